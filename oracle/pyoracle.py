@@ -1,0 +1,256 @@
+"""ctypes/numpy front-end for the CPU checkers -- TEST INFRASTRUCTURE ONLY.
+
+`oracle`  = oracle/liboracle.so      (plain-C restatement, oracle/oracle.c)
+`ref`     = oracle/_ref/libadseis_ref.so (the reference's own C++ op bodies, oracle/ref_shim.cpp), may be absent.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module; the product package
+(adseismic.jl_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_i64 = C.c_longlong
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(_i64)
+
+
+def build(quiet=True):
+    """(Re)build liboracle.so and, when /root/reference is present, _ref/libadseis_ref.so."""
+    subprocess.run(["make", "-C", _HERE], check=True, stdout=subprocess.DEVNULL if quiet else None)
+
+
+def _load(path):
+    return C.CDLL(path) if os.path.exists(path) else None
+
+
+def lib():
+    p = os.path.join(_HERE, "liboracle.so")
+    if not os.path.exists(p):
+        build()
+    return C.CDLL(p)
+
+
+def ref_lib():
+    return _load(os.path.join(_HERE, "_ref", "libadseis_ref.so"))
+
+
+def has_ref():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libadseis_ref.so"))
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    return a, a.ctypes.data_as(_ip)
+
+
+# ----------------------------------------------------------------------------------------------
+# input builders
+# ----------------------------------------------------------------------------------------------
+def ricker(nt, a, shift, amp=1.0):
+    out = np.empty(nt)
+    lib().orc_ricker(_i64(nt), C.c_double(a), C.c_double(shift), C.c_double(amp), out.ctypes.data_as(_dp))
+    return out
+
+
+def gauss(nt, dt, a, shift=None, amp=1.0):
+    if shift is None:
+        shift = 1.2 / a
+    out = np.empty(nt)
+    lib().orc_gauss(_i64(nt), C.c_double(dt), C.c_double(a), C.c_double(shift), C.c_double(amp),
+                    out.ctypes.data_as(_dp))
+    return out
+
+
+def acoustic_pml_1d(NX, NY, dx, dy, npml=12, Rcoef=1e-3, vp_ref=1000.0, use=(True, True, True, True)):
+    sx = np.empty(NX + 2)
+    ty = np.empty(NY + 2)
+    lib().orc_acoustic_pml_1d(_i64(NX), _i64(NY), C.c_double(dx), C.c_double(dy), _i64(npml), C.c_double(Rcoef),
+                              C.c_double(vp_ref), *[C.c_int(int(u)) for u in use], sx.ctypes.data_as(_dp),
+                              ty.ctypes.data_as(_dp))
+    return sx, ty
+
+
+def acoustic_pml(NX, NY, dx, dy, npml=12, Rcoef=1e-3, vp_ref=1000.0, use=(True, True, True, True)):
+    N = (NX + 2) * (NY + 2)
+    s = np.empty(N)
+    t = np.empty(N)
+    lib().orc_acoustic_pml(_i64(NX), _i64(NY), C.c_double(dx), C.c_double(dy), _i64(npml), C.c_double(Rcoef),
+                           C.c_double(vp_ref), *[C.c_int(int(u)) for u in use], s.ctypes.data_as(_dp),
+                           t.ctypes.data_as(_dp))
+    return s, t
+
+
+def elastic_cpml_1d(n, h, dt, npml=12, npower=2.0, kmax=1.0, alpha_max=2 * np.pi * 2.5, Rcoef=1e-3,
+                    vp_ref=2000.0, use_min=True, use_max=True):
+    a = np.empty(2 * n)
+    b = np.empty(2 * n)
+    lib().orc_elastic_cpml_1d(_i64(n), C.c_double(h), C.c_double(dt), _i64(npml), C.c_double(npower),
+                              C.c_double(kmax), C.c_double(alpha_max), C.c_double(Rcoef), C.c_double(vp_ref),
+                              C.c_int(int(use_min)), C.c_int(int(use_max)), a.ctypes.data_as(_dp),
+                              b.ctypes.data_as(_dp))
+    return a, b
+
+
+# ----------------------------------------------------------------------------------------------
+# acoustic
+# ----------------------------------------------------------------------------------------------
+def acoustic_step_fwd(w, wold, phi, psi, sigma, tau, c2, dt, hx, hy, NX, NY, which="oracle"):
+    N = (NX + 2) * (NY + 2)
+    u, phio, psio = np.empty(N), np.empty(N), np.empty(N)
+    args = [_d(x)[1] for x in (w, wold, phi, psi, sigma, tau, c2)] + [C.c_double(dt), C.c_double(hx), C.c_double(hy),
+                                                                   _i64(NX), _i64(NY)] + \
+           [x.ctypes.data_as(_dp) for x in (u, phio, psio)]
+    if which == "oracle":
+        lib().orc_acoustic_step_fwd(*args)
+    else:
+        ref_lib().ref_op_acoustic_step_fwd(*args)
+    return u, phio, psio
+
+
+def acoustic_step_bwd(gu, gphio, gpsio, w, sigma, tau, c2, dt, hx, hy, NX, NY, which="oracle"):
+    N = (NX + 2) * (NY + 2)
+    outs = [np.empty(N) for _ in range(5)]
+    op = [x.ctypes.data_as(_dp) for x in outs]
+    sc = [C.c_double(dt), C.c_double(hx), C.c_double(hy), _i64(NX), _i64(NY)]
+    if which == "oracle":
+        lib().orc_acoustic_step_bwd(*op, _d(gu)[1], _d(gphio)[1], _d(gpsio)[1], _d(w)[1], _d(sigma)[1],
+                                    _d(tau)[1], _d(c2)[1], *sc)
+    else:
+        z = np.zeros(N)
+        ref_lib().ref_op_acoustic_step_bwd(*op, _d(gu)[1], _d(gphio)[1], _d(gpsio)[1], _d(w)[1], _d(z)[1],
+                                           _d(z)[1], _d(z)[1], _d(sigma)[1], _d(tau)[1], _d(c2)[1], *sc)
+    return outs  # gw, gwold, gphi, gpsi, gc
+
+
+def acoustic_forward(NX, NY, NSTEP, dt, hx, hy, sigma, tau, c, srci, srcj, srcv, rcvi, rcvj, mpi_convention=False,
+                     which="oracle"):
+    """-> (u_hist[(NSTEP+1), NX+2, NY+2], rcvv[(NSTEP+1), nrcv])"""
+    N = (NX + 2) * (NY + 2)
+    srci, psi_ = _i(srci)
+    srcj, psj_ = _i(srcj)
+    rcvi, pri_ = _i(rcvi)
+    rcvj, prj_ = _i(rcvj)
+    srcv = np.ascontiguousarray(srcv, dtype=np.float64)
+    assert srcv.shape[0] >= NSTEP and srcv.shape[1] == len(srci)
+    u = np.empty((NSTEP + 1) * N)
+    rcvv = np.empty((NSTEP + 1, len(rcvi)))
+    if which == "oracle":
+        lib().orc_acoustic_forward(_i64(NX), _i64(NY), _i64(NSTEP), C.c_double(dt), C.c_double(hx), C.c_double(hy),
+                                   _d(sigma)[1], _d(tau)[1], _d(c)[1], C.c_int(int(mpi_convention)),
+                                   _i64(len(srci)), psi_, psj_, srcv.ctypes.data_as(_dp), _i64(len(rcvi)), pri_, prj_,
+                                   u.ctypes.data_as(_dp), rcvv.ctypes.data_as(_dp))
+    else:
+        assert not mpi_convention
+        ref_lib().ref_drv_acoustic_forward(_i64(NX), _i64(NY), _i64(NSTEP), C.c_double(dt), C.c_double(hx),
+                                           C.c_double(hy), _d(sigma)[1], _d(tau)[1], _d(c)[1], _i64(len(srci)), psi_,
+                                           psj_, srcv.ctypes.data_as(_dp), _i64(len(rcvi)), pri_, prj_,
+                                           u.ctypes.data_as(_dp), rcvv.ctypes.data_as(_dp))
+    return u.reshape(NSTEP + 1, NX + 2, NY + 2), rcvv
+
+
+def acoustic_misfit_grad(NX, NY, NSTEP, dt, hx, hy, sigma, tau, c, srci, srcj, rcvi, rcvj, obs, u_hist,
+                         mpi_convention=False, which="oracle"):
+    """-> (loss, grad_c[NX+2, NY+2], grad_srcv[NSTEP, nsrc])"""
+    N = (NX + 2) * (NY + 2)
+    srci, psi_ = _i(srci)
+    srcj, psj_ = _i(srcj)
+    rcvi, pri_ = _i(rcvi)
+    rcvj, prj_ = _i(rcvj)
+    loss = C.c_double(0.0)
+    gc = np.empty(N)
+    gs = np.empty((NSTEP, len(srci)))
+    obs = np.ascontiguousarray(obs, dtype=np.float64)
+    u_hist = np.ascontiguousarray(u_hist, dtype=np.float64)
+    if which == "oracle":
+        lib().orc_acoustic_misfit_grad(_i64(NX), _i64(NY), _i64(NSTEP), C.c_double(dt), C.c_double(hx),
+                                       C.c_double(hy), _d(sigma)[1], _d(tau)[1], _d(c)[1],
+                                       C.c_int(int(mpi_convention)), _i64(len(srci)), psi_, psj_, _i64(len(rcvi)),
+                                       pri_, prj_, obs.ctypes.data_as(_dp), u_hist.ctypes.data_as(_dp),
+                                       C.byref(loss), gc.ctypes.data_as(_dp), gs.ctypes.data_as(_dp))
+    else:
+        assert not mpi_convention
+        ref_lib().ref_drv_acoustic_gradient(_i64(NX), _i64(NY), _i64(NSTEP), C.c_double(dt), C.c_double(hx),
+                                            C.c_double(hy), _d(sigma)[1], _d(tau)[1], _d(c)[1], _i64(len(srci)),
+                                            psi_, psj_, _i64(len(rcvi)), pri_, prj_, obs.ctypes.data_as(_dp),
+                                            u_hist.ctypes.data_as(_dp), C.byref(loss), gc.ctypes.data_as(_dp),
+                                            gs.ctypes.data_as(_dp))
+    return loss.value, gc.reshape(NX + 2, NY + 2), gs
+
+
+def ref_mpi_acoustic_forward(NX, NY, n, NSTEP, dt, hx, hy, sigma, tau, c2g, srci, srcj, srcv, keep_history=True,
+                             nthreads=1):
+    """Block-decomposed reference loop (MPI ranks emulated by threads).  -> u[(NSTEP+1) or 3, NX, NY]"""
+    srci, psi_ = _i(srci)
+    srcj, psj_ = _i(srcj)
+    srcv = np.ascontiguousarray(srcv, dtype=np.float64)
+    nslots = NSTEP + 1 if keep_history else 3
+    u = np.zeros(nslots * NX * NY)
+    ref_lib().ref_drv_mpi_acoustic_forward(_i64(NX), _i64(NY), _i64(n), _i64(NSTEP), C.c_double(dt), C.c_double(hx),
+                                           C.c_double(hy), _d(sigma)[1], _d(tau)[1], _d(c2g)[1], _i64(len(srci)), psi_,
+                                           psj_, srcv.ctypes.data_as(_dp), u.ctypes.data_as(_dp),
+                                           C.c_int(int(keep_history)), C.c_int(nthreads))
+    return u.reshape(nslots, NX, NY)
+
+
+# ----------------------------------------------------------------------------------------------
+# elastic
+# ----------------------------------------------------------------------------------------------
+def elastic_dims(variant, NX, NY):
+    H, W = _i64(0), _i64(0)
+    lib().orc_elastic_dims(C.c_int(variant), _i64(NX), _i64(NY), C.byref(H), C.byref(W))
+    return H.value, W.value
+
+
+def elastic_forward(variant, NX, NY, NSTEP, dt, dx, dy, ax, bx, ay, by, rho, lam, mu, srci, srcj, srctype, srcv,
+                    rcvi, rcvj, rcvtype, want_hist=False):
+    """-> (rcvv[nrcv, NSTEP+1], hist[5, NSTEP+1, H, W] or None); rho/lam/mu are H x W (padded) arrays."""
+    H, W = elastic_dims(variant, NX, NY)
+    srci, p1 = _i(srci)
+    srcj, p2 = _i(srcj)
+    srctype, p3 = _i(srctype)
+    rcvi, p4 = _i(rcvi)
+    rcvj, p5 = _i(rcvj)
+    rcvtype, p6 = _i(rcvtype)
+    srcv = np.ascontiguousarray(srcv, dtype=np.float64)
+    assert srcv.shape[0] >= NSTEP and srcv.shape[1] == len(srci)
+    rcvv = np.zeros((len(rcvi), NSTEP + 1))
+    hist = np.zeros((5, NSTEP + 1, H, W)) if want_hist else None
+    lib().orc_elastic_forward(C.c_int(variant), _i64(NX), _i64(NY), _i64(NSTEP), C.c_double(dt), C.c_double(dx),
+                              C.c_double(dy), _d(ax)[1], _d(bx)[1], _d(ay)[1], _d(by)[1], _d(rho)[1], _d(lam)[1],
+                              _d(mu)[1], _i64(len(srci)), p1, p2, p3, srcv.ctypes.data_as(_dp), _i64(len(rcvi)), p4,
+                              p5, p6, rcvv.ctypes.data_as(_dp), hist.ctypes.data_as(_dp) if want_hist else None)
+    return rcvv, hist
+
+
+def elastic_misfit_grad(variant, NX, NY, NSTEP, dt, dx, dy, ax, bx, ay, by, rho, lam, mu, srci, srcj, srctype, srcv,
+                        rcvi, rcvj, rcvtype, obs):
+    """-> dict(loss, rcvv, grad_rho, grad_lam, grad_mu [H,W], grad_srcv [NSTEP,nsrc])"""
+    H, W = elastic_dims(variant, NX, NY)
+    srci, p1 = _i(srci)
+    srcj, p2 = _i(srcj)
+    srctype, p3 = _i(srctype)
+    rcvi, p4 = _i(rcvi)
+    rcvj, p5 = _i(rcvj)
+    rcvtype, p6 = _i(rcvtype)
+    srcv = np.ascontiguousarray(srcv, dtype=np.float64)
+    obs = np.ascontiguousarray(obs, dtype=np.float64)
+    loss = C.c_double(0)
+    rcvv = np.zeros((len(rcvi), NSTEP + 1))
+    gr, gl, gm = np.zeros((H, W)), np.zeros((H, W)), np.zeros((H, W))
+    gs = np.zeros((NSTEP, len(srci)))
+    lib().orc_elastic_misfit_grad(C.c_int(variant), _i64(NX), _i64(NY), _i64(NSTEP), C.c_double(dt), C.c_double(dx),
+                                  C.c_double(dy), _d(ax)[1], _d(bx)[1], _d(ay)[1], _d(by)[1], _d(rho)[1], _d(lam)[1],
+                                  _d(mu)[1], _i64(len(srci)), p1, p2, p3, srcv.ctypes.data_as(_dp), _i64(len(rcvi)),
+                                  p4, p5, p6, obs.ctypes.data_as(_dp), C.byref(loss), rcvv.ctypes.data_as(_dp),
+                                  gr.ctypes.data_as(_dp), gl.ctypes.data_as(_dp), gm.ctypes.data_as(_dp),
+                                  gs.ctypes.data_as(_dp))
+    return dict(loss=loss.value, rcvv=rcvv, grad_rho=gr, grad_lam=gl, grad_mu=gm, grad_srcv=gs)

@@ -1,0 +1,286 @@
+// oracle/ref_shim.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product library).
+//
+// Builds oracle/_ref/libadseis_ref.so from the reference's OWN numerical C++ bodies, which are
+// #included in place from /root/reference at build time (nothing is copied into this repo):
+//   deps/CustomOps/AcousticOneStepCpu/AcousticOneStepCpu.h   (AcousticOneStepCpuForward/Backward)
+//   deps/CustomOps/MPIAcousticOneStepCpu/MpiAcousticOneStep.h (MpiAcousticOneStepCpuForward/Backward)
+//   deps/CustomOps/SourceOps/AddSource.cpp                    (forwardCPU/backwardCPU)
+//   deps/CustomOps/ReceiveOps/GetReceive.cpp                  (forward/backward)
+//   deps/CustomOps/GatherOps/GatherOps.h, ScatterAddOps/ScatterAddOps.h, ScatterNdOps/ScatterNdOps.h
+// The TensorFlow #includes of the two .cpp files resolve to the empty headers in oracle/tf_stubs.
+//
+// What is mine in this file: thin extern "C" wrappers (ref_op_*) and "drivers" (ref_drv_*) that call
+// those bodies in the order the reference's Julia graph builders do (src/Core.jl:562-620 for the
+// acoustic loop, src/Core.jl:31-228 for the elastic loop, src/MPIAcoustic.jl:251-404 for the block
+// decomposed loop).  The drivers are what bench.py times as the "reference" CPU arm and what the
+// C oracle (oracle/oracle.c) is pinned against in tests/test_oracle_vs_ref.py.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef long long int64;
+namespace tensorflow {}
+
+#include "AcousticOneStepCpu/AcousticOneStepCpu.h"
+#include "MPIAcousticOneStepCpu/MpiAcousticOneStep.h"
+#include "GatherOps/GatherOps.h"
+#include "ScatterAddOps/ScatterAddOps.h"
+#include "ScatterNdOps/ScatterNdOps.h"
+namespace ref_source {
+#include "SourceOps/AddSource.cpp"
+}
+// AddSource.cpp leaves its accessor macros defined; drop them before the next body.
+#undef vx
+#undef vy
+#undef vx_
+#undef vy_
+#undef sigmaxx
+#undef sigmaxx_
+#undef sigmayy
+#undef sigmayy_
+#undef sigmaxy
+#undef sigmaxy_
+#undef g_vx
+#undef g_vy
+#undef g_vx_
+#undef g_vy_
+#undef g_sigmaxx
+#undef g_sigmaxx_
+#undef g_sigmayy
+#undef g_sigmayy_
+#undef g_sigmaxy
+#undef g_sigmaxy_
+namespace ref_receive {
+#include "ReceiveOps/GetReceive.cpp"
+}
+
+#define API extern "C" __attribute__((visibility("default")))
+
+// ------------------------------------------------------------------------------------------------
+// op-level wrappers (argument order = the reference bodies')
+// ------------------------------------------------------------------------------------------------
+API void ref_op_acoustic_step_fwd(const double* w, const double* wold, const double* phi, const double* psi,
+                                  const double* sigma, const double* tau, const double* c, double dt, double hx,
+                                  double hy, int64 NX, int64 NY, double* u, double* phiout, double* psiout) {
+  AcousticOneStepCpuForward(w, wold, phi, psi, sigma, tau, c, dt, hx, hy, NX, NY, u, phiout, psiout);
+}
+
+// Outputs are zeroed first, as AcousticOneStepCpu.cpp:363-367 does before calling the body.
+API void ref_op_acoustic_step_bwd(double* grad_w, double* grad_wold, double* grad_phi, double* grad_psi,
+                                  double* grad_c, const double* grad_u, const double* grad_phiout,
+                                  const double* grad_psiout, const double* w, const double* wold,
+                                  const double* phi, const double* psi, const double* sigma, const double* tau,
+                                  const double* c, double dt, double hx, double hy, int64 NX, int64 NY) {
+  size_t N = (size_t)(NX + 2) * (NY + 2);
+  memset(grad_w, 0, N * 8); memset(grad_wold, 0, N * 8); memset(grad_phi, 0, N * 8);
+  memset(grad_psi, 0, N * 8); memset(grad_c, 0, N * 8);
+  AcousticOneStepCpuBackward(grad_w, grad_wold, grad_phi, grad_psi, grad_c, grad_u, grad_phiout, grad_psiout,
+                             w, wold, phi, psi, sigma, tau, c, dt, hx, hy, NX, NY, nullptr, nullptr, nullptr);
+}
+
+API void ref_op_mpi_acoustic_step_fwd(const double* w, const double* wold, const double* phi, const double* psi,
+                                      const double* sigma, const double* tau, const double* c, double dt,
+                                      double hx, double hy, int64 NX, int64 NY, double* u, double* phiout,
+                                      double* psiout) {
+  MpiAcousticOneStepCpuForward(w, wold, phi, psi, sigma, tau, c, dt, hx, hy, NX, NY, u, phiout, psiout);
+}
+
+API void ref_op_add_source_fwd(double* vx_, double* vy_, double* sxx_, double* syy_, double* sxy_, const double* vx,
+                               const double* vy, const double* sxx, const double* syy, const double* sxy,
+                               const int64* srci, const int64* srcj, const double* srcv, const int64* srctype,
+                               int64 nsrc, int64 NX, int64 NY) {
+  ref_source::forwardCPU(vx_, vy_, sxx_, syy_, sxy_, vx, vy, sxx, syy, sxy, srci, srcj, srcv, srctype, nsrc, NX, NY);
+}
+
+API void ref_op_add_source_bwd(double* g_vx, double* g_vy, double* g_sxx, double* g_syy, double* g_sxy,
+                               double* grad_srcv, const double* g_vx_, const double* g_vy_, const double* g_sxx_,
+                               const double* g_syy_, const double* g_sxy_, const int64* srci, const int64* srcj,
+                               const double* srcv, const int64* srctype, int64 nsrc, int64 NX, int64 NY) {
+  ref_source::backwardCPU(g_vx, g_vy, g_sxx, g_syy, g_sxy, grad_srcv, g_vx_, g_vy_, g_sxx_, g_syy_, g_sxy_, srci,
+                          srcj, srcv, srctype, nsrc, NX, NY);
+}
+
+API void ref_op_get_receive_fwd(double* out, const double* vx, const double* vy, const double* sxx,
+                                const double* syy, const double* sxy, int64 nt, const int64* rcvi,
+                                const int64* rcvj, const int64* rcvtype, int64 nrcv, int64 NX, int64 NY) {
+  ref_receive::forward(out, vx, vy, sxx, syy, sxy, nt, rcvi, rcvj, rcvtype, nrcv, NX, NY);
+}
+
+API void ref_op_get_receive_bwd(double* d_vx, double* d_vy, double* d_sxx, double* d_syy, double* d_sxy,
+                                const double* d_out, int64 nt, const int64* rcvi, const int64* rcvj,
+                                const int64* rcvtype, int64 nrcv, int64 NX, int64 NY) {
+  ref_receive::backward(d_vx, d_vy, d_sxx, d_syy, d_sxy, d_out, nt, rcvi, rcvj, rcvtype, nrcv, NX, NY);
+}
+
+API void ref_op_gather_fwd(double* out, const double* v, const int64* ii, int n) { GatherOps_forward(out, v, ii, n); }
+API void ref_op_scatter_add_fwd(double* out, const double* ipt, const int64* ii, const double* upd, int d, int n) {
+  ScatterAddOps_forward(out, ipt, ii, upd, d, n);
+}
+API void ref_op_scatter_nd_fwd(double* out, const int64* ii, const double* upd, int n, int m) {
+  memset(out, 0, sizeof(double) * (size_t)m);  // ScatterNdOps.cpp:92 zero-fills before the body
+  ScatterNdOps_forward(out, ii, upd, n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Driver: single-process acoustic loop, PropagatorKernel=1 on CPU  (src/Core.jl:562-620, 726-730)
+// 0-based slots: u[0]=u[1]=0; s=2..NSTEP: step, then u[s][src] += srcv0[s-1]*dt^2
+// ------------------------------------------------------------------------------------------------
+API void ref_drv_acoustic_forward(int64 NX, int64 NY, int64 NSTEP, double dt, double hx, double hy,
+                                  const double* sigma, const double* tau, const double* c /* velocity */,
+                                  int64 nsrc, const int64* srci, const int64* srcj, const double* srcv,
+                                  int64 nrcv, const int64* rcvi, const int64* rcvj,
+                                  double* u /* (NSTEP+1)*N */, double* rcvv /* (NSTEP+1)*nrcv or NULL */) {
+  const int64 N = (NX + 2) * (NY + 2);
+  std::vector<double> c2(N), phi(N, 0.0), psi(N, 0.0), phin(N), psin(N), ut(N), upd(nsrc > 0 ? nsrc : 1);
+  std::vector<int64> sidx(nsrc > 0 ? nsrc : 1);
+  for (int64 k = 0; k < N; k++) c2[k] = c[k] * c[k];                       // Core.jl:564
+  for (int64 k = 0; k < nsrc; k++) sidx[k] = (srci[k] - 1) * (NY + 2) + srcj[k];  // Core.jl:600 (1-based)
+  memset(u, 0, sizeof(double) * 2 * N);                                     // Core.jl:607-612
+  for (int64 s = 2; s <= NSTEP; s++) {
+    AcousticOneStepCpuForward(u + (s - 1) * N, u + (s - 2) * N, phi.data(), psi.data(), sigma, tau, c2.data(), dt,
+                              hx, hy, NX, NY, ut.data(), phin.data(), psin.data());
+    for (int64 k = 0; k < nsrc; k++) upd[k] = srcv[(s - 1) * nsrc + k] * (dt * dt);  // Core.jl:601
+    ScatterAddOps_forward(u + s * N, ut.data(), sidx.data(), upd.data(), (int)N, (int)nsrc);
+    phi.swap(phin);
+    psi.swap(psin);
+  }
+  if (rcvv)
+    for (int64 s = 0; s <= NSTEP; s++)
+      for (int64 r = 0; r < nrcv; r++)                                       // Core.jl:727-728
+        rcvv[s * nrcv + r] = u[s * N + (rcvi[r] - 1) * (NY + 2) + rcvj[r] - 1];
+}
+
+// loss = sum (rcvv-obs)^2 (src/Utils.jl:308) and its gradient w.r.t. c (velocity) and srcv, by composing the
+// reference backward bodies in reverse graph order.  u must hold the forward history.
+API void ref_drv_acoustic_gradient(int64 NX, int64 NY, int64 NSTEP, double dt, double hx, double hy,
+                                   const double* sigma, const double* tau, const double* c, int64 nsrc,
+                                   const int64* srci, const int64* srcj, int64 nrcv, const int64* rcvi,
+                                   const int64* rcvj, const double* obs, const double* u, double* loss_out,
+                                   double* grad_c /* N */, double* grad_srcv /* NSTEP*nsrc or NULL */) {
+  const int64 N = (NX + 2) * (NY + 2);
+  std::vector<double> c2(N), G(N, 0.0), gphi(N, 0.0), gpsi(N, 0.0);
+  std::vector<double> gw(N), gwold(N), gphi_in(N), gpsi_in(N), gc(N);
+  std::vector<double> ub[3] = {std::vector<double>(N), std::vector<double>(N), std::vector<double>(N)};
+  for (int64 k = 0; k < N; k++) c2[k] = c[k] * c[k];
+  double loss = 0.0;
+  for (int64 s = 0; s <= NSTEP; s++)
+    for (int64 r = 0; r < nrcv; r++) {
+      double d = u[s * N + (rcvi[r] - 1) * (NY + 2) + rcvj[r] - 1] - obs[s * nrcv + r];
+      loss += d * d;
+    }
+  *loss_out = loss;
+  auto seed = [&](std::vector<double>& b, int64 s) {  // d loss / d u[s] through the receiver gather
+    std::fill(b.begin(), b.end(), 0.0);
+    for (int64 r = 0; r < nrcv; r++) {
+      int64 id = (rcvi[r] - 1) * (NY + 2) + rcvj[r] - 1;
+      b[id] += 2.0 * (u[s * N + id] - obs[s * nrcv + r]);
+    }
+  };
+  if (grad_srcv) memset(grad_srcv, 0, sizeof(double) * NSTEP * nsrc);
+  seed(ub[NSTEP % 3], NSTEP);
+  if (NSTEP >= 1) seed(ub[(NSTEP - 1) % 3], NSTEP - 1);
+  for (int64 s = NSTEP; s >= 2; s--) {
+    std::vector<double>& gu = ub[s % 3];
+    seed(ub[(s - 2) % 3], s - 2);
+    // ScatterAddOps_backward: grad_ipt = grad_out (pass-through), grad_update[k] = grad_out[ii[k]-1]
+    if (grad_srcv)
+      for (int64 k = 0; k < nsrc; k++)
+        grad_srcv[(s - 1) * nsrc + k] = gu[(srci[k] - 1) * (NY + 2) + srcj[k] - 1] * (dt * dt);
+    std::fill(gw.begin(), gw.end(), 0.0); std::fill(gwold.begin(), gwold.end(), 0.0);
+    std::fill(gphi_in.begin(), gphi_in.end(), 0.0); std::fill(gpsi_in.begin(), gpsi_in.end(), 0.0);
+    std::fill(gc.begin(), gc.end(), 0.0);
+    AcousticOneStepCpuBackward(gw.data(), gwold.data(), gphi_in.data(), gpsi_in.data(), gc.data(), gu.data(),
+                               gphi.data(), gpsi.data(), u + (s - 1) * N, u + (s - 2) * N, nullptr, nullptr, sigma,
+                               tau, c2.data(), dt, hx, hy, NX, NY, nullptr, nullptr, nullptr);
+    std::vector<double>& g1 = ub[(s - 1) % 3];
+    std::vector<double>& g2 = ub[(s - 2) % 3];
+    for (int64 k = 0; k < N; k++) { g1[k] += gw[k]; g2[k] += gwold[k]; G[k] += gc[k]; }
+    gphi.swap(gphi_in);
+    gpsi.swap(gpsi_in);
+  }
+  for (int64 k = 0; k < N; k++) grad_c[k] = 2.0 * c[k] * G[k];  // d(c^2)/dc, Core.jl:564
+}
+
+// ------------------------------------------------------------------------------------------------
+// Driver: block-decomposed acoustic loop, PropagatorKernel=1 (src/MPIAcoustic.jl:251-294, 334-404) with the
+// MPI ranks emulated by OpenMP threads (one block each) and mpi_halo_exchange by in-memory copies with a zero
+// fill at physical edges.  Global grid NX x NY (unpadded), blocks n x n, M=NX/n, N=NY/n.  c2g is c^2 (the MPI
+// solver does not square, MPIAcoustic.jl:336), global unpadded NX*NY.  sigma/tau are GLOBAL (NX+2)*(NY+2)
+// profiles (MPIAcoustic.jl:177-185 evaluates the same pml_helper at global coordinates).
+// Output ug: (NSTEP+1) * NX*NY global unpadded history (or only the last 3 slots if keep_history==0).
+// ------------------------------------------------------------------------------------------------
+API void ref_drv_mpi_acoustic_forward(int64 NX, int64 NY, int64 n, int64 NSTEP, double dt, double hx, double hy,
+                                      const double* sigma, const double* tau, const double* c2g, int64 nsrc,
+                                      const int64* srci, const int64* srcj, const double* srcv,
+                                      double* ug, int keep_history, int nthreads) {
+  const int64 M = NX / n, Nb = NY / n, P = (n + 2) * (n + 2), B = M * Nb;
+  const int64 NG = NX * NY;
+  // per-block state (unpadded n*n): u at slot s-1, s-2; phi, psi
+  std::vector<std::vector<double>> w(B), wold(B), phi(B), psi(B), un(B), phin(B), psin(B), cb(B), sg(B), tg(B);
+  for (int64 b = 0; b < B; b++) {
+    int64 I = b / Nb, J = b % Nb;
+    w[b].assign(n * n, 0.0); wold[b].assign(n * n, 0.0); phi[b].assign(n * n, 0.0); psi[b].assign(n * n, 0.0);
+    un[b].resize(n * n); phin[b].resize(n * n); psin[b].resize(n * n); cb[b].resize(n * n);
+    sg[b].resize(P); tg[b].resize(P);
+    for (int64 i = 0; i < n; i++)
+      for (int64 j = 0; j < n; j++) cb[b][i * n + j] = c2g[(I * n + i) * NY + J * n + j];
+    for (int64 i = 0; i < n + 2; i++)
+      for (int64 j = 0; j < n + 2; j++) {
+        sg[b][i * (n + 2) + j] = sigma[(I * n + i) * (NY + 2) + J * n + j];
+        tg[b][i * (n + 2) + j] = tau[(I * n + i) * (NY + 2) + J * n + j];
+      }
+  }
+  auto halo = [&](const std::vector<std::vector<double>>& f, int64 b, double* out) {  // n*n -> (n+2)^2
+    int64 I = b / Nb, J = b % Nb;
+    memset(out, 0, sizeof(double) * P);
+    for (int64 i = 0; i < n; i++) memcpy(out + (i + 1) * (n + 2) + 1, f[b].data() + i * n, sizeof(double) * n);
+    if (I > 0) memcpy(out + 1, f[b - Nb].data() + (n - 1) * n, sizeof(double) * n);
+    if (I < M - 1) memcpy(out + (n + 1) * (n + 2) + 1, f[b + Nb].data(), sizeof(double) * n);
+    if (J > 0) for (int64 i = 0; i < n; i++) out[(i + 1) * (n + 2)] = f[b - 1][i * n + n - 1];
+    if (J < Nb - 1) for (int64 i = 0; i < n; i++) out[(i + 1) * (n + 2) + n + 1] = f[b + 1][i * n];
+  };
+  auto store = [&](int64 s) {
+    double* dst = ug + (keep_history ? s : (s % 3)) * NG;
+    for (int64 b = 0; b < B; b++) {
+      int64 I = b / Nb, J = b % Nb;
+      for (int64 i = 0; i < n; i++) memcpy(dst + (I * n + i) * NY + J * n, w[b].data() + i * n, sizeof(double) * n);
+    }
+  };
+  memset(ug, 0, sizeof(double) * NG * (keep_history ? 2 : 3));
+  if (nthreads < 1) nthreads = 1;
+  std::vector<std::vector<double>> pw(B), pwold(B), pphi(B), ppsi(B);
+  for (int64 b = 0; b < B; b++) { pw[b].resize(P); pwold[b].resize(P); pphi[b].resize(P); ppsi[b].resize(P); }
+  for (int64 s = 2; s <= NSTEP; s++) {
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (int64 b = 0; b < B; b++) {  // 4 halo exchanges (MPIAcoustic.jl:260-263)
+      halo(w, b, pw[b].data()); halo(wold, b, pwold[b].data());
+      halo(phi, b, pphi[b].data()); halo(psi, b, ppsi[b].data());
+    }
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (int64 b = 0; b < B; b++) {
+      int64 I = b / Nb, J = b % Nb;
+      MpiAcousticOneStepCpuForward(pw[b].data(), pwold[b].data(), pphi[b].data(), ppsi[b].data(), sg[b].data(),
+                                   tg[b].data(), cb[b].data(), dt, hx, hy, n, n, un[b].data(), phin[b].data(),
+                                   psin[b].data());
+      for (int64 k = 0; k < nsrc; k++) {  // MPIAcoustic.jl:71-78, 377-381 (global 1-based src index)
+        int64 li = srci[k] - I * n, lj = srcj[k] - J * n;
+        if (li >= 1 && li <= n && lj >= 1 && lj <= n) un[b][(li - 1) * n + lj - 1] += srcv[(s - 1) * nsrc + k] * (dt * dt);
+      }
+    }
+    for (int64 b = 0; b < B; b++) { wold[b].swap(w[b]); w[b].swap(un[b]); phi[b].swap(phin[b]); psi[b].swap(psin[b]); }
+    store(s);
+  }
+}
+
+API int ref_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
