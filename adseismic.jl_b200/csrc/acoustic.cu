@@ -1,0 +1,669 @@
+// acoustic.cu -- acoustic plan: device state, time loops (forward, checkpointed reverse sweep), C ABI.
+// Reference behaviour restated: src/Core.jl:562-620 (loop), :622-655 (PML), :726-730 (receivers),
+// src/Utils.jl:308 (misfit), src/MPIAcoustic.jl:334-431 (MPI-convention inputs); adjoint = SURVEY Appendix A.
+#include <math.h>
+
+#include "acoustic_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------------------
+// small utility kernels
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_square(double* __restrict__ dst, const double* __restrict__ src, i64 n) {
+  i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) dst[k] = src[k] * src[k];
+}
+
+// res = 2 (rcvv - obs) for the receivers in `mask` (owned), 0 elsewhere; loss = sum (rcvv-obs)^2 (owned only).
+// One CTA, fixed summation order -> deterministic.
+__global__ void k_residual_loss(const double* __restrict__ rcvv, const double* __restrict__ obs,
+                                const unsigned char* __restrict__ owned, int ncol, int col_is_fast, i64 n,
+                                double* __restrict__ res, double* __restrict__ loss) {
+  __shared__ double sh[1024];
+  double acc = 0.0;
+  for (i64 k = threadIdx.x; k < n; k += blockDim.x) {
+    const int r = col_is_fast ? (int)(k % ncol) : (int)(k / (n / ncol));
+    double d = 0.0;
+    if (owned[r]) d = rcvv[k] - obs[k];
+    res[k] = 2.0 * d;
+    acc += d * d;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = sh[0];
+}
+
+// whole-array point injection / sampling (used once per sweep for the last slot)
+__global__ void k_points_inject(double* __restrict__ field, PointSetDev ps, const double* __restrict__ val,
+                                double scale) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < ps.nu) {
+    const int cell = ps.cell[k];
+    double v = field[cell];
+    for (int m = ps.start[k]; m < ps.start[k + 1]; m++) v += val[ps.perm[m]] * scale;
+    field[cell] = v;
+  }
+}
+__global__ void k_points_sample(const double* __restrict__ field, PointSetDev ps, double* __restrict__ out,
+                                double scale) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < ps.nu) {
+    const double v = field[ps.cell[k]] * scale;
+    for (int m = ps.start[k]; m < ps.start[k + 1]; m++) out[ps.perm[m]] = v;
+  }
+}
+
+// grad wrt the caller's model array from the accumulated d loss / d c^2 (pitched local rows)
+//   mpi_convention=0: out[(gi)*(W)+j] = 2*c*G   (chain rule of Core.jl:564)     (dense padded)
+//   mpi_convention=1: out[(gi-1)*NY + j-1] = G                                   (dense unpadded)
+__global__ void k_grad_finalize(const double* __restrict__ G, const double* __restrict__ cvel, int ld, int goff,
+                                int l0, int l1, int H, int W, int mpi, double* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int li = l0 + blockIdx.y;
+  if (li >= l1 || j >= W) return;
+  const int gi = goff + li;
+  const i64 IJ = (i64)li * ld + j;
+  if (!mpi) {
+    out[(i64)gi * W + j] = 2.0 * cvel[IJ] * G[IJ];
+  } else if (gi >= 1 && gi <= H - 2 && j >= 1 && j <= W - 2) {
+    out[(i64)(gi - 1) * (W - 2) + (j - 1)] = G[IJ];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------------------
+struct adseis_acoustic_plan {
+  adseis_ctx* ctx;
+  adseis_acoustic_params p;
+  adseis_slab slab;
+  AcGeom g;
+  int own0, own1;  // owned local rows [own0, own1)
+  i64 model_elems; // elements of the caller's model array
+  // static fields (pitched, local rows)
+  double *c2 = nullptr, *cvel = nullptr, *sigx = nullptr, *tauy = nullptr;
+  double *phi[2] = {nullptr, nullptr}, *psi[2] = {nullptr, nullptr};
+  // history window + checkpoints
+  double* hist = nullptr;
+  i64 win = 0;  // window capacity in slots
+  std::vector<i64> seg_b, seg_e;
+  std::vector<double*> ckpt;  // per segment (index k>=1): 4 planes
+  i64 win_base = -1, win_last = -1;  // slots currently valid in the window: [win_base, win_last]
+  // points
+  i64 nsrc = 0, nrcv = 0;
+  PointSetStorage src, rcv;
+  unsigned char* rcv_owned = nullptr;
+  double *srcv = nullptr, *rcvv = nullptr, *obs = nullptr, *res = nullptr, *loss = nullptr;
+  i64 srcv_rows = 0;
+  // adjoint state
+  double *ub[3] = {nullptr, nullptr, nullptr}, *phib[2] = {nullptr, nullptr}, *psib[2] = {nullptr, nullptr};
+  double *G = nullptr, *gradc = nullptr, *gradsrcv = nullptr;
+  bool have_model = false, have_srcv = false, have_obs = false, have_grad = false, have_fwd = false;
+  // stats
+  i64 last_launches = 0, last_segments = 0, last_recomputed = 0;
+};
+
+static inline double* win_slot(adseis_acoustic_plan* P, i64 base, i64 s) { return P->hist + (s - base) * P->g.plane; }
+
+#define LAUNCH_CHECK(P)                   \
+  do {                                    \
+    (P)->ctx->launches++;                 \
+    (P)->last_launches++;                 \
+    CUDA_TRY(cudaGetLastError());         \
+  } while (0)
+
+static int plan_segments(adseis_acoustic_plan* P, size_t budget_bytes, bool count_checkpoints) {
+  // The wavefield history window holds `win` snapshots.  If NSTEP+1 snapshots fit, the whole history is kept;
+  // otherwise the reverse sweep proceeds segment by segment (win-2 steps each) from checkpoints of 4 planes.
+  // count_checkpoints: the checkpoints must also fit into budget_bytes (auto mode); else only the window does.
+  const i64 NSTEP = P->p.NSTEP;
+  const size_t plane_bytes = (size_t)P->g.plane * sizeof(double);
+  i64 slots = (i64)(budget_bytes / plane_bytes);
+  if (slots >= NSTEP + 1) {
+    P->win = NSTEP + 1;
+  } else {
+    i64 best = -1;
+    for (i64 W = slots; W >= 4; W--) {
+      i64 nseg = (NSTEP - 1 + (W - 2) - 1) / (W - 2);
+      if (!count_checkpoints || W + 4 * (nseg - 1) <= slots) { best = W; break; }
+    }
+    if (best < 0) {
+      adseis_set_error("acoustic plan: a history budget of %zu bytes (%lld snapshots of %zu bytes) is too small",
+                       budget_bytes, (long long)slots, plane_bytes);
+      return ADSEIS_ENOMEM;
+    }
+    P->win = best;
+  }
+  P->seg_b.clear(); P->seg_e.clear();
+  i64 b = 0;
+  while (true) {
+    i64 e = std::min(b + P->win - 1, NSTEP);
+    P->seg_b.push_back(b); P->seg_e.push_back(e);
+    if (e >= NSTEP) break;
+    b = e - 1;
+  }
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_acoustic_plan_destroy(adseis_acoustic_plan* P) {
+  if (!P) return ADSEIS_OK;
+  cudaSetDevice(P->ctx->device);
+  cudaStreamSynchronize(P->ctx->stream);
+  cudaFree(P->c2); cudaFree(P->cvel); cudaFree(P->sigx); cudaFree(P->tauy);
+  for (int k = 0; k < 2; k++) { cudaFree(P->phi[k]); cudaFree(P->psi[k]); cudaFree(P->phib[k]); cudaFree(P->psib[k]); }
+  for (int k = 0; k < 3; k++) cudaFree(P->ub[k]);
+  cudaFree(P->hist);
+  for (double* c : P->ckpt) cudaFree(c);
+  free_point_set(&P->src); free_point_set(&P->rcv);
+  cudaFree(P->rcv_owned);
+  cudaFree(P->srcv); cudaFree(P->rcvv); cudaFree(P->obs); cudaFree(P->res); cudaFree(P->loss);
+  cudaFree(P->G); cudaFree(P->gradc); cudaFree(P->gradsrcv);
+  delete P;
+  return ADSEIS_OK;
+}
+
+static int validate_params(const adseis_acoustic_params* p) {
+  REQUIRE(p, "acoustic: null params");
+  REQUIRE(p->NX >= 3 && p->NY >= 3 && p->NSTEP >= 2, "acoustic: need NX,NY >= 3 and NSTEP >= 2 (got %lld,%lld,%lld)",
+          (long long)p->NX, (long long)p->NY, (long long)p->NSTEP);
+  REQUIRE((p->NX + 2) * (p->NY + 18) < 2147483647LL, "acoustic: grid too large for 32-bit cell offsets");
+  REQUIRE(p->DELTAX > 0 && p->DELTAY > 0 && p->DELTAT > 0, "acoustic: DELTAX/DELTAY/DELTAT must be > 0");
+  REQUIRE(p->NPOINTS_PML >= 1 && p->Rcoef > 0 && p->vp_ref > 0, "acoustic: bad PML parameters");
+  REQUIRE(p->PropagatorKernel == 1,
+          "acoustic: PropagatorKernel=%d not supported; this library implements the custom-op scheme (1)",
+          p->PropagatorKernel);
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acoustic_params* p, const adseis_slab* slab,
+                                           int64_t nsrc, const int64_t* srci, const int64_t* srcj, int64_t nrcv,
+                                           const int64_t* rcvi, const int64_t* rcvj, size_t hist_bytes_budget,
+                                           adseis_acoustic_plan** out) {
+  REQUIRE(ctx && out, "acoustic_plan_create: null ctx/out");
+  *out = nullptr;
+  TRY(validate_params(p));
+  REQUIRE(nsrc >= 0 && nrcv >= 0 && (nsrc == 0 || (srci && srcj)) && (nrcv == 0 || (rcvi && rcvj)),
+          "acoustic_plan_create: bad source/receiver arrays");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  adseis_acoustic_plan* P = new adseis_acoustic_plan();
+  P->ctx = ctx;
+  P->p = *p;
+  const int H = (int)p->NX + 2, W = (int)p->NY + 2;
+  if (slab) P->slab = *slab; else { P->slab.rank = 0; P->slab.nranks = 1; P->slab.row0 = 0; P->slab.row1 = H; }
+  const adseis_slab& sl = P->slab;
+  if (!(sl.nranks >= 1 && sl.rank >= 0 && sl.rank < sl.nranks && sl.row0 >= 0 && sl.row1 <= H && sl.row0 < sl.row1 &&
+        (sl.rank > 0 || sl.row0 == 0) && (sl.rank < sl.nranks - 1 || sl.row1 == H))) {
+    delete P;
+    adseis_set_error("acoustic_plan_create: inconsistent slab {rank %d/%d rows [%lld,%lld)}", sl.rank, sl.nranks,
+                     (long long)sl.row0, (long long)sl.row1);
+    return ADSEIS_EINVAL;
+  }
+  const int halo_lo = sl.rank > 0 ? 1 : 0, halo_hi = sl.rank < sl.nranks - 1 ? 1 : 0;
+  AcGeom& g = P->g;
+  g.H = H; g.W = W;
+  g.goff = (int)sl.row0 - halo_lo;
+  g.Hl = (int)(sl.row1 - sl.row0) + halo_lo + halo_hi;
+  g.ld = round_up(W, 16);
+  g.plane = (i64)g.Hl * g.ld;
+  P->own0 = halo_lo;
+  P->own1 = halo_lo + (int)(sl.row1 - sl.row0);
+  const double dt = p->DELTAT, hx = p->DELTAX, hy = p->DELTAY;
+  g.dt = dt; g.hx = hx; g.hy = hy;
+  g.kx2 = 2 * dt * dt / hx / hx; g.ky2 = 2 * dt * dt / hy / hy;
+  g.rx = dt / hx; g.ry = dt / hy;
+  g.px = dt * dt / (2.0 * hx); g.py = dt * dt / (2.0 * hy);
+  g.dt2 = dt * dt;
+  P->model_elems = p->mpi_convention ? p->NX * p->NY : (i64)H * W;
+
+  // PML profiles and the PML-free box
+  std::vector<double> sx(H), ty(W);
+  int rc = adseis_acoustic_pml_profiles(p, sx.data(), ty.data());
+  if (rc) { delete P; return rc; }
+  auto box = [](const std::vector<double>& v, int n, int* a, int* b) {  // maximal zero run inside 1..n
+    int lo = 1;
+    while (lo <= n && v[lo] != 0.0) lo++;
+    int hi = n;
+    while (hi >= 1 && v[hi] != 0.0) hi--;
+    for (int k = lo; k <= hi; k++)
+      if (v[k] != 0.0) { lo = 1; hi = 0; break; }  // not a single box: no fast region
+    *a = lo; *b = hi;
+  };
+  int ia, ib, ja, jb;
+  box(sx, (int)p->NX, &ia, &ib);
+  box(ty, (int)p->NY, &ja, &jb);
+  g.fi0 = ia + 1; g.fi1 = ib - 1; g.fj0 = ja + 1; g.fj1 = jb - 1;
+  if (g.fj0 > g.fj1) { g.fi0 = 1; g.fi1 = 0; }
+
+#define PTRY(expr)                                   \
+  do {                                               \
+    int _r = (expr);                                 \
+    if (_r != ADSEIS_OK) {                           \
+      adseis_acoustic_plan_destroy(P);               \
+      return _r;                                     \
+    }                                                \
+  } while (0)
+  PTRY(dev_upload(&P->sigx, sx, st));
+  PTRY(dev_upload(&P->tauy, ty, st));
+  PTRY(dev_alloc_zero(&P->c2, (size_t)g.plane, st));
+  PTRY(dev_alloc_zero(&P->cvel, (size_t)g.plane, st));
+  for (int k = 0; k < 2; k++) {
+    PTRY(dev_alloc_zero(&P->phi[k], (size_t)g.plane, st));
+    PTRY(dev_alloc_zero(&P->psi[k], (size_t)g.plane, st));
+  }
+
+  // sources / receivers: keep the points whose padded row is owned (MPIAcoustic.jl:71-78, 98-104)
+  P->nsrc = nsrc; P->nrcv = nrcv;
+  const int ioff = p->mpi_convention ? 0 : -1;  // 1-based padded -> 0-based padded ; 1-based unpadded -> padded
+  auto build = [&](i64 n, const int64_t* pi, const int64_t* pj, PointSetStorage* dst, std::vector<unsigned char>* owned,
+                   const char* what) -> int {
+    std::vector<int> rows, cols, gid, none;
+    if (owned) owned->assign((size_t)n, 0);
+    for (i64 k = 0; k < n; k++) {
+      i64 gi = pi[k] + ioff, gj = pj[k] + ioff;
+      REQUIRE(gi >= 0 && gi < H && gj >= 0 && gj < W, "acoustic_plan_create: %s %lld at (%lld,%lld) is outside the grid",
+              what, (long long)k, (long long)pi[k], (long long)pj[k]);
+      if (gi >= sl.row0 && gi < sl.row1) {
+        rows.push_back((int)(gi - g.goff)); cols.push_back((int)gj); gid.push_back((int)k);
+        if (owned) (*owned)[k] = 1;
+      }
+    }
+    PointSetHost h;
+    build_point_set(rows, cols, gid, none, g.ld, g.plane, AC_TILE_COLS, &h);
+    return upload_point_set(h, dst, st);
+  };
+  std::vector<unsigned char> owned;
+  PTRY(build(nsrc, srci, srcj, &P->src, nullptr, "source"));
+  PTRY(build(nrcv, rcvi, rcvj, &P->rcv, &owned, "receiver"));
+  PTRY(dev_upload(&P->rcv_owned, owned, st));
+  PTRY(dev_alloc_zero(&P->rcvv, (size_t)((p->NSTEP + 1) * nrcv), st));
+  PTRY(dev_alloc_zero(&P->loss, 1, st));
+
+  // adjoint state is allocated lazily (first gradient); history sizing now
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  const size_t plane_bytes = (size_t)g.plane * sizeof(double);
+  // reserve: adjoint state (3 ubar + 2 phib + 2 psib + G + gradc) + slack
+  const size_t reserve = 10 * plane_bytes + (size_t)(2 * (p->NSTEP + 1) * nrcv + 2 * p->NSTEP * nsrc) * 8 + (512u << 20);
+  size_t budget = hist_bytes_budget;
+  if (budget == 0) budget = free_b > reserve ? free_b - reserve : 0;
+  if (budget > free_b) budget = free_b;
+  PTRY(plan_segments(P, budget, hist_bytes_budget == 0));
+  {
+    cudaError_t e = cudaMalloc((void**)&P->hist, (size_t)P->win * plane_bytes);
+    if (e != cudaSuccess) {
+      adseis_set_error("acoustic_plan_create: cannot allocate %lld history snapshots of %zu bytes: %s",
+                       (long long)P->win, plane_bytes, cudaGetErrorString(e));
+      adseis_acoustic_plan_destroy(P);
+      return ADSEIS_ENOMEM;
+    }
+  }
+  for (size_t k = 1; k < P->seg_b.size(); k++) {
+    double* c = nullptr;
+    PTRY(dev_alloc(&c, (size_t)4 * g.plane));
+    P->ckpt.push_back(c);
+  }
+  *out = P;
+  return ADSEIS_OK;
+}
+
+// copy the caller's dense model into a pitched local array (rows of this slab, halo rows included)
+static int load_model_plane(adseis_acoustic_plan* P, const double* src, double* dst) {
+  const AcGeom& g = P->g;
+  cudaStream_t st = P->ctx->stream;
+  CUDA_TRY(cudaMemsetAsync(dst, 0, (size_t)g.plane * 8, st));
+  if (!P->p.mpi_convention) {
+    // local row li <-> global padded row goff+li ; all W columns
+    int l0 = std::max(0, -g.goff), l1 = std::min(g.Hl, g.H - g.goff);
+    CUDA_TRY(cudaMemcpy2DAsync(dst + (i64)l0 * g.ld, (size_t)g.ld * 8, src + (i64)(g.goff + l0) * g.W, (size_t)g.W * 8,
+                               (size_t)g.W * 8, (size_t)(l1 - l0), cudaMemcpyDefault, st));
+  } else {
+    const int NY = g.W - 2;
+    int l0 = std::max(0, 1 - g.goff), l1 = std::min(g.Hl, g.H - 1 - g.goff);  // global rows 1..NX
+    if (l1 > l0)
+      CUDA_TRY(cudaMemcpy2DAsync(dst + (i64)l0 * g.ld + 1, (size_t)g.ld * 8, src + (i64)(g.goff + l0 - 1) * NY,
+                                 (size_t)NY * 8, (size_t)NY * 8, (size_t)(l1 - l0), cudaMemcpyDefault, st));
+  }
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_acoustic_plan_set_model(adseis_acoustic_plan* P, const double* c, int on_device) {
+  (void)on_device;
+  REQUIRE(P && c, "acoustic_plan_set_model: null");
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  if (!P->p.mpi_convention) {
+    TRY(load_model_plane(P, c, P->cvel));
+    const i64 n = P->g.plane;
+    k_square<<<(unsigned)((n + 255) / 256), 256, 0, P->ctx->stream>>>(P->c2, P->cvel, n);  // Core.jl:564
+    P->ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+  } else {
+    TRY(load_model_plane(P, c, P->c2));  // MPIAcoustic.jl:336: no squaring
+  }
+  P->have_model = true;
+  P->have_fwd = P->have_grad = false;
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_acoustic_plan_set_srcv(adseis_acoustic_plan* P, const double* srcv, int64_t rows, int on_device) {
+  (void)on_device;
+  REQUIRE(P && (srcv || P->nsrc == 0), "acoustic_plan_set_srcv: null");
+  REQUIRE(rows >= P->p.NSTEP, "acoustic_plan_set_srcv: srcv has %lld rows, need >= NSTEP=%lld", (long long)rows,
+          (long long)P->p.NSTEP);
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  if (P->srcv_rows != P->p.NSTEP || !P->srcv) {
+    cudaFree(P->srcv);
+    P->srcv = nullptr;
+    TRY(dev_alloc(&P->srcv, (size_t)(P->p.NSTEP * P->nsrc)));
+    P->srcv_rows = P->p.NSTEP;
+  }
+  if (P->nsrc > 0)
+    CUDA_TRY(cudaMemcpyAsync(P->srcv, srcv, (size_t)(P->p.NSTEP * P->nsrc) * 8, cudaMemcpyDefault, P->ctx->stream));
+  P->have_srcv = true;
+  P->have_fwd = P->have_grad = false;
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_acoustic_plan_set_obs(adseis_acoustic_plan* P, const double* obs, int on_device) {
+  (void)on_device;
+  REQUIRE(P && (obs || P->nrcv == 0), "acoustic_plan_set_obs: null");
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  const size_t n = (size_t)((P->p.NSTEP + 1) * P->nrcv);
+  if (!P->obs) {
+    TRY(dev_alloc(&P->obs, n));
+    TRY(dev_alloc(&P->res, n));
+  }
+  if (n > 0) CUDA_TRY(cudaMemcpyAsync(P->obs, obs, n * 8, cudaMemcpyDefault, P->ctx->stream));
+  P->have_obs = true;
+  P->have_grad = false;
+  return ADSEIS_OK;
+}
+
+// ---- forward steps s_first..s_last of segment k into the window (slot s at index s - base) -----------------
+static int run_forward_steps(adseis_acoustic_plan* P, i64 base, i64 s_first, i64 s_last, bool sample) {
+  const AcGeom& g = P->g;
+  cudaStream_t st = P->ctx->stream;
+  dim3 grid((unsigned)((g.ld + AC_TILE_COLS - 1) / AC_TILE_COLS), (unsigned)((P->own1 - P->own0 + AC_RB - 1) / AC_RB));
+  PointSetDev none{};
+  for (i64 s = s_first; s <= s_last; s++) {
+    ac_fwd_kernel<<<grid, AC_THREADS, 0, st>>>(
+        g, P->own0, P->own1, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, P->phi[(s - 1) & 1],
+        P->psi[(s - 1) & 1], P->sigx, P->tauy, win_slot(P, base, s), P->phi[s & 1], P->psi[s & 1], P->src.dev,
+        P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, sample ? P->rcv.dev : none,
+        (sample && P->nrcv > 0) ? P->rcvv + s * P->nrcv : nullptr);
+    LAUNCH_CHECK(P);
+  }
+  return ADSEIS_OK;
+}
+
+typedef int (*segment_cb)(adseis_acoustic_plan* P, size_t k, void* user);
+
+// Full forward sweep, segment by segment.  After segment k finishes (slots seg_b[k]..seg_e[k] in the window)
+// `cb` is invoked (may be null).  Saves the start state of every later segment when save_ckpt.
+static int forward_sweep(adseis_acoustic_plan* P, bool save_ckpt, segment_cb cb, void* user) {
+  const AcGeom& g = P->g;
+  cudaStream_t st = P->ctx->stream;
+  const size_t pb = (size_t)g.plane * 8;
+  for (int k = 0; k < 2; k++) {
+    CUDA_TRY(cudaMemsetAsync(P->phi[k], 0, pb, st));
+    CUDA_TRY(cudaMemsetAsync(P->psi[k], 0, pb, st));
+  }
+  CUDA_TRY(cudaMemsetAsync(P->hist, 0, 2 * pb, st));  // slots 0,1 = 0 (Core.jl:607-612)
+  if (P->nrcv > 0) CUDA_TRY(cudaMemsetAsync(P->rcvv, 0, (size_t)(2 * P->nrcv) * 8, st));
+  const size_t nseg = P->seg_b.size();
+  for (size_t k = 0; k < nseg; k++) {
+    const i64 b = P->seg_b[k], e = P->seg_e[k];
+    if (k > 0) {
+      // window index 0,1 <- slots b, b+1 (the last two slots of the previous segment)
+      const i64 pbse = P->seg_b[k - 1];
+      double* s0 = win_slot(P, pbse, b);
+      double* s1 = win_slot(P, pbse, b + 1);
+      if (save_ckpt) {
+        double* c = P->ckpt[k - 1];
+        CUDA_TRY(cudaMemcpyAsync(c, s0, pb, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c + g.plane, s1, pb, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c + 2 * g.plane, P->phi[(b + 1) & 1], pb, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c + 3 * g.plane, P->psi[(b + 1) & 1], pb, cudaMemcpyDeviceToDevice, st));
+      }
+      CUDA_TRY(cudaMemcpyAsync(P->hist, s0, pb, cudaMemcpyDeviceToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(P->hist + g.plane, s1, pb, cudaMemcpyDeviceToDevice, st));
+    }
+    TRY(run_forward_steps(P, b, b + 2, e, true));
+    P->win_base = b; P->win_last = e;
+    if (cb) TRY(cb(P, k, user));
+  }
+  return ADSEIS_OK;
+}
+
+static int check_ready(adseis_acoustic_plan* P, bool need_obs) {
+  if (!P->have_model || (!P->have_srcv && P->nsrc > 0) || (need_obs && !P->have_obs)) {
+    adseis_set_error("acoustic plan: set_model / set_srcv%s must be called first", need_obs ? " / set_obs" : "");
+    return ADSEIS_ESTATE;
+  }
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_acoustic_plan_forward(adseis_acoustic_plan* P) {
+  REQUIRE(P, "acoustic_plan_forward: null");
+  TRY(check_ready(P, false));
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  P->last_launches = 0; P->last_recomputed = 0;
+  TRY(forward_sweep(P, false, nullptr, nullptr));
+  P->last_segments = (i64)P->seg_b.size();
+  P->have_fwd = true;
+  return ADSEIS_OK;
+}
+
+static int ensure_adjoint_state(adseis_acoustic_plan* P) {
+  if (P->G) return ADSEIS_OK;
+  const size_t n = (size_t)P->g.plane;
+  cudaStream_t st = P->ctx->stream;
+  for (int k = 0; k < 3; k++) TRY(dev_alloc_zero(&P->ub[k], n, st));
+  for (int k = 0; k < 2; k++) { TRY(dev_alloc_zero(&P->phib[k], n, st)); TRY(dev_alloc_zero(&P->psib[k], n, st)); }
+  TRY(dev_alloc_zero(&P->G, n, st));
+  TRY(dev_alloc_zero(&P->gradc, (size_t)P->model_elems, st));
+  TRY(dev_alloc_zero(&P->gradsrcv, (size_t)(P->p.NSTEP * P->nsrc), st));
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
+  REQUIRE(P, "acoustic_plan_gradient: null");
+  TRY(check_ready(P, true));
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  const AcGeom& g = P->g;
+  cudaStream_t st = P->ctx->stream;
+  const i64 NSTEP = P->p.NSTEP;
+  const size_t pb = (size_t)g.plane * 8;
+  P->last_launches = 0; P->last_recomputed = 0;
+  TRY(ensure_adjoint_state(P));
+  // ---- forward, keeping checkpoints; the last segment stays in the window
+  TRY(forward_sweep(P, true, nullptr, nullptr));
+  const size_t nseg = P->seg_b.size();
+  P->last_segments = (i64)nseg;
+  // ---- misfit and adjoint sources
+  const i64 nr = (NSTEP + 1) * P->nrcv;
+  k_residual_loss<<<1, 1024, 0, st>>>(P->rcvv, P->obs, P->rcv_owned, (int)std::max<i64>(P->nrcv, 1), 1, nr, P->res, P->loss);
+  LAUNCH_CHECK(P);
+  // ---- reverse sweep
+  for (int k = 0; k < 3; k++) CUDA_TRY(cudaMemsetAsync(P->ub[k], 0, pb, st));
+  for (int k = 0; k < 2; k++) { CUDA_TRY(cudaMemsetAsync(P->phib[k], 0, pb, st)); CUDA_TRY(cudaMemsetAsync(P->psib[k], 0, pb, st)); }
+  CUDA_TRY(cudaMemsetAsync(P->G, 0, pb, st));
+  if (P->nsrc > 0) CUDA_TRY(cudaMemsetAsync(P->gradsrcv, 0, (size_t)(NSTEP * P->nsrc) * 8, st));
+  // ubar[NSTEP] = receiver term only; grad_srcv row NSTEP-1
+  if (P->rcv.dev.nu > 0) {
+    k_points_inject<<<(P->rcv.dev.nu + 127) / 128, 128, 0, st>>>(P->ub[NSTEP % 3], P->rcv.dev, P->res + NSTEP * P->nrcv, 1.0);
+    LAUNCH_CHECK(P);
+  }
+  if (P->src.dev.nu > 0 && NSTEP - 1 >= 1) {
+    k_points_sample<<<(P->src.dev.nu + 127) / 128, 128, 0, st>>>(P->ub[NSTEP % 3], P->src.dev,
+                                                                 P->gradsrcv + (NSTEP - 1) * P->nsrc, g.dt2);
+    LAUNCH_CHECK(P);
+  }
+  dim3 grid((unsigned)((g.ld + AC_TILE_COLS - 1) / AC_TILE_COLS), (unsigned)((P->own1 - P->own0 + AC_RB - 1) / AC_RB));
+  PointSetDev none{};
+  for (i64 k = (i64)nseg - 1; k >= 0; k--) {
+    const i64 b = P->seg_b[k], e = P->seg_e[k];
+    if (k != (i64)nseg - 1) {
+      // restore the start state of segment k and recompute its forward steps (bit-identical replay)
+      if (k == 0) {
+        CUDA_TRY(cudaMemsetAsync(P->hist, 0, 2 * pb, st));
+        CUDA_TRY(cudaMemsetAsync(P->phi[1], 0, pb, st));
+        CUDA_TRY(cudaMemsetAsync(P->psi[1], 0, pb, st));
+      } else {
+        double* c = P->ckpt[k - 1];
+        CUDA_TRY(cudaMemcpyAsync(P->hist, c, pb, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(P->hist + g.plane, c + g.plane, pb, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(P->phi[(b + 1) & 1], c + 2 * g.plane, pb, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(P->psi[(b + 1) & 1], c + 3 * g.plane, pb, cudaMemcpyDeviceToDevice, st));
+      }
+      TRY(run_forward_steps(P, b, b + 2, e, false));
+      P->last_recomputed += e - (b + 2) + 1;
+      P->win_base = b; P->win_last = e;
+    }
+    for (i64 s = e; s >= b + 2; s--) {
+      if (s < 2) break;
+      ac_adj_kernel<<<grid, AC_THREADS, 0, st>>>(
+          g, P->own0, P->own1, P->ub[s % 3], P->ub[(s + 1) % 3], win_slot(P, b, s - 1), P->c2, P->phib[s & 1],
+          P->psib[s & 1], P->sigx, P->tauy, P->ub[(s + 2) % 3] /* == (s-1)%3 */, P->phib[(s - 1) & 1],
+          P->psib[(s - 1) & 1], P->G, P->rcv.dev, P->nrcv > 0 ? P->res + (s - 1) * P->nrcv : nullptr,
+          (s - 2 >= 1) ? P->src.dev : none, (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr);
+      LAUNCH_CHECK(P);
+    }
+  }
+  CUDA_TRY(cudaMemsetAsync(P->gradc, 0, (size_t)P->model_elems * 8, st));
+  {
+    dim3 gg((unsigned)((g.W + 127) / 128), (unsigned)(P->own1 - P->own0));
+    k_grad_finalize<<<gg, 128, 0, st>>>(P->G, P->cvel, g.ld, g.goff, P->own0, P->own1, g.H, g.W,
+                                        P->p.mpi_convention, P->gradc);
+    LAUNCH_CHECK(P);
+  }
+  P->have_fwd = true;
+  P->have_grad = true;
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_acoustic_plan_get(adseis_acoustic_plan* P, int what, double* dst, int to_device) {
+  (void)to_device;
+  REQUIRE(P && dst, "acoustic_plan_get: null");
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  const double* src = nullptr;
+  size_t n = 0;
+  switch (what) {
+    case ADSEIS_GET_RCVV:
+      if (!P->have_fwd) { adseis_set_error("acoustic_plan_get: no forward results yet"); return ADSEIS_ESTATE; }
+      src = P->rcvv; n = (size_t)((P->p.NSTEP + 1) * P->nrcv); break;
+    case ADSEIS_GET_LOSS: src = P->loss; n = 1; break;
+    case ADSEIS_GET_GRAD_C: src = P->gradc; n = (size_t)P->model_elems; break;
+    case ADSEIS_GET_GRAD_SRCV: src = P->gradsrcv; n = (size_t)(P->p.NSTEP * P->nsrc); break;
+    default: adseis_set_error("acoustic_plan_get: unknown item %d", what); return ADSEIS_EINVAL;
+  }
+  if (what != ADSEIS_GET_RCVV && !P->have_grad) {
+    adseis_set_error("acoustic_plan_get: no gradient results yet");
+    return ADSEIS_ESTATE;
+  }
+  if (n > 0) CUDA_TRY(cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyDefault, P->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(P->ctx->stream));
+  return ADSEIS_OK;
+}
+
+static int copy_snapshot_out(adseis_acoustic_plan* P, const double* plane, double* dst) {
+  const AcGeom& g = P->g;
+  cudaStream_t st = P->ctx->stream;
+  if (!P->p.mpi_convention) {
+    CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)g.W * 8, plane, (size_t)g.ld * 8, (size_t)g.W * 8, (size_t)g.H,
+                               cudaMemcpyDefault, st));
+  } else {
+    const int NY = g.W - 2;
+    CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)NY * 8, plane + g.ld + 1, (size_t)g.ld * 8, (size_t)NY * 8,
+                               (size_t)(g.H - 2), cudaMemcpyDefault, st));
+  }
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_acoustic_plan_get_snapshot(adseis_acoustic_plan* P, int64_t slot, double* dst, int to_device) {
+  (void)to_device;
+  REQUIRE(P && dst, "acoustic_plan_get_snapshot: null");
+  REQUIRE(P->slab.nranks == 1, "acoustic_plan_get_snapshot: single-GPU plans only");
+  if (!P->have_fwd || slot < P->win_base || slot > P->win_last) {
+    adseis_set_error("acoustic_plan_get_snapshot: slot %lld is not resident (window holds [%lld,%lld])",
+                     (long long)slot, (long long)P->win_base, (long long)P->win_last);
+    return ADSEIS_ESTATE;
+  }
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  TRY(copy_snapshot_out(P, win_slot(P, P->win_base, slot), dst));
+  CUDA_TRY(cudaStreamSynchronize(P->ctx->stream));
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_acoustic_plan_info(adseis_acoustic_plan* P, int64_t info[8]) {
+  REQUIRE(P && info, "acoustic_plan_info: null");
+  info[0] = P->win; info[1] = P->last_segments; info[2] = P->last_launches; info[3] = P->g.Hl; info[4] = P->g.ld;
+  info[5] = P->last_recomputed; info[6] = (i64)P->seg_b.size(); info[7] = P->g.fi1 - P->g.fi0 + 1;
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_acoustic_plan_ipc_export(adseis_acoustic_plan* P, void* handle_out) {
+  (void)P; (void)handle_out;
+  adseis_set_error("acoustic_plan_ipc_export: peer halo exchange is not available in this build");
+  return ADSEIS_ECOMM;
+}
+ADSEIS_API int adseis_acoustic_plan_ipc_connect(adseis_acoustic_plan* P, const void* lo, const void* hi) {
+  (void)P; (void)lo; (void)hi;
+  adseis_set_error("acoustic_plan_ipc_connect: peer halo exchange is not available in this build");
+  return ADSEIS_ECOMM;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// one-call host-buffer entry points
+// ------------------------------------------------------------------------------------------------------------
+struct hist_copy_ctx { double* out; };
+static int hist_copy_cb(adseis_acoustic_plan* P, size_t k, void* user) {
+  hist_copy_ctx* h = (hist_copy_ctx*)user;
+  const i64 b = P->seg_b[k], e = P->seg_e[k];
+  for (i64 s = (k == 0 ? b : b + 2); s <= e; s++)
+    TRY(copy_snapshot_out(P, win_slot(P, b, s), h->out + s * P->model_elems));
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_acoustic_forward(adseis_ctx* ctx, const adseis_acoustic_params* p, const double* c, int64_t nsrc,
+                                       const int64_t* srci, const int64_t* srcj, const double* srcv,
+                                       int64_t srcv_rows, int64_t nrcv, const int64_t* rcvi, const int64_t* rcvj,
+                                       double* rcvv_out, double* u_hist_out) {
+  adseis_acoustic_plan* P = nullptr;
+  TRY(adseis_acoustic_plan_create(ctx, p, nullptr, nsrc, srci, srcj, nrcv, rcvi, rcvj, 0, &P));
+  int rc = adseis_acoustic_plan_set_model(P, c, 0);
+  if (!rc) rc = adseis_acoustic_plan_set_srcv(P, srcv, srcv_rows, 0);
+  if (!rc) {
+    P->last_launches = 0;
+    hist_copy_ctx h{u_hist_out};
+    rc = forward_sweep(P, false, u_hist_out ? hist_copy_cb : nullptr, &h);
+    P->have_fwd = (rc == 0);
+  }
+  if (!rc && rcvv_out && nrcv > 0) rc = adseis_acoustic_plan_get(P, ADSEIS_GET_RCVV, rcvv_out, 0);
+  if (!rc) rc = adseis_ctx_sync(ctx);
+  adseis_acoustic_plan_destroy(P);
+  return rc;
+}
+
+ADSEIS_API int adseis_acoustic_misfit_grad(adseis_ctx* ctx, const adseis_acoustic_params* p, const double* c,
+                                           int64_t nsrc, const int64_t* srci, const int64_t* srcj, const double* srcv,
+                                           int64_t srcv_rows, int64_t nrcv, const int64_t* rcvi, const int64_t* rcvj,
+                                           const double* obs, double* loss_out, double* rcvv_out, double* grad_c_out,
+                                           double* grad_srcv_out) {
+  adseis_acoustic_plan* P = nullptr;
+  TRY(adseis_acoustic_plan_create(ctx, p, nullptr, nsrc, srci, srcj, nrcv, rcvi, rcvj, 0, &P));
+  int rc = adseis_acoustic_plan_set_model(P, c, 0);
+  if (!rc) rc = adseis_acoustic_plan_set_srcv(P, srcv, srcv_rows, 0);
+  if (!rc) rc = adseis_acoustic_plan_set_obs(P, obs, 0);
+  if (!rc) rc = adseis_acoustic_plan_gradient(P);
+  if (!rc && loss_out) rc = adseis_acoustic_plan_get(P, ADSEIS_GET_LOSS, loss_out, 0);
+  if (!rc && rcvv_out && nrcv > 0) rc = adseis_acoustic_plan_get(P, ADSEIS_GET_RCVV, rcvv_out, 0);
+  if (!rc && grad_c_out) rc = adseis_acoustic_plan_get(P, ADSEIS_GET_GRAD_C, grad_c_out, 0);
+  if (!rc && grad_srcv_out && nsrc > 0) rc = adseis_acoustic_plan_get(P, ADSEIS_GET_GRAD_SRCV, grad_srcv_out, 0);
+  if (!rc) rc = adseis_ctx_sync(ctx);
+  adseis_acoustic_plan_destroy(P);
+  return rc;
+}

@@ -166,5 +166,5 @@ def elastic_misfit_grad(variant, NX, NY, NSTEP, dt, dx, dy, ax, bx, ay, by, rho,
     loss.backward()
     H, W = (NX + 2, NY + 2) if variant == 0 else (NX + 4, NY + 4)
     g = lambda x: (x.grad.numpy().copy() if x.grad is not None else np.zeros(x.shape))
-    return dict(loss=float(loss), rcvv=rcvv.detach().numpy(), grad_rho=g(rho_t).reshape(H, W),
+    return dict(loss=float(loss.detach()), rcvv=rcvv.detach().numpy(), grad_rho=g(rho_t).reshape(H, W),
                 grad_lam=g(lam_t).reshape(H, W), grad_mu=g(mu_t).reshape(H, W), grad_srcv=g(srcv_t))

@@ -1,0 +1,163 @@
+"""GPU parity tests for the acoustic path, through the C ABI, against the CPU oracle and the golden vectors.
+Tolerances: forward wavefields / traces are BIT-IDENTICAL to the reference op (same expression order, no FMA);
+misfit and gradients <= 1e-10 relative (BASELINE.json), typically 1e-14 (the gather-form adjoint sums in a
+different order than the scatter-form reference)."""
+import numpy as np
+import pytest
+
+from conftest import golden, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _params(A, G):
+    use = [bool(x) for x in G["use"]]
+    return A.AcousticPropagatorParams(NX=int(G["NX"]), NY=int(G["NY"]), NSTEP=int(G["NSTEP"]), DELTAX=float(G["dx"]),
+                                      DELTAY=float(G["dy"]), DELTAT=float(G["dt"]), NPOINTS_PML=int(G["npml"]),
+                                      vp_ref=float(G["vp_ref"]), USE_PML_XMIN=use[0], USE_PML_XMAX=use[1],
+                                      USE_PML_YMIN=use[2], USE_PML_YMAX=use[3])
+
+
+@pytest.mark.parametrize("name", ["acoustic_small.npz", "acoustic_nopml_y.npz"])
+def test_golden(A, ctx, name):
+    G = golden(name)
+    p = _params(A, G)
+    src = A.AcousticSource(G["srci"], G["srcj"], G["srcv"])
+    rcv = A.AcousticReceiver(G["rcvi"], G["rcvj"])
+    ap = A.AcousticPropagatorSolver(p, src, G["c"], ctx=ctx)
+    A.SimulatedObservation_(ap, rcv)
+    assert np.array_equal(rcv.rcvv, G["rcvv"])
+    u = ap.u
+    assert np.array_equal(u[-1], G["u_last"]) and np.array_equal(u[p.NSTEP // 2], G["u_mid"])
+    R = A.acoustic_misfit_grad(p, src, G["c"], rcv, G["obs"], ctx=ctx)
+    assert np.array_equal(R["rcvv"], G["rcvv"])
+    assert abs(R["loss"] - float(G["loss"])) / float(G["loss"]) < 1e-13
+    assert relerr(R["grad_c"], G["grad_c"]) < TOL
+    assert relerr(R["grad_srcv"], G["grad_srcv"]) < TOL
+
+
+def _case(po, rng, NX, NY, NSTEP, dx, dy, dt, npml, vp_ref, nsrc=2, nrcv=40, use=(True,) * 4):
+    sig, tau = po.acoustic_pml(NX, NY, dx, dy, npml=npml, vp_ref=vp_ref, use=use)
+    c = vp_ref * (1 + 0.1 * rng.random((NX + 2, NY + 2)))
+    srci = rng.integers(2, NX, nsrc)
+    srcj = rng.integers(2, NY, nsrc)
+    srcv = np.stack([po.ricker(NSTEP, 8.0 + k, 20.0 + 3 * k, 1e6) for k in range(nsrc)], 1)
+    rcvi = rng.integers(1, NX + 2, nrcv)
+    rcvj = rng.integers(1, NY + 2, nrcv)
+    return sig, tau, c, srci, srcj, srcv, rcvi, rcvj
+
+
+@pytest.mark.parametrize("shape", [(150, 700, 60), (403 - 2, 135 - 2, 80), (70, 1100, 40), (300, 64, 50)])
+def test_vs_oracle_random(A, ctx, po, shape):
+    """Grids wide enough to exercise the register-marching fast path, ragged widths (not multiples of 64/512), the
+    PML frame on all sides, sources/receivers anywhere (including the ring), duplicates."""
+    NX, NY, NSTEP = shape
+    rng = np.random.default_rng(NX * 7 + NY)
+    dx, dy, dt, vp = 10.0, 8.0, 1e-3, 2500.0
+    sig, tau, c, srci, srcj, srcv, rcvi, rcvj = _case(po, rng, NX, NY, NSTEP, dx, dy, dt, 12, vp)
+    srci[0], srcj[0] = 1, NY // 2           # a source on the ring row
+    rcvi[:2], rcvj[:2] = srci[1], srcj[1]   # duplicate receivers on a source cell
+    u0, r0 = po.acoustic_forward(NX, NY, NSTEP, dt, dx, dy, sig, tau, c, srci, srcj, srcv, rcvi, rcvj)
+    p = A.AcousticPropagatorParams(NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dy, DELTAT=dt, vp_ref=vp)
+    src, rcv = A.AcousticSource(srci, srcj, srcv), A.AcousticReceiver(rcvi, rcvj)
+    plan = A.AcousticPlan(p, srci, srcj, rcvi, rcvj, ctx=ctx)
+    assert plan.info()["fast_rows"] > 0
+    plan.set_model(c)
+    plan.set_srcv(srcv)
+    plan.forward()
+    assert np.array_equal(plan.rcvv(), r0)
+    for s in (2, NSTEP // 2, NSTEP):
+        assert np.array_equal(plan.snapshot(s), u0[s])
+    obs = 0.7 * r0 + 0.02 * np.abs(r0).max() * rng.standard_normal(r0.shape)
+    L0, gc0, gs0 = po.acoustic_misfit_grad(NX, NY, NSTEP, dt, dx, dy, sig, tau, c, srci, srcj, rcvi, rcvj, obs, u0)
+    plan.set_obs(obs)
+    plan.gradient()
+    assert abs(plan.loss() - L0) / L0 < 1e-13
+    assert relerr(plan.grad_c(), gc0) < TOL
+    assert relerr(plan.grad_srcv(), gs0) < TOL
+    plan.close()
+
+
+def test_checkpointed_gradient_equals_full_history(A, ctx, po):
+    """Segment checkpointing replays the forward bit-identically: gradients with a 9-snapshot window are equal to
+    the full-history ones to the last bit, and both match the oracle."""
+    rng = np.random.default_rng(77)
+    NX, NY, NSTEP, dx, dt, vp = 90, 600, 75, 10.0, 1e-3, 2000.0
+    sig, tau, c, srci, srcj, srcv, rcvi, rcvj = _case(po, rng, NX, NY, NSTEP, dx, dx, dt, 10, vp)
+    p = A.AcousticPropagatorParams(NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dx, DELTAT=dt, vp_ref=vp,
+                                   NPOINTS_PML=10)
+    u0, r0 = po.acoustic_forward(NX, NY, NSTEP, dt, dx, dx, sig, tau, c, srci, srcj, srcv, rcvi, rcvj)
+    obs = 0.5 * r0
+    res = []
+    for budget in (0, None):
+        plan = A.AcousticPlan(p, srci, srcj, rcvi, rcvj, ctx=ctx,
+                              hist_bytes_budget=0 if budget == 0 else 13 * plan_bytes)
+        if budget == 0:
+            plan_bytes = plan.info()["local_rows"] * plan.info()["pitch"] * 8
+        plan.set_model(c); plan.set_srcv(srcv); plan.set_obs(obs)
+        plan.gradient()
+        info = plan.info()
+        res.append((plan.loss(), plan.grad_c(), plan.grad_srcv(), plan.rcvv(), info))
+        plan.close()
+    assert res[0][4]["segments"] == 1 and res[1][4]["segments"] > 3 and res[1][4]["recomputed_steps"] > 0
+    assert res[0][0] == res[1][0]
+    for k in (1, 2, 3):
+        assert np.array_equal(res[0][k], res[1][k])
+    L0, gc0, gs0 = po.acoustic_misfit_grad(NX, NY, NSTEP, dt, dx, dx, sig, tau, c, srci, srcj, rcvi, rcvj, obs, u0)
+    assert relerr(res[1][1], gc0) < TOL and relerr(res[1][2], gs0) < TOL
+
+
+def test_mpi_convention(A, ctx, po):
+    """MPIAcousticPropagatorSolver inputs: c given as c^2 on the unpadded grid, unpadded 1-based indices."""
+    rng = np.random.default_rng(5)
+    NX, NY, NSTEP, dx, dt = 200, 640, 50, 10.0, 0.004
+    sig, tau = po.acoustic_pml(NX, NY, dx, dx, npml=12, vp_ref=1000.0, Rcoef=0.2)
+    c2 = 1.0e6 * (1 + 0.2 * rng.random((NX, NY)))
+    srci, srcj = np.array([NX // 5, 1]), np.array([NY // 2, 1])
+    srcv = np.stack([po.ricker(NSTEP, 6.0, 15.0, 1e4)] * 2, 1)
+    rcvi, rcvj = np.full(100, NX // 5), np.arange(20, 120)
+    c2p = np.zeros((NX + 2, NY + 2)); c2p[1:-1, 1:-1] = c2
+    u0, r0 = po.acoustic_forward(NX, NY, NSTEP, dt, dx, dx, sig, tau, c2p, srci, srcj, srcv, rcvi, rcvj,
+                                 mpi_convention=True)
+    obs = 0.9 * r0
+    L0, g0, s0 = po.acoustic_misfit_grad(NX, NY, NSTEP, dt, dx, dx, sig, tau, c2p, srci, srcj, rcvi, rcvj, obs, u0,
+                                         mpi_convention=True)
+    p = A.AcousticPropagatorParams(NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dx, DELTAT=dt, vp_ref=1000.0,
+                                   Rcoef=0.2, mpi_convention=True)
+    R = A.acoustic_misfit_grad(p, A.AcousticSource(srci, srcj, srcv), c2, A.AcousticReceiver(rcvi, rcvj), obs, ctx=ctx)
+    assert np.array_equal(R["rcvv"], r0)
+    assert abs(R["loss"] - L0) / L0 < 1e-13
+    assert relerr(R["grad_c"], g0[1:-1, 1:-1]) < TOL and relerr(R["grad_srcv"], s0) < TOL
+
+
+def test_op_level_step(A, ctx, po):
+    """The reference's own op test inputs (deps/CustomOps/AcousticOneStepCpu/gradtest.jl:15-31) through the
+    op-level C ABI with device pointers."""
+    import torch
+    G = golden("acoustic_step_gradtest.npz")
+    dev = torch.device("cuda")
+    ins = [torch.tensor(x, device=dev) for x in G["ins"]]
+    g = [torch.tensor(x, device=dev) for x in G["g"]]
+    outs = [torch.empty_like(ins[0]) for _ in range(3)]
+    A.acoustic_one_step(ctx, *ins, 0.1, 0.1, 0.1, 10, 10, *outs)
+    ctx.sync()
+    assert np.array_equal(torch.stack(outs).cpu().numpy(), G["fwd"])
+    gout = [torch.empty_like(ins[0]) for _ in range(5)]
+    A.acoustic_one_step_grad(ctx, *gout, *g, ins[0], ins[4], ins[5], ins[6], 0.1, 0.1, 0.1, 10, 10)
+    ctx.sync()
+    assert relerr(torch.stack(gout).cpu().numpy(), G["bwd"]) < 1e-14
+
+
+def test_errors_are_reported(A, ctx):
+    p = A.AcousticPropagatorParams(NX=50, NY=50, NSTEP=10, PropagatorKernel=0)
+    with pytest.raises(A.AdseisError):
+        A.AcousticPlan(p, [5], [5], [6], [6], ctx=ctx)
+    p = A.AcousticPropagatorParams(NX=50, NY=50, NSTEP=10)
+    with pytest.raises(A.AdseisError):
+        A.AcousticPlan(p, [500], [5], [6], [6], ctx=ctx)       # source outside the grid
+    plan = A.AcousticPlan(p, [5], [5], [6], [6], ctx=ctx)
+    with pytest.raises(A.AdseisError):
+        plan.forward()                                          # no model yet
+    with pytest.raises(A.AdseisError):
+        plan.set_srcv(np.zeros((3, 1)))                         # too few rows
