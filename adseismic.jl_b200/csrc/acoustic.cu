@@ -37,20 +37,20 @@ __global__ void k_residual_loss(const double* __restrict__ rcvv, const double* _
 }
 
 // whole-array point injection / sampling (used once per sweep for the last slot)
-__global__ void k_points_inject(double* __restrict__ field, PointSetDev ps, const double* __restrict__ val,
+__global__ void k_points_inject(double* __restrict__ field, AcPoints ps, int nu, const double* __restrict__ val,
                                 double scale) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < ps.nu) {
+  if (k < nu) {
     const int cell = ps.cell[k];
     double v = field[cell];
     for (int m = ps.start[k]; m < ps.start[k + 1]; m++) v += val[ps.perm[m]] * scale;
     field[cell] = v;
   }
 }
-__global__ void k_points_sample(const double* __restrict__ field, PointSetDev ps, double* __restrict__ out,
+__global__ void k_points_sample(const double* __restrict__ field, AcPoints ps, int nu, double* __restrict__ out,
                                 double scale) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < ps.nu) {
+  if (k < nu) {
     const double v = field[ps.cell[k]] * scale;
     for (int m = ps.start[k]; m < ps.start[k + 1]; m++) out[ps.perm[m]] = v;
   }
@@ -81,6 +81,9 @@ struct adseis_acoustic_plan {
   adseis_acoustic_params p;
   adseis_slab slab;
   AcGeom g;
+  AcTiling t;
+  int nblocks = 0;   // CTAs per time-step launch
+  int fast_rows = 0; // rows of the PML-free box owned by this GPU
   int own0, own1;  // owned local rows [own0, own1)
   i64 model_elems; // elements of the caller's model array
   // static fields (pitched, local rows)
@@ -95,6 +98,7 @@ struct adseis_acoustic_plan {
   // points
   i64 nsrc = 0, nrcv = 0;
   PointSetStorage src, rcv;
+  AcPoints srcp{}, rcvp{};
   unsigned char* rcv_owned = nullptr;
   double *srcv = nullptr, *rcvv = nullptr, *obs = nullptr, *res = nullptr, *loss = nullptr;
   i64 srcv_rows = 0;
@@ -235,8 +239,46 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
   int ia, ib, ja, jb;
   box(sx, (int)p->NX, &ia, &ib);
   box(ty, (int)p->NY, &ja, &jb);
-  g.fi0 = ia + 1; g.fi1 = ib - 1; g.fj0 = ja + 1; g.fj1 = jb - 1;
-  if (g.fj0 > g.fj1) { g.fi0 = 1; g.fi1 = 0; }
+  {
+    // fast region = box shrunk by one cell: every stencil neighbour is PML-free, interior, and has phi=psi=0
+    const int fi0 = ia + 1, fi1 = ib - 1, fj0 = ja + 1, fj1 = jb - 1;
+    AcTiling& t = P->t;
+    memset(&t, 0, sizeof(t));
+    // marched local rows: owned rows whose global index lies in [fi0, fi1]
+    int mr0 = std::max(P->own0, fi0 - g.goff), mr1 = std::min(P->own1, fi1 + 1 - g.goff);
+    int mc0 = round_up(std::max(fj0, 1), 16);
+    int mc_end = mc0 + 2 * ((fj1 + 1 - mc0) / 2);
+    if (fj1 + 1 - mc0 < 2 || mr1 - mr0 < 1) { mr0 = mr1 = P->own0; mc0 = mc_end = 0; }
+    t.mr0 = mr0; t.mr1 = mr1; t.mc0 = mc0; t.mc_end = mc_end;
+    P->fast_rows = mr1 - mr0;
+    const int nwarpcols = (mc_end - mc0 + AC_WCOLS - 1) / AC_WCOLS;
+    t.nct = (nwarpcols + AC_WARPS - 1) / AC_WARPS;
+    // rows per marching CTA: aim at >= 4 CTAs per SM so that every SM has work and the tail is short
+    int rb = 32;
+    if (t.nct > 0 && mr1 > mr0) {
+      const int want_tr = std::max(1, (4 * ctx->sm_count + t.nct - 1) / t.nct);
+      rb = (mr1 - mr0 + want_tr - 1) / want_tr;
+      rb = std::min(64, std::max(AC_U, round_up(rb, AC_U)));  // AC_U is a multiple of AC_UA
+    }
+    t.rb = rb;
+    t.ntr = (mr1 > mr0) ? (mr1 - mr0 + rb - 1) / rb : 0;
+    t.nmarch = t.nct * t.ntr;
+    // frame rectangles: rows above / below the marched rows (all columns), columns left / right of the marched ones
+    auto add_rect = [&](int r0, int r1, int c0, int c1) {
+      if (r1 <= r0 || c1 <= c0) return;
+      const int k = t.nrect++;
+      t.rr0[k] = r0; t.rr1[k] = r1; t.rc0[k] = c0; t.rc1[k] = c1;
+      const i64 cells = (i64)(r1 - r0) * (c1 - c0);
+      t.rblk[k + 1] = t.rblk[k] + (int)((cells + AC_FRAME_CELLS - 1) / AC_FRAME_CELLS);
+    };
+    t.rblk[0] = 0;
+    add_rect(P->own0, mr0, 0, g.ld);
+    add_rect(mr1, P->own1, 0, g.ld);
+    add_rect(mr0, mr1, 0, mc0);
+    add_rect(mr0, mr1, mc_end, g.ld);
+    for (int k = t.nrect; k < 4; k++) { t.rblk[k + 1] = t.rblk[t.nrect]; t.rr0[k] = t.rr1[k] = t.rc0[k] = 0; t.rc1[k] = 1; }
+    P->nblocks = t.nmarch + t.rblk[t.nrect];
+  }
 
 #define PTRY(expr)                                   \
   do {                                               \
@@ -258,26 +300,40 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
   // sources / receivers: keep the points whose padded row is owned (MPIAcoustic.jl:71-78, 98-104)
   P->nsrc = nsrc; P->nrcv = nrcv;
   const int ioff = p->mpi_convention ? 0 : -1;  // 1-based padded -> 0-based padded ; 1-based unpadded -> padded
+  auto owner_cta = [&](int li, int j) -> int {
+    const AcTiling& t = P->t;
+    if (li >= t.mr0 && li < t.mr1 && j >= t.mc0 && j < t.mc_end)
+      return ((li - t.mr0) / t.rb) * t.nct + (j - t.mc0) / AC_TILE_COLS;
+    for (int k = 0; k < t.nrect; k++)
+      if (li >= t.rr0[k] && li < t.rr1[k] && j >= t.rc0[k] && j < t.rc1[k])
+        return t.nmarch + t.rblk[k] + (int)(((i64)(li - t.rr0[k]) * (t.rc1[k] - t.rc0[k]) + (j - t.rc0[k])) / AC_FRAME_CELLS);
+    return -1;
+  };
   auto build = [&](i64 n, const int64_t* pi, const int64_t* pj, PointSetStorage* dst, std::vector<unsigned char>* owned,
                    const char* what) -> int {
-    std::vector<int> rows, cols, gid, none;
+    std::vector<int> own, cells, gid, none;
     if (owned) owned->assign((size_t)n, 0);
     for (i64 k = 0; k < n; k++) {
       i64 gi = pi[k] + ioff, gj = pj[k] + ioff;
       REQUIRE(gi >= 0 && gi < H && gj >= 0 && gj < W, "acoustic_plan_create: %s %lld at (%lld,%lld) is outside the grid",
               what, (long long)k, (long long)pi[k], (long long)pj[k]);
       if (gi >= sl.row0 && gi < sl.row1) {
-        rows.push_back((int)(gi - g.goff)); cols.push_back((int)gj); gid.push_back((int)k);
+        const int li = (int)(gi - g.goff);
+        const int o = owner_cta(li, (int)gj);
+        REQUIRE(o >= 0, "acoustic_plan_create: internal error: cell (%d,%d) has no owner CTA", li, (int)gj);
+        own.push_back(o); cells.push_back(li * g.ld + (int)gj); gid.push_back((int)k);
         if (owned) (*owned)[k] = 1;
       }
     }
     PointSetHost h;
-    build_point_set(rows, cols, gid, none, g.ld, g.plane, AC_TILE_COLS, &h);
+    build_point_set(own, cells, gid, none, P->nblocks, &h);
     return upload_point_set(h, dst, st);
   };
   std::vector<unsigned char> owned;
   PTRY(build(nsrc, srci, srcj, &P->src, nullptr, "source"));
   PTRY(build(nrcv, rcvi, rcvj, &P->rcv, &owned, "receiver"));
+  if (P->src.nu > 0) P->srcp = AcPoints{P->src.blk, P->src.cell, P->src.start, P->src.perm};
+  if (P->rcv.nu > 0) P->rcvp = AcPoints{P->rcv.blk, P->rcv.cell, P->rcv.start, P->rcv.perm};
   PTRY(dev_upload(&P->rcv_owned, owned, st));
   PTRY(dev_alloc_zero(&P->rcvv, (size_t)((p->NSTEP + 1) * nrcv), st));
   PTRY(dev_alloc_zero(&P->loss, 1, st));
@@ -386,13 +442,12 @@ ADSEIS_API int adseis_acoustic_plan_set_obs(adseis_acoustic_plan* P, const doubl
 static int run_forward_steps(adseis_acoustic_plan* P, i64 base, i64 s_first, i64 s_last, bool sample) {
   const AcGeom& g = P->g;
   cudaStream_t st = P->ctx->stream;
-  dim3 grid((unsigned)((g.ld + AC_TILE_COLS - 1) / AC_TILE_COLS), (unsigned)((P->own1 - P->own0 + AC_RB - 1) / AC_RB));
-  PointSetDev none{};
+  AcPoints none{};
   for (i64 s = s_first; s <= s_last; s++) {
-    ac_fwd_kernel<<<grid, AC_THREADS, 0, st>>>(
-        g, P->own0, P->own1, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, P->phi[(s - 1) & 1],
-        P->psi[(s - 1) & 1], P->sigx, P->tauy, win_slot(P, base, s), P->phi[s & 1], P->psi[s & 1], P->src.dev,
-        P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, sample ? P->rcv.dev : none,
+    ac_fwd_kernel<<<P->nblocks, AC_THREADS, 0, st>>>(
+        g, P->t, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, P->phi[(s - 1) & 1], P->psi[(s - 1) & 1],
+        P->sigx, P->tauy, win_slot(P, base, s), P->phi[s & 1], P->psi[s & 1], P->srcp,
+        P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, sample ? P->rcvp : none,
         (sample && P->nrcv > 0) ? P->rcvv + s * P->nrcv : nullptr);
     LAUNCH_CHECK(P);
   }
@@ -493,17 +548,17 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
   CUDA_TRY(cudaMemsetAsync(P->G, 0, pb, st));
   if (P->nsrc > 0) CUDA_TRY(cudaMemsetAsync(P->gradsrcv, 0, (size_t)(NSTEP * P->nsrc) * 8, st));
   // ubar[NSTEP] = receiver term only; grad_srcv row NSTEP-1
-  if (P->rcv.dev.nu > 0) {
-    k_points_inject<<<(P->rcv.dev.nu + 127) / 128, 128, 0, st>>>(P->ub[NSTEP % 3], P->rcv.dev, P->res + NSTEP * P->nrcv, 1.0);
+  if (P->rcv.nu > 0) {
+    k_points_inject<<<(P->rcv.nu + 127) / 128, 128, 0, st>>>(P->ub[NSTEP % 3], P->rcvp, P->rcv.nu,
+                                                             P->res + NSTEP * P->nrcv, 1.0);
     LAUNCH_CHECK(P);
   }
-  if (P->src.dev.nu > 0 && NSTEP - 1 >= 1) {
-    k_points_sample<<<(P->src.dev.nu + 127) / 128, 128, 0, st>>>(P->ub[NSTEP % 3], P->src.dev,
-                                                                 P->gradsrcv + (NSTEP - 1) * P->nsrc, g.dt2);
+  if (P->src.nu > 0 && NSTEP - 1 >= 1) {
+    k_points_sample<<<(P->src.nu + 127) / 128, 128, 0, st>>>(P->ub[NSTEP % 3], P->srcp, P->src.nu,
+                                                             P->gradsrcv + (NSTEP - 1) * P->nsrc, g.dt2);
     LAUNCH_CHECK(P);
   }
-  dim3 grid((unsigned)((g.ld + AC_TILE_COLS - 1) / AC_TILE_COLS), (unsigned)((P->own1 - P->own0 + AC_RB - 1) / AC_RB));
-  PointSetDev none{};
+  AcPoints none{};
   for (i64 k = (i64)nseg - 1; k >= 0; k--) {
     const i64 b = P->seg_b[k], e = P->seg_e[k];
     if (k != (i64)nseg - 1) {
@@ -525,11 +580,11 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
     }
     for (i64 s = e; s >= b + 2; s--) {
       if (s < 2) break;
-      ac_adj_kernel<<<grid, AC_THREADS, 0, st>>>(
-          g, P->own0, P->own1, P->ub[s % 3], P->ub[(s + 1) % 3], win_slot(P, b, s - 1), P->c2, P->phib[s & 1],
-          P->psib[s & 1], P->sigx, P->tauy, P->ub[(s + 2) % 3] /* == (s-1)%3 */, P->phib[(s - 1) & 1],
-          P->psib[(s - 1) & 1], P->G, P->rcv.dev, P->nrcv > 0 ? P->res + (s - 1) * P->nrcv : nullptr,
-          (s - 2 >= 1) ? P->src.dev : none, (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr);
+      ac_adj_kernel<<<P->nblocks, AC_THREADS, 0, st>>>(
+          g, P->t, P->ub[s % 3], P->ub[(s + 1) % 3], win_slot(P, b, s - 1), P->c2, P->phib[s & 1], P->psib[s & 1],
+          P->sigx, P->tauy, P->ub[(s + 2) % 3] /* == (s-1)%3 */, P->phib[(s - 1) & 1], P->psib[(s - 1) & 1], P->G,
+          P->rcvp, P->nrcv > 0 ? P->res + (s - 1) * P->nrcv : nullptr, (s - 2 >= 1) ? P->srcp : none,
+          (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr);
       LAUNCH_CHECK(P);
     }
   }
@@ -601,7 +656,7 @@ ADSEIS_API int adseis_acoustic_plan_get_snapshot(adseis_acoustic_plan* P, int64_
 ADSEIS_API int adseis_acoustic_plan_info(adseis_acoustic_plan* P, int64_t info[8]) {
   REQUIRE(P && info, "acoustic_plan_info: null");
   info[0] = P->win; info[1] = P->last_segments; info[2] = P->last_launches; info[3] = P->g.Hl; info[4] = P->g.ld;
-  info[5] = P->last_recomputed; info[6] = (i64)P->seg_b.size(); info[7] = P->g.fi1 - P->g.fi0 + 1;
+  info[5] = P->last_recomputed; info[6] = (i64)P->seg_b.size(); info[7] = P->fast_rows;
   return ADSEIS_OK;
 }
 

@@ -1,6 +1,6 @@
 // acoustic_kernels.cuh -- fused acoustic time-step kernels (forward and exact adjoint) for sm_100a.
 //
-// One launch = one time step over a range of local rows:
+// One launch = one time step over the rows this GPU owns:
 //   forward : u[s]   = Step(u[s-1], u[s-2], phi, psi; c^2, sigma_x(i), tau_y(j))  + source injection into u[s]
 //                      + receiver sampling of u[s]                       (reference: AcousticOneStepCpu.h:1-48,
 //                      ScatterAddOps.h:1-7 via Core.jl:600-601, gather via Core.jl:727-728)
@@ -8,29 +8,39 @@
 //                      + cross-correlation gbar_c2 += cbar_s in the same pass
 //                      + receiver-residual injection into ubar[s-1] + grad_srcv sampling
 //
-// Mapping (HBM-bound fp64 stencil, no tensor cores): a warp owns 64 consecutive columns (one double2 per lane,
-// 512 B per row -> fully coalesced 128 B lines) and marches down AC_RB rows keeping the 3-row window of the
-// stencil in registers; left/right neighbours come from warp shuffles, the two warp-edge values from one
-// predicated 8-byte load that hits L1/L2.  Every array element is therefore requested from DRAM once per step:
-// 32 B/cell forward (w, wold, c^2 read + u written), 56 B/cell adjoint.  PML work (phi/psi traffic, the fp64
-// divide) is confined to the rows/warps that intersect the absorbing frame; the frame test is warp-uniform.
-// Arithmetic in the forward kernel is written in the reference's evaluation order and the library is compiled
-// with -fmad=false, so forward wavefields and traces are bit-identical to the CPU op.
+// Work decomposition (HBM-bound fp64 stencil, no tensor cores).  The grid of one launch holds two kinds of CTAs:
+//   * MARCHING CTAs cover the PML-free box.  A warp owns 64 consecutive columns (one double2 per lane, 512 B per
+//     row -> whole 128 B lines) and marches down `rb` rows keeping the 3-row stencil window in registers;
+//     left/right neighbours come from warp shuffles, the two warp-edge values from one predicated 8-byte load
+//     that hits L1/L2.  Every element is requested from DRAM once per step: 32 B/cell forward (w, wold, c^2 in,
+//     u out), 56 B/cell adjoint.  Loads of AC_U rows are issued back to back before their arithmetic.
+//   * FRAME CTAs cover everything else (absorbing frame, ring, pitch padding) one cell per thread-iteration with
+//     the full reference expression (phi/psi traffic, sigma/tau profiles, the fp64 divide).  The frame is ~1 % of
+//     a 4096^2 grid, so it is mapped for parallelism, not reuse.
+// Sources and receivers are injected / sampled by the CTA that owns their cell, after a CTA barrier, through
+// per-CTA CSR lists built on the host (no atomics; duplicates accumulate in the reference's sequential order).
+// Forward arithmetic is written in the reference's evaluation order and the library is compiled with
+// -fmad=false, so forward wavefields and traces are bit-identical to the CPU op.
 #pragma once
 #include "common.cuh"
 
 #define AC_WARPS 8
 #define AC_THREADS (AC_WARPS * 32)
-#define AC_WCOLS 64                       // columns per warp
-#define AC_TILE_COLS (AC_WARPS * AC_WCOLS)  // columns per CTA
-#define AC_RB 32                          // rows per CTA
-#define AC_U 4                            // rows whose loads are issued together (memory-level parallelism)
+#define AC_WCOLS 64                         // columns per warp
+#define AC_TILE_COLS (AC_WARPS * AC_WCOLS)  // columns per marching CTA
+#ifndef AC_U
+#define AC_U 4                              // forward: rows whose loads are issued together
+#endif
+#ifndef AC_UA
+#define AC_UA 2                             // adjoint: rows whose loads are issued together
+#endif
+#define AC_FRAME_CPT 4                      // frame cells per thread
+#define AC_FRAME_CELLS (AC_THREADS * AC_FRAME_CPT)
 
 struct AcGeom {
   int H, W;    // global padded rows (NX+2) and columns (NY+2)
   int Hl, ld;  // local rows held by this GPU (incl. halo rows) and pitch in doubles
   int goff;    // global row index of local row 0
-  int fi0, fi1, fj0, fj1;  // inclusive global rows / columns of the PML-free fast region (empty if fi0 > fi1)
   double dt, hx, hy;
   double kx2, ky2;  // 2*dt*dt/hx/hx , 2*dt*dt/hy/hy
   double rx, ry;    // dt/hx , dt/hy
@@ -39,13 +49,25 @@ struct AcGeom {
   i64 plane;        // Hl*ld
 };
 
-// Peer-memory halo targets of a slab (all null on a single GPU).  After finishing a tile that contains its first
-// (last) owned row, a CTA stores that row into the lower (upper) neighbour's halo row of the same array.
-struct AcPeer {
-  double* lo_u;    // address of the row in rank-1's array that mirrors my first owned row (its upper halo row)
-  double* hi_u;    // address of the row in rank+1's array that mirrors my last owned row (its lower halo row)
-  double* lo_phi;
-  double* hi_phi;
+// CTA -> work mapping of one launch (built on the host, passed by value)
+struct AcTiling {
+  int mr0, mr1;       // marched local rows [mr0, mr1)
+  int mc0, mc_end;    // marched columns [mc0, mc_end), mc0 % 16 == 0, both even
+  int rb;             // rows per marching CTA (multiple of AC_U)
+  int nct, ntr;       // marching column tiles / row tiles; marching CTA id = tr*nct + ct
+  int nmarch;         // nct*ntr
+  int nrect;          // frame rectangles (local rows [rr0,rr1) x columns [rc0,rc1))
+  int rr0[4], rr1[4], rc0[4], rc1[4];
+  int rblk[5];        // CTA-id prefix of the rectangles, relative to nmarch
+};
+
+// Per-CTA point lists: points (sources or receivers) owned by CTA b are entries [blk[b], blk[b+1]) of the
+// unique-cell arrays; start/perm give the original point indices on each cell (see PointSet in common.cuh).
+struct AcPoints {
+  const int* blk;    // [nblocks+1] or null when the set is empty
+  const int* cell;
+  const int* start;
+  const int* perm;
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -77,23 +99,24 @@ __device__ __forceinline__ void ac_fwd_general_cell(const AcGeom& g, int li, int
   psio[IJ] = (1. - dt * ta) * psi[IJ] + dt * c * (sg - ta) / 2.0 / g.hy * (w[IJp] - w[IJn]);
 }
 
-// Tile epilogue shared by both kernels: add `scale * val[perm]` into field[cell] for the points of set `inj` that
-// lie in this tile (sequentially per cell, in original point order), then sample field[cell] * sscale into
-// out[perm] for the points of set `smp`.
-__device__ __forceinline__ void ac_tile_epilogue(double* __restrict__ field, const PointSetDev& inj,
-                                                 const double* __restrict__ inj_val, double inj_scale, int ia, int ib,
-                                                 const PointSetDev& smp, double* __restrict__ smp_out,
-                                                 double smp_scale, int sa, int sb) {
-  if (inj_val != nullptr) {
-    for (int k = ia + threadIdx.x; k < ib; k += blockDim.x) {
-      const int cell = inj.cell[k];
-      double v = field[cell];
-      for (int m = inj.start[k]; m < inj.start[k + 1]; m++) v += inj_val[inj.perm[m]] * inj_scale;
-      field[cell] = v;
-    }
+// CTA epilogue shared by both kernels: add `scale * val[perm]` into field[cell] for the injected points this CTA
+// owns (sequentially per cell, in original point order), then sample field[cell]*scale into out[perm].
+__device__ __forceinline__ void ac_cta_epilogue(int bid, double* __restrict__ field, const AcPoints& inj,
+                                                const double* __restrict__ inj_val, double inj_scale,
+                                                const AcPoints& smp, double* __restrict__ smp_out, double smp_scale) {
+  int ia = 0, ib = 0, sa = 0, sb = 0;
+  if (inj.blk != nullptr && inj_val != nullptr) { ia = inj.blk[bid]; ib = inj.blk[bid + 1]; }
+  if (smp.blk != nullptr && smp_out != nullptr) { sa = smp.blk[bid]; sb = smp.blk[bid + 1]; }
+  if (ib == ia && sb == sa) return;  // CTA-uniform
+  __syncthreads();                   // all cells of this CTA are written
+  for (int k = ia + threadIdx.x; k < ib; k += blockDim.x) {
+    const int cell = inj.cell[k];
+    double v = field[cell];
+    for (int m = inj.start[k]; m < inj.start[k + 1]; m++) v += inj_val[inj.perm[m]] * inj_scale;
+    field[cell] = v;
   }
-  if (smp_out != nullptr && sb > sa) {
-    __syncthreads();  // sb>sa is CTA-uniform
+  if (sb > sa) {
+    __syncthreads();
     for (int k = sa + threadIdx.x; k < sb; k += blockDim.x) {
       const double v = field[smp.cell[k]] * smp_scale;
       for (int m = smp.start[k]; m < smp.start[k + 1]; m++) smp_out[smp.perm[m]] = v;
@@ -101,83 +124,93 @@ __device__ __forceinline__ void ac_tile_epilogue(double* __restrict__ field, con
   }
 }
 
-// Store one finished row into a neighbour GPU's halo row over NVLink (peer pointer), 16 B per lane.
-__device__ __forceinline__ void ac_push_row(double* __restrict__ peer_row, const double* __restrict__ my_row, int ct,
-                                            int ld) {
-  const int j = ct * AC_TILE_COLS + 2 * threadIdx.x;
-  if (j < ld) st2(peer_row + j, ld2(my_row + j));
+// frame CTA -> (rect, first linear cell)
+__device__ __forceinline__ void ac_frame_locate(const AcTiling& t, int fb, int* rect, int* idx0) {
+  int r = 0;
+#pragma unroll
+  for (int k = 1; k < 4; k++)
+    if (k < t.nrect && fb >= t.rblk[k]) r = k;
+  *rect = r;
+  *idx0 = (fb - t.rblk[r]) * AC_FRAME_CELLS;
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // forward kernel
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(AC_THREADS)
-ac_fwd_kernel(AcGeom g, int l0, int l1, const double* __restrict__ w, const double* __restrict__ wold,
+__global__ void __launch_bounds__(AC_THREADS, 2)
+ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* __restrict__ wold,
               const double* __restrict__ c2, const double* __restrict__ phi, const double* __restrict__ psi,
               const double* __restrict__ sigx, const double* __restrict__ tauy, double* __restrict__ u,
-              double* __restrict__ phio, double* __restrict__ psio, PointSetDev src,
-              const double* __restrict__ srcv_row, PointSetDev rcv, double* __restrict__ rcvv_row) {
-  __shared__ int s_rng[4];
-  const int ct = blockIdx.x;
-  const int r0 = l0 + blockIdx.y * AC_RB;
-  const int r1 = min(l1, r0 + AC_RB);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int jb = ct * AC_TILE_COLS + warp * AC_WCOLS;
-  const int j = jb + 2 * lane;
+              double* __restrict__ phio, double* __restrict__ psio, AcPoints src,
+              const double* __restrict__ srcv_row, AcPoints rcv, double* __restrict__ rcvv_row) {
+  const int bid = blockIdx.x;
   const int ld = g.ld;
-  if (threadIdx.x == 0) ps_range(src, ct, r0, r1, ld, g.plane, &s_rng[0], &s_rng[1]);
-  if (threadIdx.x == 32) ps_range(rcv, ct, r0, r1, ld, g.plane, &s_rng[2], &s_rng[3]);
-
-  if (j < ld) {
-    const bool fastcols = (jb >= g.fj0) && (jb + AC_WCOLS - 1 <= g.fj1) && (g.fi0 <= g.fi1);
-    if (!fastcols) {
-      for (int li = r0; li < r1; li++) {
+  if (bid >= t.nmarch) {
+    // ---------------- frame CTA ----------------
+    int rect, idx0;
+    ac_frame_locate(t, bid - t.nmarch, &rect, &idx0);
+    const int wdt = t.rc1[rect] - t.rc0[rect];
+    const int ncell = (t.rr1[rect] - t.rr0[rect]) * wdt;
+#pragma unroll
+    for (int k = 0; k < AC_FRAME_CPT; k++) {
+      const int idx = idx0 + k * AC_THREADS + threadIdx.x;
+      if (idx < ncell) {
+        const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
         ac_fwd_general_cell(g, li, j, w, wold, c2, phi, psi, sigx, tauy, u, phio, psio);
-        ac_fwd_general_cell(g, li, j + 1, w, wold, c2, phi, psi, sigx, tauy, u, phio, psio);
       }
-    } else {
+    }
+  } else {
+    // ---------------- marching CTA ----------------
+    const int ct = bid % t.nct, tr = bid / t.nct;
+    const int r0 = t.mr0 + tr * t.rb;
+    const int r1 = min(t.mr1, r0 + t.rb);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int jb = t.mc0 + ct * AC_TILE_COLS + warp * AC_WCOLS;
+    const int j = jb + 2 * lane;
+    const bool ldok = j < ld;       // may load
+    const bool act = j < t.mc_end;  // computes and stores (both columns j, j+1 are inside the box)
+    if (jb < t.mc_end) {
       const double2 z2 = make_double2(0.0, 0.0);
-      double2 wm = (r0 > 0) ? ld2(w + (i64)(r0 - 1) * ld + j) : z2;
-      double2 wc = ld2(w + (i64)r0 * ld + j);
-      for (int rb = r0; rb < r1; rb += AC_U) {
+      const double kx2 = g.kx2, ky2 = g.ky2, rx = g.rx, ry = g.ry;
+      double2 wm = ldok ? ld2(w + (i64)(r0 - 1) * ld + j) : z2;  // r0 >= 1: the box never contains row 0
+      double2 wc = ldok ? ld2(w + (i64)r0 * ld + j) : z2;
+      for (int rbase = r0; rbase < r1; rbase += AC_U) {
         double2 wn[AC_U], wo[AC_U], cc[AC_U];
         double we[AC_U];
 #pragma unroll
         for (int k = 0; k < AC_U; k++) {
-          const int li = rb + k;
+          const int li = rbase + k;
+          wn[k] = z2; wo[k] = z2; cc[k] = z2; we[k] = 0.0;
           if (li < r1) {
             const i64 ro = (i64)li * ld;
-            wn[k] = (li + 1 < g.Hl) ? ld2(w + ro + ld + j) : z2;
-            wo[k] = ld2_stream(wold + ro + j);
-            cc[k] = ld2(c2 + ro + j);
-            we[k] = 0.0;
-            if (lane == 0) we[k] = w[ro + jb - 1];
-            if (lane == 31) we[k] = w[ro + jb + AC_WCOLS];
+            if (ldok) wn[k] = ld2(w + ro + ld + j);  // li+1 <= Hl-1: the box never contains the last row
+            if (act) {
+              wo[k] = ld2_stream(wold + ro + j);
+              cc[k] = ld2(c2 + ro + j);
+              if (lane == 0) we[k] = w[ro + jb - 1];
+              if (lane == 31) we[k] = w[ro + jb + AC_WCOLS];
+            }
           }
         }
 #pragma unroll
         for (int k = 0; k < AC_U; k++) {
-          const int li = rb + k;
+          const int li = rbase + k;
           if (li < r1) {
-            const int gi = g.goff + li;
-            if (gi < g.fi0 || gi > g.fi1) {
-              ac_fwd_general_cell(g, li, j, w, wold, c2, phi, psi, sigx, tauy, u, phio, psio);
-              ac_fwd_general_cell(g, li, j + 1, w, wold, c2, phi, psi, sigx, tauy, u, phio, psio);
-            } else {
-              double lft = __shfl_up_sync(0xffffffffu, wc.y, 1);
-              double rgt = __shfl_down_sync(0xffffffffu, wc.x, 1);
-              if (lane == 0) lft = we[k];
-              if (lane == 31) rgt = we[k];
+            double lft = __shfl_up_sync(0xffffffffu, wc.y, 1);
+            double rgt = __shfl_down_sync(0xffffffffu, wc.x, 1);
+            if (lane == 0) lft = we[k];
+            if (lane == 31) rgt = we[k];
+            if (act) {
               double2 o;
               {
                 const double c = cc[k].x;
-                o.x = (2 - g.kx2 * c - g.ky2 * c) * wc.x + c * g.rx * g.rx * (wn[k].x + wm.x) +
-                      c * g.ry * g.ry * (wc.y + lft) - wo[k].x;
+                o.x = (2 - kx2 * c - ky2 * c) * wc.x + c * rx * rx * (wn[k].x + wm.x) + c * ry * ry * (wc.y + lft) -
+                      wo[k].x;
               }
               {
                 const double c = cc[k].y;
-                o.y = (2 - g.kx2 * c - g.ky2 * c) * wc.y + c * g.rx * g.rx * (wn[k].y + wm.y) +
-                      c * g.ry * g.ry * (rgt + wc.x) - wo[k].y;
+                o.y = (2 - kx2 * c - ky2 * c) * wc.y + c * rx * rx * (wn[k].y + wm.y) + c * ry * ry * (rgt + wc.x) -
+                      wo[k].y;
               }
               st2(u + (i64)li * ld + j, o);
             }
@@ -188,22 +221,12 @@ ac_fwd_kernel(AcGeom g, int l0, int l1, const double* __restrict__ w, const doub
       }
     }
   }
-  __syncthreads();
-  ac_tile_epilogue(u, src, srcv_row, g.dt2, s_rng[0], s_rng[1], rcv, rcvv_row, 1.0, s_rng[2], s_rng[3]);
+  ac_cta_epilogue(bid, u, src, srcv_row, g.dt2, rcv, rcvv_row, 1.0);
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// adjoint helpers
+// adjoint, general cell (gather form of AcousticOneStepCpu.h:76-124)
 // ------------------------------------------------------------------------------------------------------------
-// g(Q) = ubar(Q) / D(Q) for interior Q, 0 otherwise (the ring is a constant output of the forward step)
-__device__ __forceinline__ double ac_g_at(const AcGeom& g, const double* __restrict__ ub,
-                                          const double* __restrict__ sigx, const double* __restrict__ tauy, int li,
-                                          int j) {
-  const int gi = g.goff + li;
-  if (gi < 1 || gi > g.H - 2 || j < 1 || j > g.W - 2) return 0.0;
-  return ub[(i64)li * g.ld + j] / (1 + (sigx[gi] + tauy[j]) / 2 * g.dt);
-}
-
 __device__ __forceinline__ void ac_adj_general_cell(const AcGeom& g, int li, int j, const double* __restrict__ ub1,
                                                     const double* __restrict__ ub2, const double* __restrict__ wf,
                                                     const double* __restrict__ c2, const double* __restrict__ phib,
@@ -215,8 +238,9 @@ __device__ __forceinline__ void ac_adj_general_cell(const AcGeom& g, int li, int
   const i64 IJ = (i64)li * g.ld + j;
   if (j >= g.W) { ub0[IJ] = 0.0; return; }
   const double dt = g.dt;
-  const bool intP = (gi >= 1 && gi <= g.H - 2 && j >= 1 && j <= g.W - 2);
   const bool colok = (j >= 1 && j <= g.W - 2);
+  const bool rowok = (gi >= 1 && gi <= g.H - 2);
+  const bool intP = rowok && colok;
   double acc = 0.0, sg = 0.0, ta = 0.0, gP = 0.0;
   if (intP) {
     sg = sigx[gi]; ta = tauy[j];
@@ -237,14 +261,13 @@ __device__ __forceinline__ void ac_adj_general_cell(const AcGeom& g, int li, int
     gxp = ub1[Q] / (1 + (sQ + tQ) / 2 * dt);
     acc += cQ * g.rx * g.rx * gxp - dt * cQ * (tQ - sQ) / 2.0 / g.hx * phib[Q];
   }
-  const bool rowok = (gi >= 1 && gi <= g.H - 2);
-  if (rowok && j - 1 >= 1) {  // Q = P - e_y : grad_w[IJp] of Q
+  if (rowok && j - 1 >= 1 && j - 1 <= g.W - 2) {  // Q = P - e_y : grad_w[IJp] of Q
     const i64 Q = IJ - 1;
     const double cQ = c2[Q], sQ = sigx[gi], tQ = tauy[j - 1];
     gym = ub1[Q] / (1 + (sQ + tQ) / 2 * dt);
     acc += cQ * g.ry * g.ry * gym + dt * cQ * (sQ - tQ) / 2.0 / g.hy * psib[Q];
   }
-  if (rowok && j + 1 <= g.W - 2) {  // Q = P + e_y : grad_w[IJn] of Q
+  if (rowok && j + 1 >= 1 && j + 1 <= g.W - 2) {  // Q = P + e_y : grad_w[IJn] of Q
     const i64 Q = IJ + 1;
     const double cQ = c2[Q], sQ = sigx[gi], tQ = tauy[j + 1];
     gyp = ub1[Q] / (1 + (sQ + tQ) / 2 * dt);
@@ -266,96 +289,96 @@ __device__ __forceinline__ void ac_adj_general_cell(const AcGeom& g, int li, int
 // ------------------------------------------------------------------------------------------------------------
 // adjoint kernel: ub0 = ubar[s-1] from ub1 = ubar[s], ub2 = ubar[s+1], wf = u[s-1]
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(AC_THREADS)
-ac_adj_kernel(AcGeom g, int l0, int l1, const double* __restrict__ ub1, const double* __restrict__ ub2,
+__global__ void __launch_bounds__(AC_THREADS, 2)
+ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double* __restrict__ ub2,
               const double* __restrict__ wf, const double* __restrict__ c2, const double* __restrict__ phib,
               const double* __restrict__ psib, const double* __restrict__ sigx, const double* __restrict__ tauy,
               double* __restrict__ ub0, double* __restrict__ phibo, double* __restrict__ psibo,
-              double* __restrict__ G, PointSetDev rcv, const double* __restrict__ res_row, PointSetDev src,
+              double* __restrict__ G, AcPoints rcv, const double* __restrict__ res_row, AcPoints src,
               double* __restrict__ gsrcv_row) {
-  __shared__ int s_rng[4];
-  const int ct = blockIdx.x;
-  const int r0 = l0 + blockIdx.y * AC_RB;
-  const int r1 = min(l1, r0 + AC_RB);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int jb = ct * AC_TILE_COLS + warp * AC_WCOLS;
-  const int j = jb + 2 * lane;
+  const int bid = blockIdx.x;
   const int ld = g.ld;
-  if (threadIdx.x == 0) ps_range(rcv, ct, r0, r1, ld, g.plane, &s_rng[0], &s_rng[1]);
-  if (threadIdx.x == 32) ps_range(src, ct, r0, r1, ld, g.plane, &s_rng[2], &s_rng[3]);
-
-  if (j < ld) {
-    const bool fastcols = (jb >= g.fj0) && (jb + AC_WCOLS - 1 <= g.fj1) && (g.fi0 <= g.fi1);
-    if (!fastcols) {
-      for (int li = r0; li < r1; li++) {
+  if (bid >= t.nmarch) {
+    int rect, idx0;
+    ac_frame_locate(t, bid - t.nmarch, &rect, &idx0);
+    const int wdt = t.rc1[rect] - t.rc0[rect];
+    const int ncell = (t.rr1[rect] - t.rr0[rect]) * wdt;
+#pragma unroll
+    for (int k = 0; k < AC_FRAME_CPT; k++) {
+      const int idx = idx0 + k * AC_THREADS + threadIdx.x;
+      if (idx < ncell) {
+        const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
         ac_adj_general_cell(g, li, j, ub1, ub2, wf, c2, phib, psib, sigx, tauy, ub0, phibo, psibo, G);
-        ac_adj_general_cell(g, li, j + 1, ub1, ub2, wf, c2, phib, psib, sigx, tauy, ub0, phibo, psibo, G);
       }
-    } else {
+    }
+  } else {
+    const int ct = bid % t.nct, tr = bid / t.nct;
+    const int r0 = t.mr0 + tr * t.rb;
+    const int r1 = min(t.mr1, r0 + t.rb);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int jb = t.mc0 + ct * AC_TILE_COLS + warp * AC_WCOLS;
+    const int j = jb + 2 * lane;
+    const bool ldok = j < ld;
+    const bool act = j < t.mc_end;
+    if (jb < t.mc_end) {
       const double2 z2 = make_double2(0.0, 0.0);
-      const double rx2 = g.rx * g.rx, ry2 = g.ry * g.ry, kk = -g.kx2 - g.ky2;
-      // windows: cg = c^2 * ubar[s] (D == 1 on every row a fast row can see), w = u[s-1]
-      double2 cgm = z2, cgc, wm = z2, wc, gc, ccen;
-      if (r0 > 0) {
-        const i64 ro = (i64)(r0 - 1) * ld + j;
+      const double rx2 = g.rx * g.rx, ry2 = g.ry * g.ry, kk = -g.kx2 - g.ky2, kx2 = g.kx2, ky2 = g.ky2;
+      // register windows: cg = c^2 * ubar[s] (D == 1 and no ring cell within one cell of the box), w = u[s-1]
+      double2 cgm = z2, cgc = z2, wm = z2, wc = z2, gc = z2, ccen = z2;
+      if (ldok) {
+        i64 ro = (i64)(r0 - 1) * ld + j;
         const double2 c_ = ld2(c2 + ro), u_ = ld2(ub1 + ro);
         cgm = make_double2(c_.x * u_.x, c_.y * u_.y);
         wm = ld2(wf + ro);
-      }
-      {
-        const i64 ro = (i64)r0 * ld + j;
+        ro += ld;
         ccen = ld2(c2 + ro);
         gc = ld2(ub1 + ro);
         cgc = make_double2(ccen.x * gc.x, ccen.y * gc.y);
         wc = ld2(wf + ro);
       }
-      for (int rb = r0; rb < r1; rb += AC_U) {
-        double2 un[AC_U], cn[AC_U], wn[AC_U], u2[AC_U], Gr[AC_U];
-        double ecg[AC_U], ew[AC_U];
+      for (int rbase = r0; rbase < r1; rbase += AC_UA) {
+        double2 un[AC_UA], cn[AC_UA], wn[AC_UA], u2[AC_UA], Gr[AC_UA];
+        double ecg[AC_UA], ew[AC_UA];
 #pragma unroll
-        for (int k = 0; k < AC_U; k++) {
-          const int li = rb + k;
+        for (int k = 0; k < AC_UA; k++) {
+          const int li = rbase + k;
+          un[k] = z2; cn[k] = z2; wn[k] = z2; u2[k] = z2; Gr[k] = z2; ecg[k] = 0.0; ew[k] = 0.0;
           if (li < r1) {
             const i64 ro = (i64)li * ld;
-            if (li + 1 < g.Hl) {
+            if (ldok) {
               un[k] = ld2(ub1 + ro + ld + j);
               cn[k] = ld2(c2 + ro + ld + j);
               wn[k] = ld2(wf + ro + ld + j);
-            } else {
-              un[k] = z2; cn[k] = z2; wn[k] = z2;
             }
-            u2[k] = ld2_stream(ub2 + ro + j);
-            Gr[k] = ld2_stream(G + ro + j);
-            ecg[k] = 0.0; ew[k] = 0.0;
-            if (lane == 0) { ecg[k] = c2[ro + jb - 1] * ub1[ro + jb - 1]; ew[k] = wf[ro + jb - 1]; }
-            if (lane == 31) { ecg[k] = c2[ro + jb + AC_WCOLS] * ub1[ro + jb + AC_WCOLS]; ew[k] = wf[ro + jb + AC_WCOLS]; }
+            if (act) {
+              u2[k] = ld2_stream(ub2 + ro + j);
+              Gr[k] = ld2_stream(G + ro + j);
+              if (lane == 0) { ecg[k] = c2[ro + jb - 1] * ub1[ro + jb - 1]; ew[k] = wf[ro + jb - 1]; }
+              if (lane == 31) { ecg[k] = c2[ro + jb + AC_WCOLS] * ub1[ro + jb + AC_WCOLS]; ew[k] = wf[ro + jb + AC_WCOLS]; }
+            }
           }
         }
 #pragma unroll
-        for (int k = 0; k < AC_U; k++) {
-          const int li = rb + k;
+        for (int k = 0; k < AC_UA; k++) {
+          const int li = rbase + k;
           if (li < r1) {
-            const int gi = g.goff + li;
             const double2 cgp = make_double2(cn[k].x * un[k].x, cn[k].y * un[k].y);
-            if (gi < g.fi0 || gi > g.fi1) {
-              ac_adj_general_cell(g, li, j, ub1, ub2, wf, c2, phib, psib, sigx, tauy, ub0, phibo, psibo, G);
-              ac_adj_general_cell(g, li, j + 1, ub1, ub2, wf, c2, phib, psib, sigx, tauy, ub0, phibo, psibo, G);
-            } else {
-              double cgl = __shfl_up_sync(0xffffffffu, cgc.y, 1);
-              double cgr = __shfl_down_sync(0xffffffffu, cgc.x, 1);
-              double wl = __shfl_up_sync(0xffffffffu, wc.y, 1);
-              double wr = __shfl_down_sync(0xffffffffu, wc.x, 1);
-              if (lane == 0) { cgl = ecg[k]; wl = ew[k]; }
-              if (lane == 31) { cgr = ecg[k]; wr = ew[k]; }
+            double cgl = __shfl_up_sync(0xffffffffu, cgc.y, 1);
+            double cgr = __shfl_down_sync(0xffffffffu, cgc.x, 1);
+            double wl = __shfl_up_sync(0xffffffffu, wc.y, 1);
+            double wr = __shfl_down_sync(0xffffffffu, wc.x, 1);
+            if (lane == 0) { cgl = ecg[k]; wl = ew[k]; }
+            if (lane == 31) { cgr = ecg[k]; wr = ew[k]; }
+            if (act) {
               double2 o, Go;
               {
                 const double c = ccen.x, gg = gc.x;
-                o.x = (2 - g.kx2 * c - g.ky2 * c) * gg + rx2 * (cgp.x + cgm.x) + ry2 * (cgc.y + cgl) - u2[k].x;
+                o.x = (2 - kx2 * c - ky2 * c) * gg + rx2 * (cgp.x + cgm.x) + ry2 * (cgc.y + cgl) - u2[k].x;
                 Go.x = Gr[k].x + (kk * wc.x + rx2 * (wn[k].x + wm.x) + ry2 * (wc.y + wl)) * gg;
               }
               {
                 const double c = ccen.y, gg = gc.y;
-                o.y = (2 - g.kx2 * c - g.ky2 * c) * gg + rx2 * (cgp.y + cgm.y) + ry2 * (cgr + cgc.x) - u2[k].y;
+                o.y = (2 - kx2 * c - ky2 * c) * gg + rx2 * (cgp.y + cgm.y) + ry2 * (cgr + cgc.x) - u2[k].y;
                 Go.y = Gr[k].y + (kk * wc.y + rx2 * (wn[k].y + wm.y) + ry2 * (wr + wc.x)) * gg;
               }
               st2(ub0 + (i64)li * ld + j, o);
@@ -369,6 +392,5 @@ ac_adj_kernel(AcGeom g, int l0, int l1, const double* __restrict__ ub1, const do
       }
     }
   }
-  __syncthreads();
-  ac_tile_epilogue(ub0, rcv, res_row, 1.0, s_rng[0], s_rng[1], src, gsrcv_row, g.dt2, s_rng[2], s_rng[3]);
+  ac_cta_epilogue(bid, ub0, rcv, res_row, 1.0, src, gsrcv_row, g.dt2);
 }

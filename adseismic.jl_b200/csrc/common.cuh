@@ -75,97 +75,71 @@ static inline int dev_upload(T** p, const std::vector<T>& h, cudaStream_t s) {
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // ---------------------------------------------------------------------------------------------------------
-// Point sets: sources and receivers grouped by grid cell so that the time-step kernels can inject / sample
-// them in their tile epilogue without atomics and in the reference's sequential order
+// Point sets: sources and receivers grouped by owning CTA and grid cell, so that the time-step kernels can
+// inject / sample them in their CTA epilogue without atomics and in the reference's sequential order
 // (ScatterAddOps.h:3-6, AddSource.cpp:57-85 add in source order; duplicates on one cell are legal).
-//   key[k]   = coltile * plane + cell   (sorted ascending; one entry per UNIQUE (cell[,field]) )
-//   cell[k]  = local flat offset row*ld + col
-//   start[k]..start[k+1] = range into perm[] of the points that sit on that cell, in original order
-//   perm[m]  = original (global) point index
+//   blk[b]..blk[b+1]       = unique-cell entries owned by CTA b
+//   cell[k]                = local flat offset row*ld + col of entry k   (elastic: field id in `field[k]`)
+//   start[k]..start[k+1]   = range into perm[] of the points that sit on that cell, in original order
+//   perm[m]                = original (global) point index
 // ---------------------------------------------------------------------------------------------------------
 struct PointSetHost {
-  std::vector<i64> key;
-  std::vector<int> cell, start, perm, field;
-};
-struct PointSetDev {
-  int nu;            // unique cells
-  int npts;          // points
-  const i64* key;
-  const int* cell;
-  const int* start;
-  const int* perm;
-  const int* field;  // elastic: field id per unique entry (else null)
+  std::vector<int> blk, cell, start, perm, field;
 };
 
-// rows/cols are local row and column of each kept point, gid its global index; field may be empty.
-static inline void build_point_set(const std::vector<int>& rows, const std::vector<int>& cols,
-                                   const std::vector<int>& gid, const std::vector<int>& field, int ld, i64 plane,
-                                   int tile_cols, PointSetHost* out) {
-  size_t n = rows.size();
+// owner/cells/gid/field describe the kept points (field may be empty); nblocks = CTAs of the launch.
+static inline void build_point_set(const std::vector<int>& owner, const std::vector<int>& cells,
+                                   const std::vector<int>& gid, const std::vector<int>& field, int nblocks,
+                                   PointSetHost* out) {
+  const size_t n = owner.size();
   std::vector<size_t> order(n);
   for (size_t k = 0; k < n; k++) order[k] = k;
-  auto keyof = [&](size_t k) -> i64 {
-    i64 cell = (i64)rows[k] * ld + cols[k];
-    i64 f = field.empty() ? 0 : field[k];
-    return ((i64)(cols[k] / tile_cols) * plane + cell) * 8 + f;
+  auto less = [&](size_t a, size_t b) {
+    if (owner[a] != owner[b]) return owner[a] < owner[b];
+    if (cells[a] != cells[b]) return cells[a] < cells[b];
+    const int fa = field.empty() ? 0 : field[a], fb = field.empty() ? 0 : field[b];
+    return fa < fb;
   };
-  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return keyof(a) < keyof(b); });
-  out->key.clear(); out->cell.clear(); out->start.clear(); out->perm.clear(); out->field.clear();
+  std::stable_sort(order.begin(), order.end(), less);
+  out->blk.assign((size_t)nblocks + 1, 0);
+  out->cell.clear(); out->start.clear(); out->perm.clear(); out->field.clear();
+  std::vector<int> ent_owner;
   for (size_t m = 0; m < n; m++) {
-    size_t k = order[m];
-    i64 key = keyof(k);
-    if (out->key.empty() || out->key.back() != key) {
-      out->key.push_back(key);
-      out->cell.push_back(rows[k] * ld + cols[k]);
-      out->field.push_back(field.empty() ? 0 : field[k]);
+    const size_t k = order[m];
+    const int f = field.empty() ? 0 : field[k];
+    if (out->cell.empty() || ent_owner.back() != owner[k] || out->cell.back() != cells[k] || out->field.back() != f) {
+      out->cell.push_back(cells[k]);
+      out->field.push_back(f);
       out->start.push_back((int)m);
+      ent_owner.push_back(owner[k]);
     }
     out->perm.push_back(gid[k]);
   }
   out->start.push_back((int)n);
+  for (int o : ent_owner) out->blk[(size_t)o + 1]++;
+  for (int b = 0; b < nblocks; b++) out->blk[(size_t)b + 1] += out->blk[(size_t)b];
 }
 
 struct PointSetStorage {
-  i64* key = nullptr;
-  int *cell = nullptr, *start = nullptr, *perm = nullptr, *field = nullptr;
-  PointSetDev dev{};
+  int *blk = nullptr, *cell = nullptr, *start = nullptr, *perm = nullptr, *field = nullptr;
+  int nu = 0, npts = 0;
 };
 static inline int upload_point_set(const PointSetHost& h, PointSetStorage* st, cudaStream_t s) {
-  TRY(dev_upload(&st->key, h.key, s));
+  TRY(dev_upload(&st->blk, h.blk, s));
   TRY(dev_upload(&st->cell, h.cell, s));
   TRY(dev_upload(&st->start, h.start, s));
   TRY(dev_upload(&st->perm, h.perm, s));
   TRY(dev_upload(&st->field, h.field, s));
-  st->dev.nu = (int)h.key.size();
-  st->dev.npts = (int)h.perm.size();
-  st->dev.key = st->key; st->dev.cell = st->cell; st->dev.start = st->start; st->dev.perm = st->perm;
-  st->dev.field = st->field;
+  st->nu = (int)h.cell.size();
+  st->npts = (int)h.perm.size();
   return ADSEIS_OK;
 }
 static inline void free_point_set(PointSetStorage* st) {
-  cudaFree(st->key); cudaFree(st->cell); cudaFree(st->start); cudaFree(st->perm); cudaFree(st->field);
+  cudaFree(st->blk); cudaFree(st->cell); cudaFree(st->start); cudaFree(st->perm); cudaFree(st->field);
   *st = PointSetStorage();
 }
 
 #ifdef __CUDACC__
-// first index k in [0,n) with key[k] >= v
-__device__ __forceinline__ int ps_lower_bound(const i64* __restrict__ key, int n, i64 v) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (key[mid] < v) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-// entries of `ps` whose cell lies in rows [r0,r1) of column tile `ct`  ->  [*a,*b)
-__device__ __forceinline__ void ps_range(const PointSetDev& ps, int ct, int r0, int r1, int ld, i64 plane, int* a,
-                                         int* b) {
-  if (ps.nu == 0) { *a = 0; *b = 0; return; }
-  i64 base = (i64)ct * plane;
-  *a = ps_lower_bound(ps.key, ps.nu, (base + (i64)r0 * ld) * 8);
-  *b = ps_lower_bound(ps.key, ps.nu, (base + (i64)r1 * ld) * 8);
-}
-
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
 // streaming (evict-first) 16-byte accesses for data touched once per time step

@@ -1,0 +1,32 @@
+"""Quick device-side timing of the acoustic kernels (not the bench contract; a development probe)."""
+import sys, os, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import adseis_b200 as A
+
+def run(NX, NY, NSTEP, reps=3, budget=0):
+    ctx = A.default_context()
+    p = A.AcousticPropagatorParams(NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=10.0, DELTAY=10.0, DELTAT=0.05, Rcoef=0.2,
+                                   vp_ref=1000.0, mpi_convention=True)
+    c2 = np.full((NX, NY), 1000.0); c2[NX//2-NX//8:NX//2+NX//8, NY//2-NY//8:NY//2+NY//8] = 2000.0
+    srcv = A.Ricker(p, 100.0, 500.0).reshape(-1, 1)
+    rcvj = np.arange(20, NY - 19); rcvi = np.full(len(rcvj), NX // 5)
+    plan = A.AcousticPlan(p, [NX // 5], [NY // 2], rcvi, rcvj, ctx=ctx, hist_bytes_budget=budget)
+    plan.set_model(c2); plan.set_srcv(srcv); plan.set_obs(np.zeros((NSTEP + 1, len(rcvj))))
+    cells = NX * NY * (NSTEP - 1)
+    for name, fn in (("forward", plan.forward), ("gradient", plan.gradient)):
+        fn(); ctx.sync()
+        ts = []
+        for _ in range(reps):
+            ctx.timer_start(); fn(); ts.append(ctx.timer_stop_ms())
+        t = min(ts)
+        info = plan.info()
+        bytes_ = cells * (32 if name == "forward" else 88 + 32 * (info["recomputed_steps"] / max(NSTEP - 1, 1)))
+        print("%dx%d nt=%d %-8s %8.2f ms  %7.2f Gcell/s  %7.1f GB/s(alg)  %s" % (NX, NY, NSTEP, name, t, cells / t / 1e6, bytes_ / t / 1e6, info), flush=True)
+    plan.close()
+
+if __name__ == "__main__":
+    run(4096, 4096, 60)
+    run(4096, 4096, 120, budget=40 * 4098 * 4112 * 8)
+    run(2000, 1000, 200)
+    run(401, 133, 1000)

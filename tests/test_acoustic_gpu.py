@@ -116,7 +116,7 @@ def test_mpi_convention(A, ctx, po):
     c2 = 1.0e6 * (1 + 0.2 * rng.random((NX, NY)))
     srci, srcj = np.array([NX // 5, 1]), np.array([NY // 2, 1])
     srcv = np.stack([po.ricker(NSTEP, 6.0, 15.0, 1e4)] * 2, 1)
-    rcvi, rcvj = np.full(100, NX // 5), np.arange(20, 120)
+    rcvi, rcvj = np.full(100, NX // 5), np.arange(NY // 2 - 50, NY // 2 + 50)
     c2p = np.zeros((NX + 2, NY + 2)); c2p[1:-1, 1:-1] = c2
     u0, r0 = po.acoustic_forward(NX, NY, NSTEP, dt, dx, dx, sig, tau, c2p, srci, srcj, srcv, rcvi, rcvj,
                                  mpi_convention=True)
