@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libadseis_b200.so")
+LIB = os.path.join(HERE, "libadseis_b200%s.so" % os.environ.get("ADSEIS_LIB_SUFFIX", ""))  # suffix: tuning variants
 SOURCES = ["ctx.cu", "acoustic.cu", "elastic.cu", "ops.cu"]
 HEADERS = ["common.cuh", "acoustic_kernels.cuh", "elastic_kernels.cuh", os.path.join("..", "..", "include", "adseis.h")]
 # -fmad=false: fp64 products and sums are rounded separately, exactly like the reference's CPU op bodies, so that
@@ -27,7 +27,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("ADSEIS_NVCC_EXTRA", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
     env.pop("CC", None), env.pop("CXX", None)
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)

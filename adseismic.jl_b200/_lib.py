@@ -73,6 +73,7 @@ SIGNATURES = {
     "adseis_acoustic_plan_get": (C.c_int, [vp, C.c_int, vp, C.c_int]),
     "adseis_acoustic_plan_get_snapshot": (C.c_int, [vp, i64, vp, C.c_int]),
     "adseis_acoustic_plan_info": (C.c_int, [vp, ip]),
+    "adseis_acoustic_plan_timings": (C.c_int, [vp, dp]),
     "adseis_acoustic_plan_ipc_export": (C.c_int, [vp, vp]),
     "adseis_acoustic_plan_ipc_connect": (C.c_int, [vp, vp, vp]),
     "adseis_acoustic_forward": (C.c_int, [vp, _PA, dp, i64, ip, ip, dp, i64, i64, ip, ip, dp, dp]),

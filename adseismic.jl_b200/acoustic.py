@@ -112,6 +112,13 @@ class AcousticPlan:
         return dict(hist_slots=int(a[0]), segments=int(a[1]), launches=int(a[2]), local_rows=int(a[3]),
                     pitch=int(a[4]), recomputed_steps=int(a[5]), planned_segments=int(a[6]), fast_rows=int(a[7]))
 
+    def timings(self):
+        """Device ms / launches of the last forward()/gradient() per phase (CUDA events on the ctx stream)."""
+        a = np.zeros(6)
+        check(self.lib.adseis_acoustic_plan_timings(self.handle, pd(a)))
+        return dict(forward_ms=a[0], recompute_ms=a[1], adjoint_ms=a[2], forward_launches=int(a[3]),
+                    recompute_launches=int(a[4]), adjoint_launches=int(a[5]))
+
     def close(self):
         if getattr(self, "handle", None) is not None:
             self.lib.adseis_acoustic_plan_destroy(self.handle)

@@ -108,7 +108,30 @@ struct adseis_acoustic_plan {
   bool have_model = false, have_srcv = false, have_obs = false, have_grad = false, have_fwd = false;
   // stats
   i64 last_launches = 0, last_segments = 0, last_recomputed = 0;
+  // per-phase device timing of the last forward()/gradient(): CUDA events on the ctx stream around each run of
+  // identical kernels (phase 0 = forward sweep, 1 = forward recomputation, 2 = adjoint sweep)
+  std::vector<cudaEvent_t> ev_pool;
+  struct Span { int phase; i64 launches; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  size_t ev_used = 0;
 };
+
+static int span_begin(adseis_acoustic_plan* P, int phase, i64 launches) {
+  while (P->ev_pool.size() < P->ev_used + 2) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    P->ev_pool.push_back(e);
+  }
+  adseis_acoustic_plan::Span sp{phase, launches, P->ev_pool[P->ev_used], P->ev_pool[P->ev_used + 1]};
+  P->ev_used += 2;
+  CUDA_TRY(cudaEventRecord(sp.a, P->ctx->stream));
+  P->spans.push_back(sp);
+  return ADSEIS_OK;
+}
+static int span_end(adseis_acoustic_plan* P) {
+  CUDA_TRY(cudaEventRecord(P->spans.back().b, P->ctx->stream));
+  return ADSEIS_OK;
+}
 
 static inline double* win_slot(adseis_acoustic_plan* P, i64 base, i64 s) { return P->hist + (s - base) * P->g.plane; }
 
@@ -165,6 +188,7 @@ ADSEIS_API int adseis_acoustic_plan_destroy(adseis_acoustic_plan* P) {
   cudaFree(P->rcv_owned);
   cudaFree(P->srcv); cudaFree(P->rcvv); cudaFree(P->obs); cudaFree(P->res); cudaFree(P->loss);
   cudaFree(P->G); cudaFree(P->gradc); cudaFree(P->gradsrcv);
+  for (cudaEvent_t e : P->ev_pool) cudaEventDestroy(e);
   delete P;
   return ADSEIS_OK;
 }
@@ -486,7 +510,9 @@ static int forward_sweep(adseis_acoustic_plan* P, bool save_ckpt, segment_cb cb,
       CUDA_TRY(cudaMemcpyAsync(P->hist, s0, pb, cudaMemcpyDeviceToDevice, st));
       CUDA_TRY(cudaMemcpyAsync(P->hist + g.plane, s1, pb, cudaMemcpyDeviceToDevice, st));
     }
+    TRY(span_begin(P, 0, e - (b + 2) + 1));
     TRY(run_forward_steps(P, b, b + 2, e, true));
+    TRY(span_end(P));
     P->win_base = b; P->win_last = e;
     if (cb) TRY(cb(P, k, user));
   }
@@ -506,6 +532,7 @@ ADSEIS_API int adseis_acoustic_plan_forward(adseis_acoustic_plan* P) {
   TRY(check_ready(P, false));
   CUDA_TRY(cudaSetDevice(P->ctx->device));
   P->last_launches = 0; P->last_recomputed = 0;
+  P->spans.clear(); P->ev_used = 0;
   TRY(forward_sweep(P, false, nullptr, nullptr));
   P->last_segments = (i64)P->seg_b.size();
   P->have_fwd = true;
@@ -533,6 +560,7 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
   const i64 NSTEP = P->p.NSTEP;
   const size_t pb = (size_t)g.plane * 8;
   P->last_launches = 0; P->last_recomputed = 0;
+  P->spans.clear(); P->ev_used = 0;
   TRY(ensure_adjoint_state(P));
   // ---- forward, keeping checkpoints; the last segment stays in the window
   TRY(forward_sweep(P, true, nullptr, nullptr));
@@ -574,12 +602,14 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
         CUDA_TRY(cudaMemcpyAsync(P->phi[(b + 1) & 1], c + 2 * g.plane, pb, cudaMemcpyDeviceToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(P->psi[(b + 1) & 1], c + 3 * g.plane, pb, cudaMemcpyDeviceToDevice, st));
       }
+      TRY(span_begin(P, 1, e - (b + 2) + 1));
       TRY(run_forward_steps(P, b, b + 2, e, false));
+      TRY(span_end(P));
       P->last_recomputed += e - (b + 2) + 1;
       P->win_base = b; P->win_last = e;
     }
+    TRY(span_begin(P, 2, e - (b + 2) + 1));
     for (i64 s = e; s >= b + 2; s--) {
-      if (s < 2) break;
       ac_adj_kernel<<<P->nblocks, AC_THREADS, 0, st>>>(
           g, P->t, P->ub[s % 3], P->ub[(s + 1) % 3], win_slot(P, b, s - 1), P->c2, P->phib[s & 1], P->psib[s & 1],
           P->sigx, P->tauy, P->ub[(s + 2) % 3] /* == (s-1)%3 */, P->phib[(s - 1) & 1], P->psib[(s - 1) & 1], P->G,
@@ -587,6 +617,7 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
           (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr);
       LAUNCH_CHECK(P);
     }
+    TRY(span_end(P));
   }
   CUDA_TRY(cudaMemsetAsync(P->gradc, 0, (size_t)P->model_elems * 8, st));
   {
@@ -660,6 +691,20 @@ ADSEIS_API int adseis_acoustic_plan_info(adseis_acoustic_plan* P, int64_t info[8
   return ADSEIS_OK;
 }
 
+ADSEIS_API int adseis_acoustic_plan_timings(adseis_acoustic_plan* P, double out[6]) {
+  REQUIRE(P && out, "acoustic_plan_timings: null");
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  for (int k = 0; k < 6; k++) out[k] = 0.0;
+  for (const auto& sp : P->spans) {
+    CUDA_TRY(cudaEventSynchronize(sp.b));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, sp.a, sp.b));
+    out[sp.phase] += ms;
+    out[3 + sp.phase] += (double)sp.launches;
+  }
+  return ADSEIS_OK;
+}
+
 ADSEIS_API int adseis_acoustic_plan_ipc_export(adseis_acoustic_plan* P, void* handle_out) {
   (void)P; (void)handle_out;
   adseis_set_error("acoustic_plan_ipc_export: peer halo exchange is not available in this build");
@@ -693,6 +738,7 @@ ADSEIS_API int adseis_acoustic_forward(adseis_ctx* ctx, const adseis_acoustic_pa
   if (!rc) rc = adseis_acoustic_plan_set_srcv(P, srcv, srcv_rows, 0);
   if (!rc) {
     P->last_launches = 0;
+    P->spans.clear(); P->ev_used = 0;
     hist_copy_ctx h{u_hist_out};
     rc = forward_sweep(P, false, u_hist_out ? hist_copy_cb : nullptr, &h);
     P->have_fwd = (rc == 0);

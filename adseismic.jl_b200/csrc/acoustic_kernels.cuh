@@ -32,7 +32,13 @@
 #define AC_U 4                              // forward: rows whose loads are issued together
 #endif
 #ifndef AC_UA
-#define AC_UA 2                             // adjoint: rows whose loads are issued together
+#define AC_UA 1                             // adjoint: rows whose loads are issued together (occupancy beats unrolling here)
+#endif
+#ifndef AC_MINB_FWD
+#define AC_MINB_FWD 2                       // __launch_bounds__ min CTAs/SM, forward
+#endif
+#ifndef AC_MINB_ADJ
+#define AC_MINB_ADJ 3                       // __launch_bounds__ min CTAs/SM, adjoint
 #endif
 #define AC_FRAME_CPT 4                      // frame cells per thread
 #define AC_FRAME_CELLS (AC_THREADS * AC_FRAME_CPT)
@@ -137,7 +143,7 @@ __device__ __forceinline__ void ac_frame_locate(const AcTiling& t, int fb, int* 
 // ------------------------------------------------------------------------------------------------------------
 // forward kernel
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(AC_THREADS, 2)
+__global__ void __launch_bounds__(AC_THREADS, AC_MINB_FWD)
 ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* __restrict__ wold,
               const double* __restrict__ c2, const double* __restrict__ phi, const double* __restrict__ psi,
               const double* __restrict__ sigx, const double* __restrict__ tauy, double* __restrict__ u,
@@ -289,7 +295,7 @@ __device__ __forceinline__ void ac_adj_general_cell(const AcGeom& g, int li, int
 // ------------------------------------------------------------------------------------------------------------
 // adjoint kernel: ub0 = ubar[s-1] from ub1 = ubar[s], ub2 = ubar[s+1], wf = u[s-1]
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(AC_THREADS, 2)
+__global__ void __launch_bounds__(AC_THREADS, AC_MINB_ADJ)
 ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double* __restrict__ ub2,
               const double* __restrict__ wf, const double* __restrict__ c2, const double* __restrict__ phib,
               const double* __restrict__ psib, const double* __restrict__ sigx, const double* __restrict__ tauy,

@@ -126,6 +126,10 @@ int adseis_acoustic_plan_get_snapshot(adseis_acoustic_plan* plan, int64_t slot, 
 /* plan facts: [0]=history slots resident, [1]=segments used by the last gradient(), [2]=kernel launches of the
  * last forward()/gradient(), [3]=local padded rows, [4]=pitch (doubles), [5]=recomputed forward steps */
 int adseis_acoustic_plan_info(adseis_acoustic_plan* plan, int64_t info[8]);
+/* Device time of the last forward()/gradient(), measured with CUDA events on the ctx stream around each run of
+ * identical time-step kernels: out[0..2] = milliseconds in {forward sweep, forward recomputation, adjoint sweep},
+ * out[3..5] = kernel launches in each.  Synchronises on the recorded events. */
+int adseis_acoustic_plan_timings(adseis_acoustic_plan* plan, double out[6]);
 
 /* ---- multi-GPU halo exchange over peer memory (NVLink): one process per GPU --------------------------------
  * Each slab plan exports a CUDA IPC handle of its device arena; the host framework (torch.distributed, MPI, ...)

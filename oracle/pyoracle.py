@@ -186,19 +186,40 @@ def acoustic_misfit_grad(NX, NY, NSTEP, dt, hx, hy, sigma, tau, c, srci, srcj, r
     return loss.value, gc.reshape(NX + 2, NY + 2), gs
 
 
-def ref_mpi_acoustic_forward(NX, NY, n, NSTEP, dt, hx, hy, sigma, tau, c2g, srci, srcj, srcv, keep_history=True,
-                             nthreads=1):
-    """Block-decomposed reference loop (MPI ranks emulated by threads).  -> u[(NSTEP+1) or 3, NX, NY]"""
+def ref_mpi_acoustic_forward(NX, NY, n, NSTEP, dt, hx, hy, sigma, tau, c2g, srci, srcj, srcv, nthreads=1):
+    """Block-decomposed reference loop (MPI ranks emulated by threads).  -> u[(NSTEP+1), NX, NY]"""
     srci, psi_ = _i(srci)
     srcj, psj_ = _i(srcj)
     srcv = np.ascontiguousarray(srcv, dtype=np.float64)
-    nslots = NSTEP + 1 if keep_history else 3
-    u = np.zeros(nslots * NX * NY)
+    u = np.zeros((NSTEP + 1) * NX * NY)
     ref_lib().ref_drv_mpi_acoustic_forward(_i64(NX), _i64(NY), _i64(n), _i64(NSTEP), C.c_double(dt), C.c_double(hx),
                                            C.c_double(hy), _d(sigma)[1], _d(tau)[1], _d(c2g)[1], _i64(len(srci)), psi_,
-                                           psj_, srcv.ctypes.data_as(_dp), u.ctypes.data_as(_dp),
-                                           C.c_int(int(keep_history)), C.c_int(nthreads))
-    return u.reshape(nslots, NX, NY)
+                                           psj_, srcv.ctypes.data_as(_dp), u.ctypes.data_as(_dp), C.c_int(nthreads))
+    return u.reshape(NSTEP + 1, NX, NY)
+
+
+def ref_mpi_acoustic_gradient(NX, NY, n, NSTEP, dt, hx, hy, sigma, tau, c2g, srci, srcj, rcvi, rcvj, obs, u,
+                              nthreads=1):
+    """-> (loss, grad_c2[NX, NY], grad_srcv[NSTEP, nsrc]) with the reference's per-block backward body."""
+    srci, psi_ = _i(srci)
+    srcj, psj_ = _i(srcj)
+    rcvi, pri_ = _i(rcvi)
+    rcvj, prj_ = _i(rcvj)
+    obs = np.ascontiguousarray(obs, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    loss = C.c_double(0.0)
+    gc = np.zeros(NX * NY)
+    gs = np.zeros((NSTEP, len(srci)))
+    ref_lib().ref_drv_mpi_acoustic_gradient(_i64(NX), _i64(NY), _i64(n), _i64(NSTEP), C.c_double(dt), C.c_double(hx),
+                                            C.c_double(hy), _d(sigma)[1], _d(tau)[1], _d(c2g)[1], _i64(len(srci)),
+                                            psi_, psj_, _i64(len(rcvi)), pri_, prj_, obs.ctypes.data_as(_dp),
+                                            u.ctypes.data_as(_dp), C.byref(loss), gc.ctypes.data_as(_dp),
+                                            gs.ctypes.data_as(_dp), C.c_int(nthreads))
+    return loss.value, gc.reshape(NX, NY), gs
+
+
+def ref_threads():
+    return int(ref_lib().ref_max_threads())
 
 
 # ----------------------------------------------------------------------------------------------

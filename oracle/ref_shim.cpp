@@ -208,72 +208,181 @@ API void ref_drv_acoustic_gradient(int64 NX, int64 NY, int64 NSTEP, double dt, d
 
 // ------------------------------------------------------------------------------------------------
 // Driver: block-decomposed acoustic loop, PropagatorKernel=1 (src/MPIAcoustic.jl:251-294, 334-404) with the
-// MPI ranks emulated by OpenMP threads (one block each) and mpi_halo_exchange by in-memory copies with a zero
-// fill at physical edges.  Global grid NX x NY (unpadded), blocks n x n, M=NX/n, N=NY/n.  c2g is c^2 (the MPI
-// solver does not square, MPIAcoustic.jl:336), global unpadded NX*NY.  sigma/tau are GLOBAL (NX+2)*(NY+2)
-// profiles (MPIAcoustic.jl:177-185 evaluates the same pml_helper at global coordinates).
-// Output ug: (NSTEP+1) * NX*NY global unpadded history (or only the last 3 slots if keep_history==0).
+// MPI ranks emulated by OpenMP threads (one n x n block per task) and mpi_halo_exchange emulated by copies out of
+// shared global arrays with a zero fill at physical edges.  Global grid NX x NY (unpadded), M=NX/n, N=NY/n blocks.
+// c2g is c^2 (the MPI solver does not square, MPIAcoustic.jl:336), global unpadded NX*NY.  sigma/tau are GLOBAL
+// (NX+2)*(NY+2) profiles (MPIAcoustic.jl:177-185 evaluates the same pml_helper at global coordinates).
+// ug: (NSTEP+1) * NX*NY global unpadded history.  Source / receiver indices are global, 1-based, unpadded.
 // ------------------------------------------------------------------------------------------------
-API void ref_drv_mpi_acoustic_forward(int64 NX, int64 NY, int64 n, int64 NSTEP, double dt, double hx, double hy,
-                                      const double* sigma, const double* tau, const double* c2g, int64 nsrc,
-                                      const int64* srci, const int64* srcj, const double* srcv,
-                                      double* ug, int keep_history, int nthreads) {
-  const int64 M = NX / n, Nb = NY / n, P = (n + 2) * (n + 2), B = M * Nb;
-  const int64 NG = NX * NY;
-  // per-block state (unpadded n*n): u at slot s-1, s-2; phi, psi
-  std::vector<std::vector<double>> w(B), wold(B), phi(B), psi(B), un(B), phin(B), psin(B), cb(B), sg(B), tg(B);
+struct BlockScratch {
+  std::vector<double> pw, pwold, pphi, ppsi, sg, tg, cb, o1, o2, o3, gw, gwold, gphi, gpsi, gc, i1, i2, i3;
+};
+
+// (n+2)^2 halo-padded copy of block (I,J) of a global unpadded field (zero outside the global grid)
+static void pad_block(const double* f, int64 NX, int64 NY, int64 n, int64 I, int64 J, double* out) {
+  for (int64 i = 0; i < n + 2; i++) {
+    const int64 gi = I * n + i - 1;
+    double* row = out + i * (n + 2);
+    if (gi < 0 || gi >= NX) { memset(row, 0, sizeof(double) * (n + 2)); continue; }
+    const int64 gj0 = J * n - 1;
+    row[0] = (gj0 >= 0) ? f[gi * NY + gj0] : 0.0;
+    memcpy(row + 1, f + gi * NY + J * n, sizeof(double) * n);
+    row[n + 1] = (gj0 + n + 1 < NY) ? f[gi * NY + gj0 + n + 1] : 0.0;
+  }
+}
+static void get_block(const double* f, int64 NY, int64 n, int64 I, int64 J, double* out) {
+  for (int64 i = 0; i < n; i++) memcpy(out + i * n, f + (I * n + i) * NY + J * n, sizeof(double) * n);
+}
+static void put_block(double* f, int64 NY, int64 n, int64 I, int64 J, const double* in) {
+  for (int64 i = 0; i < n; i++) memcpy(f + (I * n + i) * NY + J * n, in + i * n, sizeof(double) * n);
+}
+
+static void init_blocks(std::vector<BlockScratch>& S, int64 NX, int64 NY, int64 n, const double* sigma,
+                        const double* tau, const double* c2g, bool backward) {
+  const int64 Nb = NY / n, P = (n + 2) * (n + 2), B = (NX / n) * Nb;
+  S.resize(B);
   for (int64 b = 0; b < B; b++) {
-    int64 I = b / Nb, J = b % Nb;
-    w[b].assign(n * n, 0.0); wold[b].assign(n * n, 0.0); phi[b].assign(n * n, 0.0); psi[b].assign(n * n, 0.0);
-    un[b].resize(n * n); phin[b].resize(n * n); psin[b].resize(n * n); cb[b].resize(n * n);
-    sg[b].resize(P); tg[b].resize(P);
-    for (int64 i = 0; i < n; i++)
-      for (int64 j = 0; j < n; j++) cb[b][i * n + j] = c2g[(I * n + i) * NY + J * n + j];
+    const int64 I = b / Nb, J = b % Nb;
+    BlockScratch& s = S[b];
+    s.pw.resize(P); s.pwold.resize(P); s.pphi.resize(P); s.ppsi.resize(P); s.sg.resize(P); s.tg.resize(P);
+    s.cb.resize(n * n); s.o1.resize(n * n); s.o2.resize(n * n); s.o3.resize(n * n);
+    if (backward) {
+      s.gw.resize(P); s.gwold.resize(P); s.gphi.resize(P); s.gpsi.resize(P); s.gc.resize(n * n);
+      s.i1.resize(n * n); s.i2.resize(n * n); s.i3.resize(n * n);
+    }
+    get_block(c2g, NY, n, I, J, s.cb.data());
     for (int64 i = 0; i < n + 2; i++)
       for (int64 j = 0; j < n + 2; j++) {
-        sg[b][i * (n + 2) + j] = sigma[(I * n + i) * (NY + 2) + J * n + j];
-        tg[b][i * (n + 2) + j] = tau[(I * n + i) * (NY + 2) + J * n + j];
+        s.sg[i * (n + 2) + j] = sigma[(I * n + i) * (NY + 2) + J * n + j];
+        s.tg[i * (n + 2) + j] = tau[(I * n + i) * (NY + 2) + J * n + j];
       }
   }
-  auto halo = [&](const std::vector<std::vector<double>>& f, int64 b, double* out) {  // n*n -> (n+2)^2
-    int64 I = b / Nb, J = b % Nb;
-    memset(out, 0, sizeof(double) * P);
-    for (int64 i = 0; i < n; i++) memcpy(out + (i + 1) * (n + 2) + 1, f[b].data() + i * n, sizeof(double) * n);
-    if (I > 0) memcpy(out + 1, f[b - Nb].data() + (n - 1) * n, sizeof(double) * n);
-    if (I < M - 1) memcpy(out + (n + 1) * (n + 2) + 1, f[b + Nb].data(), sizeof(double) * n);
-    if (J > 0) for (int64 i = 0; i < n; i++) out[(i + 1) * (n + 2)] = f[b - 1][i * n + n - 1];
-    if (J < Nb - 1) for (int64 i = 0; i < n; i++) out[(i + 1) * (n + 2) + n + 1] = f[b + 1][i * n];
-  };
-  auto store = [&](int64 s) {
-    double* dst = ug + (keep_history ? s : (s % 3)) * NG;
-    for (int64 b = 0; b < B; b++) {
-      int64 I = b / Nb, J = b % Nb;
-      for (int64 i = 0; i < n; i++) memcpy(dst + (I * n + i) * NY + J * n, w[b].data() + i * n, sizeof(double) * n);
-    }
-  };
-  memset(ug, 0, sizeof(double) * NG * (keep_history ? 2 : 3));
+}
+
+API void ref_drv_mpi_acoustic_forward(int64 NX, int64 NY, int64 n, int64 NSTEP, double dt, double hx, double hy,
+                                      const double* sigma, const double* tau, const double* c2g, int64 nsrc,
+                                      const int64* srci, const int64* srcj, const double* srcv, double* ug,
+                                      int nthreads) {
+  const int64 Nb = NY / n, B = (NX / n) * Nb, NG = NX * NY;
+  std::vector<BlockScratch> S;
+  init_blocks(S, NX, NY, n, sigma, tau, c2g, false);
+  std::vector<double> phi[2] = {std::vector<double>(NG, 0.0), std::vector<double>(NG, 0.0)};
+  std::vector<double> psi[2] = {std::vector<double>(NG, 0.0), std::vector<double>(NG, 0.0)};
+  memset(ug, 0, sizeof(double) * NG * 2);
   if (nthreads < 1) nthreads = 1;
-  std::vector<std::vector<double>> pw(B), pwold(B), pphi(B), ppsi(B);
-  for (int64 b = 0; b < B; b++) { pw[b].resize(P); pwold[b].resize(P); pphi[b].resize(P); ppsi[b].resize(P); }
   for (int64 s = 2; s <= NSTEP; s++) {
-#pragma omp parallel for num_threads(nthreads) schedule(static)
-    for (int64 b = 0; b < B; b++) {  // 4 halo exchanges (MPIAcoustic.jl:260-263)
-      halo(w, b, pw[b].data()); halo(wold, b, pwold[b].data());
-      halo(phi, b, pphi[b].data()); halo(psi, b, ppsi[b].data());
-    }
-#pragma omp parallel for num_threads(nthreads) schedule(static)
+    const double *w = ug + (s - 1) * NG, *wold = ug + (s - 2) * NG;
+    double* un = ug + s * NG;
+    const std::vector<double>&ph = phi[(s - 1) & 1], &ps = psi[(s - 1) & 1];
+    std::vector<double>&pho = phi[s & 1], &pso = psi[s & 1];
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1)
     for (int64 b = 0; b < B; b++) {
-      int64 I = b / Nb, J = b % Nb;
-      MpiAcousticOneStepCpuForward(pw[b].data(), pwold[b].data(), pphi[b].data(), ppsi[b].data(), sg[b].data(),
-                                   tg[b].data(), cb[b].data(), dt, hx, hy, n, n, un[b].data(), phin[b].data(),
-                                   psin[b].data());
-      for (int64 k = 0; k < nsrc; k++) {  // MPIAcoustic.jl:71-78, 377-381 (global 1-based src index)
-        int64 li = srci[k] - I * n, lj = srcj[k] - J * n;
-        if (li >= 1 && li <= n && lj >= 1 && lj <= n) un[b][(li - 1) * n + lj - 1] += srcv[(s - 1) * nsrc + k] * (dt * dt);
+      const int64 I = b / Nb, J = b % Nb;
+      BlockScratch& k = S[b];
+      pad_block(w, NX, NY, n, I, J, k.pw.data());       // 4 halo exchanges (MPIAcoustic.jl:260-263)
+      pad_block(wold, NX, NY, n, I, J, k.pwold.data());
+      pad_block(ph.data(), NX, NY, n, I, J, k.pphi.data());
+      pad_block(ps.data(), NX, NY, n, I, J, k.ppsi.data());
+      MpiAcousticOneStepCpuForward(k.pw.data(), k.pwold.data(), k.pphi.data(), k.ppsi.data(), k.sg.data(), k.tg.data(),
+                                   k.cb.data(), dt, hx, hy, n, n, k.o1.data(), k.o2.data(), k.o3.data());
+      for (int64 q = 0; q < nsrc; q++) {  // MPIAcoustic.jl:71-78, 377-381
+        const int64 li = srci[q] - I * n, lj = srcj[q] - J * n;
+        if (li >= 1 && li <= n && lj >= 1 && lj <= n) k.o1[(li - 1) * n + lj - 1] += srcv[(s - 1) * nsrc + q] * (dt * dt);
       }
+      put_block(un, NY, n, I, J, k.o1.data());
+      put_block(pho.data(), NY, n, I, J, k.o2.data());
+      put_block(pso.data(), NY, n, I, J, k.o3.data());
     }
-    for (int64 b = 0; b < B; b++) { wold[b].swap(w[b]); w[b].swap(un[b]); phi[b].swap(phin[b]); psi[b].swap(psin[b]); }
-    store(s);
+  }
+}
+
+// loss = sum (rcvv-obs)^2 over all blocks (mpi_sum of the local losses) and its gradient w.r.t. c^2 [NX*NY] and
+// srcv [NSTEP*nsrc], composing MpiAcousticOneStepCpuBackward (MpiAcousticOneStep.h:45-122) per block with the
+// transpose of the halo exchange (halo contributions are added into the neighbour's edge cells).  NOTE: the
+// reference registers an EMPTY gradient op for this kernel (MpiAcousticOneStep.cpp:347-350); the body used here is
+// the one it ships but never calls, so this driver is an optimistic stand-in for "the reference on all cores".
+API void ref_drv_mpi_acoustic_gradient(int64 NX, int64 NY, int64 n, int64 NSTEP, double dt, double hx, double hy,
+                                       const double* sigma, const double* tau, const double* c2g, int64 nsrc,
+                                       const int64* srci, const int64* srcj, int64 nrcv, const int64* rcvi,
+                                       const int64* rcvj, const double* obs, const double* ug, double* loss_out,
+                                       double* grad_c2, double* grad_srcv, int nthreads) {
+  const int64 Nb = NY / n, M = NX / n, B = M * Nb, NG = NX * NY, n2 = n + 2;
+  std::vector<BlockScratch> S;
+  init_blocks(S, NX, NY, n, sigma, tau, c2g, true);
+  std::vector<double> ub[3] = {std::vector<double>(NG, 0.0), std::vector<double>(NG, 0.0), std::vector<double>(NG, 0.0)};
+  std::vector<double> gphi[2] = {std::vector<double>(NG, 0.0), std::vector<double>(NG, 0.0)};
+  std::vector<double> gpsi[2] = {std::vector<double>(NG, 0.0), std::vector<double>(NG, 0.0)};
+  std::vector<double> add1(NG), add2(NG);
+  memset(grad_c2, 0, sizeof(double) * NG);
+  if (grad_srcv) memset(grad_srcv, 0, sizeof(double) * NSTEP * nsrc);
+  if (nthreads < 1) nthreads = 1;
+  double loss = 0.0;
+  for (int64 s = 0; s <= NSTEP; s++)
+    for (int64 r = 0; r < nrcv; r++) {
+      const double d = ug[s * NG + (rcvi[r] - 1) * NY + rcvj[r] - 1] - obs[s * nrcv + r];
+      loss += d * d;
+    }
+  *loss_out = loss;
+  auto seed = [&](std::vector<double>& bfr, int64 s) {
+    std::fill(bfr.begin(), bfr.end(), 0.0);
+    for (int64 r = 0; r < nrcv; r++) {
+      const int64 id = (rcvi[r] - 1) * NY + rcvj[r] - 1;
+      bfr[id] += 2.0 * (ug[s * NG + id] - obs[s * nrcv + r]);
+    }
+  };
+  seed(ub[NSTEP % 3], NSTEP);
+  seed(ub[(NSTEP - 1) % 3], NSTEP - 1);
+  for (int64 s = NSTEP; s >= 2; s--) {
+    std::vector<double>& gu = ub[s % 3];
+    seed(ub[(s - 2) % 3], s - 2);
+    if (grad_srcv)
+      for (int64 q = 0; q < nsrc; q++) grad_srcv[(s - 1) * nsrc + q] = gu[(srci[q] - 1) * NY + srcj[q] - 1] * (dt * dt);
+    const double* w = ug + (s - 1) * NG;
+    const std::vector<double>&gpo = gphi[s & 1], &gso = gpsi[s & 1];
+    std::vector<double>&gpn = gphi[(s - 1) & 1], &gsn = gpsi[(s - 1) & 1];
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1)
+    for (int64 b = 0; b < B; b++) {
+      const int64 I = b / Nb, J = b % Nb;
+      BlockScratch& k = S[b];
+      pad_block(w, NX, NY, n, I, J, k.pw.data());
+      get_block(gu.data(), NY, n, I, J, k.i1.data());
+      get_block(gpo.data(), NY, n, I, J, k.i2.data());
+      get_block(gso.data(), NY, n, I, J, k.i3.data());
+      std::fill(k.gw.begin(), k.gw.end(), 0.0); std::fill(k.gwold.begin(), k.gwold.end(), 0.0);
+      std::fill(k.gphi.begin(), k.gphi.end(), 0.0); std::fill(k.gpsi.begin(), k.gpsi.end(), 0.0);
+      std::fill(k.gc.begin(), k.gc.end(), 0.0);
+      MpiAcousticOneStepCpuBackward(k.gw.data(), k.gwold.data(), k.gphi.data(), k.gpsi.data(), k.gc.data(), k.i1.data(),
+                                    k.i2.data(), k.i3.data(), k.pw.data(), nullptr, nullptr, nullptr, k.sg.data(),
+                                    k.tg.data(), k.cb.data(), dt, hx, hy, n, n, nullptr, nullptr, nullptr);
+    }
+    // transpose of the halo exchanges: own interior + the neighbours' halo cells that mirror my edge cells
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1)
+    for (int64 b = 0; b < B; b++) {
+      const int64 I = b / Nb, J = b % Nb;
+      auto gather = [&](std::vector<double> BlockScratch::*fld, double* out_nn) {
+        const std::vector<double>& me = S[b].*fld;
+        for (int64 i = 0; i < n; i++)
+          for (int64 j = 0; j < n; j++) out_nn[i * n + j] = me[(i + 1) * n2 + j + 1];
+        if (I > 0) { const std::vector<double>& o = S[b - Nb].*fld; for (int64 j = 0; j < n; j++) out_nn[j] += o[(n + 1) * n2 + j + 1]; }
+        if (I < M - 1) { const std::vector<double>& o = S[b + Nb].*fld; for (int64 j = 0; j < n; j++) out_nn[(n - 1) * n + j] += o[j + 1]; }
+        if (J > 0) { const std::vector<double>& o = S[b - 1].*fld; for (int64 i = 0; i < n; i++) out_nn[i * n] += o[(i + 1) * n2 + n + 1]; }
+        if (J < Nb - 1) { const std::vector<double>& o = S[b + 1].*fld; for (int64 i = 0; i < n; i++) out_nn[i * n + n - 1] += o[(i + 1) * n2]; }
+      };
+      BlockScratch& k = S[b];
+      gather(&BlockScratch::gw, k.o1.data());
+      put_block(add1.data(), NY, n, I, J, k.o1.data());
+      gather(&BlockScratch::gwold, k.o1.data());
+      put_block(add2.data(), NY, n, I, J, k.o1.data());
+      gather(&BlockScratch::gphi, k.o2.data());
+      put_block(gpn.data(), NY, n, I, J, k.o2.data());
+      gather(&BlockScratch::gpsi, k.o3.data());
+      put_block(gsn.data(), NY, n, I, J, k.o3.data());
+      for (int64 i = 0; i < n; i++)
+        for (int64 j = 0; j < n; j++) grad_c2[(I * n + i) * NY + J * n + j] += k.gc[i * n + j];
+    }
+    std::vector<double>&g1 = ub[(s - 1) % 3], &g2 = ub[(s - 2) % 3];
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (int64 q = 0; q < NG; q++) { g1[q] += add1[q]; g2[q] += add2[q]; }
   }
 }
 

@@ -26,6 +26,13 @@ def run(NX, NY, NSTEP, reps=3, budget=0):
     plan.close()
 
 if __name__ == "__main__":
+    if "--quick" in sys.argv:
+        print("variant", os.environ.get("ADSEIS_LIB_SUFFIX", "(default)"))
+        run(4096, 4096, 60)
+        sys.exit(0)
+    if "--one" in sys.argv:
+        run(4096, 4096, 24, reps=1)
+        sys.exit(0)
     run(4096, 4096, 60)
     run(4096, 4096, 120, budget=40 * 4098 * 4112 * 8)
     run(2000, 1000, 200)
