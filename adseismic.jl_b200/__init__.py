@@ -6,10 +6,23 @@ from . import _lib
 from ._lib import AdseisError, Context, default_context
 from .structs import (AcousticPropagatorParams, AcousticReceiver, AcousticSource, ElasticPropagatorParams,
                       ElasticReceiver, ElasticSource)
-from .acoustic import (AcousticPlan, AcousticPropagator, AcousticPropagatorSolver, SimulatedObservation_,
+from .acoustic import (AcousticPlan, AcousticPropagator, AcousticPropagatorSolver,
                        acoustic_forward, acoustic_misfit_grad, acoustic_one_step, acoustic_one_step_grad,
                        compute_PML_Params_)
+from . import acoustic as _ac
+from . import elastic as _el
+from .elastic import (ElasticPlan, ElasticPropagator, ElasticPropagatorSolver, compute_PML_Params, elastic_forward,
+                      elastic_misfit_grad)
 from .utils import Gauss, Ricker, compute_lame_parameters
+
+
+def SimulatedObservation_(prop, rcv):
+    """SimulatedObservation!(propagator, receiver): src/Core.jl:726-730 (acoustic, rcvv [(NSTEP+1), nrcv]) and
+    src/Core.jl:701-712 (elastic, rcvv [nrcv, (NSTEP+1)])."""
+    if isinstance(prop, ElasticPropagator):
+        rcv.rcvv = elastic_forward(prop.param, prop.src, prop.rho, prop.lam, prop.mu, rcv, False, prop.ctx)[0]
+        return rcv.rcvv
+    return _ac.SimulatedObservation_(prop, rcv)
 
 
 def build(force=False, verbose=False):

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libadseis_b200%s.so" % os.environ.get("ADSEIS_LIB_SUFFIX", ""))  # suffix: tuning variants
 SOURCES = ["ctx.cu", "acoustic.cu", "elastic.cu", "ops.cu"]
-HEADERS = ["common.cuh", "acoustic_kernels.cuh", "elastic_kernels.cuh", os.path.join("..", "..", "include", "adseis.h")]
+HEADERS = ["common.cuh", "acoustic_kernels.cuh", "elastic_kernels.cuh", "util_kernels.cuh", os.path.join("..", "..", "include", "adseis.h")]
 # -fmad=false: fp64 products and sums are rounded separately, exactly like the reference's CPU op bodies, so that
 # forward wavefields are bit-identical to the oracle.  The kernels are HBM-bound; the extra DMUL/DADD issue slots
 # are not on the critical path.

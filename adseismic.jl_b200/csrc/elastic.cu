@@ -1,17 +1,736 @@
-// elastic.cu -- placeholder; replaced by the real implementation.
-#include "common.cuh"
-#define NOTYET(name) { adseis_set_error(name ": elastic path not built yet"); return ADSEIS_ESTATE; }
-ADSEIS_API int adseis_elastic_plan_create(adseis_ctx*, const adseis_elastic_params*, const adseis_slab*, int64_t, const int64_t*, const int64_t*, const int64_t*, int64_t, const int64_t*, const int64_t*, const int64_t*, size_t, adseis_elastic_plan**) NOTYET("elastic_plan_create")
-ADSEIS_API int adseis_elastic_plan_destroy(adseis_elastic_plan*) { return ADSEIS_OK; }
-ADSEIS_API int adseis_elastic_plan_set_model(adseis_elastic_plan*, const double*, const double*, const double*, int) NOTYET("elastic")
-ADSEIS_API int adseis_elastic_plan_set_srcv(adseis_elastic_plan*, const double*, int64_t, int) NOTYET("elastic")
-ADSEIS_API int adseis_elastic_plan_set_obs(adseis_elastic_plan*, const double*, int) NOTYET("elastic")
-ADSEIS_API int adseis_elastic_plan_forward(adseis_elastic_plan*) NOTYET("elastic")
-ADSEIS_API int adseis_elastic_plan_gradient(adseis_elastic_plan*, int) NOTYET("elastic")
-ADSEIS_API int adseis_elastic_plan_get(adseis_elastic_plan*, int, double*, int) NOTYET("elastic")
-ADSEIS_API int adseis_elastic_plan_get_snapshot(adseis_elastic_plan*, int, int64_t, double*, int) NOTYET("elastic")
-ADSEIS_API int adseis_elastic_plan_info(adseis_elastic_plan*, int64_t*) NOTYET("elastic")
-ADSEIS_API int adseis_elastic_plan_ipc_export(adseis_elastic_plan*, void*) NOTYET("elastic")
-ADSEIS_API int adseis_elastic_plan_ipc_connect(adseis_elastic_plan*, const void*, const void*) NOTYET("elastic")
-ADSEIS_API int adseis_elastic_forward(adseis_ctx*, const adseis_elastic_params*, const double*, const double*, const double*, int64_t, const int64_t*, const int64_t*, const int64_t*, const double*, int64_t, int64_t, const int64_t*, const int64_t*, const int64_t*, double*, double*) NOTYET("elastic")
-ADSEIS_API int adseis_elastic_misfit_grad(adseis_ctx*, const adseis_elastic_params*, const double*, const double*, const double*, int64_t, const int64_t*, const int64_t*, const int64_t*, const double*, int64_t, int64_t, const int64_t*, const int64_t*, const int64_t*, const double*, double*, double*, double*, double*, double*, double*) NOTYET("elastic")
+// elastic.cu -- elastic plan: device state, time loops (forward, checkpointed reverse sweep), C ABI.
+// Reference behaviour restated: src/Core.jl:31-228 (variant 0), src/MPIElastic.jl:374-682 on the global grid
+// (variant 1), CPML coefficients src/Core.jl:231-407, receivers src/Core.jl:701-712 + ReceiveOps/GetReceive.cpp,
+// sources SourceOps/AddSource.cpp, misfit src/Utils.jl:308; adjoint = SURVEY Appendix B.
+#include <map>
+
+#include "elastic_kernels.cuh"
+#include "util_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------------------
+// material pre-processing and gradient post-processing
+// ------------------------------------------------------------------------------------------------------------
+// Averaged materials exactly as fw1/fw2/fw4 form them (Core.jl:109-111, 141, 200); variant M: no averaging.
+__global__ void k_el_materials(int Hl, int ld, int W, int avg, const double* __restrict__ rho,
+                               const double* __restrict__ lam, const double* __restrict__ mu,
+                               double* __restrict__ lamb, double* __restrict__ lmb, double* __restrict__ mub2,
+                               double* __restrict__ rhob, double* __restrict__ rinv, double* __restrict__ rbinv) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int li = blockIdx.y;
+  if (q >= ld || li >= Hl) return;
+  const i64 c = (i64)li * ld + q;
+  if (q >= W) { lamb[c] = lmb[c] = mub2[c] = rhob[c] = rinv[c] = rbinv[c] = 0.0; return; }
+  double l_, m1, m2, rb;
+  if (avg) {
+    const bool dn = li + 1 < Hl, rt = q + 1 < W;
+    l_ = dn ? 0.5 * (lam[c + ld] + lam[c]) : lam[c];
+    m1 = dn ? 0.5 * (mu[c + ld] + mu[c]) : mu[c];
+    m2 = rt ? 0.5 * (mu[c] + mu[c + 1]) : mu[c];
+    rb = (dn && rt) ? 0.25 * (rho[c] + rho[c + ld] + rho[c + ld + 1] + rho[c + 1]) : rho[c];
+  } else {
+    l_ = lam[c]; m1 = mu[c]; m2 = mu[c]; rb = rho[c];
+  }
+  lamb[c] = l_;
+  lmb[c] = l_ + 2 * m1;
+  mub2[c] = m2;
+  rhob[c] = rb;
+  rinv[c] = rho[c] != 0.0 ? 1.0 / rho[c] : 0.0;
+  rbinv[c] = rb != 0.0 ? 1.0 / rb : 0.0;
+}
+
+// d loss / d (rho, lambda, mu) in the caller's layout from the accumulators w.r.t. the averaged materials.
+__global__ void k_el_grad_finalize(ElGeom g, int avg, int off /* rows/cols to strip: 0 (S) or 2 (M) */,
+                                   const double* __restrict__ Gl, const double* __restrict__ Gm1,
+                                   const double* __restrict__ Gm2, const double* __restrict__ Gr3,
+                                   const double* __restrict__ Gr4, double* __restrict__ grho,
+                                   double* __restrict__ glam, double* __restrict__ gmu) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int li = g.own0 + blockIdx.y;
+  if (q >= g.W || li >= g.own1) return;
+  const int gp = g.goff + li;
+  const i64 c = (i64)li * g.ld + q;
+  double gl, gm, gr;
+  if (avg) {
+    const bool up = li - 1 >= 0, lf = q - 1 >= 0;
+    gl = 0.5 * (Gl[c] + (up ? Gl[c - g.ld] : 0.0));
+    gm = 0.5 * (Gm1[c] + (up ? Gm1[c - g.ld] : 0.0)) + 0.5 * (Gm2[c] + (lf ? Gm2[c - 1] : 0.0));
+    gr = Gr3[c] + 0.25 * (Gr4[c] + (up ? Gr4[c - g.ld] : 0.0) + ((up && lf) ? Gr4[c - g.ld - 1] : 0.0) +
+                          (lf ? Gr4[c - 1] : 0.0));
+  } else {
+    gl = Gl[c]; gm = Gm1[c] + Gm2[c]; gr = Gr3[c] + Gr4[c];
+  }
+  const int op = gp - off, oq = q - off, OW = g.W - 2 * off, OH = g.H - 2 * off;
+  if (op < 0 || op >= OH || oq < 0 || oq >= OW) return;
+  const i64 o = (i64)op * OW + oq;
+  grho[o] = gr; glam[o] = gl; gmu[o] = gm;
+}
+
+// post-injection value of a stress plane for snapshot output: plane += pending stress sources of that slot
+__global__ void k_el_apply_stress_sources(double* __restrict__ plane, int field, ElPoints src, int nu,
+                                          const double* __restrict__ srcv_row) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nu && src.field[k] == field) {
+    double v = plane[src.cell[k]];
+    for (int m = src.start[k]; m < src.start[k + 1]; m++) v += srcv_row[src.perm[m]];
+    plane[src.cell[k]] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------------------
+struct ElPointStore {
+  PointSetStorage ps;
+  int *xstart = nullptr, *xperm = nullptr;
+  ElPoints dev{};
+};
+
+struct adseis_elastic_plan {
+  adseis_ctx* ctx;
+  adseis_elastic_params p;
+  adseis_slab slab;
+  ElGeom g;
+  int nblocks = 0;
+  int off = 0;          // 0 (S) / 2 (M): offset between the caller's model array and the internal array
+  i64 model_elems = 0;
+  i64 slot_sz = 0;      // doubles per slot
+  // materials
+  double *rho = nullptr, *lam = nullptr, *mu = nullptr, *lamb = nullptr, *lmb = nullptr, *mub2 = nullptr,
+         *rhob = nullptr, *rinv = nullptr, *rbinv = nullptr;
+  double *ax = nullptr, *bx = nullptr, *ay = nullptr, *by = nullptr;
+  // history window + checkpoints
+  double* hist = nullptr;
+  i64 win = 0;
+  std::vector<i64> seg_b, seg_e;
+  std::vector<double*> ckpt;
+  i64 win_base = -1, win_last = -1;
+  bool inplace_last = false;  // last forward ran in place (only the final slot is resident)
+  // points
+  i64 nsrc = 0, nrcv = 0;
+  ElPointStore src, rcv;
+  unsigned char* rcv_owned = nullptr;
+  double *srcv = nullptr, *rcvv = nullptr, *obs = nullptr, *res = nullptr, *loss = nullptr;
+  // adjoint state: fields in place + two memory sides
+  double* adj = nullptr;       // 5 planes + 2 * (4 xm + 4 ym)
+  double *Gl = nullptr, *Gm1 = nullptr, *Gm2 = nullptr, *Gr3 = nullptr, *Gr4 = nullptr;
+  double *grho = nullptr, *glam = nullptr, *gmu = nullptr, *gradsrcv = nullptr;
+  bool have_model = false, have_srcv = false, have_obs = false, have_fwd = false, have_grad = false,
+       have_matgrad = false;
+  i64 last_launches = 0, last_segments = 0, last_recomputed = 0;
+};
+
+#define EL_LAUNCH_CHECK(P)        \
+  do {                            \
+    (P)->ctx->launches++;         \
+    (P)->last_launches++;         \
+    CUDA_TRY(cudaGetLastError()); \
+  } while (0)
+
+static ElSlot slot_at(const adseis_elastic_plan* P, double* base) {
+  const ElGeom& g = P->g;
+  ElSlot s;
+  s.vx = base; s.vy = base + g.plane; s.sxx = base + 2 * g.plane; s.syy = base + 3 * g.plane;
+  s.sxy = base + 4 * g.plane; s.xm = base + 5 * g.plane; s.ym = s.xm + 4 * g.xm_sz;
+  return s;
+}
+static inline double* win_ptr(adseis_elastic_plan* P, i64 base, i64 s) { return P->hist + (s - base) * P->slot_sz; }
+static ElMat mat_of(const adseis_elastic_plan* P) {
+  return ElMat{P->lamb, P->lmb, P->mub2, P->rho, P->rhob, P->rinv, P->rbinv};
+}
+static ElCoef coef_of(const adseis_elastic_plan* P) { return ElCoef{P->ax, P->bx, P->ay, P->by}; }
+
+static void free_points(ElPointStore* s) {
+  free_point_set(&s->ps);
+  cudaFree(s->xstart); cudaFree(s->xperm);
+  *s = ElPointStore();
+}
+
+ADSEIS_API int adseis_elastic_plan_destroy(adseis_elastic_plan* P) {
+  if (!P) return ADSEIS_OK;
+  cudaSetDevice(P->ctx->device);
+  cudaStreamSynchronize(P->ctx->stream);
+  double* arr[] = {P->rho, P->lam, P->mu, P->lamb, P->lmb, P->mub2, P->rhob, P->rinv, P->rbinv, P->ax, P->bx, P->ay,
+                   P->by, P->hist, P->srcv, P->rcvv, P->obs, P->res, P->loss, P->adj, P->Gl, P->Gm1, P->Gm2, P->Gr3,
+                   P->Gr4, P->grho, P->glam, P->gmu, P->gradsrcv};
+  for (double* a : arr) cudaFree(a);
+  for (double* c : P->ckpt) cudaFree(c);
+  cudaFree(P->rcv_owned);
+  free_points(&P->src); free_points(&P->rcv);
+  delete P;
+  return ADSEIS_OK;
+}
+
+static int el_validate(const adseis_elastic_params* p) {
+  REQUIRE(p, "elastic: null params");
+  REQUIRE(p->variant == 0 || p->variant == 1, "elastic: variant must be 0 (Core.jl) or 1 (MPIElastic.jl)");
+  REQUIRE(p->NX >= 6 && p->NY >= 6 && p->NSTEP >= 1, "elastic: need NX,NY >= 6 and NSTEP >= 1");
+  REQUIRE((p->NX + 4) * (p->NY + 20) < 2147483647LL, "elastic: grid too large for 32-bit cell offsets");
+  REQUIRE(p->DELTAX > 0 && p->DELTAY > 0 && p->DELTAT > 0, "elastic: DELTAX/DELTAY/DELTAT must be > 0");
+  REQUIRE(p->NPOINTS_PML >= 1 && p->Rcoef > 0 && p->vp_ref > 0, "elastic: bad PML parameters");
+  REQUIRE(p->K_MAX_PML == 1.0, "elastic: K_MAX_PML must be 1 (the reference ignores K, Core.jl:686-693)");
+  return ADSEIS_OK;
+}
+
+// segments over slots 0..NSTEP with a window of `win` slots; consecutive segments share one slot
+static void el_make_segments(adseis_elastic_plan* P) {
+  P->seg_b.clear(); P->seg_e.clear();
+  i64 b = 0;
+  while (true) {
+    i64 e = std::min(b + P->win - 1, (i64)P->p.NSTEP);
+    P->seg_b.push_back(b); P->seg_e.push_back(e);
+    if (e >= P->p.NSTEP) break;
+    b = e;
+  }
+}
+
+ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_params* p, const adseis_slab* slab,
+                                          int64_t nsrc, const int64_t* srci, const int64_t* srcj,
+                                          const int64_t* srctype, int64_t nrcv, const int64_t* rcvi,
+                                          const int64_t* rcvj, const int64_t* rcvtype, size_t hist_bytes_budget,
+                                          adseis_elastic_plan** out) {
+  REQUIRE(ctx && out, "elastic_plan_create: null ctx/out");
+  *out = nullptr;
+  TRY(el_validate(p));
+  REQUIRE(nsrc >= 0 && nrcv >= 0 && (nsrc == 0 || (srci && srcj && srctype)) && (nrcv == 0 || (rcvi && rcvj && rcvtype)),
+          "elastic_plan_create: bad source/receiver arrays");
+  REQUIRE(slab == nullptr || slab->nranks == 1, "elastic_plan_create: slab decomposition of the elastic path is not "
+          "available in this build (single-GPU and shot-parallel only)");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  adseis_elastic_plan* P = new adseis_elastic_plan();
+  P->ctx = ctx;
+  P->p = *p;
+  const int NX = (int)p->NX, NY = (int)p->NY;
+  ElGeom& g = P->g;
+  memset(&g, 0, sizeof(g));
+  g.NX = NX; g.NY = NY;
+  if (p->variant == 0) {
+    g.H = NX + 2; g.W = NY + 2; g.cx = g.cy = 1; P->off = 0;
+    // fw1 Core.jl:100-107; fw2 :132-139; fw3 :162-169; fw4 :190-198 (1-based getid ranges -> 0-based)
+    g.p0[0] = 1; g.p1[0] = NX - 1; g.q0[0] = 2; g.q1[0] = NY;
+    g.p0[1] = 2; g.p1[1] = NX;     g.q0[1] = 1; g.q1[1] = NY - 1;
+    g.p0[2] = 2; g.p1[2] = NX;     g.q0[2] = 2; g.q1[2] = NY;
+    g.p0[3] = 1; g.p1[3] = NX - 1; g.q0[3] = 1; g.q1[3] = NY - 1;
+    P->model_elems = (i64)(NX + 2) * (NY + 2);
+  } else {
+    g.H = NX + 4; g.W = NY + 4; g.cx = g.cy = 2; P->off = 2;
+    for (int k = 0; k < 4; k++) { g.p0[k] = 2; g.p1[k] = NX + 1; g.q0[k] = 2; g.q1[k] = NY + 1; }  // MPIElastic.jl:175-189
+    P->model_elems = (i64)NX * NY;
+  }
+  P->slab.rank = 0; P->slab.nranks = 1; P->slab.row0 = 0; P->slab.row1 = g.H;
+  g.goff = 0; g.Hl = g.H; g.own0 = 0; g.own1 = g.H;
+  g.ld = round_up(g.W, 16);
+  g.plane = (i64)g.Hl * g.ld;
+  g.dt = p->DELTAT; g.dx = p->DELTAX; g.dy = p->DELTAY;
+
+#define EPTRY(expr)                       \
+  do {                                    \
+    int _r = (expr);                      \
+    if (_r != ADSEIS_OK) {                \
+      adseis_elastic_plan_destroy(P);     \
+      return _r;                          \
+    }                                     \
+  } while (0)
+
+  // CPML coefficients and the index ranges on which they are non-trivial
+  std::vector<double> ax(2 * NX), bx(2 * NX), ay(2 * NY), by(2 * NY);
+  EPTRY(adseis_elastic_cpml_profiles(p, 0, ax.data(), bx.data()));
+  EPTRY(adseis_elastic_cpml_profiles(p, 1, ay.data(), by.data()));
+  auto strip = [](const std::vector<double>& a, int n, int* lo, int* hi) {
+    auto nz = [&](int k) { return a[k] != 0.0 || a[n + k] != 0.0; };
+    int l = 0;
+    while (l < n && nz(l)) l++;
+    int h = n;
+    while (h > l && nz(h - 1)) h--;
+    for (int k = l; k < h; k++)
+      if (nz(k)) { l = n; h = n; break; }  // profile is not "two strips": treat every index as PML
+    *lo = l; *hi = h;
+  };
+  strip(ax, NX, &g.xlo, &g.xhi);
+  strip(ay, NY, &g.ylo, &g.yhi);
+  g.nxr = g.xlo + (NX - g.xhi);
+  const int nyc = g.ylo + (NY - g.yhi);
+  g.ycp = std::max(1, nyc);
+  g.xm_sz = (i64)std::max(1, g.nxr) * g.ld;
+  g.ym_sz = (i64)g.Hl * g.ycp;
+  P->slot_sz = 5 * g.plane + 4 * g.xm_sz + 4 * g.ym_sz;
+  g.ntc = (g.ld + EL_BX - 1) / EL_BX;
+  g.ntr = (g.own1 - g.own0 + EL_ROWS - 1) / EL_ROWS;
+  P->nblocks = g.ntc * g.ntr;
+  EPTRY(dev_upload(&P->ax, ax, st)); EPTRY(dev_upload(&P->bx, bx, st));
+  EPTRY(dev_upload(&P->ay, ay, st)); EPTRY(dev_upload(&P->by, by, st));
+  double** mats[] = {&P->rho, &P->lam, &P->mu, &P->lamb, &P->lmb, &P->mub2, &P->rhob, &P->rinv, &P->rbinv};
+  for (double** m : mats) EPTRY(dev_alloc_zero(m, (size_t)g.plane, st));
+
+  // sources / receivers (1-based indices: S -> padded grid, M -> unpadded global grid; MPIElastic.jl:85-86)
+  P->nsrc = nsrc; P->nrcv = nrcv;
+  const int ioff = p->variant == 0 ? -1 : 1;
+  struct Pt { int cell, field, gid; };
+  auto collect = [&](i64 n, const int64_t* pi, const int64_t* pj, const int64_t* pt, std::vector<Pt>* v,
+                     const char* what) -> int {
+    for (i64 k = 0; k < n; k++) {
+      const i64 gi = pi[k] + ioff, gj = pj[k] + ioff;
+      REQUIRE(gi >= 0 && gi < g.H && gj >= 0 && gj < g.W, "elastic_plan_create: %s %lld at (%lld,%lld) is outside the grid",
+              what, (long long)k, (long long)pi[k], (long long)pj[k]);
+      if (pt[k] < 0 || pt[k] > 4) continue;  // AddSource.cpp:83 / GetReceive.cpp:43: other types are ignored
+      v->push_back(Pt{(int)(gi * g.ld + gj), (int)pt[k], (int)k});
+    }
+    return ADSEIS_OK;
+  };
+  std::vector<Pt> sp, rp;
+  EPTRY(collect(nsrc, srci, srcj, srctype, &sp, "source"));
+  EPTRY(collect(nrcv, rcvi, rcvj, rcvtype, &rp, "receiver"));
+  auto upload = [&](const std::vector<Pt>& mine, const std::vector<Pt>& other, ElPointStore* dst) -> int {
+    std::vector<int> own, cells, gid, field;
+    for (const Pt& t : mine) {
+      const int li = t.cell / g.ld, q = t.cell % g.ld;
+      own.push_back(((li - g.own0) / EL_ROWS) * g.ntc + q / EL_BX);
+      cells.push_back(t.cell); gid.push_back(t.gid); field.push_back(t.field);
+    }
+    PointSetHost h;
+    build_point_set(own, cells, gid, field, P->nblocks, &h);
+    std::map<std::pair<int, int>, std::vector<int>> idx;
+    for (const Pt& t : other) idx[{t.cell, t.field}].push_back(t.gid);
+    std::vector<int> xs(1, 0), xp;
+    for (size_t k = 0; k < h.cell.size(); k++) {
+      auto it = idx.find({h.cell[k], h.field[k]});
+      if (it != idx.end()) xp.insert(xp.end(), it->second.begin(), it->second.end());
+      xs.push_back((int)xp.size());
+    }
+    TRY(upload_point_set(h, &dst->ps, st));
+    TRY(dev_upload(&dst->xstart, xs, st));
+    TRY(dev_upload(&dst->xperm, xp, st));
+    if (dst->ps.nu > 0)
+      dst->dev = ElPoints{dst->ps.blk, dst->ps.cell, dst->ps.field, dst->ps.start, dst->ps.perm, dst->xstart, dst->xperm};
+    return ADSEIS_OK;
+  };
+  EPTRY(upload(sp, rp, &P->src));
+  EPTRY(upload(rp, sp, &P->rcv));
+  std::vector<unsigned char> owned((size_t)std::max<i64>(nrcv, 1), 0);
+  for (const Pt& t : rp) owned[t.gid] = 1;
+  EPTRY(dev_upload(&P->rcv_owned, owned, st));
+  EPTRY(dev_alloc_zero(&P->rcvv, (size_t)((p->NSTEP + 1) * nrcv), st));
+  EPTRY(dev_alloc_zero(&P->loss, 1, st));
+
+  // history window
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  const size_t slot_bytes = (size_t)P->slot_sz * 8;
+  const size_t reserve = 16 * (size_t)g.plane * 8 + 4 * slot_bytes +
+                         (size_t)(3 * (p->NSTEP + 1) * nrcv + 2 * p->NSTEP * nsrc) * 8 + (512u << 20);
+  size_t budget = hist_bytes_budget ? hist_bytes_budget : (free_b > reserve ? free_b - reserve : 0);
+  if (budget > free_b) budget = free_b;
+  i64 slots = (i64)(budget / slot_bytes);
+  if (slots >= p->NSTEP + 1) {
+    P->win = p->NSTEP + 1;
+  } else if (hist_bytes_budget) {
+    P->win = std::max<i64>(slots, 2);
+  } else {
+    i64 best = 2;
+    for (i64 W = slots; W >= 2; W--) {
+      i64 nseg = (p->NSTEP + (W - 1) - 1) / (W - 1);
+      if (W + (nseg - 1) <= slots) { best = W; break; }
+    }
+    P->win = best;
+  }
+  el_make_segments(P);
+  {
+    cudaError_t e = cudaMalloc((void**)&P->hist, (size_t)P->win * slot_bytes);
+    if (e != cudaSuccess) {
+      adseis_set_error("elastic_plan_create: cannot allocate %lld history slots of %zu bytes: %s", (long long)P->win,
+                       slot_bytes, cudaGetErrorString(e));
+      adseis_elastic_plan_destroy(P);
+      return ADSEIS_ENOMEM;
+    }
+    CUDA_TRY(cudaMemsetAsync(P->hist, 0, (size_t)P->win * slot_bytes, st));
+  }
+  for (size_t k = 1; k < P->seg_b.size(); k++) {
+    double* c = nullptr;
+    EPTRY(dev_alloc(&c, (size_t)P->slot_sz));
+    P->ckpt.push_back(c);
+  }
+  *out = P;
+  return ADSEIS_OK;
+}
+
+// caller's dense model array -> pitched internal plane (ghost / pad entries zero)
+static int el_load_plane(adseis_elastic_plan* P, const double* src, double* dst) {
+  const ElGeom& g = P->g;
+  cudaStream_t st = P->ctx->stream;
+  CUDA_TRY(cudaMemsetAsync(dst, 0, (size_t)g.plane * 8, st));
+  const int off = P->off, OW = g.W - 2 * off, OH = g.H - 2 * off;
+  CUDA_TRY(cudaMemcpy2DAsync(dst + (i64)off * g.ld + off, (size_t)g.ld * 8, src, (size_t)OW * 8, (size_t)OW * 8,
+                             (size_t)OH, cudaMemcpyDefault, st));
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_elastic_plan_set_model(adseis_elastic_plan* P, const double* rho, const double* lambda,
+                                             const double* mu, int on_device) {
+  (void)on_device;
+  REQUIRE(P && rho && lambda && mu, "elastic_plan_set_model: null");
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  TRY(el_load_plane(P, rho, P->rho));
+  TRY(el_load_plane(P, lambda, P->lam));
+  TRY(el_load_plane(P, mu, P->mu));
+  const ElGeom& g = P->g;
+  dim3 grid((unsigned)((g.ld + 127) / 128), (unsigned)g.Hl);
+  k_el_materials<<<grid, 128, 0, P->ctx->stream>>>(g.Hl, g.ld, g.W, P->p.variant == 0, P->rho, P->lam, P->mu, P->lamb,
+                                                   P->lmb, P->mub2, P->rhob, P->rinv, P->rbinv);
+  P->ctx->launches++;
+  CUDA_TRY(cudaGetLastError());
+  P->have_model = true;
+  P->have_fwd = P->have_grad = false;
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_elastic_plan_set_srcv(adseis_elastic_plan* P, const double* srcv, int64_t rows, int on_device) {
+  (void)on_device;
+  REQUIRE(P && (srcv || P->nsrc == 0), "elastic_plan_set_srcv: null");
+  REQUIRE(rows >= P->p.NSTEP, "elastic_plan_set_srcv: srcv has %lld rows, need >= NSTEP=%lld", (long long)rows,
+          (long long)P->p.NSTEP);
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  if (!P->srcv) TRY(dev_alloc(&P->srcv, (size_t)(P->p.NSTEP * P->nsrc)));
+  if (P->nsrc > 0)
+    CUDA_TRY(cudaMemcpyAsync(P->srcv, srcv, (size_t)(P->p.NSTEP * P->nsrc) * 8, cudaMemcpyDefault, P->ctx->stream));
+  P->have_srcv = true;
+  P->have_fwd = P->have_grad = false;
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_elastic_plan_set_obs(adseis_elastic_plan* P, const double* obs, int on_device) {
+  (void)on_device;
+  REQUIRE(P && (obs || P->nrcv == 0), "elastic_plan_set_obs: null");
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  const size_t n = (size_t)((P->p.NSTEP + 1) * P->nrcv);
+  if (!P->obs) { TRY(dev_alloc(&P->obs, n)); TRY(dev_alloc(&P->res, n)); }
+  if (n > 0) CUDA_TRY(cudaMemcpyAsync(P->obs, obs, n * 8, cudaMemcpyDefault, P->ctx->stream));
+  P->have_obs = true;
+  P->have_grad = false;
+  return ADSEIS_OK;
+}
+
+// one forward step s: slot `in` (s-1) -> slot `out` (s); in == out is allowed (in-place stepping)
+static int el_step_forward(adseis_elastic_plan* P, i64 s, double* in, double* out, bool sample) {
+  cudaStream_t st = P->ctx->stream;
+  const ElSlot si = slot_at(P, in), so = slot_at(P, out);
+  const ElMat mt = mat_of(P);
+  const ElCoef cf = coef_of(P);
+  dim3 blk(EL_BX, EL_BY);
+  ElPoints none{};
+  const double* row = P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr;
+  const double* prev = (P->nsrc > 0 && s >= 2) ? P->srcv + (s - 2) * P->nsrc : nullptr;
+  el_sigma_fwd<<<P->nblocks, blk, 0, st>>>(P->g, si, so, mt, cf, P->src.dev, prev);
+  EL_LAUNCH_CHECK(P);
+  el_vel_fwd<<<P->nblocks, blk, 0, st>>>(P->g, si, so, mt, cf, P->src.dev, row, sample ? P->rcv.dev : none,
+                                         (sample && P->nrcv > 0) ? P->rcvv : nullptr, (int)(P->p.NSTEP + 1), (int)s);
+  EL_LAUNCH_CHECK(P);
+  return ADSEIS_OK;
+}
+
+static int el_check_ready(adseis_elastic_plan* P, bool need_obs) {
+  if (!P->have_model || (!P->have_srcv && P->nsrc > 0) || (need_obs && !P->have_obs)) {
+    adseis_set_error("elastic plan: set_model / set_srcv%s must be called first", need_obs ? " / set_obs" : "");
+    return ADSEIS_ESTATE;
+  }
+  return ADSEIS_OK;
+}
+
+// forward sweep through the segments of the history window (keep==true) or in place in slot 0 (keep==false)
+static int el_forward_sweep(adseis_elastic_plan* P, bool keep, bool save_ckpt) {
+  cudaStream_t st = P->ctx->stream;
+  const size_t sb = (size_t)P->slot_sz * 8;
+  CUDA_TRY(cudaMemsetAsync(P->hist, 0, sb, st));  // slot 0 = zeros (Core.jl:37-45)
+  if (P->nrcv > 0) CUDA_TRY(cudaMemsetAsync(P->rcvv, 0, (size_t)((P->p.NSTEP + 1) * P->nrcv) * 8, st));
+  if (!keep) {
+    for (i64 s = 1; s <= P->p.NSTEP; s++) TRY(el_step_forward(P, s, P->hist, P->hist, true));
+    P->win_base = P->win_last = P->p.NSTEP;
+    P->inplace_last = true;
+    return ADSEIS_OK;
+  }
+  const size_t nseg = P->seg_b.size();
+  for (size_t k = 0; k < nseg; k++) {
+    const i64 b = P->seg_b[k], e = P->seg_e[k];
+    if (k > 0) {
+      double* last = win_ptr(P, P->seg_b[k - 1], b);
+      if (save_ckpt) CUDA_TRY(cudaMemcpyAsync(P->ckpt[k - 1], last, sb, cudaMemcpyDeviceToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(P->hist, last, sb, cudaMemcpyDeviceToDevice, st));
+    }
+    // memory strips of a slot that a step does not write must be zero: slots were zero-filled at creation and
+    // every step writes the same (region x PML) cells, so nothing else to do.
+    for (i64 s = b + 1; s <= e; s++) TRY(el_step_forward(P, s, win_ptr(P, b, s - 1), win_ptr(P, b, s), true));
+    P->win_base = b; P->win_last = e;
+  }
+  P->inplace_last = false;
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_elastic_plan_forward(adseis_elastic_plan* P) {
+  REQUIRE(P, "elastic_plan_forward: null");
+  TRY(el_check_ready(P, false));
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  P->last_launches = 0; P->last_recomputed = 0;
+  // keep the history when all of it fits (so that snapshots can be fetched); otherwise step in place
+  TRY(el_forward_sweep(P, P->win >= P->p.NSTEP + 1, false));
+  P->last_segments = 1;
+  P->have_fwd = true;
+  return ADSEIS_OK;
+}
+
+static int el_ensure_adjoint(adseis_elastic_plan* P, bool mat) {
+  cudaStream_t st = P->ctx->stream;
+  const ElGeom& g = P->g;
+  if (!P->adj) {
+    TRY(dev_alloc_zero(&P->adj, (size_t)(5 * g.plane + 2 * (4 * g.xm_sz + 4 * g.ym_sz)), st));
+    TRY(dev_alloc_zero(&P->gradsrcv, (size_t)(P->p.NSTEP * P->nsrc), st));
+  }
+  if (mat && !P->Gl) {
+    double** a[] = {&P->Gl, &P->Gm1, &P->Gm2, &P->Gr3, &P->Gr4};
+    for (double** x : a) TRY(dev_alloc_zero(x, (size_t)g.plane, st));
+    TRY(dev_alloc_zero(&P->grho, (size_t)P->model_elems, st));
+    TRY(dev_alloc_zero(&P->glam, (size_t)P->model_elems, st));
+    TRY(dev_alloc_zero(&P->gmu, (size_t)P->model_elems, st));
+  }
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_elastic_plan_gradient(adseis_elastic_plan* P, int want_material_grads) {
+  REQUIRE(P, "elastic_plan_gradient: null");
+  TRY(el_check_ready(P, true));
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  const ElGeom& g = P->g;
+  cudaStream_t st = P->ctx->stream;
+  const i64 NSTEP = P->p.NSTEP;
+  const bool mat = want_material_grads != 0;
+  P->last_launches = 0; P->last_recomputed = 0;
+  TRY(el_ensure_adjoint(P, mat));
+  // ---- forward: with history only when material gradients are wanted ----
+  TRY(el_forward_sweep(P, mat, mat));
+  const size_t nseg = mat ? P->seg_b.size() : 1;
+  P->last_segments = (i64)nseg;
+  const i64 nr = (NSTEP + 1) * P->nrcv;
+  k_residual_loss<<<1, 1024, 0, st>>>(P->rcvv, P->obs, P->rcv_owned, (int)std::max<i64>(P->nrcv, 1), 0, nr, P->res,
+                                      P->loss);
+  EL_LAUNCH_CHECK(P);
+  // ---- reverse sweep ----
+  const size_t msz = (size_t)(4 * g.xm_sz + 4 * g.ym_sz);
+  CUDA_TRY(cudaMemsetAsync(P->adj, 0, (size_t)(5 * g.plane + 2 * msz) * 8, st));
+  if (P->nsrc > 0) CUDA_TRY(cudaMemsetAsync(P->gradsrcv, 0, (size_t)(NSTEP * P->nsrc) * 8, st));
+  if (mat) {
+    double* a[] = {P->Gl, P->Gm1, P->Gm2, P->Gr3, P->Gr4};
+    for (double* x : a) CUDA_TRY(cudaMemsetAsync(x, 0, (size_t)g.plane * 8, st));
+  }
+  ElSlot side[2];
+  for (int k = 0; k < 2; k++) {
+    side[k] = slot_at(P, P->adj);  // fields are shared (updated in place) ...
+    side[k].xm = P->adj + 5 * g.plane + k * msz;  // ... the adjoint memories ping-pong
+    side[k].ym = side[k].xm + 4 * g.xm_sz;
+  }
+  const ElMat mt = mat_of(P);
+  const ElCoef cf = coef_of(P);
+  dim3 blk(EL_BX, EL_BY);
+  const int stride = (int)(NSTEP + 1);
+  ElPoints none{};
+  // start: velocity residuals of slot NSTEP into vbar; grad_srcv row NSTEP-1
+  el_adj_start<<<P->nblocks, blk, 0, st>>>(g, side[0], P->rcv.dev, P->nrcv > 0 ? P->res : nullptr, stride, (int)NSTEP,
+                                           P->src.dev, P->nsrc > 0 ? P->gradsrcv + (NSTEP - 1) * P->nsrc : nullptr);
+  EL_LAUNCH_CHECK(P);
+  const size_t sb = (size_t)P->slot_sz * 8;
+  ElSlot zero{};
+  for (i64 k = (i64)nseg - 1; k >= 0; k--) {
+    i64 b = 0, e = NSTEP;
+    if (mat) {
+      b = P->seg_b[k]; e = P->seg_e[k];
+      if (k != (i64)nseg - 1) {  // restore the first slot of segment k and replay its forward steps
+        if (k == 0) CUDA_TRY(cudaMemsetAsync(P->hist, 0, sb, st));
+        else CUDA_TRY(cudaMemcpyAsync(P->hist, P->ckpt[k - 1], sb, cudaMemcpyDeviceToDevice, st));
+        for (i64 s = b + 1; s <= e; s++) TRY(el_step_forward(P, s, win_ptr(P, b, s - 1), win_ptr(P, b, s), false));
+        P->last_recomputed += e - b;
+        P->win_base = b; P->win_last = e;
+      }
+    }
+    for (i64 s = e; s >= b + 1; s--) {
+      const ElSlot& bi = side[s & 1];
+      const ElSlot& bo = side[(s & 1) ^ 1];
+      const ElSlot fs = mat ? slot_at(P, win_ptr(P, b, s)) : zero;
+      const ElSlot fp = mat ? slot_at(P, win_ptr(P, b, s - 1)) : zero;
+      const double* resp = P->nrcv > 0 ? P->res : nullptr;
+      double* grow = (s - 2 >= 0 && P->nsrc > 0 && s >= 2) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr;
+      if (mat) {
+        el_vel_adj<true><<<P->nblocks, blk, 0, st>>>(g, bi, bo, fs, mt, cf, P->Gr3, P->Gr4, P->rcv.dev, resp, stride, (int)s);
+        EL_LAUNCH_CHECK(P);
+        el_sigma_adj<true><<<P->nblocks, blk, 0, st>>>(g, bi, bo, fp, fs, mt, cf, P->Gl, P->Gm1, P->Gm2,
+                                                       s >= 2 ? P->rcv.dev : none, s >= 2 ? resp : nullptr, stride,
+                                                       (int)(s - 1), s >= 2 ? P->src.dev : none, grow);
+        EL_LAUNCH_CHECK(P);
+      } else {
+        el_vel_adj<false><<<P->nblocks, blk, 0, st>>>(g, bi, bo, zero, mt, cf, nullptr, nullptr, P->rcv.dev, resp, stride, (int)s);
+        EL_LAUNCH_CHECK(P);
+        el_sigma_adj<false><<<P->nblocks, blk, 0, st>>>(g, bi, bo, zero, zero, mt, cf, nullptr, nullptr, nullptr,
+                                                        s >= 2 ? P->rcv.dev : none, s >= 2 ? resp : nullptr, stride,
+                                                        (int)(s - 1), s >= 2 ? P->src.dev : none, grow);
+        EL_LAUNCH_CHECK(P);
+      }
+    }
+  }
+  if (mat) {
+    CUDA_TRY(cudaMemsetAsync(P->grho, 0, (size_t)P->model_elems * 8, st));
+    CUDA_TRY(cudaMemsetAsync(P->glam, 0, (size_t)P->model_elems * 8, st));
+    CUDA_TRY(cudaMemsetAsync(P->gmu, 0, (size_t)P->model_elems * 8, st));
+    dim3 gg((unsigned)((g.W + 127) / 128), (unsigned)(g.own1 - g.own0));
+    k_el_grad_finalize<<<gg, 128, 0, st>>>(g, P->p.variant == 0, P->off, P->Gl, P->Gm1, P->Gm2, P->Gr3, P->Gr4, P->grho,
+                                           P->glam, P->gmu);
+    EL_LAUNCH_CHECK(P);
+  }
+  P->have_fwd = true;
+  P->have_grad = true;
+  P->have_matgrad = mat;
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_elastic_plan_get(adseis_elastic_plan* P, int what, double* dst, int to_device) {
+  (void)to_device;
+  REQUIRE(P && dst, "elastic_plan_get: null");
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  const double* src = nullptr;
+  size_t n = 0;
+  bool need_grad = true, need_mat = false;
+  switch (what) {
+    case ADSEIS_GET_RCVV: src = P->rcvv; n = (size_t)((P->p.NSTEP + 1) * P->nrcv); need_grad = false; break;
+    case ADSEIS_GET_LOSS: src = P->loss; n = 1; break;
+    case ADSEIS_GET_GRAD_SRCV: src = P->gradsrcv; n = (size_t)(P->p.NSTEP * P->nsrc); break;
+    case ADSEIS_GET_GRAD_RHO: src = P->grho; n = (size_t)P->model_elems; need_mat = true; break;
+    case ADSEIS_GET_GRAD_LAMBDA: src = P->glam; n = (size_t)P->model_elems; need_mat = true; break;
+    case ADSEIS_GET_GRAD_MU: src = P->gmu; n = (size_t)P->model_elems; need_mat = true; break;
+    default: adseis_set_error("elastic_plan_get: unknown item %d", what); return ADSEIS_EINVAL;
+  }
+  if ((!need_grad && !P->have_fwd) || (need_grad && !P->have_grad) || (need_mat && !P->have_matgrad)) {
+    adseis_set_error("elastic_plan_get: item %d has not been computed yet", what);
+    return ADSEIS_ESTATE;
+  }
+  if (n > 0) CUDA_TRY(cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyDefault, P->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(P->ctx->stream));
+  return ADSEIS_OK;
+}
+
+// copy one field of a resident slot out in the caller's layout (stress planes get their pending sources added)
+static int el_copy_field_out(adseis_elastic_plan* P, const double* slot_base, int field, i64 slot, double* dst,
+                             double* scratch) {
+  const ElGeom& g = P->g;
+  cudaStream_t st = P->ctx->stream;
+  const double* plane = slot_base + (i64)field * g.plane;
+  if (field >= 2 && P->src.ps.nu > 0 && slot >= 1) {
+    CUDA_TRY(cudaMemcpyAsync(scratch, plane, (size_t)g.plane * 8, cudaMemcpyDeviceToDevice, st));
+    k_el_apply_stress_sources<<<(P->src.ps.nu + 127) / 128, 128, 0, st>>>(scratch, field, P->src.dev, P->src.ps.nu,
+                                                                          P->srcv + (slot - 1) * P->nsrc);
+    P->ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    plane = scratch;
+  }
+  const int off = P->off, OW = g.W - 2 * off, OH = g.H - 2 * off;
+  CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)OW * 8, plane + (i64)off * g.ld + off, (size_t)g.ld * 8, (size_t)OW * 8,
+                             (size_t)OH, cudaMemcpyDefault, st));
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_elastic_plan_get_snapshot(adseis_elastic_plan* P, int field, int64_t slot, double* dst,
+                                                int to_device) {
+  (void)to_device;
+  REQUIRE(P && dst && field >= 0 && field <= 4, "elastic_plan_get_snapshot: bad argument");
+  if (!P->have_fwd || slot < P->win_base || slot > P->win_last) {
+    adseis_set_error("elastic_plan_get_snapshot: slot %lld is not resident (window holds [%lld,%lld])",
+                     (long long)slot, (long long)P->win_base, (long long)P->win_last);
+    return ADSEIS_ESTATE;
+  }
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  double* scratch = nullptr;
+  TRY(dev_alloc(&scratch, (size_t)P->g.plane));
+  const double* base = P->inplace_last ? P->hist : win_ptr(P, P->win_base, slot);
+  int rc = el_copy_field_out(P, base, field, slot, dst, scratch);
+  cudaStreamSynchronize(P->ctx->stream);
+  cudaFree(scratch);
+  return rc;
+}
+
+ADSEIS_API int adseis_elastic_plan_info(adseis_elastic_plan* P, int64_t info[8]) {
+  REQUIRE(P && info, "elastic_plan_info: null");
+  info[0] = P->win; info[1] = P->last_segments; info[2] = P->last_launches; info[3] = P->g.Hl; info[4] = P->g.ld;
+  info[5] = P->last_recomputed; info[6] = (i64)P->seg_b.size(); info[7] = P->slot_sz;
+  return ADSEIS_OK;
+}
+
+ADSEIS_API int adseis_elastic_plan_ipc_export(adseis_elastic_plan* P, void* handle_out) {
+  (void)P; (void)handle_out;
+  adseis_set_error("elastic_plan_ipc_export: slab decomposition of the elastic path is not available in this build");
+  return ADSEIS_ECOMM;
+}
+ADSEIS_API int adseis_elastic_plan_ipc_connect(adseis_elastic_plan* P, const void* lo, const void* hi) {
+  (void)P; (void)lo; (void)hi;
+  adseis_set_error("elastic_plan_ipc_connect: slab decomposition of the elastic path is not available in this build");
+  return ADSEIS_ECOMM;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// one-call host-buffer entry points
+// ------------------------------------------------------------------------------------------------------------
+ADSEIS_API int adseis_elastic_forward(adseis_ctx* ctx, const adseis_elastic_params* p, const double* rho,
+                                      const double* lambda, const double* mu, int64_t nsrc, const int64_t* srci,
+                                      const int64_t* srcj, const int64_t* srctype, const double* srcv,
+                                      int64_t srcv_rows, int64_t nrcv, const int64_t* rcvi, const int64_t* rcvj,
+                                      const int64_t* rcvtype, double* rcvv_out, double* hist_out) {
+  adseis_elastic_plan* P = nullptr;
+  // without a history request two slots are enough (in-place stepping uses one)
+  TRY(adseis_elastic_plan_create(ctx, p, nullptr, nsrc, srci, srcj, srctype, nrcv, rcvi, rcvj, rcvtype,
+                                 hist_out ? 0 : 1, &P));
+  int rc = adseis_elastic_plan_set_model(P, rho, lambda, mu, 0);
+  if (!rc) rc = adseis_elastic_plan_set_srcv(P, srcv, srcv_rows, 0);
+  if (!rc && !hist_out) rc = adseis_elastic_plan_forward(P);
+  if (!rc && hist_out) {
+    // field histories for the caller: [5][(NSTEP+1)][model]; step in place and copy each slot out
+    cudaStream_t st = ctx->stream;
+    double* scratch = nullptr;
+    rc = dev_alloc(&scratch, (size_t)P->g.plane);
+    if (!rc) rc = el_check_ready(P, false);
+    if (!rc) {
+      cudaMemsetAsync(P->hist, 0, (size_t)P->slot_sz * 8, st);
+      if (P->nrcv > 0) cudaMemsetAsync(P->rcvv, 0, (size_t)((p->NSTEP + 1) * P->nrcv) * 8, st);
+      for (i64 s = 0; s <= p->NSTEP && !rc; s++) {
+        if (s >= 1) rc = el_step_forward(P, s, P->hist, P->hist, true);
+        for (int f = 0; f < 5 && !rc; f++)
+          rc = el_copy_field_out(P, P->hist, f, s, hist_out + ((i64)f * (p->NSTEP + 1) + s) * P->model_elems, scratch);
+      }
+      P->have_fwd = (rc == 0);
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(scratch);
+  }
+  if (!rc && rcvv_out && nrcv > 0) rc = adseis_elastic_plan_get(P, ADSEIS_GET_RCVV, rcvv_out, 0);
+  if (!rc) rc = adseis_ctx_sync(ctx);
+  adseis_elastic_plan_destroy(P);
+  return rc;
+}
+
+ADSEIS_API int adseis_elastic_misfit_grad(adseis_ctx* ctx, const adseis_elastic_params* p, const double* rho,
+                                          const double* lambda, const double* mu, int64_t nsrc, const int64_t* srci,
+                                          const int64_t* srcj, const int64_t* srctype, const double* srcv,
+                                          int64_t srcv_rows, int64_t nrcv, const int64_t* rcvi, const int64_t* rcvj,
+                                          const int64_t* rcvtype, const double* obs, double* loss_out,
+                                          double* rcvv_out, double* grad_rho_out, double* grad_lambda_out,
+                                          double* grad_mu_out, double* grad_srcv_out) {
+  adseis_elastic_plan* P = nullptr;
+  const bool mat = grad_rho_out || grad_lambda_out || grad_mu_out;
+  TRY(adseis_elastic_plan_create(ctx, p, nullptr, nsrc, srci, srcj, srctype, nrcv, rcvi, rcvj, rcvtype, mat ? 0 : 1,
+                                 &P));
+  int rc = adseis_elastic_plan_set_model(P, rho, lambda, mu, 0);
+  if (!rc) rc = adseis_elastic_plan_set_srcv(P, srcv, srcv_rows, 0);
+  if (!rc) rc = adseis_elastic_plan_set_obs(P, obs, 0);
+  if (!rc) rc = adseis_elastic_plan_gradient(P, mat ? 1 : 0);
+  if (!rc && loss_out) rc = adseis_elastic_plan_get(P, ADSEIS_GET_LOSS, loss_out, 0);
+  if (!rc && rcvv_out && nrcv > 0) rc = adseis_elastic_plan_get(P, ADSEIS_GET_RCVV, rcvv_out, 0);
+  if (!rc && grad_rho_out) rc = adseis_elastic_plan_get(P, ADSEIS_GET_GRAD_RHO, grad_rho_out, 0);
+  if (!rc && grad_lambda_out) rc = adseis_elastic_plan_get(P, ADSEIS_GET_GRAD_LAMBDA, grad_lambda_out, 0);
+  if (!rc && grad_mu_out) rc = adseis_elastic_plan_get(P, ADSEIS_GET_GRAD_MU, grad_mu_out, 0);
+  if (!rc && grad_srcv_out && nsrc > 0) rc = adseis_elastic_plan_get(P, ADSEIS_GET_GRAD_SRCV, grad_srcv_out, 0);
+  if (!rc) rc = adseis_ctx_sync(ctx);
+  adseis_elastic_plan_destroy(P);
+  return rc;
+}
