@@ -119,6 +119,18 @@ class AcousticPlan:
         return dict(forward_ms=a[0], recompute_ms=a[1], adjoint_ms=a[2], forward_launches=int(a[3]),
                     recompute_launches=int(a[4]), adjoint_launches=int(a[5]))
 
+    def ipc_export(self):
+        """64-byte CUDA IPC handle of this slab plan's device arena (to be all-gathered by the host framework)."""
+        buf = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        check(self.lib.adseis_acoustic_plan_ipc_export(self.handle, C.cast(buf, C.c_void_p)))
+        return bytes(buf.raw)
+
+    def ipc_connect(self, handle_lo, handle_hi):
+        lo = C.create_string_buffer(handle_lo, _lib.IPC_HANDLE_BYTES) if handle_lo is not None else None
+        hi = C.create_string_buffer(handle_hi, _lib.IPC_HANDLE_BYTES) if handle_hi is not None else None
+        check(self.lib.adseis_acoustic_plan_ipc_connect(self.handle, C.cast(lo, C.c_void_p) if lo else None,
+                                                        C.cast(hi, C.c_void_p) if hi else None))
+
     def close(self):
         if getattr(self, "handle", None) is not None:
             self.lib.adseis_acoustic_plan_destroy(self.handle)

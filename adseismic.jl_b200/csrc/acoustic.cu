@@ -52,6 +52,59 @@ __global__ void k_grad_finalize(const double* __restrict__ G, const double* __re
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// slab decomposition: peer-memory halo exchange over NVLink (one process per GPU, CUDA IPC)
+// ------------------------------------------------------------------------------------------------------------
+// Every slab plan keeps the arrays that have halo rows in ONE device arena whose IPC handle is exported; the
+// descriptor at the start of the arena tells a neighbour where each array lives.
+struct AcDesc {
+  unsigned long long magic;
+  long long Hl, ld, plane, win, own0, own1;
+  long long off_flags, off_hist, off_phi[2], off_psi[2], off_ub[3], off_phib[2], off_psib[2];
+};
+#define AC_DESC_MAGIC 0xAD5E15B200ULL
+#define AC_HX_BLOCKS 8
+#define AC_HX_SPIN_LIMIT (1ULL << 26)
+
+struct AcHaloArgs {
+  int nrow;                 // rows to push (0 = pure barrier)
+  const double* src[4];     // my rows (ld doubles each)
+  double* dst[4];           // the neighbour's halo rows (peer pointers)
+  int ld;
+  int has_lo, has_hi;
+  unsigned long long* sig_lo;   // neighbour's "flag_from_hi" / "flag_from_lo" (peer pointers)
+  unsigned long long* sig_hi;
+  unsigned long long* my_flags; // [0] = written by rank-1, [1] = written by rank+1, [2] = error
+  unsigned long long expect;    // AC_HX_BLOCKS * epoch
+};
+
+// Push my edge rows into the neighbours' halo rows (plain 16-byte stores over NVLink), publish them with a
+// system-scope fence + atomic on the neighbour's flag, then wait until both neighbours have published theirs.
+// All ranks run the same sequence of exchanges, so a single monotonically increasing epoch orders everything.
+__global__ void __launch_bounds__(256) k_halo_exchange(AcHaloArgs a) {
+  const int per = (a.ld / 2 + AC_HX_BLOCKS - 1) / AC_HX_BLOCKS;  // double2 elements per CTA
+  const int j0 = blockIdx.x * per, j1 = min(a.ld / 2, j0 + per);
+  for (int r = 0; r < a.nrow; r++) {
+    const double2* s = reinterpret_cast<const double2*>(a.src[r]);
+    double2* d = reinterpret_cast<double2*>(a.dst[r]);
+    for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) d[j] = s[j];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (a.has_lo) atomicAdd_system(a.sig_lo, 1ULL);
+    if (a.has_hi) atomicAdd_system(a.sig_hi, 1ULL);
+    if (blockIdx.x == 0) {
+      volatile unsigned long long* f = a.my_flags;
+      unsigned long long spins = 0;
+      while ((a.has_lo && f[0] < a.expect) || (a.has_hi && f[1] < a.expect)) {
+        if (++spins > AC_HX_SPIN_LIMIT) { f[2] = 1ULL; break; }  // neighbour lost: report, do not hang
+      }
+      __threadfence_system();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------------------
 struct adseis_acoustic_plan {
@@ -84,6 +137,14 @@ struct adseis_acoustic_plan {
   double *ub[3] = {nullptr, nullptr, nullptr}, *phib[2] = {nullptr, nullptr}, *psib[2] = {nullptr, nullptr};
   double *G = nullptr, *gradc = nullptr, *gradsrcv = nullptr;
   bool have_model = false, have_srcv = false, have_obs = false, have_grad = false, have_fwd = false;
+  // slab decomposition (nranks > 1): arena, neighbours
+  double* arena = nullptr;
+  size_t arena_bytes = 0;
+  AcDesc desc{};
+  AcDesc dpeer[2];                           // descriptors of rank-1 / rank+1
+  char* peer[2] = {nullptr, nullptr};        // their arenas mapped into this process
+  unsigned long long epoch = 0;              // exchanges issued so far
+  bool connected = false;
   // stats
   i64 last_launches = 0, last_segments = 0, last_recomputed = 0;
   // per-phase device timing of the last forward()/gradient(): CUDA events on the ctx stream around each run of
@@ -119,6 +180,10 @@ static inline double* win_slot(adseis_acoustic_plan* P, i64 base, i64 s) { retur
     (P)->last_launches++;                 \
     CUDA_TRY(cudaGetLastError());         \
   } while (0)
+
+enum AcArr { AR_HIST, AR_PHI, AR_PSI, AR_UB, AR_PHIB, AR_PSIB };  // arrays with halo rows (slab plans)
+static int halo_exchange(adseis_acoustic_plan* P, int narr, const int* arr, const i64* idx);
+static int halo_check(adseis_acoustic_plan* P);
 
 static int plan_segments(adseis_acoustic_plan* P, size_t budget_bytes, bool count_checkpoints) {
   // The wavefield history window holds `win` snapshots.  If NSTEP+1 snapshots fit, the whole history is kept;
@@ -158,9 +223,14 @@ ADSEIS_API int adseis_acoustic_plan_destroy(adseis_acoustic_plan* P) {
   cudaSetDevice(P->ctx->device);
   cudaStreamSynchronize(P->ctx->stream);
   cudaFree(P->c2); cudaFree(P->cvel); cudaFree(P->sigx); cudaFree(P->tauy);
-  for (int k = 0; k < 2; k++) { cudaFree(P->phi[k]); cudaFree(P->psi[k]); cudaFree(P->phib[k]); cudaFree(P->psib[k]); }
-  for (int k = 0; k < 3; k++) cudaFree(P->ub[k]);
-  cudaFree(P->hist);
+  if (P->arena) {
+    for (int k = 0; k < 2; k++) if (P->peer[k]) cudaIpcCloseMemHandle(P->peer[k]);
+    cudaFree(P->arena);
+  } else {
+    for (int k = 0; k < 2; k++) { cudaFree(P->phi[k]); cudaFree(P->psi[k]); cudaFree(P->phib[k]); cudaFree(P->psib[k]); }
+    for (int k = 0; k < 3; k++) cudaFree(P->ub[k]);
+    cudaFree(P->hist);
+  }
   for (double* c : P->ckpt) cudaFree(c);
   free_point_set(&P->src); free_point_set(&P->rcv);
   cudaFree(P->rcv_owned);
@@ -294,10 +364,11 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
   PTRY(dev_upload(&P->tauy, ty, st));
   PTRY(dev_alloc_zero(&P->c2, (size_t)g.plane, st));
   PTRY(dev_alloc_zero(&P->cvel, (size_t)g.plane, st));
-  for (int k = 0; k < 2; k++) {
-    PTRY(dev_alloc_zero(&P->phi[k], (size_t)g.plane, st));
-    PTRY(dev_alloc_zero(&P->psi[k], (size_t)g.plane, st));
-  }
+  if (sl.nranks == 1)
+    for (int k = 0; k < 2; k++) {
+      PTRY(dev_alloc_zero(&P->phi[k], (size_t)g.plane, st));
+      PTRY(dev_alloc_zero(&P->psi[k], (size_t)g.plane, st));
+    }
 
   // sources / receivers: keep the points whose padded row is owned (MPIAcoustic.jl:71-78, 98-104)
   P->nsrc = nsrc; P->nrcv = nrcv;
@@ -350,7 +421,7 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
   if (budget == 0) budget = free_b > reserve ? free_b - reserve : 0;
   if (budget > free_b) budget = free_b;
   PTRY(plan_segments(P, budget, hist_bytes_budget == 0));
-  {
+  if (sl.nranks == 1) {
     cudaError_t e = cudaMalloc((void**)&P->hist, (size_t)P->win * plane_bytes);
     if (e != cudaSuccess) {
       adseis_set_error("acoustic_plan_create: cannot allocate %lld history snapshots of %zu bytes: %s",
@@ -358,6 +429,41 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
       adseis_acoustic_plan_destroy(P);
       return ADSEIS_ENOMEM;
     }
+  } else {
+    // one arena: [descriptor | flags | history window | phi,psi x2 | ubar x3 | phibar,psibar x2]
+    if (P->win < 6) {
+      adseis_set_error("acoustic_plan_create: slab plans need a history window of >= 6 snapshots (got %lld)",
+                       (long long)P->win);
+      adseis_acoustic_plan_destroy(P);
+      return ADSEIS_ENOMEM;
+    }
+    AcDesc& d = P->desc;
+    d.magic = AC_DESC_MAGIC; d.Hl = g.Hl; d.ld = g.ld; d.plane = g.plane; d.win = P->win; d.own0 = P->own0; d.own1 = P->own1;
+    long long off = 512;  // bytes; descriptor lives in [0,512)
+    d.off_flags = off; off += 512;
+    auto take = [&](long long nplanes) { long long o = off; off += nplanes * (long long)plane_bytes; return o; };
+    d.off_hist = take(P->win);
+    for (int k = 0; k < 2; k++) d.off_phi[k] = take(1);
+    for (int k = 0; k < 2; k++) d.off_psi[k] = take(1);
+    for (int k = 0; k < 3; k++) d.off_ub[k] = take(1);
+    for (int k = 0; k < 2; k++) d.off_phib[k] = take(1);
+    for (int k = 0; k < 2; k++) d.off_psib[k] = take(1);
+    P->arena_bytes = (size_t)off;
+    cudaError_t e = cudaMalloc((void**)&P->arena, P->arena_bytes);
+    if (e != cudaSuccess) {
+      adseis_set_error("acoustic_plan_create: cannot allocate the %zu-byte slab arena: %s", P->arena_bytes,
+                       cudaGetErrorString(e));
+      adseis_acoustic_plan_destroy(P);
+      return ADSEIS_ENOMEM;
+    }
+    CUDA_TRY(cudaMemsetAsync(P->arena, 0, P->arena_bytes, st));
+    CUDA_TRY(cudaMemcpyAsync(P->arena, &d, sizeof(d), cudaMemcpyHostToDevice, st));
+    char* base = (char*)P->arena;
+    P->hist = (double*)(base + d.off_hist);
+    for (int k = 0; k < 2; k++) { P->phi[k] = (double*)(base + d.off_phi[k]); P->psi[k] = (double*)(base + d.off_psi[k]); }
+    for (int k = 0; k < 3; k++) P->ub[k] = (double*)(base + d.off_ub[k]);
+    for (int k = 0; k < 2; k++) { P->phib[k] = (double*)(base + d.off_phib[k]); P->psib[k] = (double*)(base + d.off_psib[k]); }
+    CUDA_TRY(cudaStreamSynchronize(st));
   }
   for (size_t k = 1; k < P->seg_b.size(); k++) {
     double* c = nullptr;
@@ -452,6 +558,11 @@ static int run_forward_steps(adseis_acoustic_plan* P, i64 base, i64 s_first, i64
         P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, sample ? P->rcvp : none,
         (sample && P->nrcv > 0) ? P->rcvv + s * P->nrcv : nullptr);
     LAUNCH_CHECK(P);
+    if (P->arena) {  // new u[s] and phi[s] edge rows -> neighbours' halo rows; wait for theirs
+      const int arr[2] = {AR_HIST, AR_PHI};
+      const i64 idx[2] = {s - base, s & 1};
+      TRY(halo_exchange(P, 2, arr, idx));
+    }
   }
   return ADSEIS_OK;
 }
@@ -470,6 +581,7 @@ static int forward_sweep(adseis_acoustic_plan* P, bool save_ckpt, segment_cb cb,
   }
   CUDA_TRY(cudaMemsetAsync(P->hist, 0, 2 * pb, st));  // slots 0,1 = 0 (Core.jl:607-612)
   if (P->nrcv > 0) CUDA_TRY(cudaMemsetAsync(P->rcvv, 0, (size_t)(2 * P->nrcv) * 8, st));
+  TRY(halo_exchange(P, 0, nullptr, nullptr));  // slab plans: nobody pushes before everybody's memsets are done
   const size_t nseg = P->seg_b.size();
   for (size_t k = 0; k < nseg; k++) {
     const i64 b = P->seg_b[k], e = P->seg_e[k];
@@ -521,8 +633,10 @@ static int ensure_adjoint_state(adseis_acoustic_plan* P) {
   if (P->G) return ADSEIS_OK;
   const size_t n = (size_t)P->g.plane;
   cudaStream_t st = P->ctx->stream;
-  for (int k = 0; k < 3; k++) TRY(dev_alloc_zero(&P->ub[k], n, st));
-  for (int k = 0; k < 2; k++) { TRY(dev_alloc_zero(&P->phib[k], n, st)); TRY(dev_alloc_zero(&P->psib[k], n, st)); }
+  if (!P->arena) {
+    for (int k = 0; k < 3; k++) TRY(dev_alloc_zero(&P->ub[k], n, st));
+    for (int k = 0; k < 2; k++) { TRY(dev_alloc_zero(&P->phib[k], n, st)); TRY(dev_alloc_zero(&P->psib[k], n, st)); }
+  }
   TRY(dev_alloc_zero(&P->G, n, st));
   TRY(dev_alloc_zero(&P->gradc, (size_t)P->model_elems, st));
   TRY(dev_alloc_zero(&P->gradsrcv, (size_t)(P->p.NSTEP * P->nsrc), st));
@@ -553,6 +667,7 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
   for (int k = 0; k < 2; k++) { CUDA_TRY(cudaMemsetAsync(P->phib[k], 0, pb, st)); CUDA_TRY(cudaMemsetAsync(P->psib[k], 0, pb, st)); }
   CUDA_TRY(cudaMemsetAsync(P->G, 0, pb, st));
   if (P->nsrc > 0) CUDA_TRY(cudaMemsetAsync(P->gradsrcv, 0, (size_t)(NSTEP * P->nsrc) * 8, st));
+  TRY(halo_exchange(P, 0, nullptr, nullptr));
   // ubar[NSTEP] = receiver term only; grad_srcv row NSTEP-1
   if (P->rcv.nu > 0) {
     k_points_inject<<<(P->rcv.nu + 127) / 128, 128, 0, st>>>(P->ub[NSTEP % 3], P->rcvp, P->rcv.nu,
@@ -563,6 +678,11 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
     k_points_sample<<<(P->src.nu + 127) / 128, 128, 0, st>>>(P->ub[NSTEP % 3], P->srcp, P->src.nu,
                                                              P->gradsrcv + (NSTEP - 1) * P->nsrc, g.dt2);
     LAUNCH_CHECK(P);
+  }
+  if (P->arena) {
+    const int arr[1] = {AR_UB};
+    const i64 idx[1] = {NSTEP % 3};
+    TRY(halo_exchange(P, 1, arr, idx));
   }
   AcPoints none{};
   for (i64 k = (i64)nseg - 1; k >= 0; k--) {
@@ -594,6 +714,11 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
           P->rcvp, P->nrcv > 0 ? P->res + (s - 1) * P->nrcv : nullptr, (s - 2 >= 1) ? P->srcp : none,
           (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr);
       LAUNCH_CHECK(P);
+      if (P->arena) {
+        const int arr[2] = {AR_UB, AR_PHIB};
+        const i64 idx[2] = {(s + 2) % 3, (s - 1) & 1};
+        TRY(halo_exchange(P, 2, arr, idx));
+      }
     }
     TRY(span_end(P));
   }
@@ -630,6 +755,7 @@ ADSEIS_API int adseis_acoustic_plan_get(adseis_acoustic_plan* P, int what, doubl
   }
   if (n > 0) CUDA_TRY(cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyDefault, P->ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(P->ctx->stream));
+  TRY(halo_check(P));
   return ADSEIS_OK;
 }
 
@@ -684,14 +810,115 @@ ADSEIS_API int adseis_acoustic_plan_timings(adseis_acoustic_plan* P, double out[
 }
 
 ADSEIS_API int adseis_acoustic_plan_ipc_export(adseis_acoustic_plan* P, void* handle_out) {
-  (void)P; (void)handle_out;
-  adseis_set_error("acoustic_plan_ipc_export: peer halo exchange is not available in this build");
-  return ADSEIS_ECOMM;
+  REQUIRE(P && handle_out, "acoustic_plan_ipc_export: null");
+  if (!P->arena) {
+    adseis_set_error("acoustic_plan_ipc_export: not a slab plan (nranks == 1)");
+    return ADSEIS_ESTATE;
+  }
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, P->arena));
+  static_assert(sizeof(h) == ADSEIS_IPC_HANDLE_BYTES, "IPC handle size");
+  memcpy(handle_out, &h, sizeof(h));
+  return ADSEIS_OK;
 }
+
 ADSEIS_API int adseis_acoustic_plan_ipc_connect(adseis_acoustic_plan* P, const void* lo, const void* hi) {
-  (void)P; (void)lo; (void)hi;
-  adseis_set_error("acoustic_plan_ipc_connect: peer halo exchange is not available in this build");
-  return ADSEIS_ECOMM;
+  REQUIRE(P, "acoustic_plan_ipc_connect: null");
+  if (!P->arena) {
+    adseis_set_error("acoustic_plan_ipc_connect: not a slab plan (nranks == 1)");
+    return ADSEIS_ESTATE;
+  }
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  const void* hs[2] = {lo, hi};
+  const bool need[2] = {P->slab.rank > 0, P->slab.rank < P->slab.nranks - 1};
+  for (int k = 0; k < 2; k++) {
+    if (!need[k]) continue;
+    REQUIRE(hs[k], "acoustic_plan_ipc_connect: missing handle of rank %d", P->slab.rank + (k ? 1 : -1));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hs[k], sizeof(h));
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      adseis_set_error("acoustic_plan_ipc_connect: cudaIpcOpenMemHandle(rank %d) -> %s", P->slab.rank + (k ? 1 : -1),
+                       cudaGetErrorString(e));
+      return ADSEIS_ECOMM;
+    }
+    P->peer[k] = (char*)ptr;
+    CUDA_TRY(cudaMemcpy(&P->dpeer[k], ptr, sizeof(AcDesc), cudaMemcpyDeviceToHost));
+    const AcDesc& d = P->dpeer[k];
+    if (d.magic != AC_DESC_MAGIC || d.ld != P->desc.ld || d.win != P->desc.win) {
+      adseis_set_error("acoustic_plan_ipc_connect: neighbour %d has an incompatible layout (magic %llx ld %lld win %lld; "
+                       "mine ld %lld win %lld)", P->slab.rank + (k ? 1 : -1), d.magic, d.ld, d.win, P->desc.ld, P->desc.win);
+      return ADSEIS_ECOMM;
+    }
+  }
+  P->connected = true;
+  return ADSEIS_OK;
+}
+
+static long long desc_off(const AcDesc& d, int arr, i64 idx) {
+  switch (arr) {
+    case AR_HIST: return d.off_hist + idx * d.plane * 8;
+    case AR_PHI: return d.off_phi[idx];
+    case AR_PSI: return d.off_psi[idx];
+    case AR_UB: return d.off_ub[idx];
+    case AR_PHIB: return d.off_phib[idx];
+    default: return d.off_psib[idx];
+  }
+}
+
+// Push the first / last owned row of up to two arrays to the neighbours and wait for theirs (nothing to do on a
+// single GPU).  narr == 0 is a pure barrier.
+static int halo_exchange(adseis_acoustic_plan* P, int narr, const int* arr, const i64* idx) {
+  if (!P->arena) return ADSEIS_OK;
+  if (!P->connected) {
+    adseis_set_error("acoustic slab plan: adseis_acoustic_plan_ipc_connect has not been called");
+    return ADSEIS_ESTATE;
+  }
+  const AcGeom& g = P->g;
+  AcHaloArgs a;
+  memset(&a, 0, sizeof(a));
+  a.ld = g.ld;
+  a.has_lo = P->peer[0] != nullptr;
+  a.has_hi = P->peer[1] != nullptr;
+  char* base = (char*)P->arena;
+  for (int k = 0; k < narr; k++) {
+    const double* mine = (const double*)(base + desc_off(P->desc, arr[k], idx[k]));
+    if (a.has_lo) {  // my first owned row -> rank-1's upper halo row (its local row Hl-1)
+      const AcDesc& d = P->dpeer[0];
+      a.src[a.nrow] = mine + (i64)P->own0 * g.ld;
+      a.dst[a.nrow] = (double*)(P->peer[0] + desc_off(d, arr[k], idx[k])) + (d.Hl - 1) * d.ld;
+      a.nrow++;
+    }
+    if (a.has_hi) {  // my last owned row -> rank+1's lower halo row (its local row 0)
+      const AcDesc& d = P->dpeer[1];
+      a.src[a.nrow] = mine + (i64)(P->own1 - 1) * g.ld;
+      a.dst[a.nrow] = (double*)(P->peer[1] + desc_off(d, arr[k], idx[k]));
+      a.nrow++;
+    }
+  }
+  // rank-1 sees me as its "hi" neighbour: I add to its flag[1]; rank+1 sees me as "lo": its flag[0]
+  if (a.has_lo) a.sig_lo = (unsigned long long*)(P->peer[0] + P->dpeer[0].off_flags) + 1;
+  if (a.has_hi) a.sig_hi = (unsigned long long*)(P->peer[1] + P->dpeer[1].off_flags) + 0;
+  a.my_flags = (unsigned long long*)(base + P->desc.off_flags);
+  P->epoch++;
+  a.expect = (unsigned long long)AC_HX_BLOCKS * P->epoch;
+  k_halo_exchange<<<AC_HX_BLOCKS, 256, 0, P->ctx->stream>>>(a);
+  LAUNCH_CHECK(P);
+  return ADSEIS_OK;
+}
+
+static int halo_check(adseis_acoustic_plan* P) {
+  if (!P->arena) return ADSEIS_OK;
+  unsigned long long f[3] = {0, 0, 0};
+  CUDA_TRY(cudaMemcpyAsync(f, (char*)P->arena + P->desc.off_flags, sizeof(f), cudaMemcpyDeviceToHost, P->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(P->ctx->stream));
+  if (f[2] != 0) {
+    adseis_set_error("acoustic slab plan (rank %d): timed out waiting for a neighbour's halo rows", P->slab.rank);
+    return ADSEIS_ECOMM;
+  }
+  return ADSEIS_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -25,7 +25,7 @@ def run(NX, NY, NSTEP, reps=3, budget=0):
         print("%dx%d nt=%d %-8s %8.2f ms  %7.2f Gcell/s  %7.1f GB/s(alg)  %s" % (NX, NY, NSTEP, name, t, cells / t / 1e6, bytes_ / t / 1e6, info), flush=True)
     plan.close()
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--elastic" not in sys.argv:
     if "--quick" in sys.argv:
         print("variant", os.environ.get("ADSEIS_LIB_SUFFIX", "(default)"))
         run(4096, 4096, 60)
@@ -37,3 +37,33 @@ if __name__ == "__main__":
     run(4096, 4096, 120, budget=40 * 4098 * 4112 * 8)
     run(2000, 1000, 200)
     run(401, 133, 1000)
+
+
+def run_elastic(NX, NY, NSTEP, variant, reps=2, mat=True):
+    ctx = A.default_context()
+    p = A.ElasticPropagatorParams(NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=1.0, DELTAY=1.0, DELTAT=1e-4, vp_ref=3300.0,
+                                  variant=variant)
+    sh = p.model_shape()
+    rho = np.full(sh, 2800.0); vp = np.full(sh, 3000.0); vp[:, sh[1] // 2:] = 3300.0; vs = vp / 1.732
+    lam, mu, rho = A.compute_lame_parameters(vp, vs, rho)
+    srcv = A.Ricker(p, 15.0, 100.0, 1e6).reshape(-1, 1)
+    rcvi = np.arange(20, NX - 20); rcvj = np.full(len(rcvi), 20); rcvt = np.arange(len(rcvi)) % 2
+    plan = A.ElasticPlan(p, [NX // 2], [NY // 2], [0], rcvi, rcvj, rcvt, ctx=ctx)
+    plan.set_model(rho, lam, mu); plan.set_srcv(srcv); plan.set_obs(np.zeros((len(rcvi), NSTEP + 1)))
+    cells = NX * NY * NSTEP
+    for name, fn, byt in (("forward", plan.forward, 144), ("gradient", lambda: plan.gradient(mat), 144 + (232 if mat else 152))):
+        fn(); ctx.sync()
+        ts = []
+        for _ in range(reps):
+            ctx.timer_start(); fn(); ts.append(ctx.timer_stop_ms())
+        t = min(ts)
+        print("elastic v%d %dx%d nt=%d %-8s mat=%d %8.2f ms  %7.2f Gcell/s  %7.1f GB/s(est)  %s" %
+              (variant, NX, NY, NSTEP, name, mat, t, cells / t / 1e6, cells * byt / t / 1e6, plan.info()), flush=True)
+    plan.close()
+
+
+if __name__ == "__main__" and "--elastic" in sys.argv:
+    run_elastic(500, 500, 200, 0)
+    run_elastic(2000, 2000, 60, 1)
+    run_elastic(2000, 2000, 60, 1, mat=False)
+    run_elastic(4096, 4096, 20, 0)
