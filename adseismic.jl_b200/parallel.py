@@ -167,7 +167,10 @@ class DomainDecomposedAcoustic:
             return
         if hist_slots is None:
             free_b, _ = self.ctx.mem_info()
-            reserve = 12 * plane_bytes + (2 * (param.NSTEP + 1) * nrcv + 2 * param.NSTEP * nsrc) * 8 + (1 << 30)
+            model_bytes = (param.NX + 2) * (param.NY + 2) * 8
+            # adjoint accumulators, checkpoints of the C side, full-size gradient buffers, torch / NCCL workspaces
+            reserve = (16 * plane_bytes + 6 * model_bytes + (4 * (param.NSTEP + 1) * nrcv + 2 * param.NSTEP * nsrc) * 8
+                       + (6 << 30))
             slots = max(0, free_b - reserve) // plane_bytes
             W = plan_window(param.NSTEP, slots)
             hist_slots = int(all_reduce_scalar(W, "min", device=self.dev))   # every rank must use the same window
