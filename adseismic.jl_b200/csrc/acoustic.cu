@@ -60,6 +60,7 @@ struct AcDesc {
   unsigned long long magic;
   long long Hl, ld, plane, win, own0, own1;
   long long off_flags, off_hist, off_phi[2], off_psi[2], off_ub[3], off_phib[2], off_psib[2];
+  long long n_edge_lo, n_edge_hi;  // CTAs of one step launch that own cells of my first / last owned row
 };
 #define AC_DESC_MAGIC 0xAD5E15B200ULL
 #define AC_HX_BLOCKS 8
@@ -144,6 +145,9 @@ struct adseis_acoustic_plan {
   AcDesc dpeer[2];                           // descriptors of rank-1 / rank+1
   char* peer[2] = {nullptr, nullptr};        // their arenas mapped into this process
   unsigned long long epoch = 0;              // exchanges issued so far
+  unsigned long long sepoch = 0;             // step kernels launched so far (same sequence on every rank)
+  int* perm = nullptr;                       // launch order -> logical CTA id (edge CTAs first)
+  int n_edge_lo = 0, n_edge_hi = 0;
   bool connected = false;
   // stats
   i64 last_launches = 0, last_segments = 0, last_recomputed = 0;
@@ -184,6 +188,8 @@ static inline double* win_slot(adseis_acoustic_plan* P, i64 base, i64 s) { retur
 enum AcArr { AR_HIST, AR_PHI, AR_PSI, AR_UB, AR_PHIB, AR_PSIB };  // arrays with halo rows (slab plans)
 static int halo_exchange(adseis_acoustic_plan* P, int narr, const int* arr, const i64* idx);
 static int halo_check(adseis_acoustic_plan* P);
+struct AcDesc;
+static long long desc_off(const AcDesc& d, int arr, i64 idx);
 
 static int plan_segments(adseis_acoustic_plan* P, size_t budget_bytes, bool count_checkpoints) {
   // The wavefield history window holds `win` snapshots.  If NSTEP+1 snapshots fit, the whole history is kept;
@@ -223,6 +229,7 @@ ADSEIS_API int adseis_acoustic_plan_destroy(adseis_acoustic_plan* P) {
   cudaSetDevice(P->ctx->device);
   cudaStreamSynchronize(P->ctx->stream);
   cudaFree(P->c2); cudaFree(P->cvel); cudaFree(P->sigx); cudaFree(P->tauy);
+  cudaFree(P->perm);
   if (P->arena) {
     for (int k = 0; k < 2; k++) if (P->peer[k]) cudaIpcCloseMemHandle(P->peer[k]);
     cudaFree(P->arena);
@@ -295,6 +302,14 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
   g.dt2 = dt * dt;
   P->model_elems = p->mpi_convention ? p->NX * p->NY : (i64)H * W;
 
+#define PTRY(expr)                                   \
+  do {                                               \
+    int _r = (expr);                                 \
+    if (_r != ADSEIS_OK) {                           \
+      adseis_acoustic_plan_destroy(P);               \
+      return _r;                                     \
+    }                                                \
+  } while (0)
   // PML profiles and the PML-free box
   std::vector<double> sx(H), ty(W);
   int rc = adseis_acoustic_pml_profiles(p, sx.data(), ty.data());
@@ -351,15 +366,33 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     for (int k = t.nrect; k < 4; k++) { t.rblk[k + 1] = t.rblk[t.nrect]; t.rr0[k] = t.rr1[k] = t.rc0[k] = 0; t.rc1[k] = 1; }
     P->nblocks = t.nmarch + t.rblk[t.nrect];
   }
+  if (sl.nranks > 1) {
+    // edge-first launch order: the CTAs that own cells of my first / last owned row next to a neighbour go first,
+    // so their halo pushes leave early and the rest of the step hides the NVLink latency
+    const AcTiling& t = P->t;
+    const int first = P->own0, last = P->own1 - 1;
+    std::vector<int> edge, rest;
+    for (int b = 0; b < P->nblocks; b++) {
+      int rlo, rhi;
+      if (b < t.nmarch) {
+        rlo = t.mr0 + (b / t.nct) * t.rb; rhi = std::min(t.mr1, rlo + t.rb) - 1;
+      } else {
+        int fb = b - t.nmarch, r = 0;
+        for (int k = 1; k < t.nrect; k++) if (fb >= t.rblk[k]) r = k;
+        const int w = t.rc1[r] - t.rc0[r];
+        const i64 ncell = (i64)(t.rr1[r] - t.rr0[r]) * w, i0 = (i64)(fb - t.rblk[r]) * AC_FRAME_CELLS;
+        rlo = t.rr0[r] + (int)(i0 / w);
+        rhi = t.rr0[r] + (int)((std::min<i64>(ncell, i0 + AC_FRAME_CELLS) - 1) / w);
+      }
+      const bool tl = halo_lo && rlo <= first && first <= rhi, th = halo_hi && rlo <= last && last <= rhi;
+      if (tl) P->n_edge_lo++;
+      if (th) P->n_edge_hi++;
+      (tl || th ? edge : rest).push_back(b);
+    }
+    edge.insert(edge.end(), rest.begin(), rest.end());
+    PTRY(dev_upload(&P->perm, edge, st));
+  }
 
-#define PTRY(expr)                                   \
-  do {                                               \
-    int _r = (expr);                                 \
-    if (_r != ADSEIS_OK) {                           \
-      adseis_acoustic_plan_destroy(P);               \
-      return _r;                                     \
-    }                                                \
-  } while (0)
   PTRY(dev_upload(&P->sigx, sx, st));
   PTRY(dev_upload(&P->tauy, ty, st));
   PTRY(dev_alloc_zero(&P->c2, (size_t)g.plane, st));
@@ -439,6 +472,7 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     }
     AcDesc& d = P->desc;
     d.magic = AC_DESC_MAGIC; d.Hl = g.Hl; d.ld = g.ld; d.plane = g.plane; d.win = P->win; d.own0 = P->own0; d.own1 = P->own1;
+    d.n_edge_lo = P->n_edge_lo; d.n_edge_hi = P->n_edge_hi;
     long long off = 512;  // bytes; descriptor lives in [0,512)
     d.off_flags = off; off += 512;
     auto take = [&](long long nplanes) { long long o = off; off += nplanes * (long long)plane_bytes; return o; };
@@ -547,22 +581,51 @@ ADSEIS_API int adseis_acoustic_plan_set_obs(adseis_acoustic_plan* P, const doubl
 }
 
 // ---- forward steps s_first..s_last of segment k into the window (slot s at index s - base) -----------------
+// Peer pointers and flag expectations of the next step launch (slab plans); arr_u/arr_p: the arrays it produces.
+static AcFuse make_fuse(adseis_acoustic_plan* P, int arr_u, i64 idx_u, int arr_p, i64 idx_p) {
+  AcFuse f;
+  memset(&f, 0, sizeof(f));
+  if (!P->arena) return f;
+  const AcGeom& g = P->g;
+  f.perm = P->perm;
+  f.own0 = P->own0; f.own_last = P->own1 - 1;
+  f.has_lo = P->peer[0] != nullptr; f.has_hi = P->peer[1] != nullptr;
+  P->sepoch++;
+  if (f.has_lo) {  // my first owned row -> rank-1's upper halo row; it bumps my flags[3], I bump its flags[4]
+    const AcDesc& d = P->dpeer[0];
+    f.lo_u = (double*)(P->peer[0] + desc_off(d, arr_u, idx_u)) + (d.Hl - 1) * d.ld;
+    f.lo_p = (double*)(P->peer[0] + desc_off(d, arr_p, idx_p)) + (d.Hl - 1) * d.ld;
+    f.sig_lo = (unsigned long long*)(P->peer[0] + d.off_flags) + 4;
+    f.expect_lo = (unsigned long long)d.n_edge_hi * (P->sepoch - 1);
+  }
+  if (f.has_hi) {  // my last owned row -> rank+1's lower halo row (its local row 0)
+    const AcDesc& d = P->dpeer[1];
+    f.hi_u = (double*)(P->peer[1] + desc_off(d, arr_u, idx_u));
+    f.hi_p = (double*)(P->peer[1] + desc_off(d, arr_p, idx_p));
+    f.sig_hi = (unsigned long long*)(P->peer[1] + d.off_flags) + 3;
+    f.expect_hi = (unsigned long long)d.n_edge_lo * (P->sepoch - 1);
+  }
+  f.my_flags = (unsigned long long*)((char*)P->arena + P->desc.off_flags);
+  (void)g;
+  return f;
+}
+
 static int run_forward_steps(adseis_acoustic_plan* P, i64 base, i64 s_first, i64 s_last, bool sample) {
   const AcGeom& g = P->g;
   cudaStream_t st = P->ctx->stream;
   AcPoints none{};
+  if (P->arena && !P->connected) {
+    adseis_set_error("acoustic slab plan: adseis_acoustic_plan_ipc_connect has not been called");
+    return ADSEIS_ESTATE;
+  }
   for (i64 s = s_first; s <= s_last; s++) {
+    const AcFuse fuse = make_fuse(P, AR_HIST, s - base, AR_PHI, s & 1);
     ac_fwd_kernel<<<P->nblocks, AC_THREADS, 0, st>>>(
         g, P->t, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, P->phi[(s - 1) & 1], P->psi[(s - 1) & 1],
         P->sigx, P->tauy, win_slot(P, base, s), P->phi[s & 1], P->psi[s & 1], P->srcp,
         P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, sample ? P->rcvp : none,
-        (sample && P->nrcv > 0) ? P->rcvv + s * P->nrcv : nullptr);
+        (sample && P->nrcv > 0) ? P->rcvv + s * P->nrcv : nullptr, fuse);
     LAUNCH_CHECK(P);
-    if (P->arena) {  // new u[s] and phi[s] edge rows -> neighbours' halo rows; wait for theirs
-      const int arr[2] = {AR_HIST, AR_PHI};
-      const i64 idx[2] = {s - base, s & 1};
-      TRY(halo_exchange(P, 2, arr, idx));
-    }
   }
   return ADSEIS_OK;
 }
@@ -586,6 +649,8 @@ static int forward_sweep(adseis_acoustic_plan* P, bool save_ckpt, segment_cb cb,
   for (size_t k = 0; k < nseg; k++) {
     const i64 b = P->seg_b[k], e = P->seg_e[k];
     if (k > 0) {
+      // slab plans: the neighbours' last pushes must have landed before halo rows are copied
+      TRY(halo_exchange(P, 0, nullptr, nullptr));
       // window index 0,1 <- slots b, b+1 (the last two slots of the previous segment)
       const i64 pbse = P->seg_b[k - 1];
       double* s0 = win_slot(P, pbse, b);
@@ -708,17 +773,13 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
     }
     TRY(span_begin(P, 2, e - (b + 2) + 1));
     for (i64 s = e; s >= b + 2; s--) {
+      const AcFuse fuse = make_fuse(P, AR_UB, (s + 2) % 3, AR_PHIB, (s - 1) & 1);
       ac_adj_kernel<<<P->nblocks, AC_THREADS, 0, st>>>(
           g, P->t, P->ub[s % 3], P->ub[(s + 1) % 3], win_slot(P, b, s - 1), P->c2, P->phib[s & 1], P->psib[s & 1],
           P->sigx, P->tauy, P->ub[(s + 2) % 3] /* == (s-1)%3 */, P->phib[(s - 1) & 1], P->psib[(s - 1) & 1], P->G,
           P->rcvp, P->nrcv > 0 ? P->res + (s - 1) * P->nrcv : nullptr, (s - 2 >= 1) ? P->srcp : none,
-          (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr);
+          (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr, fuse);
       LAUNCH_CHECK(P);
-      if (P->arena) {
-        const int arr[2] = {AR_UB, AR_PHIB};
-        const i64 idx[2] = {(s + 2) % 3, (s - 1) & 1};
-        TRY(halo_exchange(P, 2, arr, idx));
-      }
     }
     TRY(span_end(P));
   }

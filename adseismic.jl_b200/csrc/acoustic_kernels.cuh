@@ -76,6 +76,45 @@ struct AcPoints {
   const int* perm;
 };
 
+// Slab decomposition, fused into the step kernels (all null / zero on a single GPU).  The CTAs whose cells include
+// my first (last) owned row are scheduled first (perm), wait until the neighbour's previous step has delivered the
+// halo row they read, and -- after their epilogue -- store their piece of the new edge row straight into the
+// neighbour's halo row over NVLink and publish it with a system-scope fence + atomic on the neighbour's flag.
+// Interior CTAs never wait, so the exchange latency is hidden behind the bulk of the step.
+struct AcFuse {
+  const int* perm;              // launch order -> logical CTA id (edge CTAs first), or null
+  int own0, own_last;           // my first / last owned local row
+  int has_lo, has_hi;
+  double *lo_u, *hi_u;          // neighbour halo rows (peer pointers) of the array this launch produces
+  double *lo_p, *hi_p;          // ... and of its phi / phibar companion
+  unsigned long long *sig_lo, *sig_hi;   // neighbour flags to bump (peer pointers)
+  unsigned long long* my_flags;          // [3] bumped by rank-1's step kernels, [4] by rank+1's, [2] error
+  unsigned long long expect_lo, expect_hi;
+};
+
+__device__ __forceinline__ void ac_fuse_wait(const AcFuse& f, bool t_lo, bool t_hi) {
+  if (!(t_lo || t_hi)) return;  // CTA-uniform
+  if (threadIdx.x == 0) {
+    volatile unsigned long long* fl = f.my_flags;
+    unsigned long long spins = 0;
+    while ((t_lo && fl[3] < f.expect_lo) || (t_hi && fl[4] < f.expect_hi)) {
+      if (++spins > (1ULL << 26)) { fl[2] = 1ULL; break; }  // neighbour lost: report, do not hang
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void ac_fuse_signal(const AcFuse& f, bool t_lo, bool t_hi) {
+  if (!(t_lo || t_hi)) return;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (t_lo) atomicAdd_system(f.sig_lo, 1ULL);
+    if (t_hi) atomicAdd_system(f.sig_hi, 1ULL);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // forward, general (PML / ring / pad) cell: literal AcousticOneStepCpu.h:27-44
 // ------------------------------------------------------------------------------------------------------------
@@ -148,15 +187,20 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
               const double* __restrict__ c2, const double* __restrict__ phi, const double* __restrict__ psi,
               const double* __restrict__ sigx, const double* __restrict__ tauy, double* __restrict__ u,
               double* __restrict__ phio, double* __restrict__ psio, AcPoints src,
-              const double* __restrict__ srcv_row, AcPoints rcv, double* __restrict__ rcvv_row) {
-  const int bid = blockIdx.x;
+              const double* __restrict__ srcv_row, AcPoints rcv, double* __restrict__ rcvv_row, AcFuse f) {
+  const int bid = f.perm ? f.perm[blockIdx.x] : blockIdx.x;
   const int ld = g.ld;
+  bool t_lo = false, t_hi = false;  // this CTA owns cells of my first / last owned row next to a neighbour
+  int rect = 0, idx0 = 0, wdt = 1, ncell = 0;
   if (bid >= t.nmarch) {
     // ---------------- frame CTA ----------------
-    int rect, idx0;
     ac_frame_locate(t, bid - t.nmarch, &rect, &idx0);
-    const int wdt = t.rc1[rect] - t.rc0[rect];
-    const int ncell = (t.rr1[rect] - t.rr0[rect]) * wdt;
+    wdt = t.rc1[rect] - t.rc0[rect];
+    ncell = (t.rr1[rect] - t.rr0[rect]) * wdt;
+    const int rlo = t.rr0[rect] + idx0 / wdt, rhi = t.rr0[rect] + (min(ncell, idx0 + AC_FRAME_CELLS) - 1) / wdt;
+    t_lo = f.has_lo && rlo <= f.own0 && f.own0 <= rhi;
+    t_hi = f.has_hi && rlo <= f.own_last && f.own_last <= rhi;
+    ac_fuse_wait(f, t_lo, t_hi);
 #pragma unroll
     for (int k = 0; k < AC_FRAME_CPT; k++) {
       const int idx = idx0 + k * AC_THREADS + threadIdx.x;
@@ -175,6 +219,9 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
     const int j = jb + 2 * lane;
     const bool ldok = j < ld;       // may load
     const bool act = j < t.mc_end;  // computes and stores (both columns j, j+1 are inside the box)
+    t_lo = f.has_lo && r0 <= f.own0 && f.own0 < r1;
+    t_hi = f.has_hi && r0 <= f.own_last && f.own_last < r1;
+    ac_fuse_wait(f, t_lo, t_hi);
     if (jb < t.mc_end) {
       const double2 z2 = make_double2(0.0, 0.0);
       const double kx2 = g.kx2, ky2 = g.ky2, rx = g.rx, ry = g.ry;
@@ -228,6 +275,29 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
     }
   }
   ac_cta_epilogue(bid, u, src, srcv_row, g.dt2, rcv, rcvv_row, 1.0);
+  if (t_lo || t_hi) {  // push my piece of the new edge row(s) into the neighbours' halo rows, then publish
+    __syncthreads();
+    if (bid >= t.nmarch) {
+#pragma unroll
+      for (int k = 0; k < AC_FRAME_CPT; k++) {
+        const int idx = idx0 + k * AC_THREADS + threadIdx.x;
+        if (idx < ncell) {
+          const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
+          const i64 IJ = (i64)li * ld + j;
+          if (t_lo && li == f.own0) { f.lo_u[j] = u[IJ]; f.lo_p[j] = phio[IJ]; }
+          if (t_hi && li == f.own_last) { f.hi_u[j] = u[IJ]; f.hi_p[j] = phio[IJ]; }
+        }
+      }
+    } else {
+      const int ct = bid % t.nct;
+      const int j = t.mc0 + ct * AC_TILE_COLS + 2 * threadIdx.x;
+      if (j < t.mc_end) {
+        if (t_lo) st2(f.lo_u + j, ld2(u + (i64)f.own0 * ld + j));
+        if (t_hi) st2(f.hi_u + j, ld2(u + (i64)f.own_last * ld + j));
+      }
+    }
+    ac_fuse_signal(f, t_lo, t_hi);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -301,14 +371,19 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
               const double* __restrict__ psib, const double* __restrict__ sigx, const double* __restrict__ tauy,
               double* __restrict__ ub0, double* __restrict__ phibo, double* __restrict__ psibo,
               double* __restrict__ G, AcPoints rcv, const double* __restrict__ res_row, AcPoints src,
-              double* __restrict__ gsrcv_row) {
-  const int bid = blockIdx.x;
+              double* __restrict__ gsrcv_row, AcFuse f) {
+  const int bid = f.perm ? f.perm[blockIdx.x] : blockIdx.x;
   const int ld = g.ld;
+  bool t_lo = false, t_hi = false;
+  int rect = 0, idx0 = 0, wdt = 1, ncell = 0;
   if (bid >= t.nmarch) {
-    int rect, idx0;
     ac_frame_locate(t, bid - t.nmarch, &rect, &idx0);
-    const int wdt = t.rc1[rect] - t.rc0[rect];
-    const int ncell = (t.rr1[rect] - t.rr0[rect]) * wdt;
+    wdt = t.rc1[rect] - t.rc0[rect];
+    ncell = (t.rr1[rect] - t.rr0[rect]) * wdt;
+    const int rlo = t.rr0[rect] + idx0 / wdt, rhi = t.rr0[rect] + (min(ncell, idx0 + AC_FRAME_CELLS) - 1) / wdt;
+    t_lo = f.has_lo && rlo <= f.own0 && f.own0 <= rhi;
+    t_hi = f.has_hi && rlo <= f.own_last && f.own_last <= rhi;
+    ac_fuse_wait(f, t_lo, t_hi);
 #pragma unroll
     for (int k = 0; k < AC_FRAME_CPT; k++) {
       const int idx = idx0 + k * AC_THREADS + threadIdx.x;
@@ -326,6 +401,9 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
     const int j = jb + 2 * lane;
     const bool ldok = j < ld;
     const bool act = j < t.mc_end;
+    t_lo = f.has_lo && r0 <= f.own0 && f.own0 < r1;
+    t_hi = f.has_hi && r0 <= f.own_last && f.own_last < r1;
+    ac_fuse_wait(f, t_lo, t_hi);
     if (jb < t.mc_end) {
       const double2 z2 = make_double2(0.0, 0.0);
       const double rx2 = g.rx * g.rx, ry2 = g.ry * g.ry, kk = -g.kx2 - g.ky2, kx2 = g.kx2, ky2 = g.ky2;
@@ -399,4 +477,27 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
     }
   }
   ac_cta_epilogue(bid, ub0, rcv, res_row, 1.0, src, gsrcv_row, g.dt2);
+  if (t_lo || t_hi) {
+    __syncthreads();
+    if (bid >= t.nmarch) {
+#pragma unroll
+      for (int k = 0; k < AC_FRAME_CPT; k++) {
+        const int idx = idx0 + k * AC_THREADS + threadIdx.x;
+        if (idx < ncell) {
+          const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
+          const i64 IJ = (i64)li * ld + j;
+          if (t_lo && li == f.own0) { f.lo_u[j] = ub0[IJ]; f.lo_p[j] = phibo[IJ]; }
+          if (t_hi && li == f.own_last) { f.hi_u[j] = ub0[IJ]; f.hi_p[j] = phibo[IJ]; }
+        }
+      }
+    } else {
+      const int ct = bid % t.nct;
+      const int j = t.mc0 + ct * AC_TILE_COLS + 2 * threadIdx.x;
+      if (j < t.mc_end) {
+        if (t_lo) st2(f.lo_u + j, ld2(ub0 + (i64)f.own0 * ld + j));
+        if (t_hi) st2(f.hi_u + j, ld2(ub0 + (i64)f.own_last * ld + j));
+      }
+    }
+    ac_fuse_signal(f, t_lo, t_hi);
+  }
 }

@@ -258,7 +258,10 @@ def main():
         from adseis_b200 import parallel
         res = parallel.bench_domain_decomposed(A, w, args, rank, world, local_rank)
         if rank == 0:
-            print(json.dumps(res))
+            print(json.dumps(res), flush=True)
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
         return
 
     ctx = A.Context(local_rank)
