@@ -271,6 +271,10 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
   REQUIRE(nsrc >= 0 && nrcv >= 0 && (nsrc == 0 || (srci && srcj)) && (nrcv == 0 || (rcvi && rcvj)),
           "acoustic_plan_create: bad source/receiver arrays");
   CUDA_TRY(cudaSetDevice(ctx->device));
+  if (AC_FWD_SMEM > 0)
+    CUDA_TRY(cudaFuncSetAttribute(ac_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_FWD_SMEM));
+  if (AC_ADJ_SMEM > 0)
+    CUDA_TRY(cudaFuncSetAttribute(ac_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_ADJ_SMEM));
   cudaStream_t st = ctx->stream;
   adseis_acoustic_plan* P = new adseis_acoustic_plan();
   P->ctx = ctx;
@@ -300,6 +304,7 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
   g.rx = dt / hx; g.ry = dt / hy;
   g.px = dt * dt / (2.0 * hx); g.py = dt * dt / (2.0 * hy);
   g.dt2 = dt * dt;
+  g.rhx = 1.0 / hx; g.rhy = 1.0 / hy;
   P->model_elems = p->mpi_convention ? p->NX * p->NY : (i64)H * W;
 
 #define PTRY(expr)                                   \
@@ -359,19 +364,22 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
       t.rblk[k + 1] = t.rblk[k] + (int)((cells + AC_FRAME_CELLS - 1) / AC_FRAME_CELLS);
     };
     t.rblk[0] = 0;
-    add_rect(P->own0, mr0, 0, g.ld);
-    add_rect(mr1, P->own1, 0, g.ld);
+    // (pitch-padding columns j >= W are never read by a cell that is stored, so nobody needs to write them)
+    add_rect(P->own0, mr0, 0, g.W);
+    add_rect(mr1, P->own1, 0, g.W);
     add_rect(mr0, mr1, 0, mc0);
-    add_rect(mr0, mr1, mc_end, g.ld);
+    add_rect(mr0, mr1, mc_end, g.W);
     for (int k = t.nrect; k < 4; k++) { t.rblk[k + 1] = t.rblk[t.nrect]; t.rr0[k] = t.rr1[k] = t.rc0[k] = 0; t.rc1[k] = 1; }
     P->nblocks = t.nmarch + t.rblk[t.nrect];
   }
-  if (sl.nranks > 1) {
-    // edge-first launch order: the CTAs that own cells of my first / last owned row next to a neighbour go first,
-    // so their halo pushes leave early and the rest of the step hides the NVLink latency
+  {
+    // Launch order (logical CTA id = perm[blockIdx.x]).  Slab plans: the CTAs that own cells of my first / last
+    // owned row next to a neighbour go first, so their halo pushes leave early and the rest of the step hides the
+    // NVLink latency.  Then the frame CTAs (latency-bound: one DRAM round trip + fp64 divides, no bandwidth) are
+    // spread evenly among the marching CTAs (bandwidth-bound) instead of forming the tail of the launch.
     const AcTiling& t = P->t;
     const int first = P->own0, last = P->own1 - 1;
-    std::vector<int> edge, rest;
+    std::vector<int> edge, march, frame;
     for (int b = 0; b < P->nblocks; b++) {
       int rlo, rhi;
       if (b < t.nmarch) {
@@ -387,10 +395,17 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
       const bool tl = halo_lo && rlo <= first && first <= rhi, th = halo_hi && rlo <= last && last <= rhi;
       if (tl) P->n_edge_lo++;
       if (th) P->n_edge_hi++;
-      (tl || th ? edge : rest).push_back(b);
+      if (tl || th) edge.push_back(b);
+      else (b < t.nmarch ? march : frame).push_back(b);
     }
-    edge.insert(edge.end(), rest.begin(), rest.end());
-    PTRY(dev_upload(&P->perm, edge, st));
+    std::vector<int> order(edge);
+    size_t im = 0, ifr = 0;
+    const size_t nm = march.size(), nf = frame.size();
+    while (im < nm || ifr < nf) {  // Bresenham merge: frame CTA k goes after ~k*nm/nf marching CTAs
+      if (ifr < nf && (im >= nm || ifr * nm <= im * nf)) order.push_back(frame[ifr++]);
+      else order.push_back(march[im++]);
+    }
+    PTRY(dev_upload(&P->perm, order, st));
   }
 
   PTRY(dev_upload(&P->sigx, sx, st));
@@ -585,9 +600,9 @@ ADSEIS_API int adseis_acoustic_plan_set_obs(adseis_acoustic_plan* P, const doubl
 static AcFuse make_fuse(adseis_acoustic_plan* P, int arr_u, i64 idx_u, int arr_p, i64 idx_p) {
   AcFuse f;
   memset(&f, 0, sizeof(f));
+  f.perm = P->perm;
   if (!P->arena) return f;
   const AcGeom& g = P->g;
-  f.perm = P->perm;
   f.own0 = P->own0; f.own_last = P->own1 - 1;
   f.has_lo = P->peer[0] != nullptr; f.has_hi = P->peer[1] != nullptr;
   P->sepoch++;
@@ -620,7 +635,7 @@ static int run_forward_steps(adseis_acoustic_plan* P, i64 base, i64 s_first, i64
   }
   for (i64 s = s_first; s <= s_last; s++) {
     const AcFuse fuse = make_fuse(P, AR_HIST, s - base, AR_PHI, s & 1);
-    ac_fwd_kernel<<<P->nblocks, AC_THREADS, 0, st>>>(
+    ac_fwd_kernel<<<P->nblocks, AC_FWD_THREADS, AC_FWD_SMEM, st>>>(
         g, P->t, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, P->phi[(s - 1) & 1], P->psi[(s - 1) & 1],
         P->sigx, P->tauy, win_slot(P, base, s), P->phi[s & 1], P->psi[s & 1], P->srcp,
         P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, sample ? P->rcvp : none,
@@ -774,7 +789,7 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
     TRY(span_begin(P, 2, e - (b + 2) + 1));
     for (i64 s = e; s >= b + 2; s--) {
       const AcFuse fuse = make_fuse(P, AR_UB, (s + 2) % 3, AR_PHIB, (s - 1) & 1);
-      ac_adj_kernel<<<P->nblocks, AC_THREADS, 0, st>>>(
+      ac_adj_kernel<<<P->nblocks, AC_ADJ_THREADS, AC_ADJ_SMEM, st>>>(
           g, P->t, P->ub[s % 3], P->ub[(s + 1) % 3], win_slot(P, b, s - 1), P->c2, P->phib[s & 1], P->psib[s & 1],
           P->sigx, P->tauy, P->ub[(s + 2) % 3] /* == (s-1)%3 */, P->phib[(s - 1) & 1], P->psib[(s - 1) & 1], P->G,
           P->rcvp, P->nrcv > 0 ? P->res + (s - 1) * P->nrcv : nullptr, (s - 2 >= 1) ? P->srcp : none,

@@ -34,14 +34,46 @@
 #ifndef AC_UA
 #define AC_UA 1                             // adjoint: rows whose loads are issued together (occupancy beats unrolling here)
 #endif
-#ifndef AC_MINB_FWD
-#define AC_MINB_FWD 2                       // __launch_bounds__ min CTAs/SM, forward
+#ifndef AC_FRAME_CPT
+#define AC_FRAME_CPT 4                      // frame cells per thread
+#endif
+#define AC_FRAME_CELLS (AC_THREADS * AC_FRAME_CPT)
+#ifndef AC_ADJ_TMA
+#define AC_ADJ_TMA 1                        // adjoint marching CTAs stage their rows through shared memory by TMA bulk copies
+#endif
+#ifndef AC_NST_ADJ
+#define AC_NST_ADJ 4                        // adjoint: ring depth (rows of the CTA tile in flight)
 #endif
 #ifndef AC_MINB_ADJ
-#define AC_MINB_ADJ 3                       // __launch_bounds__ min CTAs/SM, adjoint
+#define AC_MINB_ADJ (AC_ADJ_TMA ? 2 : 3)    // __launch_bounds__ min CTAs/SM, adjoint (TMA: bounded by shared memory)
 #endif
-#define AC_FRAME_CPT 4                      // frame cells per thread
-#define AC_FRAME_CELLS (AC_THREADS * AC_FRAME_CPT)
+#define AC_ADJ_THREADS (AC_THREADS + 32 * AC_ADJ_TMA)  // + one producer warp
+#define AC_HCOLS (AC_TILE_COLS + 4)         // staged columns of an array with y-neighbours: 16-byte halo on each side
+
+// One ring stage of an adjoint marching CTA: row `li` of its 512-column tile (iteration li - r0).  Filled by five
+// 4-KB bulk copies (one UBLKCP per array: the TMA unit retires ~one op per 45 cycles whatever its size, so the
+// copies must be CTA-wide, not per warp), completion on the stage's `full` mbarrier; the eight consumer warps
+// release it through the `empty` mbarrier.
+struct __align__(128) AcAdjStage {
+  double ub1[AC_HCOLS], c2[AC_HCOLS], wf[AC_HCOLS];  // row li+1, columns c0-2 .. c0+513
+  double ub2[AC_TILE_COLS], G[AC_TILE_COLS];         // row li,   columns c0   .. c0+511
+};
+#ifndef AC_FWD_TMA
+#define AC_FWD_TMA 1                        // forward marching CTAs: same TMA row ring
+#endif
+#ifndef AC_MINB_FWD
+#define AC_MINB_FWD (AC_FWD_TMA ? 3 : 2)    // __launch_bounds__ min CTAs/SM, forward
+#endif
+#ifndef AC_NST_FWD
+#define AC_NST_FWD 4
+#endif
+#define AC_FWD_THREADS (AC_THREADS + 32 * AC_FWD_TMA)
+struct __align__(128) AcFwdStage {
+  double w[AC_HCOLS];                                // row li+1, columns c0-2 .. c0+513
+  double wold[AC_TILE_COLS], c2[AC_TILE_COLS];       // row li
+};
+#define AC_FWD_SMEM (AC_FWD_TMA ? (int)(AC_NST_FWD * (sizeof(AcFwdStage) + 16)) : 0)
+#define AC_ADJ_SMEM (AC_ADJ_TMA ? (int)(AC_NST_ADJ * (sizeof(AcAdjStage) + 16)) : 0)
 
 struct AcGeom {
   int H, W;    // global padded rows (NX+2) and columns (NY+2)
@@ -52,6 +84,7 @@ struct AcGeom {
   double rx, ry;    // dt/hx , dt/hy
   double px, py;    // dt*dt/(2.0*hx) , dt*dt/(2.0*hy)
   double dt2;       // dt*dt
+  double rhx, rhy;  // RN(1/hx), RN(1/hy)
   i64 plane;        // Hl*ld
 };
 
@@ -115,6 +148,20 @@ __device__ __forceinline__ void ac_fuse_signal(const AcFuse& f, bool t_lo, bool 
   }
 }
 
+// RN(x / h) from rh = RN(1/h) computed once on the host: q0 = x*rh is within 2 ulp, one FMA correction makes it a
+// faithful quotient and a second one the correctly rounded quotient (Markstein's theorem; the remainders
+// r = x - q*h are exact in an FMA).  Five issue slots instead of the ~40-instruction divide sequence, whose slow
+// path is also taken for every zero wavefield value.  Numerators near the denormal range (inexact remainders)
+// use the divide sequence, so the result is bit-identical to `x / h` for all inputs.
+__device__ __forceinline__ double ac_div_by(double x, double h, double rh) {
+  if (x != 0.0 && fabs(x) < 1e-280) return x / h;
+  double q = x * rh;
+  double r = fma(-q, h, x);
+  q = fma(r, rh, q);
+  r = fma(-q, h, x);
+  return fma(r, rh, q);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // forward, general (PML / ring / pad) cell: literal AcousticOneStepCpu.h:27-44
 // ------------------------------------------------------------------------------------------------------------
@@ -139,9 +186,9 @@ __device__ __forceinline__ void ac_fwd_general_cell(const AcGeom& g, int li, int
              g.px * (phi[IpJ] - phi[InJ]) +
              g.py * (psi[IJp] - psi[IJn]) -
              (1 - (sg + ta) * dt / 2) * wold[IJ];
-  u[IJ] = v / (1 + (sg + ta) / 2 * dt);
-  phio[IJ] = (1. - dt * sg) * phi[IJ] + dt * c * (ta - sg) / 2.0 / g.hx * (w[IpJ] - w[InJ]);
-  psio[IJ] = (1. - dt * ta) * psi[IJ] + dt * c * (sg - ta) / 2.0 / g.hy * (w[IJp] - w[IJn]);
+  u[IJ] = (v == 0.0) ? v : v / (1 + (sg + ta) / 2 * dt);  // zero numerators would take the divide's slow path
+  phio[IJ] = (1. - dt * sg) * phi[IJ] + ac_div_by(dt * c * (ta - sg) / 2.0, g.hx, g.rhx) * (w[IpJ] - w[InJ]);
+  psio[IJ] = (1. - dt * ta) * psi[IJ] + ac_div_by(dt * c * (sg - ta) / 2.0, g.hy, g.rhy) * (w[IJp] - w[IJn]);
 }
 
 // CTA epilogue shared by both kernels: add `scale * val[perm]` into field[cell] for the injected points this CTA
@@ -182,7 +229,7 @@ __device__ __forceinline__ void ac_frame_locate(const AcTiling& t, int fb, int* 
 // ------------------------------------------------------------------------------------------------------------
 // forward kernel
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(AC_THREADS, AC_MINB_FWD)
+__global__ void __launch_bounds__(AC_FWD_THREADS, AC_MINB_FWD)
 ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* __restrict__ wold,
               const double* __restrict__ c2, const double* __restrict__ phi, const double* __restrict__ psi,
               const double* __restrict__ sigx, const double* __restrict__ tauy, double* __restrict__ u,
@@ -204,7 +251,7 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
 #pragma unroll
     for (int k = 0; k < AC_FRAME_CPT; k++) {
       const int idx = idx0 + k * AC_THREADS + threadIdx.x;
-      if (idx < ncell) {
+      if (idx < ncell && threadIdx.x < AC_THREADS) {
         const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
         ac_fwd_general_cell(g, li, j, w, wold, c2, phi, psi, sigx, tauy, u, phio, psio);
       }
@@ -215,13 +262,94 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
     const int r0 = t.mr0 + tr * t.rb;
     const int r1 = min(t.mr1, r0 + t.rb);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int jb = t.mc0 + ct * AC_TILE_COLS + warp * AC_WCOLS;
+    const int c0 = t.mc0 + ct * AC_TILE_COLS;
+    const int jb = c0 + warp * AC_WCOLS;
     const int j = jb + 2 * lane;
     const bool ldok = j < ld;       // may load
     const bool act = j < t.mc_end;  // computes and stores (both columns j, j+1 are inside the box)
     t_lo = f.has_lo && r0 <= f.own0 && f.own0 < r1;
     t_hi = f.has_hi && r0 <= f.own_last && f.own_last < r1;
     ac_fuse_wait(f, t_lo, t_hi);
+#if AC_FWD_TMA
+    extern __shared__ __align__(128) unsigned char ac_smem[];
+    AcFwdStage* stg = reinterpret_cast<AcFwdStage*>(ac_smem);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(ac_smem + AC_NST_FWD * sizeof(AcFwdStage));
+    unsigned long long* empty = full + AC_NST_FWD;
+    const int nrows = r1 - r0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < AC_NST_FWD; k++) { mbar_init(full + k, 1); mbar_init(empty + k, AC_WARPS); }
+      mbar_init_fence();
+    }
+    __syncthreads();
+    if (warp == AC_WARPS) {
+      // producer warp: one 4-KB bulk copy per streamed array and row, AC_NST_FWD rows ahead of the consumers
+      if (lane == 0) {
+        const unsigned hbytes = (unsigned)min(AC_HCOLS, ld - (c0 - 2)) * 8u;  // never read past the end of a row
+        const unsigned cbytes = (unsigned)min(AC_TILE_COLS, ld - c0) * 8u;
+        for (int it = 0; it < nrows; it++) {
+          const int sidx = it % AC_NST_FWD;
+          if (it >= AC_NST_FWD) mbar_wait(empty + sidx, (unsigned)(it / AC_NST_FWD - 1) & 1u);
+          AcFwdStage& s = stg[sidx];
+          const i64 ro = (i64)(r0 + it) * ld + c0;
+          mbar_arrive_expect_tx(full + sidx, hbytes + 2u * cbytes);
+          bulk_g2s(s.w, w + ro + ld - 2, hbytes, full + sidx);  // li+1 <= Hl-1: the box never contains the last row
+          bulk_g2s(s.wold, wold + ro, cbytes, full + sidx);
+          bulk_g2s(s.c2, c2 + ro, cbytes, full + sidx);
+        }
+      }
+    } else {
+      const bool wact = jb < t.mc_end;  // this warp's strip intersects the box
+      const double2 z2 = make_double2(0.0, 0.0);
+      const double kx2 = g.kx2, ky2 = g.ky2, rx = g.rx, ry = g.ry;
+      double2 wm = z2, wc = z2;
+      double we = 0.0;  // warp-edge neighbour of the centre row (lanes 0 and 31)
+      if (wact && ldok) {
+        wm = ld2(w + (i64)(r0 - 1) * ld + j);  // r0 >= 1: the box never contains row 0
+        wc = ld2(w + (i64)r0 * ld + j);
+        if (act) {
+          if (lane == 0) we = w[(i64)r0 * ld + jb - 1];
+          if (lane == 31) we = w[(i64)r0 * ld + jb + AC_WCOLS];
+        }
+      }
+      const int so = 2 + warp * AC_WCOLS + 2 * lane;
+      for (int it = 0; it < nrows; it++) {
+        const int li = r0 + it, sidx = it % AC_NST_FWD;
+        mbar_wait(full + sidx, (unsigned)(it / AC_NST_FWD) & 1u);
+        const AcFwdStage& s = stg[sidx];
+        double2 wn = z2, wo = z2, cc = z2;
+        double we_n = 0.0;
+        if (wact) {
+          wn = ld2(s.w + so); wo = ld2(s.wold + so - 2); cc = ld2(s.c2 + so - 2);
+          if (lane == 0) we_n = s.w[so - 1];
+          if (lane == 31) we_n = s.w[so + 2];
+        }
+        __syncwarp();  // every lane has read the stage
+        if (lane == 0) mbar_arrive(empty + sidx);
+        if (wact) {
+          double lft = __shfl_up_sync(0xffffffffu, wc.y, 1);
+          double rgt = __shfl_down_sync(0xffffffffu, wc.x, 1);
+          if (lane == 0) lft = we;
+          if (lane == 31) rgt = we;
+          if (act) {
+            double2 o;
+            {
+              const double c = cc.x;
+              o.x = (2 - kx2 * c - ky2 * c) * wc.x + c * rx * rx * (wn.x + wm.x) + c * ry * ry * (wc.y + lft) - wo.x;
+            }
+            {
+              const double c = cc.y;
+              o.y = (2 - kx2 * c - ky2 * c) * wc.y + c * rx * rx * (wn.y + wm.y) + c * ry * ry * (rgt + wc.x) - wo.y;
+            }
+            st2(u + (i64)li * ld + j, o);
+          }
+          wm = wc;
+          wc = wn;
+          we = we_n;
+        }
+      }
+    }
+#else
     if (jb < t.mc_end) {
       const double2 z2 = make_double2(0.0, 0.0);
       const double kx2 = g.kx2, ky2 = g.ky2, rx = g.rx, ry = g.ry;
@@ -273,6 +401,7 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
         }
       }
     }
+#endif
   }
   ac_cta_epilogue(bid, u, src, srcv_row, g.dt2, rcv, rcvv_row, 1.0);
   if (t_lo || t_hi) {  // push my piece of the new edge row(s) into the neighbours' halo rows, then publish
@@ -281,7 +410,7 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
 #pragma unroll
       for (int k = 0; k < AC_FRAME_CPT; k++) {
         const int idx = idx0 + k * AC_THREADS + threadIdx.x;
-        if (idx < ncell) {
+        if (idx < ncell && threadIdx.x < AC_THREADS) {
           const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
           const i64 IJ = (i64)li * ld + j;
           if (t_lo && li == f.own0) { f.lo_u[j] = u[IJ]; f.lo_p[j] = phio[IJ]; }
@@ -291,7 +420,7 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
     } else {
       const int ct = bid % t.nct;
       const int j = t.mc0 + ct * AC_TILE_COLS + 2 * threadIdx.x;
-      if (j < t.mc_end) {
+      if (j < t.mc_end && threadIdx.x < AC_THREADS) {
         if (t_lo) st2(f.lo_u + j, ld2(u + (i64)f.own0 * ld + j));
         if (t_hi) st2(f.hi_u + j, ld2(u + (i64)f.own_last * ld + j));
       }
@@ -310,6 +439,9 @@ __device__ __forceinline__ void ac_adj_general_cell(const AcGeom& g, int li, int
                                                     const double* __restrict__ sigx, const double* __restrict__ tauy,
                                                     double* __restrict__ ub0, double* __restrict__ phibo,
                                                     double* __restrict__ psibo, double* __restrict__ G) {
+  // All loads are issued up front from always-valid (clamped) addresses and the validity predicates only select
+  // terms afterwards: a frame cell then costs ONE memory round trip instead of one per neighbour branch (the
+  // frame is ~2 % of the cells but its dependent DRAM round trips used to form the tail of every launch).
   const int gi = g.goff + li;
   const i64 IJ = (i64)li * g.ld + j;
   if (j >= g.W) { ub0[IJ] = 0.0; return; }
@@ -317,47 +449,52 @@ __device__ __forceinline__ void ac_adj_general_cell(const AcGeom& g, int li, int
   const bool colok = (j >= 1 && j <= g.W - 2);
   const bool rowok = (gi >= 1 && gi <= g.H - 2);
   const bool intP = rowok && colok;
-  double acc = 0.0, sg = 0.0, ta = 0.0, gP = 0.0;
+  const bool vxm = colok && gi - 1 >= 1 && gi - 1 <= g.H - 2;  // Q = P - e_x is an interior cell
+  const bool vxp = colok && gi + 1 >= 1 && gi + 1 <= g.H - 2;  // Q = P + e_x
+  const bool vym = rowok && j - 1 >= 1 && j - 1 <= g.W - 2;    // Q = P - e_y
+  const bool vyp = rowok && j + 1 >= 1 && j + 1 <= g.W - 2;    // Q = P + e_y
+  const i64 Qxm = vxm ? IJ - g.ld : IJ, Qxp = vxp ? IJ + g.ld : IJ, Qym = vym ? IJ - 1 : IJ, Qyp = vyp ? IJ + 1 : IJ;
+  const i64 Wu = intP ? IJ + g.ld : IJ, Wd = intP ? IJ - g.ld : IJ, Wr = intP ? IJ + 1 : IJ, Wl = intP ? IJ - 1 : IJ;
+  const double sg = sigx[gi], sgm = sigx[vxm ? gi - 1 : gi], sgp = sigx[vxp ? gi + 1 : gi];
+  const double ta = tauy[j], tam = tauy[vym ? j - 1 : j], tap = tauy[vyp ? j + 1 : j];
+  const double cP = c2[IJ], uP = ub1[IJ], u2P = ub2[IJ], pb = phib[IJ], qb = psib[IJ], GP = G[IJ];
+  const double cxm = c2[Qxm], uxm = ub1[Qxm], pxm = phib[Qxm];
+  const double cxp = c2[Qxp], uxp = ub1[Qxp], pxp = phib[Qxp];
+  const double cym = c2[Qym], uym = ub1[Qym], qym = psib[Qym];
+  const double cyp = c2[Qyp], uyp = ub1[Qyp], qyp = psib[Qyp];
+  const double wC = wf[IJ], wU = wf[Wu], wD = wf[Wd], wR = wf[Wr], wL = wf[Wl];
+  // the adjoint is compared with the reference at 1e-10, not bit for bit: D in [1,2) is inverted once per cell
+  // (fast path of the reciprocal sequence) and the constant divisors are folded into rhx, rhy
+  const double kx = dt * 0.5 * g.rhx, ky = dt * 0.5 * g.rhy;
+  double acc = 0.0, gP = 0.0;
   if (intP) {
-    sg = sigx[gi]; ta = tauy[j];
-    const double c = c2[IJ];
-    gP = ub1[IJ] / (1 + (sg + ta) / 2 * dt);
-    acc = (2 - sg * ta * dt * dt - g.kx2 * c - g.ky2 * c) * gP;
+    gP = uP * (1.0 / (1 + (sg + ta) / 2 * dt));
+    acc = (2 - sg * ta * dt * dt - g.kx2 * cP - g.ky2 * cP) * gP;
   }
   double gxm = 0.0, gxp = 0.0, gym = 0.0, gyp = 0.0;
-  if (colok && gi - 1 >= 1 && gi - 1 <= g.H - 2) {  // Q = P - e_x : grad_w[IpJ] of Q
-    const i64 Q = IJ - g.ld;
-    const double cQ = c2[Q], sQ = sigx[gi - 1], tQ = tauy[j];
-    gxm = ub1[Q] / (1 + (sQ + tQ) / 2 * dt);
-    acc += cQ * g.rx * g.rx * gxm + dt * cQ * (tQ - sQ) / 2.0 / g.hx * phib[Q];
+  if (vxm) {  // grad_w[IpJ] of Q = P - e_x
+    gxm = uxm * (1.0 / (1 + (sgm + ta) / 2 * dt));
+    acc += cxm * g.rx * g.rx * gxm + cxm * (ta - sgm) * kx * pxm;
   }
-  if (colok && gi + 1 >= 1 && gi + 1 <= g.H - 2) {  // Q = P + e_x : grad_w[InJ] of Q
-    const i64 Q = IJ + g.ld;
-    const double cQ = c2[Q], sQ = sigx[gi + 1], tQ = tauy[j];
-    gxp = ub1[Q] / (1 + (sQ + tQ) / 2 * dt);
-    acc += cQ * g.rx * g.rx * gxp - dt * cQ * (tQ - sQ) / 2.0 / g.hx * phib[Q];
+  if (vxp) {  // grad_w[InJ] of Q = P + e_x
+    gxp = uxp * (1.0 / (1 + (sgp + ta) / 2 * dt));
+    acc += cxp * g.rx * g.rx * gxp - cxp * (ta - sgp) * kx * pxp;
   }
-  if (rowok && j - 1 >= 1 && j - 1 <= g.W - 2) {  // Q = P - e_y : grad_w[IJp] of Q
-    const i64 Q = IJ - 1;
-    const double cQ = c2[Q], sQ = sigx[gi], tQ = tauy[j - 1];
-    gym = ub1[Q] / (1 + (sQ + tQ) / 2 * dt);
-    acc += cQ * g.ry * g.ry * gym + dt * cQ * (sQ - tQ) / 2.0 / g.hy * psib[Q];
+  if (vym) {  // grad_w[IJp] of Q = P - e_y
+    gym = uym * (1.0 / (1 + (sg + tam) / 2 * dt));
+    acc += cym * g.ry * g.ry * gym + cym * (sg - tam) * ky * qym;
   }
-  if (rowok && j + 1 >= 1 && j + 1 <= g.W - 2) {  // Q = P + e_y : grad_w[IJn] of Q
-    const i64 Q = IJ + 1;
-    const double cQ = c2[Q], sQ = sigx[gi], tQ = tauy[j + 1];
-    gyp = ub1[Q] / (1 + (sQ + tQ) / 2 * dt);
-    acc += cQ * g.ry * g.ry * gyp - dt * cQ * (sQ - tQ) / 2.0 / g.hy * psib[Q];
+  if (vyp) {  // grad_w[IJn] of Q = P + e_y
+    gyp = uyp * (1.0 / (1 + (sg + tap) / 2 * dt));
+    acc += cyp * g.ry * g.ry * gyp - cyp * (sg - tap) * ky * qyp;
   }
   if (intP) {
-    acc += -(1 - (sg + ta) * dt / 2) * (ub2[IJ] / (1 + (sg + ta) / 2 * dt));  // grad_wold of step s+1
-    const double pb = phib[IJ], qb = psib[IJ];
+    acc += -(1 - (sg + ta) * dt / 2) * (u2P * (1.0 / (1 + (sg + ta) / 2 * dt)));  // grad_wold of step s+1
     phibo[IJ] = (1. - dt * sg) * pb + g.px * (gxm - gxp);
     psibo[IJ] = (1. - dt * ta) * qb + g.py * (gym - gyp);
-    const double wC = wf[IJ], wU = wf[IJ + g.ld], wD = wf[IJ - g.ld], wR = wf[IJ + 1], wL = wf[IJ - 1];
     const double cb = ((-g.kx2 - g.ky2) * wC + g.rx * g.rx * (wU + wD) + g.ry * g.ry * (wR + wL)) * gP +
-                      dt * (ta - sg) / 2.0 / g.hx * (wU - wD) * pb + dt * (sg - ta) / 2.0 / g.hy * (wR - wL) * qb;
-    G[IJ] += cb;
+                      (ta - sg) * kx * (wU - wD) * pb + (sg - ta) * ky * (wR - wL) * qb;
+    G[IJ] = GP + cb;
   }
   ub0[IJ] = acc;
 }
@@ -365,7 +502,7 @@ __device__ __forceinline__ void ac_adj_general_cell(const AcGeom& g, int li, int
 // ------------------------------------------------------------------------------------------------------------
 // adjoint kernel: ub0 = ubar[s-1] from ub1 = ubar[s], ub2 = ubar[s+1], wf = u[s-1]
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(AC_THREADS, AC_MINB_ADJ)
+__global__ void __launch_bounds__(AC_ADJ_THREADS, AC_MINB_ADJ)
 ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double* __restrict__ ub2,
               const double* __restrict__ wf, const double* __restrict__ c2, const double* __restrict__ phib,
               const double* __restrict__ psib, const double* __restrict__ sigx, const double* __restrict__ tauy,
@@ -373,11 +510,20 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
               double* __restrict__ G, AcPoints rcv, const double* __restrict__ res_row, AcPoints src,
               double* __restrict__ gsrcv_row, AcFuse f) {
   const int bid = f.perm ? f.perm[blockIdx.x] : blockIdx.x;
+#ifdef AC_DEBUG_SKIP_FRAME   // timing experiments only (wrong results)
+  if (bid >= t.nmarch) return;
+#endif
+#ifdef AC_DEBUG_SKIP_MARCH
+  if (bid < t.nmarch) return;
+#endif
   const int ld = g.ld;
   bool t_lo = false, t_hi = false;
   int rect = 0, idx0 = 0, wdt = 1, ncell = 0;
   if (bid >= t.nmarch) {
     ac_frame_locate(t, bid - t.nmarch, &rect, &idx0);
+#ifdef AC_DEBUG_RECTS
+    if (!((AC_DEBUG_RECTS >> rect) & 1)) return;
+#endif
     wdt = t.rc1[rect] - t.rc0[rect];
     ncell = (t.rr1[rect] - t.rr0[rect]) * wdt;
     const int rlo = t.rr0[rect] + idx0 / wdt, rhi = t.rr0[rect] + (min(ncell, idx0 + AC_FRAME_CELLS) - 1) / wdt;
@@ -387,7 +533,7 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
 #pragma unroll
     for (int k = 0; k < AC_FRAME_CPT; k++) {
       const int idx = idx0 + k * AC_THREADS + threadIdx.x;
-      if (idx < ncell) {
+      if (idx < ncell && threadIdx.x < AC_THREADS) {
         const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
         ac_adj_general_cell(g, li, j, ub1, ub2, wf, c2, phib, psib, sigx, tauy, ub0, phibo, psibo, G);
       }
@@ -397,13 +543,114 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
     const int r0 = t.mr0 + tr * t.rb;
     const int r1 = min(t.mr1, r0 + t.rb);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int jb = t.mc0 + ct * AC_TILE_COLS + warp * AC_WCOLS;
+    const int c0 = t.mc0 + ct * AC_TILE_COLS;
+    const int jb = c0 + warp * AC_WCOLS;
     const int j = jb + 2 * lane;
     const bool ldok = j < ld;
     const bool act = j < t.mc_end;
     t_lo = f.has_lo && r0 <= f.own0 && f.own0 < r1;
     t_hi = f.has_hi && r0 <= f.own_last && f.own_last < r1;
     ac_fuse_wait(f, t_lo, t_hi);
+#if AC_ADJ_TMA
+    extern __shared__ __align__(128) unsigned char ac_smem[];
+    AcAdjStage* stg = reinterpret_cast<AcAdjStage*>(ac_smem);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(ac_smem + AC_NST_ADJ * sizeof(AcAdjStage));
+    unsigned long long* empty = full + AC_NST_ADJ;
+    const int nrows = r1 - r0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < AC_NST_ADJ; k++) { mbar_init(full + k, 1); mbar_init(empty + k, AC_WARPS); }
+      mbar_init_fence();
+    }
+    __syncthreads();
+    if (warp == AC_WARPS) {
+      // ---------------- producer warp: keeps AC_NST_ADJ rows of the five streamed arrays in flight ----------------
+      if (lane == 0) {
+        const unsigned hbytes = (unsigned)min(AC_HCOLS, ld - (c0 - 2)) * 8u;  // never read past the end of a row
+        const unsigned cbytes = (unsigned)min(AC_TILE_COLS, ld - c0) * 8u;
+        for (int it = 0; it < nrows; it++) {
+          const int sidx = it % AC_NST_ADJ;
+          if (it >= AC_NST_ADJ) mbar_wait(empty + sidx, (unsigned)(it / AC_NST_ADJ - 1) & 1u);
+          AcAdjStage& s = stg[sidx];
+          const i64 ro = (i64)(r0 + it) * ld + c0;
+          mbar_arrive_expect_tx(full + sidx, 3u * hbytes + 2u * cbytes);
+          bulk_g2s(s.ub1, ub1 + ro + ld - 2, hbytes, full + sidx);
+          bulk_g2s(s.c2, c2 + ro + ld - 2, hbytes, full + sidx);
+          bulk_g2s(s.wf, wf + ro + ld - 2, hbytes, full + sidx);
+          bulk_g2s(s.ub2, ub2 + ro, cbytes, full + sidx);
+          bulk_g2s(s.G, G + ro, cbytes, full + sidx);
+        }
+      }
+    } else {
+      // ---------------- consumer warps: 64 columns each, 3-row windows in registers ----------------
+      const bool wact = jb < t.mc_end;  // this warp's strip intersects the box
+      const double2 z2 = make_double2(0.0, 0.0);
+      const double rx2 = g.rx * g.rx, ry2 = g.ry * g.ry, kk = -g.kx2 - g.ky2, kx2 = g.kx2, ky2 = g.ky2;
+      // register windows: cg = c^2 * ubar[s] (D == 1 and no ring cell within one cell of the box), w = u[s-1]
+      double2 cgm = z2, cgc = z2, wm = z2, wc = z2, gc = z2, ccen = z2;
+      double ecg = 0.0, ew = 0.0;  // warp-edge neighbours of the centre row (lanes 0 and 31)
+      if (wact && ldok) {
+        i64 ro = (i64)(r0 - 1) * ld + j;
+        const double2 c_ = ld2(c2 + ro), u_ = ld2(ub1 + ro);
+        cgm = make_double2(c_.x * u_.x, c_.y * u_.y);
+        wm = ld2(wf + ro);
+        ro += ld;
+        ccen = ld2(c2 + ro);
+        gc = ld2(ub1 + ro);
+        cgc = make_double2(ccen.x * gc.x, ccen.y * gc.y);
+        wc = ld2(wf + ro);
+        if (act) {
+          const i64 rc = (i64)r0 * ld;
+          if (lane == 0) { ecg = c2[rc + jb - 1] * ub1[rc + jb - 1]; ew = wf[rc + jb - 1]; }
+          if (lane == 31) { ecg = c2[rc + jb + AC_WCOLS] * ub1[rc + jb + AC_WCOLS]; ew = wf[rc + jb + AC_WCOLS]; }
+        }
+      }
+      const int so = 2 + warp * AC_WCOLS + 2 * lane;  // this lane's column pair inside a halo'd stage row
+      for (int it = 0; it < nrows; it++) {
+        const int li = r0 + it, sidx = it % AC_NST_ADJ;
+        mbar_wait(full + sidx, (unsigned)(it / AC_NST_ADJ) & 1u);
+        const AcAdjStage& s = stg[sidx];
+        double2 un = z2, cn = z2, wn = z2, u2 = z2, Gr = z2;
+        double ecg_n = 0.0, ew_n = 0.0;  // edge neighbours of the next centre row
+        if (wact) {
+          un = ld2(s.ub1 + so); cn = ld2(s.c2 + so); wn = ld2(s.wf + so);
+          u2 = ld2(s.ub2 + so - 2); Gr = ld2(s.G + so - 2);
+          if (lane == 0) { ecg_n = s.c2[so - 1] * s.ub1[so - 1]; ew_n = s.wf[so - 1]; }
+          if (lane == 31) { ecg_n = s.c2[so + 2] * s.ub1[so + 2]; ew_n = s.wf[so + 2]; }
+        }
+        __syncwarp();  // every lane has read the stage
+        if (lane == 0) mbar_arrive(empty + sidx);
+        if (wact) {
+          const double2 cgp = make_double2(cn.x * un.x, cn.y * un.y);
+          double cgl = __shfl_up_sync(0xffffffffu, cgc.y, 1);
+          double cgr = __shfl_down_sync(0xffffffffu, cgc.x, 1);
+          double wl = __shfl_up_sync(0xffffffffu, wc.y, 1);
+          double wr = __shfl_down_sync(0xffffffffu, wc.x, 1);
+          if (lane == 0) { cgl = ecg; wl = ew; }
+          if (lane == 31) { cgr = ecg; wr = ew; }
+          if (act) {
+            double2 o, Go;
+            {
+              const double c = ccen.x, gg = gc.x;
+              o.x = (2 - kx2 * c - ky2 * c) * gg + rx2 * (cgp.x + cgm.x) + ry2 * (cgc.y + cgl) - u2.x;
+              Go.x = Gr.x + (kk * wc.x + rx2 * (wn.x + wm.x) + ry2 * (wc.y + wl)) * gg;
+            }
+            {
+              const double c = ccen.y, gg = gc.y;
+              o.y = (2 - kx2 * c - ky2 * c) * gg + rx2 * (cgp.y + cgm.y) + ry2 * (cgr + cgc.x) - u2.y;
+              Go.y = Gr.y + (kk * wc.y + rx2 * (wn.y + wm.y) + ry2 * (wr + wc.x)) * gg;
+            }
+            st2(ub0 + (i64)li * ld + j, o);
+            st2(G + (i64)li * ld + j, Go);
+          }
+          cgm = cgc; cgc = cgp;
+          wm = wc; wc = wn;
+          gc = un; ccen = cn;
+          ecg = ecg_n; ew = ew_n;
+        }
+      }
+    }
+#else
     if (jb < t.mc_end) {
       const double2 z2 = make_double2(0.0, 0.0);
       const double rx2 = g.rx * g.rx, ry2 = g.ry * g.ry, kk = -g.kx2 - g.ky2, kx2 = g.kx2, ky2 = g.ky2;
@@ -475,6 +722,7 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
         }
       }
     }
+#endif
   }
   ac_cta_epilogue(bid, ub0, rcv, res_row, 1.0, src, gsrcv_row, g.dt2);
   if (t_lo || t_hi) {
@@ -483,7 +731,7 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
 #pragma unroll
       for (int k = 0; k < AC_FRAME_CPT; k++) {
         const int idx = idx0 + k * AC_THREADS + threadIdx.x;
-        if (idx < ncell) {
+        if (idx < ncell && threadIdx.x < AC_THREADS) {
           const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
           const i64 IJ = (i64)li * ld + j;
           if (t_lo && li == f.own0) { f.lo_u[j] = ub0[IJ]; f.lo_p[j] = phibo[IJ]; }
@@ -493,7 +741,7 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
     } else {
       const int ct = bid % t.nct;
       const int j = t.mc0 + ct * AC_TILE_COLS + 2 * threadIdx.x;
-      if (j < t.mc_end) {
+      if (j < t.mc_end && threadIdx.x < AC_THREADS) {
         if (t_lo) st2(f.lo_u + j, ld2(ub0 + (i64)f.own0 * ld + j));
         if (t_hi) st2(f.hi_u + j, ld2(ub0 + (i64)f.own_last * ld + j));
       }

@@ -145,4 +145,46 @@ __device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<do
 // streaming (evict-first) 16-byte accesses for data touched once per time step
 __device__ __forceinline__ double2 ld2_stream(const double* p) { return __ldcs(reinterpret_cast<const double2*>(p)); }
 __device__ __forceinline__ void st2_stream(double* p, double2 v) { __stcs(reinterpret_cast<double2*>(p), v); }
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA row staging (sm_90+/sm_100a): 1-D bulk asynchronous copies global -> shared (`cp.async.bulk`, SASS UBLKCP)
+// completing on an mbarrier.  The marching kernels keep a ring of row stages per CTA: a producer warp arms the
+// stage's `full` mbarrier with the byte count and issues one multi-KB bulk copy per streamed array several rows
+// ahead; the consumer warps wait on the barrier's phase parity, read the stage and release it through an `empty`
+// mbarrier.  Memory-level parallelism is then set by the ring depth (shared memory), not by registers/occupancy.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = smem_u32(bar);
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// bytes: multiple of 16; src and dst 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 #endif

@@ -22,7 +22,11 @@ def run(NX, NY, NSTEP, reps=3, budget=0):
         t = min(ts)
         info = plan.info()
         bytes_ = cells * (32 if name == "forward" else 88 + 32 * (info["recomputed_steps"] / max(NSTEP - 1, 1)))
-        print("%dx%d nt=%d %-8s %8.2f ms  %7.2f Gcell/s  %7.1f GB/s(alg)  %s" % (NX, NY, NSTEP, name, t, cells / t / 1e6, bytes_ / t / 1e6, info), flush=True)
+        tm = plan.timings()
+        per = lambda k: tm[k + "_ms"] * 1e3 / max(tm[k + "_launches"], 1)
+        print("%dx%d nt=%d %-8s %8.2f ms  %7.2f Gcell/s  %7.1f GB/s(alg) | us/launch fwd %.1f adj %.1f | slots %d segs %d" %
+              (NX, NY, NSTEP, name, t, cells / t / 1e6, bytes_ / t / 1e6, per("forward"), per("adjoint"),
+               info["hist_slots"], info["segments"]), flush=True)
     plan.close()
 
 if __name__ == "__main__" and "--elastic" not in sys.argv:

@@ -5,6 +5,7 @@ set -e
 cd "$(dirname "$0")/.."
 for v in "$@"; do
   tag="${v%%:*}"; flags="${v#*:}"
-  ADSEIS_LIB_SUFFIX="_$tag" ADSEIS_NVCC_EXTRA="$flags" python "adseismic.jl_b200/_build.py" --force 2>&1 | grep -A2 "ac_adj_kernel\|ac_fwd_kernel\|el_" | grep -E "spill|Used" | tr '\n' ' '
-  echo " <- $tag"
+  ADSEIS_LIB_SUFFIX="_$tag" ADSEIS_NVCC_EXTRA="$flags" python "adseismic.jl_b200/_build.py" --force >/dev/null 2>&1
+  echo "== $tag ($flags)"
+  grep -A2 "Compiling entry function '_Z1[0-9]*\(ac_\|el_\)" adseismic.jl_b200/build.log | grep -E "Compiling|spill|Used" | sed -e "s/.*function '_Z[0-9]*\([a-z_0-9]*kernel\|el_[a-z_]*\).*/\1/" | paste - - - | awk '{print "   ", $0}' | sed -e 's/ptxas info    ://' -e 's/bytes stack frame/B stack/' | cut -c1-200
 done
