@@ -63,6 +63,7 @@ SIGNATURES = {
     "adseis_ctx_mem_info": (C.c_int, [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "adseis_acoustic_pml_profiles": (C.c_int, [_PA, dp, dp]),
     "adseis_slab_partition": (C.c_int, [i64, C.c_int32, C.c_int32, _PS]),
+    "adseis_elastic_slab_partition": (C.c_int, [_PE, C.c_int32, C.c_int32, _PS]),
     "adseis_acoustic_plan_create": (C.c_int, [vp, _PA, _PS, i64, ip, ip, i64, ip, ip, C.c_size_t, C.POINTER(vp)]),
     "adseis_acoustic_plan_destroy": (C.c_int, [vp]),
     "adseis_acoustic_plan_set_model": (C.c_int, [vp, vp, C.c_int]),

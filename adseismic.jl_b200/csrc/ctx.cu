@@ -191,3 +191,18 @@ ADSEIS_API int adseis_slab_partition(int64_t NX, int32_t nranks, int32_t rank, a
   out->row1 = (rank == nranks - 1) ? NX + 2 : start + cnt;
   return ADSEIS_OK;
 }
+
+ADSEIS_API int adseis_elastic_slab_partition(const adseis_elastic_params* p, int32_t nranks, int32_t rank,
+                                             adseis_slab* out) {
+  REQUIRE(p && out && nranks >= 1 && rank >= 0 && rank < nranks && p->NX >= 4 * (i64)nranks,
+          "adseis_elastic_slab_partition: bad argument");
+  const i64 ghost = p->variant == 0 ? 1 : 2, NX = p->NX;
+  i64 base = NX / nranks, rem = NX % nranks;
+  i64 start = ghost + rank * base + (rank < rem ? rank : rem);
+  i64 cnt = base + (rank < rem ? 1 : 0);
+  out->rank = rank;
+  out->nranks = nranks;
+  out->row0 = (rank == 0) ? 0 : start;
+  out->row1 = (rank == nranks - 1) ? NX + 2 * ghost : start + cnt;
+  return ADSEIS_OK;
+}

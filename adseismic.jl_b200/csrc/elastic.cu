@@ -11,7 +11,7 @@
 // material pre-processing and gradient post-processing
 // ------------------------------------------------------------------------------------------------------------
 // Averaged materials exactly as fw1/fw2/fw4 form them (Core.jl:109-111, 141, 200); variant M: no averaging.
-__global__ void k_el_materials(int Hl, int ld, int W, int avg, const double* __restrict__ rho,
+__global__ void k_el_materials(int Hl, int ld, int W, int goff, int H, int avg, const double* __restrict__ rho,
                                const double* __restrict__ lam, const double* __restrict__ mu,
                                double* __restrict__ lamb, double* __restrict__ lmb, double* __restrict__ mub2,
                                double* __restrict__ rhob, double* __restrict__ rinv, double* __restrict__ rbinv) {
@@ -22,7 +22,7 @@ __global__ void k_el_materials(int Hl, int ld, int W, int avg, const double* __r
   if (q >= W) { lamb[c] = lmb[c] = mub2[c] = rhob[c] = rinv[c] = rbinv[c] = 0.0; return; }
   double l_, m1, m2, rb;
   if (avg) {
-    const bool dn = li + 1 < Hl, rt = q + 1 < W;
+    const bool dn = goff + li + 1 < H, rt = q + 1 < W;  // raw planes hold Hl+1 local rows: row li+1 is always there
     l_ = dn ? 0.5 * (lam[c + ld] + lam[c]) : lam[c];
     m1 = dn ? 0.5 * (mu[c + ld] + mu[c]) : mu[c];
     m2 = rt ? 0.5 * (mu[c] + mu[c + 1]) : mu[c];
@@ -51,7 +51,7 @@ __global__ void k_el_grad_finalize(ElGeom g, int avg, int off /* rows/cols to st
   const i64 c = (i64)li * g.ld + q;
   double gl, gm, gr;
   if (avg) {
-    const bool up = li - 1 >= 0, lf = q - 1 >= 0;
+    const bool up = gp - 1 >= 0, lf = q - 1 >= 0;  // slab plans: row li-1 of an accumulator may be a halo row
     gl = 0.5 * (Gl[c] + (up ? Gl[c - g.ld] : 0.0));
     gm = 0.5 * (Gm1[c] + (up ? Gm1[c - g.ld] : 0.0)) + 0.5 * (Gm2[c] + (lf ? Gm2[c - 1] : 0.0));
     gr = Gr3[c] + 0.25 * (Gr4[c] + (up ? Gr4[c - g.ld] : 0.0) + ((up && lf) ? Gr4[c - g.ld - 1] : 0.0) +
@@ -117,7 +117,23 @@ struct adseis_elastic_plan {
   bool have_model = false, have_srcv = false, have_obs = false, have_fwd = false, have_grad = false,
        have_matgrad = false;
   i64 last_launches = 0, last_segments = 0, last_recomputed = 0;
+  // slab decomposition (nranks > 1): one IPC-exported arena holds every array with halo rows
+  double* arena = nullptr;
+  size_t arena_bytes = 0;
+  struct Desc {
+    unsigned long long magic;
+    long long Hl, ld, plane, slot_sz, win, own0, own1;
+    long long off_flags, off_hist, off_adj, off_gacc;
+    long long n_edge_lo, n_edge_hi;
+  } desc{}, dpeer[2];
+  char* peer[2] = {nullptr, nullptr};
+  unsigned long long epoch = 0, sepoch = 0;
+  int* perm = nullptr;
+  int n_edge_lo = 0, n_edge_hi = 0;
+  bool connected = false;
 };
+#define EL_DESC_MAGIC 0xAD5E15E1A5ULL
+#define EL_HX_BLOCKS 8
 
 #define EL_LAUNCH_CHECK(P)        \
   do {                            \
@@ -149,6 +165,12 @@ ADSEIS_API int adseis_elastic_plan_destroy(adseis_elastic_plan* P) {
   if (!P) return ADSEIS_OK;
   cudaSetDevice(P->ctx->device);
   cudaStreamSynchronize(P->ctx->stream);
+  if (P->arena) {  // hist, adj and the accumulators live inside the arena
+    for (int k = 0; k < 2; k++) if (P->peer[k]) cudaIpcCloseMemHandle(P->peer[k]);
+    cudaFree(P->arena);
+    P->hist = P->adj = P->Gl = P->Gm1 = P->Gm2 = P->Gr3 = P->Gr4 = nullptr;
+  }
+  cudaFree(P->perm);
   double* arr[] = {P->rho, P->lam, P->mu, P->lamb, P->lmb, P->mub2, P->rhob, P->rinv, P->rbinv, P->ax, P->bx, P->ay,
                    P->by, P->hist, P->srcv, P->rcvv, P->obs, P->res, P->loss, P->adj, P->Gl, P->Gm1, P->Gm2, P->Gr3,
                    P->Gr4, P->grho, P->glam, P->gmu, P->gradsrcv};
@@ -193,8 +215,6 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
   TRY(el_validate(p));
   REQUIRE(nsrc >= 0 && nrcv >= 0 && (nsrc == 0 || (srci && srcj && srctype)) && (nrcv == 0 || (rcvi && rcvj && rcvtype)),
           "elastic_plan_create: bad source/receiver arrays");
-  REQUIRE(slab == nullptr || slab->nranks == 1, "elastic_plan_create: slab decomposition of the elastic path is not "
-          "available in this build (single-GPU and shot-parallel only)");
   CUDA_TRY(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   adseis_elastic_plan* P = new adseis_elastic_plan();
@@ -217,8 +237,22 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
     for (int k = 0; k < 4; k++) { g.p0[k] = 2; g.p1[k] = NX + 1; g.q0[k] = 2; g.q1[k] = NY + 1; }  // MPIElastic.jl:175-189
     P->model_elems = (i64)NX * NY;
   }
-  P->slab.rank = 0; P->slab.nranks = 1; P->slab.row0 = 0; P->slab.row1 = g.H;
-  g.goff = 0; g.Hl = g.H; g.own0 = 0; g.own1 = g.H;
+  // slab of a 1-D decomposition along i: rows [row0,row1) of the INTERNAL array (variant 0: the padded grid,
+  // variant 1: the global grid plus its 2 ghost rows on each side), EL_HALO halo rows per interior side
+  if (slab && slab->nranks > 1) P->slab = *slab;
+  else { P->slab.rank = 0; P->slab.nranks = 1; P->slab.row0 = 0; P->slab.row1 = g.H; }
+  const adseis_slab& sl = P->slab;
+  if (!(sl.rank >= 0 && sl.rank < sl.nranks && sl.row0 >= 0 && sl.row1 <= g.H && sl.row1 - sl.row0 >= 2 * EL_HALO &&
+        (sl.rank > 0 || sl.row0 == 0) && (sl.rank < sl.nranks - 1 || sl.row1 == g.H))) {
+    adseis_set_error("elastic_plan_create: inconsistent slab {rank %d/%d rows [%lld,%lld)} for %d internal rows",
+                     sl.rank, sl.nranks, (long long)sl.row0, (long long)sl.row1, g.H);
+    delete P;
+    return ADSEIS_EINVAL;
+  }
+  const int halo_lo = sl.rank > 0 ? EL_HALO : 0, halo_hi = sl.rank < sl.nranks - 1 ? EL_HALO : 0;
+  g.goff = (int)sl.row0 - halo_lo;
+  g.Hl = (int)(sl.row1 - sl.row0) + halo_lo + halo_hi;
+  g.own0 = halo_lo; g.own1 = halo_lo + (int)(sl.row1 - sl.row0);
   g.ld = round_up(g.W, 16);
   g.plane = (i64)g.Hl * g.ld;
   g.dt = p->DELTAT; g.dx = p->DELTAX; g.dy = p->DELTAY;
@@ -248,6 +282,20 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
   };
   strip(ax, NX, &g.xlo, &g.xhi);
   strip(ay, NY, &g.ylo, &g.yhi);
+  if (sl.nranks > 1) {
+    // x-memories are stored compactly with GLOBAL strip rows and have no halo: an interior slab boundary must keep
+    // EL_HALO rows of distance from the x-PML strips (coefficient index kx = row - cx)
+    const int b_lo = (int)sl.row0 - g.cx, b_hi = (int)sl.row1 - g.cx;  // first kx owned / first kx of rank+1
+    const bool bad_lo = sl.rank > 0 && (b_lo - EL_HALO < g.xlo || b_lo + EL_HALO > g.xhi);
+    const bool bad_hi = sl.rank < sl.nranks - 1 && (b_hi - EL_HALO < g.xlo || b_hi + EL_HALO > g.xhi);
+    if (bad_lo || bad_hi) {
+      adseis_set_error("elastic_plan_create: slab boundary of rank %d lies inside (or within %d rows of) an x-PML strip "
+                       "(PML-free coefficient rows [%d,%d)); use fewer ranks or a thinner PML", sl.rank, EL_HALO, g.xlo,
+                       g.xhi);
+      adseis_elastic_plan_destroy(P);
+      return ADSEIS_EINVAL;
+    }
+  }
   g.nxr = g.xlo + (NX - g.xhi);
   const int nyc = g.ylo + (NY - g.yhi);
   g.ycp = std::max(1, nyc);
@@ -260,7 +308,21 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
   EPTRY(dev_upload(&P->ax, ax, st)); EPTRY(dev_upload(&P->bx, bx, st));
   EPTRY(dev_upload(&P->ay, ay, st)); EPTRY(dev_upload(&P->by, by, st));
   double** mats[] = {&P->rho, &P->lam, &P->mu, &P->lamb, &P->lmb, &P->mub2, &P->rhob, &P->rinv, &P->rbinv};
-  for (double** m : mats) EPTRY(dev_alloc_zero(m, (size_t)g.plane, st));
+  for (double** m : mats) EPTRY(dev_alloc_zero(m, (size_t)g.plane + g.ld, st));  // raw planes: one extra row (averaging)
+  if (sl.nranks > 1) {
+    // launch order: edge row tiles (they wait for / push halo rows) first, so the NVLink latency hides behind the rest
+    std::vector<int> edge, rest;
+    for (int b = 0; b < P->nblocks; b++) {
+      const int tr = b / g.ntc;
+      const int ra = g.own0 + tr * EL_ROWS, rb = std::min(g.own1, ra + EL_ROWS);
+      const bool tl = halo_lo && ra < g.own0 + EL_HALO, th = halo_hi && rb > g.own1 - EL_HALO;
+      if (tl) P->n_edge_lo++;
+      if (th) P->n_edge_hi++;
+      (tl || th ? edge : rest).push_back(b);
+    }
+    edge.insert(edge.end(), rest.begin(), rest.end());
+    EPTRY(dev_upload(&P->perm, edge, st));
+  }
 
   // sources / receivers (1-based indices: S -> padded grid, M -> unpadded global grid; MPIElastic.jl:85-86)
   P->nsrc = nsrc; P->nrcv = nrcv;
@@ -273,7 +335,8 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
       REQUIRE(gi >= 0 && gi < g.H && gj >= 0 && gj < g.W, "elastic_plan_create: %s %lld at (%lld,%lld) is outside the grid",
               what, (long long)k, (long long)pi[k], (long long)pj[k]);
       if (pt[k] < 0 || pt[k] > 4) continue;  // AddSource.cpp:83 / GetReceive.cpp:43: other types are ignored
-      v->push_back(Pt{(int)(gi * g.ld + gj), (int)pt[k], (int)k});
+      if (gi < sl.row0 || gi >= sl.row1) continue;  // owned by another slab (MPIElastic.jl:71-86, 116-131)
+      v->push_back(Pt{(int)((gi - g.goff) * g.ld + gj), (int)pt[k], (int)k});
     }
     return ADSEIS_OK;
   };
@@ -334,7 +397,34 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
     P->win = best;
   }
   el_make_segments(P);
-  {
+  const size_t adj_elems = (size_t)(5 * g.plane + 2 * (4 * g.xm_sz + 4 * g.ym_sz));
+  if (sl.nranks > 1) {
+    // one arena: [descriptor | flags | history window | adjoint state | 5 gradient accumulators]
+    adseis_elastic_plan::Desc& d = P->desc;
+    d.magic = EL_DESC_MAGIC; d.Hl = g.Hl; d.ld = g.ld; d.plane = g.plane; d.slot_sz = P->slot_sz; d.win = P->win;
+    d.own0 = g.own0; d.own1 = g.own1; d.n_edge_lo = P->n_edge_lo; d.n_edge_hi = P->n_edge_hi;
+    long long off = 512;
+    d.off_flags = off; off += 512;
+    d.off_hist = off; off += (long long)((size_t)P->win * slot_bytes);
+    d.off_adj = off; off += (long long)(adj_elems * 8);
+    d.off_gacc = off; off += (long long)(5 * (size_t)g.plane * 8);
+    P->arena_bytes = (size_t)off;
+    cudaError_t e = cudaMalloc((void**)&P->arena, P->arena_bytes);
+    if (e != cudaSuccess) {
+      adseis_set_error("elastic_plan_create: cannot allocate the %zu-byte slab arena: %s", P->arena_bytes,
+                       cudaGetErrorString(e));
+      adseis_elastic_plan_destroy(P);
+      return ADSEIS_ENOMEM;
+    }
+    CUDA_TRY(cudaMemsetAsync(P->arena, 0, P->arena_bytes, st));
+    CUDA_TRY(cudaMemcpyAsync(P->arena, &d, sizeof(d), cudaMemcpyHostToDevice, st));
+    char* base = (char*)P->arena;
+    P->hist = (double*)(base + d.off_hist);
+    P->adj = (double*)(base + d.off_adj);
+    double* ga = (double*)(base + d.off_gacc);
+    P->Gl = ga; P->Gm1 = ga + g.plane; P->Gm2 = ga + 2 * g.plane; P->Gr3 = ga + 3 * g.plane; P->Gr4 = ga + 4 * g.plane;
+    CUDA_TRY(cudaStreamSynchronize(st));
+  } else {
     cudaError_t e = cudaMalloc((void**)&P->hist, (size_t)P->win * slot_bytes);
     if (e != cudaSuccess) {
       adseis_set_error("elastic_plan_create: cannot allocate %lld history slots of %zu bytes: %s", (long long)P->win,
@@ -353,14 +443,17 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
   return ADSEIS_OK;
 }
 
-// caller's dense model array -> pitched internal plane (ghost / pad entries zero)
+// caller's dense model array -> pitched internal plane of this slab's rows plus one extra row (ghost / pad zero)
 static int el_load_plane(adseis_elastic_plan* P, const double* src, double* dst) {
   const ElGeom& g = P->g;
   cudaStream_t st = P->ctx->stream;
-  CUDA_TRY(cudaMemsetAsync(dst, 0, (size_t)g.plane * 8, st));
+  CUDA_TRY(cudaMemsetAsync(dst, 0, (size_t)(g.plane + g.ld) * 8, st));
   const int off = P->off, OW = g.W - 2 * off, OH = g.H - 2 * off;
-  CUDA_TRY(cudaMemcpy2DAsync(dst + (i64)off * g.ld + off, (size_t)g.ld * 8, src, (size_t)OW * 8, (size_t)OW * 8,
-                             (size_t)OH, cudaMemcpyDefault, st));
+  // local row li <-> internal row goff+li <-> caller row goff+li-off, for li in [0, Hl]
+  const int l0 = std::max(0, off - g.goff), l1 = std::min(g.Hl + 1, OH + off - g.goff);
+  if (l1 > l0)
+    CUDA_TRY(cudaMemcpy2DAsync(dst + (i64)l0 * g.ld + off, (size_t)g.ld * 8, src + (i64)(g.goff + l0 - off) * OW,
+                               (size_t)OW * 8, (size_t)OW * 8, (size_t)(l1 - l0), cudaMemcpyDefault, st));
   return ADSEIS_OK;
 }
 
@@ -374,7 +467,7 @@ ADSEIS_API int adseis_elastic_plan_set_model(adseis_elastic_plan* P, const doubl
   TRY(el_load_plane(P, mu, P->mu));
   const ElGeom& g = P->g;
   dim3 grid((unsigned)((g.ld + 127) / 128), (unsigned)g.Hl);
-  k_el_materials<<<grid, 128, 0, P->ctx->stream>>>(g.Hl, g.ld, g.W, P->p.variant == 0, P->rho, P->lam, P->mu, P->lamb,
+  k_el_materials<<<grid, 128, 0, P->ctx->stream>>>(g.Hl, g.ld, g.W, g.goff, g.H, P->p.variant == 0, P->rho, P->lam, P->mu, P->lamb,
                                                    P->lmb, P->mub2, P->rhob, P->rinv, P->rbinv);
   P->ctx->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -409,6 +502,125 @@ ADSEIS_API int adseis_elastic_plan_set_obs(adseis_elastic_plan* P, const double*
   return ADSEIS_OK;
 }
 
+// ---- slab decomposition: peer pointers of the next fused launch, standalone exchange / barrier ----------------
+// A plane with halo rows is named by (array, index, field) because the neighbours' arenas have the same structure
+// but not the same plane size (their slabs may hold a different number of rows).
+enum ElArr { EA_HIST, EA_ADJ, EA_GACC };
+struct ElPlaneRef { int arr; i64 idx; int field; };  // HIST: idx = window index, field 0..4; ADJ: field 0..4; GACC: field 0..4
+static inline long long el_plane_off(const adseis_elastic_plan::Desc& d, const ElPlaneRef& r) {
+  const long long base = r.arr == EA_HIST ? d.off_hist + r.idx * d.slot_sz * 8 : (r.arr == EA_ADJ ? d.off_adj : d.off_gacc);
+  return base + (long long)r.field * d.plane * 8;
+}
+
+static ElFuse el_make_fuse(adseis_elastic_plan* P, int nf, const ElPlaneRef* planes) {
+  ElFuse f;
+  memset(&f, 0, sizeof(f));
+  if (!P->arena) return f;
+  f.perm = P->perm;
+  f.has_lo = P->peer[0] != nullptr; f.has_hi = P->peer[1] != nullptr;
+  f.nf = nf;
+  P->sepoch++;
+  for (int k = 0; k < nf; k++) {
+    f.src[k] = (const double*)((char*)P->arena + el_plane_off(P->desc, planes[k]));
+    if (f.has_lo) f.lo[k] = (double*)(P->peer[0] + el_plane_off(P->dpeer[0], planes[k])) + (P->dpeer[0].Hl - EL_HALO) * P->dpeer[0].ld;
+    if (f.has_hi) f.hi[k] = (double*)(P->peer[1] + el_plane_off(P->dpeer[1], planes[k]));
+  }
+  if (f.has_lo) {
+    f.sig_lo = (unsigned long long*)(P->peer[0] + P->dpeer[0].off_flags) + 4;
+    f.expect_lo = (unsigned long long)P->dpeer[0].n_edge_hi * (P->sepoch - 1);
+  }
+  if (f.has_hi) {
+    f.sig_hi = (unsigned long long*)(P->peer[1] + P->dpeer[1].off_flags) + 3;
+    f.expect_hi = (unsigned long long)P->dpeer[1].n_edge_lo * (P->sepoch - 1);
+  }
+  f.my_flags = (unsigned long long*)((char*)P->arena + P->desc.off_flags);
+  return f;
+}
+
+struct ElHaloArgs {
+  int nf;
+  const double* src[5];
+  double* lo[5];
+  double* hi[5];
+  int ld, own0, own1;
+  int has_lo, has_hi;
+  unsigned long long *sig_lo, *sig_hi, *my_flags;
+  unsigned long long expect;
+};
+
+// Standalone exchange: push my EL_HALO edge rows of up to five planes into the neighbours' halo rows, publish, then
+// wait for theirs.  nf == 0 is a pure barrier (guards host-enqueued memsets / copies of arrays with halo rows).
+__global__ void __launch_bounds__(256) k_el_halo_exchange(ElHaloArgs a) {
+  const int n2 = EL_HALO * a.ld / 2;  // double2 elements per (plane, side)
+  const int per = (n2 + EL_HX_BLOCKS - 1) / EL_HX_BLOCKS;
+  const int j0 = blockIdx.x * per, j1 = min(n2, j0 + per);
+  for (int k = 0; k < a.nf; k++) {
+    if (a.has_lo) {
+      const double2* s2 = reinterpret_cast<const double2*>(a.src[k] + (i64)a.own0 * a.ld);
+      double2* d2 = reinterpret_cast<double2*>(a.lo[k]);
+      for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) d2[j] = s2[j];
+    }
+    if (a.has_hi) {
+      const double2* s2 = reinterpret_cast<const double2*>(a.src[k] + (i64)(a.own1 - EL_HALO) * a.ld);
+      double2* d2 = reinterpret_cast<double2*>(a.hi[k]);
+      for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) d2[j] = s2[j];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (a.has_lo) atomicAdd_system(a.sig_lo, 1ULL);
+    if (a.has_hi) atomicAdd_system(a.sig_hi, 1ULL);
+    if (blockIdx.x == 0) {
+      volatile unsigned long long* f = a.my_flags;
+      unsigned long long spins = 0;
+      while ((a.has_lo && f[0] < a.expect) || (a.has_hi && f[1] < a.expect)) {
+        if (++spins > (1ULL << 26)) { f[2] = 1ULL; break; }  // neighbour lost: report, do not hang
+      }
+      __threadfence_system();
+    }
+  }
+}
+
+static int el_halo_exchange(adseis_elastic_plan* P, int nf, const ElPlaneRef* planes) {
+  if (!P->arena) return ADSEIS_OK;
+  if (!P->connected) {
+    adseis_set_error("elastic slab plan: adseis_elastic_plan_ipc_connect has not been called");
+    return ADSEIS_ESTATE;
+  }
+  const ElGeom& g = P->g;
+  ElHaloArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nf = nf; a.ld = g.ld; a.own0 = g.own0; a.own1 = g.own1;
+  a.has_lo = P->peer[0] != nullptr; a.has_hi = P->peer[1] != nullptr;
+  for (int k = 0; k < nf; k++) {
+    a.src[k] = (const double*)((char*)P->arena + el_plane_off(P->desc, planes[k]));
+    if (a.has_lo) a.lo[k] = (double*)(P->peer[0] + el_plane_off(P->dpeer[0], planes[k])) + (P->dpeer[0].Hl - EL_HALO) * g.ld;
+    if (a.has_hi) a.hi[k] = (double*)(P->peer[1] + el_plane_off(P->dpeer[1], planes[k]));
+  }
+  if (a.has_lo) a.sig_lo = (unsigned long long*)(P->peer[0] + P->dpeer[0].off_flags) + 1;
+  if (a.has_hi) a.sig_hi = (unsigned long long*)(P->peer[1] + P->dpeer[1].off_flags) + 0;
+  a.my_flags = (unsigned long long*)((char*)P->arena + P->desc.off_flags);
+  P->epoch++;
+  a.expect = (unsigned long long)EL_HX_BLOCKS * P->epoch;
+  k_el_halo_exchange<<<EL_HX_BLOCKS, 256, 0, P->ctx->stream>>>(a);
+  EL_LAUNCH_CHECK(P);
+  return ADSEIS_OK;
+}
+static int el_barrier(adseis_elastic_plan* P) { return el_halo_exchange(P, 0, nullptr); }
+
+static int el_halo_check(adseis_elastic_plan* P) {
+  if (!P->arena) return ADSEIS_OK;
+  unsigned long long f[3] = {0, 0, 0};
+  CUDA_TRY(cudaMemcpyAsync(f, (char*)P->arena + P->desc.off_flags, sizeof(f), cudaMemcpyDeviceToHost, P->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(P->ctx->stream));
+  if (f[2] != 0) {
+    adseis_set_error("elastic slab plan (rank %d): timed out waiting for a neighbour's halo rows", P->slab.rank);
+    return ADSEIS_ECOMM;
+  }
+  return ADSEIS_OK;
+}
+
 // one forward step s: slot `in` (s-1) -> slot `out` (s); in == out is allowed (in-place stepping)
 static int el_step_forward(adseis_elastic_plan* P, i64 s, double* in, double* out, bool sample) {
   cudaStream_t st = P->ctx->stream;
@@ -419,10 +631,14 @@ static int el_step_forward(adseis_elastic_plan* P, i64 s, double* in, double* ou
   ElPoints none{};
   const double* row = P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr;
   const double* prev = (P->nsrc > 0 && s >= 2) ? P->srcv + (s - 2) * P->nsrc : nullptr;
-  el_sigma_fwd<<<P->nblocks, blk, 0, st>>>(P->g, si, so, mt, cf, P->src.dev, prev);
+  const i64 widx = (out - P->hist) / P->slot_sz;
+  const ElPlaneRef sig_planes[2] = {{EA_HIST, widx, 2}, {EA_HIST, widx, 4}};  // fw3/fw4 difference sxx, sxy along x
+  el_sigma_fwd<<<P->nblocks, blk, 0, st>>>(P->g, si, so, mt, cf, P->src.dev, prev, el_make_fuse(P, 2, sig_planes));
   EL_LAUNCH_CHECK(P);
+  const ElPlaneRef vel_planes[2] = {{EA_HIST, widx, 0}, {EA_HIST, widx, 1}};
   el_vel_fwd<<<P->nblocks, blk, 0, st>>>(P->g, si, so, mt, cf, P->src.dev, row, sample ? P->rcv.dev : none,
-                                         (sample && P->nrcv > 0) ? P->rcvv : nullptr, (int)(P->p.NSTEP + 1), (int)s);
+                                         (sample && P->nrcv > 0) ? P->rcvv : nullptr, (int)(P->p.NSTEP + 1), (int)s,
+                                         el_make_fuse(P, 2, vel_planes));
   EL_LAUNCH_CHECK(P);
   return ADSEIS_OK;
 }
@@ -441,6 +657,7 @@ static int el_forward_sweep(adseis_elastic_plan* P, bool keep, bool save_ckpt) {
   const size_t sb = (size_t)P->slot_sz * 8;
   CUDA_TRY(cudaMemsetAsync(P->hist, 0, sb, st));  // slot 0 = zeros (Core.jl:37-45)
   if (P->nrcv > 0) CUDA_TRY(cudaMemsetAsync(P->rcvv, 0, (size_t)((P->p.NSTEP + 1) * P->nrcv) * 8, st));
+  TRY(el_barrier(P));  // slab plans: nobody pushes halo rows before everybody's memsets are done
   if (!keep) {
     for (i64 s = 1; s <= P->p.NSTEP; s++) TRY(el_step_forward(P, s, P->hist, P->hist, true));
     P->win_base = P->win_last = P->p.NSTEP;
@@ -451,6 +668,7 @@ static int el_forward_sweep(adseis_elastic_plan* P, bool keep, bool save_ckpt) {
   for (size_t k = 0; k < nseg; k++) {
     const i64 b = P->seg_b[k], e = P->seg_e[k];
     if (k > 0) {
+      TRY(el_barrier(P));  // slab plans: the neighbours' last pushes must have landed before halo rows are copied
       double* last = win_ptr(P, P->seg_b[k - 1], b);
       if (save_ckpt) CUDA_TRY(cudaMemcpyAsync(P->ckpt[k - 1], last, sb, cudaMemcpyDeviceToDevice, st));
       CUDA_TRY(cudaMemcpyAsync(P->hist, last, sb, cudaMemcpyDeviceToDevice, st));
@@ -479,13 +697,13 @@ ADSEIS_API int adseis_elastic_plan_forward(adseis_elastic_plan* P) {
 static int el_ensure_adjoint(adseis_elastic_plan* P, bool mat) {
   cudaStream_t st = P->ctx->stream;
   const ElGeom& g = P->g;
-  if (!P->adj) {
-    TRY(dev_alloc_zero(&P->adj, (size_t)(5 * g.plane + 2 * (4 * g.xm_sz + 4 * g.ym_sz)), st));
-    TRY(dev_alloc_zero(&P->gradsrcv, (size_t)(P->p.NSTEP * P->nsrc), st));
-  }
+  if (!P->adj) TRY(dev_alloc_zero(&P->adj, (size_t)(5 * g.plane + 2 * (4 * g.xm_sz + 4 * g.ym_sz)), st));
+  if (!P->gradsrcv) TRY(dev_alloc_zero(&P->gradsrcv, (size_t)(P->p.NSTEP * P->nsrc), st));
   if (mat && !P->Gl) {
     double** a[] = {&P->Gl, &P->Gm1, &P->Gm2, &P->Gr3, &P->Gr4};
     for (double** x : a) TRY(dev_alloc_zero(x, (size_t)g.plane, st));
+  }
+  if (mat && !P->grho) {
     TRY(dev_alloc_zero(&P->grho, (size_t)P->model_elems, st));
     TRY(dev_alloc_zero(&P->glam, (size_t)P->model_elems, st));
     TRY(dev_alloc_zero(&P->gmu, (size_t)P->model_elems, st));
@@ -530,10 +748,14 @@ ADSEIS_API int adseis_elastic_plan_gradient(adseis_elastic_plan* P, int want_mat
   dim3 blk(EL_BX, EL_BY);
   const int stride = (int)(NSTEP + 1);
   ElPoints none{};
+  TRY(el_barrier(P));  // slab plans: the memsets above are done everywhere before anybody pushes adjoint halo rows
   // start: velocity residuals of slot NSTEP into vbar; grad_srcv row NSTEP-1
   el_adj_start<<<P->nblocks, blk, 0, st>>>(g, side[0], P->rcv.dev, P->nrcv > 0 ? P->res : nullptr, stride, (int)NSTEP,
                                            P->src.dev, P->nsrc > 0 ? P->gradsrcv + (NSTEP - 1) * P->nsrc : nullptr);
   EL_LAUNCH_CHECK(P);
+  const ElPlaneRef vb_planes[2] = {{EA_ADJ, 0, 0}, {EA_ADJ, 0, 1}};               // vbar_x, vbar_y
+  const ElPlaneRef sb_planes[3] = {{EA_ADJ, 0, 2}, {EA_ADJ, 0, 3}, {EA_ADJ, 0, 4}};  // sigma_bar xx, yy, xy
+  TRY(el_halo_exchange(P, 2, vb_planes));
   const size_t sb = (size_t)P->slot_sz * 8;
   ElSlot zero{};
   for (i64 k = (i64)nseg - 1; k >= 0; k--) {
@@ -556,18 +778,22 @@ ADSEIS_API int adseis_elastic_plan_gradient(adseis_elastic_plan* P, int want_mat
       const double* resp = P->nrcv > 0 ? P->res : nullptr;
       double* grow = (s - 2 >= 0 && P->nsrc > 0 && s >= 2) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr;
       if (mat) {
-        el_vel_adj<true><<<P->nblocks, blk, 0, st>>>(g, bi, bo, fs, mt, cf, P->Gr3, P->Gr4, P->rcv.dev, resp, stride, (int)s);
+        el_vel_adj<true><<<P->nblocks, blk, 0, st>>>(g, bi, bo, fs, mt, cf, P->Gr3, P->Gr4, P->rcv.dev, resp, stride, (int)s,
+                                                     el_make_fuse(P, 3, sb_planes));
         EL_LAUNCH_CHECK(P);
         el_sigma_adj<true><<<P->nblocks, blk, 0, st>>>(g, bi, bo, fp, fs, mt, cf, P->Gl, P->Gm1, P->Gm2,
                                                        s >= 2 ? P->rcv.dev : none, s >= 2 ? resp : nullptr, stride,
-                                                       (int)(s - 1), s >= 2 ? P->src.dev : none, grow);
+                                                       (int)(s - 1), s >= 2 ? P->src.dev : none, grow,
+                                                       el_make_fuse(P, 2, vb_planes));
         EL_LAUNCH_CHECK(P);
       } else {
-        el_vel_adj<false><<<P->nblocks, blk, 0, st>>>(g, bi, bo, zero, mt, cf, nullptr, nullptr, P->rcv.dev, resp, stride, (int)s);
+        el_vel_adj<false><<<P->nblocks, blk, 0, st>>>(g, bi, bo, zero, mt, cf, nullptr, nullptr, P->rcv.dev, resp, stride,
+                                                      (int)s, el_make_fuse(P, 3, sb_planes));
         EL_LAUNCH_CHECK(P);
         el_sigma_adj<false><<<P->nblocks, blk, 0, st>>>(g, bi, bo, zero, zero, mt, cf, nullptr, nullptr, nullptr,
                                                         s >= 2 ? P->rcv.dev : none, s >= 2 ? resp : nullptr, stride,
-                                                        (int)(s - 1), s >= 2 ? P->src.dev : none, grow);
+                                                        (int)(s - 1), s >= 2 ? P->src.dev : none, grow,
+                                                        el_make_fuse(P, 2, vb_planes));
         EL_LAUNCH_CHECK(P);
       }
     }
@@ -576,6 +802,10 @@ ADSEIS_API int adseis_elastic_plan_gradient(adseis_elastic_plan* P, int want_mat
     CUDA_TRY(cudaMemsetAsync(P->grho, 0, (size_t)P->model_elems * 8, st));
     CUDA_TRY(cudaMemsetAsync(P->glam, 0, (size_t)P->model_elems * 8, st));
     CUDA_TRY(cudaMemsetAsync(P->gmu, 0, (size_t)P->model_elems * 8, st));
+    if (P->p.variant == 0) {  // un-averaging reads the accumulator row above my first owned row
+      const ElPlaneRef gp[3] = {{EA_GACC, 0, 0}, {EA_GACC, 0, 1}, {EA_GACC, 0, 4}};
+      TRY(el_halo_exchange(P, 3, gp));
+    }
     dim3 gg((unsigned)((g.W + 127) / 128), (unsigned)(g.own1 - g.own0));
     k_el_grad_finalize<<<gg, 128, 0, st>>>(g, P->p.variant == 0, P->off, P->Gl, P->Gm1, P->Gm2, P->Gr3, P->Gr4, P->grho,
                                            P->glam, P->gmu);
@@ -609,6 +839,7 @@ ADSEIS_API int adseis_elastic_plan_get(adseis_elastic_plan* P, int what, double*
   }
   if (n > 0) CUDA_TRY(cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyDefault, P->ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(P->ctx->stream));
+  TRY(el_halo_check(P));
   return ADSEIS_OK;
 }
 
@@ -659,14 +890,51 @@ ADSEIS_API int adseis_elastic_plan_info(adseis_elastic_plan* P, int64_t info[8])
 }
 
 ADSEIS_API int adseis_elastic_plan_ipc_export(adseis_elastic_plan* P, void* handle_out) {
-  (void)P; (void)handle_out;
-  adseis_set_error("elastic_plan_ipc_export: slab decomposition of the elastic path is not available in this build");
-  return ADSEIS_ECOMM;
+  REQUIRE(P && handle_out, "elastic_plan_ipc_export: null");
+  if (!P->arena) {
+    adseis_set_error("elastic_plan_ipc_export: not a slab plan (nranks == 1)");
+    return ADSEIS_ESTATE;
+  }
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, P->arena));
+  static_assert(sizeof(h) == ADSEIS_IPC_HANDLE_BYTES, "IPC handle size");
+  memcpy(handle_out, &h, sizeof(h));
+  return ADSEIS_OK;
 }
+
 ADSEIS_API int adseis_elastic_plan_ipc_connect(adseis_elastic_plan* P, const void* lo, const void* hi) {
-  (void)P; (void)lo; (void)hi;
-  adseis_set_error("elastic_plan_ipc_connect: slab decomposition of the elastic path is not available in this build");
-  return ADSEIS_ECOMM;
+  REQUIRE(P, "elastic_plan_ipc_connect: null");
+  if (!P->arena) {
+    adseis_set_error("elastic_plan_ipc_connect: not a slab plan (nranks == 1)");
+    return ADSEIS_ESTATE;
+  }
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  const void* hs[2] = {lo, hi};
+  const bool need[2] = {P->slab.rank > 0, P->slab.rank < P->slab.nranks - 1};
+  for (int k = 0; k < 2; k++) {
+    if (!need[k]) continue;
+    REQUIRE(hs[k], "elastic_plan_ipc_connect: missing handle of rank %d", P->slab.rank + (k ? 1 : -1));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hs[k], sizeof(h));
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      adseis_set_error("elastic_plan_ipc_connect: cudaIpcOpenMemHandle(rank %d) -> %s", P->slab.rank + (k ? 1 : -1),
+                       cudaGetErrorString(e));
+      return ADSEIS_ECOMM;
+    }
+    P->peer[k] = (char*)ptr;
+    CUDA_TRY(cudaMemcpy(&P->dpeer[k], ptr, sizeof(P->dpeer[k]), cudaMemcpyDeviceToHost));
+    const adseis_elastic_plan::Desc& d = P->dpeer[k];
+    if (d.magic != EL_DESC_MAGIC || d.ld != P->desc.ld || d.win != P->desc.win) {
+      adseis_set_error("elastic_plan_ipc_connect: neighbour %d has an incompatible layout (magic %llx ld %lld win %lld; "
+                       "mine ld %lld win %lld)", P->slab.rank + (k ? 1 : -1), d.magic, d.ld, d.win, P->desc.ld, P->desc.win);
+      return ADSEIS_ECOMM;
+    }
+  }
+  P->connected = true;
+  return ADSEIS_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -67,6 +67,74 @@ struct ElPoints {
   const int *xstart, *xperm;  // per unique entry: points of the OTHER set on the same (cell, field)
 };
 
+// Slab decomposition (rows are split over GPUs, halo = 2 rows per interior side), fused into the step kernels; all
+// null / zero on a single GPU.  The row tiles that contain my first / last owned rows are launched first (perm),
+// wait until the neighbour's PREVIOUS launch has delivered the halo rows they read, and -- after their epilogue --
+// store their columns of my two edge rows of every field this launch produces straight into the neighbour's halo
+// rows over NVLink, then publish with a system-scope fence + atomic on the neighbour's flag.  Replaces the 18
+// mpi_halo_exchange2 ops per step of src/MPIElastic.jl:411-436, 515-516, 551, 582, 618.
+#define EL_HALO 2
+struct ElFuse {
+  const int* perm;              // launch order -> logical CTA id (edge row tiles first), or null
+  int has_lo, has_hi;
+  int nf;                       // fields pushed by this launch (0..3)
+  const double* src[3];         // my planes
+  double* lo[3];                // rank-1: its upper halo rows (local rows Hl'-2, Hl'-1) of the same plane
+  double* hi[3];                // rank+1: its lower halo rows (local rows 0, 1)
+  unsigned long long *sig_lo, *sig_hi;   // neighbour flags to bump (peer pointers)
+  unsigned long long* my_flags;          // [3] bumped by rank-1's step kernels, [4] by rank+1's, [2] error
+  unsigned long long expect_lo, expect_hi;
+};
+
+__device__ __forceinline__ int el_bid(const ElFuse& f) { return f.perm ? f.perm[blockIdx.x] : blockIdx.x; }
+
+__device__ __forceinline__ void el_fuse_wait(const ElFuse& f, bool t_lo, bool t_hi) {
+  if (!(t_lo || t_hi)) return;  // CTA-uniform
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    volatile unsigned long long* fl = f.my_flags;
+    unsigned long long spins = 0;
+    while ((t_lo && fl[3] < f.expect_lo) || (t_hi && fl[4] < f.expect_hi)) {
+      if (++spins > (1ULL << 26)) { fl[2] = 1ULL; break; }  // neighbour lost: report, do not hang
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+
+// A row tile is an edge tile when it holds one of my first / last EL_HALO owned rows next to a neighbour: those are
+// the rows it must push, and (a superset of) the tiles whose stencils read halo rows.
+__device__ __forceinline__ void el_tile_edges(const ElGeom& g, const ElFuse& f, int tr, bool* t_lo, bool* t_hi) {
+  const int ra = g.own0 + tr * EL_ROWS, rb = min(g.own1, ra + EL_ROWS);
+  *t_lo = f.has_lo && ra < g.own0 + EL_HALO;
+  *t_hi = f.has_hi && rb > g.own1 - EL_HALO;
+}
+
+// push this tile's columns of my edge rows, then signal (called by all threads of an edge CTA)
+__device__ __forceinline__ void el_fuse_push(const ElGeom& g, const ElFuse& f, bool t_lo, bool t_hi, int tr, int q) {
+  if (!(t_lo || t_hi)) return;
+  __syncthreads();  // all cells (and point injections) of this CTA are written
+  if (q < g.ld) {
+    const int ra = g.own0 + tr * EL_ROWS, rb = min(g.own1, ra + EL_ROWS);
+    for (int k = 0; k < f.nf; k++) {
+      // threadIdx.y = 0..3 -> (row 0/1) x (lo/hi)
+      const int r = threadIdx.y & 1;
+      if ((threadIdx.y >> 1) == 0) {
+        const int li = g.own0 + r;
+        if (t_lo && li >= ra && li < rb) f.lo[k][(i64)r * g.ld + q] = f.src[k][(i64)li * g.ld + q];
+      } else {
+        const int li = g.own1 - EL_HALO + r;
+        if (t_hi && li >= ra && li < rb) f.hi[k][(i64)r * g.ld + q] = f.src[k][(i64)li * g.ld + q];
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    if (t_lo) atomicAdd_system(f.sig_lo, 1ULL);
+    if (t_hi) atomicAdd_system(f.sig_hi, 1ULL);
+  }
+}
+
 __device__ __forceinline__ bool el_in(const ElGeom& g, int k, int gp, int q) {
   return gp >= g.p0[k] && gp <= g.p1[k] && q >= g.q0[k] && q <= g.q1[k];
 }
@@ -104,10 +172,14 @@ __device__ __forceinline__ double* el_field(const ElSlot& s, int f) {
 //   `src`/`srcv_prev`: stress sources of step s-1 that are still pending (null for s == 1)
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(EL_THREADS)
-el_sigma_fwd(ElGeom g, ElSlot in, ElSlot out, ElMat mt, ElCoef cf, ElPoints src, const double* __restrict__ srcv_prev) {
-  const int bid = blockIdx.x;
+el_sigma_fwd(ElGeom g, ElSlot in, ElSlot out, ElMat mt, ElCoef cf, ElPoints src, const double* __restrict__ srcv_prev,
+             ElFuse f) {
+  const int bid = el_bid(f);
   const int tc = bid % g.ntc, tr = bid / g.ntc;
   const int q = tc * EL_BX + threadIdx.x;
+  bool t_lo, t_hi;
+  el_tile_edges(g, f, tr, &t_lo, &t_hi);
+  el_fuse_wait(f, t_lo, t_hi);
   int sa = 0, sb = 0;
   if (src.blk != nullptr && srcv_prev != nullptr) { sa = src.blk[bid]; sb = src.blk[bid + 1]; }
   const double* __restrict__ vx = in.vx;
@@ -166,6 +238,7 @@ el_sigma_fwd(ElGeom g, ElSlot in, ElSlot out, ElMat mt, ElCoef cf, ElPoints src,
     }
     out.sxx[c] = sxx; out.syy[c] = syy; out.sxy[c] = sxy;
   }
+  el_fuse_push(g, f, t_lo, t_hi, tr, q);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -175,10 +248,13 @@ el_sigma_fwd(ElGeom g, ElSlot in, ElSlot out, ElMat mt, ElCoef cf, ElPoints src,
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(EL_THREADS)
 el_vel_fwd(ElGeom g, ElSlot in, ElSlot out, ElMat mt, ElCoef cf, ElPoints src, const double* __restrict__ srcv_row,
-           ElPoints rcv, double* __restrict__ rcvv, int rcv_stride, int slot) {
-  const int bid = blockIdx.x;
+           ElPoints rcv, double* __restrict__ rcvv, int rcv_stride, int slot, ElFuse f) {
+  const int bid = el_bid(f);
   const int tc = bid % g.ntc, tr = bid / g.ntc;
   const int q = tc * EL_BX + threadIdx.x;
+  bool t_lo, t_hi;
+  el_tile_edges(g, f, tr, &t_lo, &t_hi);
+  el_fuse_wait(f, t_lo, t_hi);
   const double* __restrict__ sxx = out.sxx;
   const double* __restrict__ syy = out.syy;
   const double* __restrict__ sxy = out.sxy;
@@ -233,28 +309,30 @@ el_vel_fwd(ElGeom g, ElSlot in, ElSlot out, ElMat mt, ElCoef cf, ElPoints src, c
   int ia = 0, ib = 0, ra = 0, rb = 0;
   if (src.blk != nullptr && srcv_row != nullptr) { ia = src.blk[bid]; ib = src.blk[bid + 1]; }
   if (rcv.blk != nullptr && rcvv != nullptr) { ra = rcv.blk[bid]; rb = rcv.blk[bid + 1]; }
-  if (ib == ia && rb == ra) return;
-  __syncthreads();
-  const int tid = threadIdx.y * EL_BX + threadIdx.x;
-  for (int k = ia + tid; k < ib; k += EL_THREADS) {
-    const int f = src.field[k];
-    if (f <= 1) {
-      double* fld = el_field(out, f);
-      double v = fld[src.cell[k]];
-      for (int m = src.start[k]; m < src.start[k + 1]; m++) v += srcv_row[src.perm[m]];
-      fld[src.cell[k]] = v;
-    }
-  }
-  if (rb > ra) {
+  if (ib != ia || rb != ra) {  // CTA-uniform
     __syncthreads();
-    for (int k = ra + tid; k < rb; k += EL_THREADS) {
-      const int f = rcv.field[k];
-      double v = el_field(out, f)[rcv.cell[k]];
-      if (f >= 2 && srcv_row != nullptr)  // post-injection value of a stress component
-        for (int m = rcv.xstart[k]; m < rcv.xstart[k + 1]; m++) v += srcv_row[rcv.xperm[m]];
-      for (int m = rcv.start[k]; m < rcv.start[k + 1]; m++) rcvv[(i64)rcv.perm[m] * rcv_stride + slot] = v;
+    const int tid = threadIdx.y * EL_BX + threadIdx.x;
+    for (int k = ia + tid; k < ib; k += EL_THREADS) {
+      const int fd = src.field[k];
+      if (fd <= 1) {
+        double* fld = el_field(out, fd);
+        double v = fld[src.cell[k]];
+        for (int m = src.start[k]; m < src.start[k + 1]; m++) v += srcv_row[src.perm[m]];
+        fld[src.cell[k]] = v;
+      }
+    }
+    if (rb > ra) {
+      __syncthreads();
+      for (int k = ra + tid; k < rb; k += EL_THREADS) {
+        const int fd = rcv.field[k];
+        double v = el_field(out, fd)[rcv.cell[k]];
+        if (fd >= 2 && srcv_row != nullptr)  // post-injection value of a stress component
+          for (int m = rcv.xstart[k]; m < rcv.xstart[k + 1]; m++) v += srcv_row[rcv.xperm[m]];
+        for (int m = rcv.start[k]; m < rcv.start[k + 1]; m++) rcvv[(i64)rcv.perm[m] * rcv_stride + slot] = v;
+      }
     }
   }
+  el_fuse_push(g, f, t_lo, t_hi, tr, q);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -363,10 +441,14 @@ __device__ __forceinline__ double el_db4(const ElAdjCtx& A, int li, int q) {
 template <bool MATGRAD>
 __global__ void __launch_bounds__(EL_THREADS)
 el_vel_adj(ElGeom g, ElSlot b, ElSlot bout, ElSlot fwd, ElMat mt, ElCoef cf, double* __restrict__ Gr3,
-           double* __restrict__ Gr4, ElPoints rcv, const double* __restrict__ res, int res_stride, int slot) {
-  const int bid = blockIdx.x;
+           double* __restrict__ Gr4, ElPoints rcv, const double* __restrict__ res, int res_stride, int slot,
+           ElFuse f) {
+  const int bid = el_bid(f);
   const int tc = bid % g.ntc, tr = bid / g.ntc;
   const int q = tc * EL_BX + threadIdx.x;
+  bool t_lo, t_hi;
+  el_tile_edges(g, f, tr, &t_lo, &t_hi);
+  el_fuse_wait(f, t_lo, t_hi);
   int ra = 0, rb = 0;
   if (rcv.blk != nullptr && res != nullptr) { ra = rcv.blk[bid]; rb = rcv.blk[bid + 1]; }
   const ElAdjCtx A{g, b, mt, cf};
@@ -441,6 +523,7 @@ el_vel_adj(ElGeom g, ElSlot b, ElSlot bout, ElSlot fwd, ElMat mt, ElCoef cf, dou
     }
     bout.sxx[c] = sxx; bout.syy[c] = syy; bout.sxy[c] = sxy;
   }
+  el_fuse_push(g, f, t_lo, t_hi, tr, q);
 }
 
 // Epilogue of the adjoint sigma pass (also launched on its own to start the reverse sweep at slot NSTEP):
@@ -448,8 +531,7 @@ el_vel_adj(ElGeom g, ElSlot b, ElSlot bout, ElSlot fwd, ElMat mt, ElCoef cf, dou
 // velocity types from vbar, stress types from sigma_bar plus the still pending stress residuals of that slot.
 __device__ __forceinline__ void el_adj_epilogue(const ElGeom& g, const ElSlot& bout, const ElPoints& rcv,
                                                 const double* __restrict__ res, int res_stride, int slot_prev,
-                                                const ElPoints& src, double* __restrict__ gsrcv_row) {
-  const int bid = blockIdx.x;
+                                                const ElPoints& src, double* __restrict__ gsrcv_row, int bid) {
   int ra = 0, rb = 0, sa = 0, sb = 0;
   if (rcv.blk != nullptr && res != nullptr) { ra = rcv.blk[bid]; rb = rcv.blk[bid + 1]; }
   if (src.blk != nullptr && gsrcv_row != nullptr) { sa = src.blk[bid]; sb = src.blk[bid + 1]; }
@@ -480,7 +562,7 @@ __device__ __forceinline__ void el_adj_epilogue(const ElGeom& g, const ElSlot& b
 __global__ void __launch_bounds__(EL_THREADS)
 el_adj_start(ElGeom g, ElSlot bout, ElPoints rcv, const double* __restrict__ res, int res_stride, int slot_prev,
              ElPoints src, double* __restrict__ gsrcv_row) {
-  el_adj_epilogue(g, bout, rcv, res, res_stride, slot_prev, src, gsrcv_row);
+  el_adj_epilogue(g, bout, rcv, res, res_stride, slot_prev, src, gsrcv_row, blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -494,10 +576,13 @@ template <bool MATGRAD>
 __global__ void __launch_bounds__(EL_THREADS)
 el_sigma_adj(ElGeom g, ElSlot b, ElSlot bout, ElSlot fwdv, ElSlot fwdm, ElMat mt, ElCoef cf, double* __restrict__ Gl,
              double* __restrict__ Gm1, double* __restrict__ Gm2, ElPoints rcv, const double* __restrict__ res,
-             int res_stride, int slot_prev, ElPoints src, double* __restrict__ gsrcv_row) {
-  const int bid = blockIdx.x;
+             int res_stride, int slot_prev, ElPoints src, double* __restrict__ gsrcv_row, ElFuse f) {
+  const int bid = el_bid(f);
   const int tc = bid % g.ntc, tr = bid / g.ntc;
   const int q = tc * EL_BX + threadIdx.x;
+  bool t_lo, t_hi;
+  el_tile_edges(g, f, tr, &t_lo, &t_hi);
+  el_fuse_wait(f, t_lo, t_hi);
   const ElAdjCtx A{g, b, mt, cf};
   const int ld = g.ld, NX = g.NX, NY = g.NY;
   const double ix = 1.0 / (24 * g.dx), iy = 1.0 / (24 * g.dy);
@@ -567,5 +652,6 @@ el_sigma_adj(ElGeom g, ElSlot b, ElSlot bout, ElSlot fwdv, ElSlot fwdm, ElMat mt
     }
     bout.vx[c] = vx; bout.vy[c] = vy;
   }
-  el_adj_epilogue(g, bout, rcv, res, res_stride, slot_prev, src, gsrcv_row);
+  el_adj_epilogue(g, bout, rcv, res, res_stride, slot_prev, src, gsrcv_row, bid);
+  el_fuse_push(g, f, t_lo, t_hi, tr, q);
 }

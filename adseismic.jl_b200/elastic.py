@@ -26,7 +26,7 @@ def compute_PML_Params(param: ElasticPropagatorParams):
 class ElasticPlan:
     """Device-resident state for one (params, sources, receivers) triple -- wraps adseis_elastic_plan_*."""
 
-    def __init__(self, param, srci, srcj, srctype, rcvi, rcvj, rcvtype, ctx=None, hist_bytes_budget=0):
+    def __init__(self, param, srci, srcj, srctype, rcvi, rcvj, rcvtype, ctx=None, hist_bytes_budget=0, slab=None):
         self.lib = _lib.load()
         self.ctx = ctx or _lib.default_context()
         self.param = param
@@ -36,7 +36,11 @@ class ElasticPlan:
         self.model_shape = param.model_shape()
         pc = param.to_c()
         h = _lib.vp()
-        check(self.lib.adseis_elastic_plan_create(self.ctx.handle, C.byref(pc), None, self.nsrc, pi(self.srci),
+        sl = None
+        if slab is not None:   # (rank, nranks, row0, row1): rows of the internal array owned by this GPU
+            self._slab = _lib.SlabC(int(slab[0]), int(slab[1]), int(slab[2]), int(slab[3]))
+            sl = C.byref(self._slab)
+        check(self.lib.adseis_elastic_plan_create(self.ctx.handle, C.byref(pc), sl, self.nsrc, pi(self.srci),
                                                   pi(self.srcj), pi(self.srctype), self.nrcv, pi(self.rcvi),
                                                   pi(self.rcvj), pi(self.rcvtype), int(hist_bytes_budget),
                                                   C.byref(h)))
@@ -109,6 +113,18 @@ class ElasticPlan:
         check(self.lib.adseis_elastic_plan_info(self.handle, pi(a)))
         return dict(hist_slots=int(a[0]), segments=int(a[1]), launches=int(a[2]), local_rows=int(a[3]),
                     pitch=int(a[4]), recomputed_steps=int(a[5]), planned_segments=int(a[6]), slot_doubles=int(a[7]))
+
+    def ipc_export(self):
+        """64-byte CUDA IPC handle of this slab plan's device arena (to be all-gathered by the host framework)."""
+        buf = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        check(self.lib.adseis_elastic_plan_ipc_export(self.handle, C.cast(buf, C.c_void_p)))
+        return bytes(buf.raw)
+
+    def ipc_connect(self, handle_lo, handle_hi):
+        lo = C.create_string_buffer(handle_lo, _lib.IPC_HANDLE_BYTES) if handle_lo is not None else None
+        hi = C.create_string_buffer(handle_hi, _lib.IPC_HANDLE_BYTES) if handle_hi is not None else None
+        check(self.lib.adseis_elastic_plan_ipc_connect(self.handle, C.cast(lo, C.c_void_p) if lo else None,
+                                                       C.cast(hi, C.c_void_p) if hi else None))
 
     def close(self):
         if getattr(self, "handle", None) is not None:

@@ -15,6 +15,7 @@ import numpy as np
 
 from . import _lib
 from .acoustic import AcousticPlan
+from .elastic import ElasticPlan
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -221,6 +222,109 @@ class DomainDecomposedAcoustic:
         import torch
         t = torch.from_numpy(self.plan.grad_srcv()).to(self.dev)
         return all_reduce_sum_(t).cpu().numpy()
+
+    def close(self):
+        self.plan.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# domain decomposition (elastic; replaces src/MPIElastic.jl's M x N blocks + 18 mpi_halo_exchange2 per step)
+# ------------------------------------------------------------------------------------------------------------
+EL_HALO = 2
+
+
+def elastic_slab_partition(param, world, rank):
+    """(row0, row1): rows of the INTERNAL elastic array ((NX+2) padded rows for variant 0, NX + 2*2 ghost rows for
+    variant 1) owned by `rank` (adseis_elastic_slab_partition)."""
+    s = _lib.SlabC()
+    pc = param.to_c()
+    _lib.check(_lib.load().adseis_elastic_slab_partition(C.byref(pc), int(world), int(rank), C.byref(s)))
+    return int(s.row0), int(s.row1)
+
+
+def elastic_owned_points(param, pi, row0, row1):
+    """Mask of sources/receivers whose internal row lies in [row0,row1): 1-based padded index (variant 0) or
+    1-based global index (variant 1, MPIElastic.jl:85-86) -> 0-based internal row."""
+    gi = np.asarray(pi, dtype=np.int64) + (-1 if param.variant == 0 else 1)
+    return (gi >= row0) & (gi < row1)
+
+
+class DomainDecomposedElastic:
+    """One slab of the elastic solver per rank of the current process group.  Inputs are the GLOBAL arrays on every
+    rank; results are reduced on request (receivers / sources are owned by exactly one slab)."""
+
+    def __init__(self, param, srci, srcj, srctype, rcvi, rcvj, rcvtype, ctx=None, hist_slots=None):
+        import torch
+        dist = _dist()
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.param = param
+        self.ctx = ctx or _lib.default_context()
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        if self.world == 1:
+            self.plan = ElasticPlan(param, srci, srcj, srctype, rcvi, rcvj, rcvtype, ctx=self.ctx)
+            return
+        self.row0, self.row1 = elastic_slab_partition(param, self.world, self.rank)
+        # every rank must use the same history window: probe the slot size with a 1-slot plan-free estimate
+        H, W = param.NX + (2 if param.variant == 0 else 4), param.NY + (2 if param.variant == 0 else 4)
+        ld = (W + 15) // 16 * 16
+        Hl = (self.row1 - self.row0) + (EL_HALO if self.rank > 0 else 0) + (EL_HALO if self.rank < self.world - 1 else 0)
+        slot_bytes_max = int(all_reduce_scalar(6 * Hl * ld * 8, "max", device=self.dev))   # 5 planes + compact memories
+        if hist_slots is None:
+            free_b, _ = self.ctx.mem_info()
+            reserve = 40 * Hl * ld * 8 + 6 * H * W * 8 + (6 << 30)
+            slots = max(2, (free_b - reserve) // slot_bytes_max) if free_b > reserve else 2
+            slots = min(slots, param.NSTEP + 1)
+            hist_slots = int(all_reduce_scalar(slots, "min", device=self.dev))
+        self.hist_slots = int(hist_slots)
+        slab = (self.rank, self.world, self.row0, self.row1)
+        # the C side sizes the window as budget // slot_bytes: ask for exactly hist_slots slots of MY slot size
+        probe = ElasticPlan(param, [], [], [], [], [], [], ctx=self.ctx, slab=slab, hist_bytes_budget=1)
+        my_slot_bytes = probe.info()["slot_doubles"] * 8
+        probe.close()
+        self.plan = ElasticPlan(param, srci, srcj, srctype, rcvi, rcvj, rcvtype, ctx=self.ctx, slab=slab,
+                                hist_bytes_budget=self.hist_slots * my_slot_bytes)
+        assert self.plan.info()["hist_slots"] == self.hist_slots, (self.plan.info(), self.hist_slots)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.plan.ipc_export())
+        lo = handles[self.rank - 1] if self.rank > 0 else None
+        hi = handles[self.rank + 1] if self.rank < self.world - 1 else None
+        self.plan.ipc_connect(lo, hi)
+        dist.barrier()
+
+    def set_model(self, rho, lam, mu):
+        self.plan.set_model(rho, lam, mu)
+
+    def set_srcv(self, srcv):
+        self.plan.set_srcv(srcv)
+
+    def set_obs(self, obs):
+        self.plan.set_obs(obs)
+
+    def forward(self):
+        self.plan.forward()
+
+    def gradient(self, material_grads=True):
+        self.plan.gradient(material_grads)
+
+    def _sum(self, a):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+        return all_reduce_sum_(t).cpu().numpy()
+
+    def loss(self):
+        return all_reduce_scalar(self.plan.loss(), "sum", device=self.dev)
+
+    def rcvv(self):
+        return self._sum(self.plan.rcvv())          # every receiver is owned by exactly one slab, the others hold 0
+
+    def grad_srcv(self):
+        return self._sum(self.plan.grad_srcv())
+
+    def grads(self, reduce=True):
+        """(grad_rho, grad_lambda, grad_mu): own rows filled, the rest zero; summed over ranks when reduce."""
+        out = (self.plan.grad_rho(), self.plan.grad_lambda(), self.plan.grad_mu())
+        return tuple(self._sum(a) for a in out) if (reduce and self.world > 1) else out
 
     def close(self):
         self.plan.close()

@@ -194,6 +194,14 @@ typedef struct adseis_elastic_plan adseis_elastic_plan;
  * (adbroadcast idx 3/4 returns its first argument, Core.jl:686-693); K_MAX_PML must be 1. */
 int adseis_elastic_cpml_profiles(const adseis_elastic_params* p, int axis, double* a, double* b);
 
+/* Suggested slab bounds over the rows of the INTERNAL elastic array (variant 0: the padded (NX+2) rows; variant 1:
+ * NX rows + 2 ghost rows per side, MPIElastic.jl:175-189), balanced on the NX interior rows.  Host-only helper.
+ * A slab plan keeps 2 halo rows per interior side (4th-order staggered stencils; the reference's
+ * mpi_halo_exchange2, MPIElastic.jl:475-480); its boundaries must stay 2 rows clear of the x-CPML strips. */
+int adseis_elastic_slab_partition(const adseis_elastic_params* p, int32_t nranks, int32_t rank, adseis_slab* out);
+
+/* slab == NULL (or nranks == 1): single GPU.  Sources / receivers are given with GLOBAL indices; a slab plan keeps
+ * the ones whose row it owns (MPIElastic.jl:71-86, 116-131). */
 int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_params* p, const adseis_slab* slab,
                                int64_t nsrc, const int64_t* srci, const int64_t* srcj, const int64_t* srctype,
                                int64_t nrcv, const int64_t* rcvi, const int64_t* rcvj, const int64_t* rcvtype,
@@ -217,6 +225,11 @@ int adseis_elastic_plan_get(adseis_elastic_plan* plan, int what, double* dst, in
 int adseis_elastic_plan_get_snapshot(adseis_elastic_plan* plan, int field, int64_t slot, double* dst,
                                      int to_device);
 int adseis_elastic_plan_info(adseis_elastic_plan* plan, int64_t info[8]);
+/* Slab plans (one process per GPU): same protocol as the acoustic one -- export the arena's IPC handle, all-gather,
+ * connect to rank-1 / rank+1.  Afterwards every time-step kernel stores its two edge rows of the fields it produced
+ * (sigma_xx, sigma_xy after the stress pass; v_x, v_y after the velocity pass; their adjoints in the reverse sweep)
+ * straight into the neighbour's halo rows over NVLink.  Results: GET_RCVV / GET_GRAD_SRCV hold zeros for points
+ * owned elsewhere, GET_GRAD_* hold this slab's rows (rest zero), GET_LOSS the partial sum -- reduce with a SUM. */
 int adseis_elastic_plan_ipc_export(adseis_elastic_plan* plan, void* handle_out);
 int adseis_elastic_plan_ipc_connect(adseis_elastic_plan* plan, const void* handle_lo, const void* handle_hi);
 

@@ -62,6 +62,63 @@ def main():
             print("DD x%d slots=%s ok: loss rel %.1e grad_c rel %.1e grad_srcv rel %.1e segments %d" %
                   (world, slots, abs(L - L0) / L0, relerr(g, g0), relerr(s, s0), info["segments"]), flush=True)
         dd.close()
+    # ---------------- elastic domain decomposition (both reference variants) ----------------
+    # the reference's own test is decomposed == undecomposed (examples/mpi_elastic/verification/verify_backward.jl)
+    for variant, (NX, NY, NSTEP) in ((1, (36 * world + 3, 150, 24)), (0, (34 * world + 1, 140, 22))):
+        rng2 = np.random.default_rng(7 + variant)
+        h, dte, npml = 1.0, 1e-4, 8
+        H, W = po.elastic_dims(variant, NX, NY)
+        ax, bx = po.elastic_cpml_1d(NX, h, dte, npml=npml, vp_ref=3300.0, alpha_max=np.pi * 15)
+        ay, by = po.elastic_cpml_1d(NY, h, dte, npml=npml, vp_ref=3300.0, alpha_max=np.pi * 15)
+        vpm = 3000.0 * (1 + 0.1 * rng2.random((H, W)))
+        vsm = vpm / 1.732 * (1 + 0.05 * rng2.random((H, W)))
+        rho = 2800.0 * (1 + 0.1 * rng2.random((H, W)))
+        mu, lam = rho * vsm * vsm, rho * (vpm * vpm - 2 * vsm * vsm)
+        pe = A.ElasticPropagatorParams(NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=h, DELTAY=h, DELTAT=dte, NPOINTS_PML=npml,
+                                       vp_ref=3300.0, ALPHA_MAX_PML=np.pi * 15, variant=variant)
+        nsrc, nrcv = 8, 40
+        srci = rng2.integers(3, NX - 2, nsrc); srcj = rng2.integers(3, NY - 2, nsrc)
+        srctype = np.arange(nsrc) % 5
+        rcvi = rng2.integers(1, NX + 1, nrcv); rcvj = rng2.integers(1, NY + 1, nrcv)
+        rcvtype = rng2.integers(0, 5, nrcv)
+        # sources and receivers of every type on the rows next to every slab boundary
+        ioff = 1 if variant == 0 else -1     # internal 0-based row -> the caller's 1-based index
+        for r in range(world - 1):
+            b = parallel.elastic_slab_partition(pe, world, r)[1]    # first internal row of slab r+1
+            for k in range(5):
+                rcvi[(10 * r + 2 * k) % nrcv] = b - 1 + ioff; rcvtype[(10 * r + 2 * k) % nrcv] = k
+                rcvi[(10 * r + 2 * k + 1) % nrcv] = b + ioff; rcvtype[(10 * r + 2 * k + 1) % nrcv] = k
+            srci[(2 * r) % nsrc] = b - 1 + ioff
+            srci[(2 * r + 1) % nsrc] = b + ioff
+        srcv = np.stack([po.ricker(NSTEP, 6.0 + k, 10.0 + k, 1e3 * (1 + k)) for k in range(nsrc)], 1)
+        args = (variant, NX, NY, NSTEP, dte, h, h, ax, bx, ay, by, rho, lam, mu, srci, srcj, srctype, srcv, rcvi, rcvj,
+                rcvtype)
+        r0, _ = po.elastic_forward(*args)
+        obs = 0.6 * r0 + 0.05 * np.abs(r0).max() * rng2.standard_normal(r0.shape)
+        O = po.elastic_misfit_grad(*args, obs)
+        unpad = (lambda a: a) if variant == 0 else (lambda a: a[2:-2, 2:-2])
+        for slots in (None, 7):
+            dd = parallel.DomainDecomposedElastic(pe, srci, srcj, srctype, rcvi, rcvj, rcvtype, ctx=ctx, hist_slots=slots)
+            dd.set_model(unpad(rho), unpad(lam), unpad(mu)); dd.set_srcv(srcv); dd.set_obs(obs)
+            dd.forward()
+            r = dd.rcvv()
+            assert np.array_equal(r, r0), "rank %d: elastic DD traces differ (max %g)" % (rank, np.abs(r - r0).max())
+            dd.gradient(True)
+            L, gs = dd.loss(), dd.grad_srcv()
+            gr, gl, gm = dd.grads()
+            assert abs(L - O["loss"]) / O["loss"] < 1e-12, (L, O["loss"])
+            errs = dict(srcv=relerr(gs, O["grad_srcv"]), rho=relerr(gr, unpad(O["grad_rho"])),
+                        lam=relerr(gl, unpad(O["grad_lam"])), mu=relerr(gm, unpad(O["grad_mu"])))
+            assert max(errs.values()) < 1e-10, errs
+            info = dd.plan.info()
+            dd.gradient(False)                      # source-time-function gradient: no forward history at all
+            assert relerr(dd.grad_srcv(), O["grad_srcv"]) < 1e-10
+            if slots:
+                assert info["segments"] > 1 and info["recomputed_steps"] > 0
+            if rank == 0:
+                print("elastic DD x%d variant %d slots=%s ok: %s segments %d" % (world, variant, slots,
+                      " ".join("%s %.1e" % kv for kv in errs.items()), info["segments"]), flush=True)
+            dd.close()
     # ---------------- shot parallelism ----------------
     nshots = 5
     NX, NY, NSTEP = 60, 300, 40

@@ -155,3 +155,24 @@ def _dd_fn(rank, world):
 def test_slab_halo_protocol_gloo():
     for err in _spawn(_dd_fn, 2):
         assert err == 0.0
+
+
+def test_elastic_slab_partition_and_ownership():
+    """Host logic of the elastic slab decomposition (MPIElastic.jl block ownership, :71-86, 116-131): the slabs tile
+    the internal rows exactly, interior rows are balanced, every source / receiver is owned by exactly one slab."""
+    import adseis_b200 as A
+    from adseis_b200 import parallel
+    rng = np.random.default_rng(3)
+    for variant, ghost in ((0, 1), (1, 2)):
+        for NX, world in ((2000, 8), (37, 2), (103, 4), (16, 4)):
+            p = A.ElasticPropagatorParams(NX=NX, NY=50, NSTEP=4, variant=variant)
+            bounds = [parallel.elastic_slab_partition(p, world, r) for r in range(world)]
+            assert bounds[0][0] == 0 and bounds[-1][1] == NX + 2 * ghost
+            for (a0, a1), (b0, b1) in zip(bounds[:-1], bounds[1:]):
+                assert a1 == b0 and a1 > a0
+            interior = [min(b1, NX + ghost) - max(b0, ghost) for b0, b1 in bounds]
+            assert sum(interior) == NX and max(interior) - min(interior) <= 1
+            lo, hi = (1, NX + 2) if variant == 0 else (1, NX)       # the caller's 1-based index range
+            pi = rng.integers(lo, hi + 1, 200)
+            own = np.stack([parallel.elastic_owned_points(p, pi, b0, b1) for b0, b1 in bounds])
+            assert np.all(own.sum(0) == 1)
