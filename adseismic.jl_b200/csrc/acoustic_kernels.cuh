@@ -148,20 +148,6 @@ __device__ __forceinline__ void ac_fuse_signal(const AcFuse& f, bool t_lo, bool 
   }
 }
 
-// RN(x / h) from rh = RN(1/h) computed once on the host: q0 = x*rh is within 2 ulp, one FMA correction makes it a
-// faithful quotient and a second one the correctly rounded quotient (Markstein's theorem; the remainders
-// r = x - q*h are exact in an FMA).  Five issue slots instead of the ~40-instruction divide sequence, whose slow
-// path is also taken for every zero wavefield value.  Numerators near the denormal range (inexact remainders)
-// use the divide sequence, so the result is bit-identical to `x / h` for all inputs.
-__device__ __forceinline__ double ac_div_by(double x, double h, double rh) {
-  if (x != 0.0 && fabs(x) < 1e-280) return x / h;
-  double q = x * rh;
-  double r = fma(-q, h, x);
-  q = fma(r, rh, q);
-  r = fma(-q, h, x);
-  return fma(r, rh, q);
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // forward, general (PML / ring / pad) cell: literal AcousticOneStepCpu.h:27-44
 // ------------------------------------------------------------------------------------------------------------
@@ -187,8 +173,8 @@ __device__ __forceinline__ void ac_fwd_general_cell(const AcGeom& g, int li, int
              g.py * (psi[IJp] - psi[IJn]) -
              (1 - (sg + ta) * dt / 2) * wold[IJ];
   u[IJ] = (v == 0.0) ? v : v / (1 + (sg + ta) / 2 * dt);  // zero numerators would take the divide's slow path
-  phio[IJ] = (1. - dt * sg) * phi[IJ] + ac_div_by(dt * c * (ta - sg) / 2.0, g.hx, g.rhx) * (w[IpJ] - w[InJ]);
-  psio[IJ] = (1. - dt * ta) * psi[IJ] + ac_div_by(dt * c * (sg - ta) / 2.0, g.hy, g.rhy) * (w[IJp] - w[IJn]);
+  phio[IJ] = (1. - dt * sg) * phi[IJ] + div_exact(dt * c * (ta - sg) / 2.0, g.hx, g.rhx) * (w[IpJ] - w[InJ]);
+  psio[IJ] = (1. - dt * ta) * psi[IJ] + div_exact(dt * c * (sg - ta) / 2.0, g.hy, g.rhy) * (w[IJp] - w[IJn]);
 }
 
 // CTA epilogue shared by both kernels: add `scale * val[perm]` into field[cell] for the injected points this CTA

@@ -146,6 +146,20 @@ __device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<do
 __device__ __forceinline__ double2 ld2_stream(const double* p) { return __ldcs(reinterpret_cast<const double2*>(p)); }
 __device__ __forceinline__ void st2_stream(double* p, double2 v) { __stcs(reinterpret_cast<double2*>(p), v); }
 
+// RN(x / h) from rh = RN(1/h) computed once on the host: q0 = x*rh is within 2 ulp, one FMA correction makes it a
+// faithful quotient and a second one the correctly rounded quotient (Markstein's theorem; the remainders
+// r = x - q*h are exact in an FMA).  Five issue slots instead of the ~40-instruction divide sequence, whose slow
+// path is also taken for every zero wavefield value.  Numerators near the denormal range (inexact remainders)
+// use the divide sequence, so the result is bit-identical to `x / h` for all inputs.
+__device__ __forceinline__ double div_exact(double x, double h, double rh) {
+  if (x != 0.0 && fabs(x) < 1e-280) return x / h;
+  double q = x * rh;
+  double r = fma(-q, h, x);
+  q = fma(r, rh, q);
+  r = fma(-q, h, x);
+  return fma(r, rh, q);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // TMA row staging (sm_90+/sm_100a): 1-D bulk asynchronous copies global -> shared (`cp.async.bulk`, SASS UBLKCP)
 // completing on an mbarrier.  The marching kernels keep a ring of row stages per CTA: a producer warp arms the

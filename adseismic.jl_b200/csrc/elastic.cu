@@ -90,7 +90,9 @@ struct adseis_elastic_plan {
   adseis_elastic_params p;
   adseis_slab slab;
   ElGeom g;
-  int nblocks = 0;
+  int nblocks = 0, nmarch = 0;
+  ElCta* ctas = nullptr;
+  int box[4] = {0, 0, 0, 0};  // marching box: local rows [box0,box1), columns [box2,box3)
   int off = 0;          // 0 (S) / 2 (M): offset between the caller's model array and the internal array
   i64 model_elems = 0;
   i64 slot_sz = 0;      // doubles per slot
@@ -170,7 +172,7 @@ ADSEIS_API int adseis_elastic_plan_destroy(adseis_elastic_plan* P) {
     cudaFree(P->arena);
     P->hist = P->adj = P->Gl = P->Gm1 = P->Gm2 = P->Gr3 = P->Gr4 = nullptr;
   }
-  cudaFree(P->perm);
+  cudaFree(P->perm); cudaFree(P->ctas);
   double* arr[] = {P->rho, P->lam, P->mu, P->lamb, P->lmb, P->mub2, P->rhob, P->rinv, P->rbinv, P->ax, P->bx, P->ay,
                    P->by, P->hist, P->srcv, P->rcvv, P->obs, P->res, P->loss, P->adj, P->Gl, P->Gm1, P->Gm2, P->Gr3,
                    P->Gr4, P->grho, P->glam, P->gmu, P->gradsrcv};
@@ -216,6 +218,15 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
   REQUIRE(nsrc >= 0 && nrcv >= 0 && (nsrc == 0 || (srci && srcj && srctype)) && (nrcv == 0 || (rcvi && rcvj && rcvtype)),
           "elastic_plan_create: bad source/receiver arrays");
   CUDA_TRY(cudaSetDevice(ctx->device));
+  {
+    const cudaFuncAttribute A = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    CUDA_TRY(cudaFuncSetAttribute(el_sigma_fwd, A, el_ring_bytes<ElSigFwdT>()));
+    CUDA_TRY(cudaFuncSetAttribute(el_vel_fwd, A, el_ring_bytes<ElVelFwdT>()));
+    CUDA_TRY(cudaFuncSetAttribute(el_vel_adj<true>, A, el_ring_bytes<ElVelAdjT<true>>()));
+    CUDA_TRY(cudaFuncSetAttribute(el_vel_adj<false>, A, el_ring_bytes<ElVelAdjT<false>>()));
+    CUDA_TRY(cudaFuncSetAttribute(el_sigma_adj<true>, A, el_ring_bytes<ElSigAdjT<true>>()));
+    CUDA_TRY(cudaFuncSetAttribute(el_sigma_adj<false>, A, el_ring_bytes<ElSigAdjT<false>>()));
+  }
   cudaStream_t st = ctx->stream;
   adseis_elastic_plan* P = new adseis_elastic_plan();
   P->ctx = ctx;
@@ -302,27 +313,100 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
   g.xm_sz = (i64)std::max(1, g.nxr) * g.ld;
   g.ym_sz = (i64)g.Hl * g.ycp;
   P->slot_sz = 5 * g.plane + 4 * g.xm_sz + 4 * g.ym_sz;
-  g.ntc = (g.ld + EL_BX - 1) / EL_BX;
-  g.ntr = (g.own1 - g.own0 + EL_ROWS - 1) / EL_ROWS;
-  P->nblocks = g.ntc * g.ntr;
+  g.h24x = 24 * g.dx; g.h24y = 24 * g.dy;
+  g.r24x = 1.0 / g.h24x; g.r24y = 1.0 / g.h24y;
   EPTRY(dev_upload(&P->ax, ax, st)); EPTRY(dev_upload(&P->bx, bx, st));
   EPTRY(dev_upload(&P->ay, ay, st)); EPTRY(dev_upload(&P->by, by, st));
   double** mats[] = {&P->rho, &P->lam, &P->mu, &P->lamb, &P->lmb, &P->mub2, &P->rhob, &P->rinv, &P->rbinv};
   for (double** m : mats) EPTRY(dev_alloc_zero(m, (size_t)g.plane + g.ld, st));  // raw planes: one extra row (averaging)
-  if (sl.nranks > 1) {
-    // launch order: edge row tiles (they wait for / push halo rows) first, so the NVLink latency hides behind the rest
-    std::vector<int> edge, rest;
+
+  // ---- CTA table of a step launch: marching tiles over the box, generic 64 x 16 tiles over the rest ----
+  std::vector<ElCta> ctas;
+  struct Rect { int r0, r1, c0, c1, base, ntc, tw, th; };
+  std::vector<Rect> rects;
+  int mrb = 0, mnct = 0;  // marching tile rows / column tiles
+  {
+    // box: inside the update regions of fw1..fw4, CPML-free, and 2 cells away from anything that is not
+    int bp0 = 0, bp1 = g.H - 1, bq0 = 0, bq1 = g.W - 1;  // inclusive, global
+    for (int k = 0; k < 4; k++) {
+      bp0 = std::max(bp0, g.p0[k]); bp1 = std::min(bp1, g.p1[k]);
+      bq0 = std::max(bq0, g.q0[k]); bq1 = std::min(bq1, g.q1[k]);
+    }
+    bp0 = std::max(bp0, g.xlo + g.cx); bp1 = std::min(bp1, g.xhi - 1 + g.cx);
+    bq0 = std::max(bq0, g.ylo + g.cy); bq1 = std::min(bq1, g.yhi - 1 + g.cy);
+    bp0 += EL_HALO; bp1 -= EL_HALO; bq0 += EL_HALO; bq1 -= EL_HALO;
+    int r0 = std::max(g.own0, bp0 - g.goff), r1 = std::min(g.own1, bp1 + 1 - g.goff);
+    int c0 = round_up(std::max(bq0, 2), 16);
+    int c1 = c0 + 2 * ((bq1 + 1 - c0) / 2);
+    // marching needs enough rows per CTA to amortise its pipeline prologue and enough CTAs to fill the GPU
+    const i64 min_cells = getenv("ADSEIS_EL_MARCH_MIN") ? atoll(getenv("ADSEIS_EL_MARCH_MIN")) : (i64)16 * EL_TCOLS * ctx->sm_count / 2;
+    if (r1 - r0 < 4 || c1 - c0 < 32 || (i64)(r1 - r0) * (c1 - c0) < min_cells) { r0 = r1 = g.own0; c0 = c1 = 0; }
+    P->box[0] = r0; P->box[1] = r1; P->box[2] = c0; P->box[3] = c1;
+    if (r1 > r0) {
+      mnct = (c1 - c0 + EL_TCOLS - 1) / EL_TCOLS;
+      const int want_tr = std::max(1, (2 * ctx->sm_count + mnct - 1) / mnct);  // ~2 CTAs per SM
+      mrb = std::min(64, std::max(8, (r1 - r0 + want_tr - 1) / want_tr));
+      const int ntr = (r1 - r0 + mrb - 1) / mrb;
+      for (int tr = 0; tr < ntr; tr++)
+        for (int tc = 0; tc < mnct; tc++)
+          ctas.push_back(ElCta{0, r0 + tr * mrb, std::min(r1, r0 + (tr + 1) * mrb), c0 + tc * EL_TCOLS,
+                               std::min(c1, c0 + (tc + 1) * EL_TCOLS), 0, 0, 0});
+    }
+    P->nmarch = (int)ctas.size();
+    auto add_rect = [&](int rr0, int rr1, int cc0, int cc1) {
+      if (rr1 <= rr0 || cc1 <= cc0) return;
+      // narrow strips get tall tiles (16 x 64, 32 x 32), wide rectangles 64 x 16: 256 threads x 4 cells each
+      const int ltw = (cc1 - cc0 <= 16) ? 4 : ((cc1 - cc0 <= 32) ? 5 : 6);
+      const int tw = 1 << ltw, th = 4 * ((EL_BX * EL_BY) >> ltw);
+      Rect R{rr0, rr1, cc0, cc1, (int)ctas.size(), (cc1 - cc0 + tw - 1) / tw, tw, th};
+      for (int a = rr0; a < rr1; a += th)
+        for (int b = cc0; b < cc1; b += tw)
+          ctas.push_back(ElCta{1, a, std::min(rr1, a + th), b, std::min(cc1, b + tw), ltw, 0, 0});
+      rects.push_back(R);
+    };
+    // (pitch-padding columns q >= W are never read by a cell that is stored: nobody writes them)
+    add_rect(g.own0, r0, 0, g.W);
+    add_rect(r1, g.own1, 0, g.W);
+    add_rect(r0, r1, 0, c0);
+    add_rect(r0, r1, c1, g.W);
+  }
+  P->nblocks = (int)ctas.size();
+  {
+    std::vector<int> tab((size_t)P->nblocks * 8);
+    memcpy(tab.data(), ctas.data(), tab.size() * sizeof(int));
+    int* dtab = nullptr;
+    EPTRY(dev_upload(&dtab, tab, st));
+    P->ctas = reinterpret_cast<ElCta*>(dtab);
+  }
+  {
+    // Launch order (logical CTA id = perm[blockIdx.x]).  Slab plans: the CTAs that own one of my first / last two
+    // rows next to a neighbour go first, so their halo pushes leave early and the rest of the step hides the NVLink
+    // latency.  Then the generic CTAs (latency-bound) are spread evenly among the marching CTAs (bandwidth-bound).
+    std::vector<int> edge, march, frame;
     for (int b = 0; b < P->nblocks; b++) {
-      const int tr = b / g.ntc;
-      const int ra = g.own0 + tr * EL_ROWS, rb = std::min(g.own1, ra + EL_ROWS);
-      const bool tl = halo_lo && ra < g.own0 + EL_HALO, th = halo_hi && rb > g.own1 - EL_HALO;
+      const bool tl = halo_lo && ctas[b].r0 < g.own0 + EL_HALO, th = halo_hi && ctas[b].r1 > g.own1 - EL_HALO;
       if (tl) P->n_edge_lo++;
       if (th) P->n_edge_hi++;
-      (tl || th ? edge : rest).push_back(b);
+      if (tl || th) edge.push_back(b);
+      else (ctas[b].kind == 0 ? march : frame).push_back(b);
     }
-    edge.insert(edge.end(), rest.begin(), rest.end());
-    EPTRY(dev_upload(&P->perm, edge, st));
+    std::vector<int> order(edge);
+    size_t im = 0, ifr = 0;
+    const size_t nm = march.size(), nf = frame.size();
+    while (im < nm || ifr < nf) {
+      if (ifr < nf && (im >= nm || ifr * nm <= im * nf)) order.push_back(frame[ifr++]);
+      else order.push_back(march[im++]);
+    }
+    EPTRY(dev_upload(&P->perm, order, st));
   }
+  auto owner_cta = [&](int li, int q) -> int {
+    if (li >= P->box[0] && li < P->box[1] && q >= P->box[2] && q < P->box[3])
+      return ((li - P->box[0]) / mrb) * mnct + (q - P->box[2]) / EL_TCOLS;
+    for (const Rect& R : rects)
+      if (li >= R.r0 && li < R.r1 && q >= R.c0 && q < R.c1)
+        return R.base + ((li - R.r0) / R.th) * R.ntc + (q - R.c0) / R.tw;
+    return -1;
+  };
 
   // sources / receivers (1-based indices: S -> padded grid, M -> unpadded global grid; MPIElastic.jl:85-86)
   P->nsrc = nsrc; P->nrcv = nrcv;
@@ -347,7 +431,9 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
     std::vector<int> own, cells, gid, field;
     for (const Pt& t : mine) {
       const int li = t.cell / g.ld, q = t.cell % g.ld;
-      own.push_back(((li - g.own0) / EL_ROWS) * g.ntc + q / EL_BX);
+      const int o = owner_cta(li, q);
+      REQUIRE(o >= 0, "elastic_plan_create: internal error: cell (%d,%d) has no owner CTA", li, q);
+      own.push_back(o);
       cells.push_back(t.cell); gid.push_back(t.gid); field.push_back(t.field);
     }
     PointSetHost h;
@@ -515,8 +601,8 @@ static inline long long el_plane_off(const adseis_elastic_plan::Desc& d, const E
 static ElFuse el_make_fuse(adseis_elastic_plan* P, int nf, const ElPlaneRef* planes) {
   ElFuse f;
   memset(&f, 0, sizeof(f));
-  if (!P->arena) return f;
   f.perm = P->perm;
+  if (!P->arena) return f;
   f.has_lo = P->peer[0] != nullptr; f.has_hi = P->peer[1] != nullptr;
   f.nf = nf;
   P->sepoch++;
@@ -627,16 +713,15 @@ static int el_step_forward(adseis_elastic_plan* P, i64 s, double* in, double* ou
   const ElSlot si = slot_at(P, in), so = slot_at(P, out);
   const ElMat mt = mat_of(P);
   const ElCoef cf = coef_of(P);
-  dim3 blk(EL_BX, EL_BY);
   ElPoints none{};
   const double* row = P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr;
   const double* prev = (P->nsrc > 0 && s >= 2) ? P->srcv + (s - 2) * P->nsrc : nullptr;
   const i64 widx = (out - P->hist) / P->slot_sz;
   const ElPlaneRef sig_planes[2] = {{EA_HIST, widx, 2}, {EA_HIST, widx, 4}};  // fw3/fw4 difference sxx, sxy along x
-  el_sigma_fwd<<<P->nblocks, blk, 0, st>>>(P->g, si, so, mt, cf, P->src.dev, prev, el_make_fuse(P, 2, sig_planes));
+  el_sigma_fwd<<<P->nblocks, EL_NT, el_ring_bytes<ElSigFwdT>(), st>>>(P->g, P->ctas, si, so, mt, cf, P->src.dev, prev, el_make_fuse(P, 2, sig_planes));
   EL_LAUNCH_CHECK(P);
   const ElPlaneRef vel_planes[2] = {{EA_HIST, widx, 0}, {EA_HIST, widx, 1}};
-  el_vel_fwd<<<P->nblocks, blk, 0, st>>>(P->g, si, so, mt, cf, P->src.dev, row, sample ? P->rcv.dev : none,
+  el_vel_fwd<<<P->nblocks, EL_NT, el_ring_bytes<ElVelFwdT>(), st>>>(P->g, P->ctas, si, so, mt, cf, P->src.dev, row, sample ? P->rcv.dev : none,
                                          (sample && P->nrcv > 0) ? P->rcvv : nullptr, (int)(P->p.NSTEP + 1), (int)s,
                                          el_make_fuse(P, 2, vel_planes));
   EL_LAUNCH_CHECK(P);
@@ -745,12 +830,11 @@ ADSEIS_API int adseis_elastic_plan_gradient(adseis_elastic_plan* P, int want_mat
   }
   const ElMat mt = mat_of(P);
   const ElCoef cf = coef_of(P);
-  dim3 blk(EL_BX, EL_BY);
   const int stride = (int)(NSTEP + 1);
   ElPoints none{};
   TRY(el_barrier(P));  // slab plans: the memsets above are done everywhere before anybody pushes adjoint halo rows
   // start: velocity residuals of slot NSTEP into vbar; grad_srcv row NSTEP-1
-  el_adj_start<<<P->nblocks, blk, 0, st>>>(g, side[0], P->rcv.dev, P->nrcv > 0 ? P->res : nullptr, stride, (int)NSTEP,
+  el_adj_start<<<P->nblocks, 256, 0, st>>>(g, side[0], P->rcv.dev, P->nrcv > 0 ? P->res : nullptr, stride, (int)NSTEP,
                                            P->src.dev, P->nsrc > 0 ? P->gradsrcv + (NSTEP - 1) * P->nsrc : nullptr);
   EL_LAUNCH_CHECK(P);
   const ElPlaneRef vb_planes[2] = {{EA_ADJ, 0, 0}, {EA_ADJ, 0, 1}};               // vbar_x, vbar_y
@@ -778,19 +862,19 @@ ADSEIS_API int adseis_elastic_plan_gradient(adseis_elastic_plan* P, int want_mat
       const double* resp = P->nrcv > 0 ? P->res : nullptr;
       double* grow = (s - 2 >= 0 && P->nsrc > 0 && s >= 2) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr;
       if (mat) {
-        el_vel_adj<true><<<P->nblocks, blk, 0, st>>>(g, bi, bo, fs, mt, cf, P->Gr3, P->Gr4, P->rcv.dev, resp, stride, (int)s,
+        el_vel_adj<true><<<P->nblocks, EL_NT, el_ring_bytes<ElVelAdjT<true>>(), st>>>(g, P->ctas, bi, bo, fs, mt, cf, P->Gr3, P->Gr4, P->rcv.dev, resp, stride, (int)s,
                                                      el_make_fuse(P, 3, sb_planes));
         EL_LAUNCH_CHECK(P);
-        el_sigma_adj<true><<<P->nblocks, blk, 0, st>>>(g, bi, bo, fp, fs, mt, cf, P->Gl, P->Gm1, P->Gm2,
+        el_sigma_adj<true><<<P->nblocks, EL_NT, el_ring_bytes<ElSigAdjT<true>>(), st>>>(g, P->ctas, bi, bo, fp, fs, mt, cf, P->Gl, P->Gm1, P->Gm2,
                                                        s >= 2 ? P->rcv.dev : none, s >= 2 ? resp : nullptr, stride,
                                                        (int)(s - 1), s >= 2 ? P->src.dev : none, grow,
                                                        el_make_fuse(P, 2, vb_planes));
         EL_LAUNCH_CHECK(P);
       } else {
-        el_vel_adj<false><<<P->nblocks, blk, 0, st>>>(g, bi, bo, zero, mt, cf, nullptr, nullptr, P->rcv.dev, resp, stride,
+        el_vel_adj<false><<<P->nblocks, EL_NT, el_ring_bytes<ElVelAdjT<false>>(), st>>>(g, P->ctas, bi, bo, zero, mt, cf, nullptr, nullptr, P->rcv.dev, resp, stride,
                                                       (int)s, el_make_fuse(P, 3, sb_planes));
         EL_LAUNCH_CHECK(P);
-        el_sigma_adj<false><<<P->nblocks, blk, 0, st>>>(g, bi, bo, zero, zero, mt, cf, nullptr, nullptr, nullptr,
+        el_sigma_adj<false><<<P->nblocks, EL_NT, el_ring_bytes<ElSigAdjT<false>>(), st>>>(g, P->ctas, bi, bo, zero, zero, mt, cf, nullptr, nullptr, nullptr,
                                                         s >= 2 ? P->rcv.dev : none, s >= 2 ? resp : nullptr, stride,
                                                         (int)(s - 1), s >= 2 ? P->src.dev : none, grow,
                                                         el_make_fuse(P, 2, vb_planes));

@@ -98,6 +98,8 @@ def main():
         O = po.elastic_misfit_grad(*args, obs)
         unpad = (lambda a: a) if variant == 0 else (lambda a: a[2:-2, 2:-2])
         for slots in (None, 7):
+            # full history: TMA-ring marching CTAs forced onto the small box; checkpointed: generic CTAs only
+            os.environ["ADSEIS_EL_MARCH_MIN"] = "0" if slots is None else str(1 << 40)
             dd = parallel.DomainDecomposedElastic(pe, srci, srcj, srctype, rcvi, rcvj, rcvtype, ctx=ctx, hist_slots=slots)
             dd.set_model(unpad(rho), unpad(lam), unpad(mu)); dd.set_srcv(srcv); dd.set_obs(obs)
             dd.forward()

@@ -64,8 +64,18 @@ def _case(po, rng, variant, NX, NY, NSTEP, npml=10):
                 srctype=srctype, srcv=srcv, rcvi=rcvi, rcvj=rcvj, rcvtype=rcvtype, npml=npml)
 
 
-@pytest.mark.parametrize("variant,shape", [(0, (150, 170, 40)), (1, (130, 200, 36)), (0, (500, 500, 12))])
-def test_vs_oracle(A, ctx, po, variant, shape):
+@pytest.fixture(params=["march", "generic"])
+def tiling(request, monkeypatch):
+    """Both CTA kinds of the step kernels: `march` forces the TMA-ring marching CTAs onto the (small) test grids'
+    PML-free box, `generic` keeps every cell on the one-cell-per-thread path (ADSEIS_EL_MARCH_MIN = minimum box
+    cells for marching; by default small grids stay generic)."""
+    monkeypatch.setenv("ADSEIS_EL_MARCH_MIN", "0" if request.param == "march" else str(1 << 40))
+    return request.param
+
+
+@pytest.mark.parametrize("variant,shape", [(0, (150, 170, 40)), (1, (130, 200, 36)), (0, (500, 500, 12)),
+                                           (1, (90, 1200, 10))])
+def test_vs_oracle(A, ctx, po, variant, shape, tiling):
     NX, NY, NSTEP = shape
     rng = np.random.default_rng(100 * variant + NX)
     K = _case(po, rng, variant, NX, NY, NSTEP)
@@ -97,7 +107,7 @@ def test_vs_oracle(A, ctx, po, variant, shape):
     plan.close()
 
 
-def test_checkpointed_gradient_equals_full_history(A, ctx, po):
+def test_checkpointed_gradient_equals_full_history(A, ctx, po, tiling):
     rng = np.random.default_rng(9)
     variant, NX, NY, NSTEP = 0, 120, 140, 30
     K = _case(po, rng, variant, NX, NY, NSTEP)
