@@ -160,6 +160,17 @@ __device__ __forceinline__ double div_exact(double x, double h, double rh) {
   return fma(r, rh, q);
 }
 
+// Branch-free core of div_exact for hot loops: the caller ORs `tiny` over all quotients of an iteration and redoes
+// the iteration with true divisions in the (rare) case that one numerator was near the denormal range.
+__device__ __forceinline__ double div_core(double x, double h, double rh, bool& tiny) {
+  tiny |= (x != 0.0) & (fabs(x) < 1e-280);
+  double q = x * rh;
+  double r = fma(-q, h, x);
+  q = fma(r, rh, q);
+  r = fma(-q, h, x);
+  return fma(r, rh, q);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // TMA row staging (sm_90+/sm_100a): 1-D bulk asynchronous copies global -> shared (`cp.async.bulk`, SASS UBLKCP)
 // completing on an mbarrier.  The marching kernels keep a ring of row stages per CTA: a producer warp arms the

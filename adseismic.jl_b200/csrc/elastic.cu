@@ -344,7 +344,8 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
     P->box[0] = r0; P->box[1] = r1; P->box[2] = c0; P->box[3] = c1;
     if (r1 > r0) {
       mnct = (c1 - c0 + EL_TCOLS - 1) / EL_TCOLS;
-      const int want_tr = std::max(1, (2 * ctx->sm_count + mnct - 1) / mnct);  // ~2 CTAs per SM
+      // ~6 marching CTAs per SM: whole waves for the kernels that fit 2 and those that fit 3 CTAs per SM
+      const int want_tr = std::max(1, (6 * ctx->sm_count + mnct - 1) / mnct);
       mrb = std::min(64, std::max(8, (r1 - r0 + want_tr - 1) / want_tr));
       const int ntr = (r1 - r0 + mrb - 1) / mrb;
       for (int tr = 0; tr < ntr; tr++)

@@ -38,20 +38,25 @@
 // Forward arithmetic follows the reference's evaluation order (bit-identical with -fmad=false; the divisions by
 // 24*dx, 24*dy of the marching CTAs use div_exact, which returns the correctly rounded quotient).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 #define EL_BX 64                    // generic tile: columns
 #define EL_BY 4                     // generic tile: thread rows
 #define EL_ROWS 16                  // generic tile: rows
-#define EL_MW 8                     // marching CTA: consumer warps (64 columns each)
+#define EL_MW 8                     // marching CTA: consumer warps (32 columns each, one column per lane)
 #define EL_NT (EL_MW * 32 + 32)     // threads per CTA: consumers + one producer warp (generic tiles use the first 256)
-#define EL_TCOLS (EL_MW * 64)       // marching CTA: columns
+#define EL_TCOLS (EL_MW * 32)       // marching CTA: columns
 #define EL_RC (EL_TCOLS + 4)        // ring row: tile columns + a 2-column (16-byte) halo on each side
 #ifndef EL_PF
 #define EL_PF 2                     // row bundles in flight beyond the one being consumed
 #endif
 #define EL_NB (EL_PF + 1)           // bundle barriers
 #define EL_HALO 2                   // slab decomposition: halo rows per interior side
+#ifndef EL_MINB_FWD
+#define EL_MINB_FWD 3                // forward kernels: CTAs per SM the register allocation aims at
+#endif
 
 struct ElGeom {
   int H, W;       // global array rows / columns (incl. ring or ghost cells)
@@ -276,7 +281,6 @@ struct ElCursor {
   }
 };
 
-__device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
 // x / r with the zero numerators of the quiet zone kept off the divide's slow path
 __device__ __forceinline__ double el_div_var(double x, double r) { return x == 0.0 ? x : x / r; }
 
@@ -361,74 +365,60 @@ __device__ __forceinline__ void el_sigma_fwd_march(const ElGeom& g, const ElCta&
     }
     return;
   }
-  const int so = 2 + warp * 64 + 2 * lane;  // this lane's column pair inside a ring row
-  const int q = d.c0 + warp * 64 + 2 * lane;
-  const bool act = q < d.c1;  // tile widths are even
-  const bool wact = d.c0 + warp * 64 < d.c1;
+  const int so = 2 + warp * 32 + lane;  // this lane's column inside a ring row
+  const int q = d.c0 + warp * 32 + lane;
+  const bool act = q < d.c1;
   const double dt = g.dt, hx = g.h24x, hy = g.h24y, rx = g.r24x, ry = g.r24y;
-  const double2 z2 = mk2(0.0, 0.0);
-  // x-direction windows (own column pair): vx rows li-1, li, li+1 (+ li+2 new), vy rows li-2, li-1, li (+ li+1 new)
-  double2 vxm1 = z2, vxc = z2, vxp1 = z2, vym2 = z2, vym1 = z2, vyc = z2;
+  // x-direction windows (own column): vx rows li-1, li, li+1 (+ li+2 new), vy rows li-2, li-1, li (+ li+1 new)
+  double vxm1 = 0.0, vxc, vxp1, vym2 = 0.0, vym1 = 0.0, vyc;
   if (act) {
-    vxm1 = ld2(in.vx + (i64)(d.r0 - 1) * ld + q);
-    vym2 = ld2(in.vy + (i64)(d.r0 - 2) * ld + q);
-    vym1 = ld2(in.vy + (i64)(d.r0 - 1) * ld + q);
+    vxm1 = in.vx[(i64)(d.r0 - 1) * ld + q];
+    vym2 = in.vy[(i64)(d.r0 - 2) * ld + q];
+    vym1 = in.vy[(i64)(d.r0 - 1) * ld + q];
   }
   mbar_wait(bars, 0);
-  if (wact) {
-    vxc = ld2(EL_RING(T, 0, 0) + so);
-    vxp1 = ld2(EL_RING(T, 0, 1) + so);
-    vyc = ld2(EL_RING(T, 1, 0) + so);
-  }
+  vxc = EL_RING(T, 0, 0)[so];
+  vxp1 = EL_RING(T, 0, 1)[so];
+  vyc = EL_RING(T, 1, 0)[so];
   ElCursor cu;
   cu.init();
   for (int it = 0; it < nrows; it++) {
     const int li = d.r0 + it, b = it % EL_NB;
     mbar_wait(bars + 1 + b, (unsigned)(it / EL_NB) & 1u);
-    double2 vxp2 = z2, vyp1 = z2, vxr = z2, vyl = z2, sxx = z2, syy = z2, sxy = z2, l_ = z2, lm = z2, m_ = z2;
-    double vxl = 0.0, vyr = 0.0;
-    if (wact) {
-      vxp2 = ld2(EL_RING(T, 0, cu.n[2]) + so);
-      vyp1 = ld2(EL_RING(T, 1, cu.n[1]) + so);
-      const double* cx_ = EL_RING(T, 0, cu.c[2]);  // centre row of vx: columns q-1, q+2, q+3
-      vxl = cx_[so - 1]; vxr = ld2(cx_ + so + 2);
-      const double* cy_ = EL_RING(T, 1, cu.c[1]);  // centre row of vy: columns q-2, q-1, q+2
-      vyl = ld2(cy_ + so - 2); vyr = cy_[so + 2];
-      sxx = ld2(EL_RING(T, 2, cu.c[0]) + so); syy = ld2(EL_RING(T, 3, cu.c[0]) + so); sxy = ld2(EL_RING(T, 4, cu.c[0]) + so);
-      l_ = ld2(EL_RING(T, 5, cu.c[0]) + so); lm = ld2(EL_RING(T, 6, cu.c[0]) + so); m_ = ld2(EL_RING(T, 7, cu.c[0]) + so);
-    }
+    const double vxp2 = EL_RING(T, 0, cu.n[2])[so];
+    const double vyp1 = EL_RING(T, 1, cu.n[1])[so];
+    const double* cx_ = EL_RING(T, 0, cu.c[2]) + so;  // centre row of vx
+    const double vx_m1 = cx_[-1], vx_p1 = cx_[1], vx_p2 = cx_[2];
+    const double* cy_ = EL_RING(T, 1, cu.c[1]) + so;  // centre row of vy
+    const double vy_m2 = cy_[-2], vy_m1 = cy_[-1], vy_p1 = cy_[1];
+    double sxx = EL_RING(T, 2, cu.c[0])[so], syy = EL_RING(T, 3, cu.c[0])[so], sxy = EL_RING(T, 4, cu.c[0])[so];
+    const double l_ = EL_RING(T, 5, cu.c[0])[so], lm = EL_RING(T, 6, cu.c[0])[so], m_ = EL_RING(T, 7, cu.c[0])[so];
     __syncwarp();  // every lane has read its ring rows
     if (lane == 0) mbar_arrive(bars + 1 + EL_NB + b);
     if (act) {
       const i64 c = (i64)li * ld + q;
       if (sb > sa) {  // pending stress injection of the previous step (AddSource.cpp:69-84)
-        sxx.x = el_apply_points(sxx.x, src, sa, sb, (int)c, 2, srcv_prev);
-        syy.x = el_apply_points(syy.x, src, sa, sb, (int)c, 3, srcv_prev);
-        sxy.x = el_apply_points(sxy.x, src, sa, sb, (int)c, 4, srcv_prev);
-        sxx.y = el_apply_points(sxx.y, src, sa, sb, (int)c + 1, 2, srcv_prev);
-        syy.y = el_apply_points(syy.y, src, sa, sb, (int)c + 1, 3, srcv_prev);
-        sxy.y = el_apply_points(sxy.y, src, sa, sb, (int)c + 1, 4, srcv_prev);
+        sxx = el_apply_points(sxx, src, sa, sb, (int)c, 2, srcv_prev);
+        syy = el_apply_points(syy, src, sa, sb, (int)c, 3, srcv_prev);
+        sxy = el_apply_points(sxy, src, sa, sb, (int)c, 4, srcv_prev);
       }
-      double2 o1, o2, o3;
-      {  // column q
-        const double d1 = div_exact(27 * vxp1.x - 27 * vxc.x - vxp2.x + vxm1.x, hx, rx);
-        const double d2 = div_exact(27 * vyc.x - 27 * vyl.y - vyc.y + vyl.x, hy, ry);
-        const double d3 = div_exact(27 * vyc.x - 27 * vym1.x - vyp1.x + vym2.x, hx, rx);
-        const double d4 = div_exact(27 * vxc.y - 27 * vxc.x - vxr.x + vxl, hy, ry);
-        o1.x = sxx.x + (lm.x * d1 + l_.x * d2) * dt;
-        o2.x = syy.x + (lm.x * d2 + l_.x * d1) * dt;
-        o3.x = sxy.x + m_.x * (d3 + d4) * dt;
-      }
-      {  // column q+1
-        const double d1 = div_exact(27 * vxp1.y - 27 * vxc.y - vxp2.y + vxm1.y, hx, rx);
-        const double d2 = div_exact(27 * vyc.y - 27 * vyc.x - vyr + vyl.y, hy, ry);
-        const double d3 = div_exact(27 * vyc.y - 27 * vym1.y - vyp1.y + vym2.y, hx, rx);
-        const double d4 = div_exact(27 * vxr.x - 27 * vxc.y - vxr.y + vxc.x, hy, ry);
-        o1.y = sxx.y + (lm.y * d1 + l_.y * d2) * dt;
-        o2.y = syy.y + (lm.y * d2 + l_.y * d1) * dt;
-        o3.y = sxy.y + m_.y * (d3 + d4) * dt;
-      }
-      st2(out.sxx + c, o1); st2(out.syy + c, o2); st2(out.sxy + c, o3);
+      // EX: true divisions (redo of a cell in which a numerator was near the denormal range); else exact
+      // reciprocal-based quotients without branches
+      auto calc = [&](auto EX) -> bool {
+        constexpr bool E = decltype(EX)::value;
+        bool tiny = false;
+        auto DX = [&](double x) { return E ? x / hx : div_core(x, hx, rx, tiny); };
+        auto DY = [&](double x) { return E ? x / hy : div_core(x, hy, ry, tiny); };
+        const double d1 = DX(27 * vxp1 - 27 * vxc - vxp2 + vxm1);
+        const double d2 = DY(27 * vyc - 27 * vy_m1 - vy_p1 + vy_m2);
+        const double d3 = DX(27 * vyc - 27 * vym1 - vyp1 + vym2);
+        const double d4 = DY(27 * vx_p1 - 27 * vxc - vx_p2 + vx_m1);
+        out.sxx[c] = sxx + (lm * d1 + l_ * d2) * dt;
+        out.syy[c] = syy + (lm * d2 + l_ * d1) * dt;
+        out.sxy[c] = sxy + m_ * (d3 + d4) * dt;
+        return tiny;
+      };
+      if (calc(std::false_type{})) calc(std::true_type{});
     }
     vxm1 = vxc; vxc = vxp1; vxp1 = vxp2;
     vym2 = vym1; vym1 = vyc; vyc = vyp1;
@@ -436,12 +426,18 @@ __device__ __forceinline__ void el_sigma_fwd_march(const ElGeom& g, const ElCta&
   }
 }
 
-__global__ void __launch_bounds__(EL_NT, 2)
+__global__ void __launch_bounds__(EL_NT, EL_MINB_FWD)
 el_sigma_fwd(ElGeom g, const ElCta* __restrict__ ctas, ElSlot in, ElSlot out, ElMat mt, ElCoef cf, ElPoints src,
              const double* __restrict__ srcv_prev, ElFuse f) {
   extern __shared__ __align__(128) unsigned char el_smem[];
   const int bid = el_bid(f);
   const ElCta d = el_cta(ctas, bid);
+#ifdef EL_DEBUG_SKIP_GENERIC  // timing experiments only (wrong results)
+  if (d.kind != 0) return;
+#endif
+#ifdef EL_DEBUG_SKIP_MARCH
+  if (d.kind == 0) return;
+#endif
   bool t_lo, t_hi;
   el_cta_edges(g, f, d, &t_lo, &t_hi);
   el_fuse_wait(f, t_lo, t_hi);
@@ -531,64 +527,52 @@ __device__ __forceinline__ void el_vel_fwd_march(const ElGeom& g, const ElCta& d
     }
     return;
   }
-  const int so = 2 + warp * 64 + 2 * lane;
-  const int q = d.c0 + warp * 64 + 2 * lane;
+  const int so = 2 + warp * 32 + lane;
+  const int q = d.c0 + warp * 32 + lane;
   const bool act = q < d.c1;
-  const bool wact = d.c0 + warp * 64 < d.c1;
   const double dt = g.dt, hx = g.h24x, hy = g.h24y, rx = g.r24x, ry = g.r24y;
-  const double2 z2 = mk2(0.0, 0.0);
   // windows: sxy rows li-1, li, li+1 (+ li+2 new) ; sxx rows li-2, li-1, li (+ li+1 new)
-  double2 qm1 = z2, qc = z2, qp1 = z2, xm2 = z2, xm1 = z2, xc = z2;
+  double qm1 = 0.0, qc, qp1, xm2 = 0.0, xm1 = 0.0, xc;
   if (act) {
-    qm1 = ld2(out.sxy + (i64)(d.r0 - 1) * ld + q);
-    xm2 = ld2(out.sxx + (i64)(d.r0 - 2) * ld + q);
-    xm1 = ld2(out.sxx + (i64)(d.r0 - 1) * ld + q);
+    qm1 = out.sxy[(i64)(d.r0 - 1) * ld + q];
+    xm2 = out.sxx[(i64)(d.r0 - 2) * ld + q];
+    xm1 = out.sxx[(i64)(d.r0 - 1) * ld + q];
   }
   mbar_wait(bars, 0);
-  if (wact) {
-    qc = ld2(EL_RING(T, 0, 0) + so);
-    qp1 = ld2(EL_RING(T, 0, 1) + so);
-    xc = ld2(EL_RING(T, 1, 0) + so);
-  }
+  qc = EL_RING(T, 0, 0)[so];
+  qp1 = EL_RING(T, 0, 1)[so];
+  xc = EL_RING(T, 1, 0)[so];
   ElCursor cu;
   cu.init();
   for (int it = 0; it < nrows; it++) {
     const int li = d.r0 + it, b = it % EL_NB;
     mbar_wait(bars + 1 + b, (unsigned)(it / EL_NB) & 1u);
-    double2 qp2 = z2, xp1 = z2, ql = z2, yy = z2, yr = z2, vx = z2, vy = z2, rh = z2, rb = z2;
-    double qr = 0.0, yl = 0.0;
-    if (wact) {
-      qp2 = ld2(EL_RING(T, 0, cu.n[2]) + so);
-      xp1 = ld2(EL_RING(T, 1, cu.n[1]) + so);
-      const double* cq = EL_RING(T, 0, cu.c[2]);  // centre row of sxy: columns q-2, q-1, q+2
-      ql = ld2(cq + so - 2); qr = cq[so + 2];
-      const double* cy_ = EL_RING(T, 2, cu.c[0]);  // syy: columns q-1, q, q+1, q+2, q+3
-      yl = cy_[so - 1]; yy = ld2(cy_ + so); yr = ld2(cy_ + so + 2);
-      vx = ld2(EL_RING(T, 3, cu.c[0]) + so); vy = ld2(EL_RING(T, 4, cu.c[0]) + so);
-      rh = ld2(EL_RING(T, 5, cu.c[0]) + so); rb = ld2(EL_RING(T, 6, cu.c[0]) + so);
-    }
+    const double qp2 = EL_RING(T, 0, cu.n[2])[so];
+    const double xp1 = EL_RING(T, 1, cu.n[1])[so];
+    const double* cq = EL_RING(T, 0, cu.c[2]) + so;  // centre row of sxy
+    const double q_m2 = cq[-2], q_m1 = cq[-1], q_p1 = cq[1];
+    const double* cy_ = EL_RING(T, 2, cu.c[0]) + so;  // syy
+    const double y_m1 = cy_[-1], y_c = cy_[0], y_p1 = cy_[1], y_p2 = cy_[2];
+    const double vx = EL_RING(T, 3, cu.c[0])[so], vy = EL_RING(T, 4, cu.c[0])[so];
+    const double rh = EL_RING(T, 5, cu.c[0])[so], rb = EL_RING(T, 6, cu.c[0])[so];
     __syncwarp();
     if (lane == 0) mbar_arrive(bars + 1 + EL_NB + b);
     if (act) {
       const i64 c = (i64)li * ld + q;
-      double2 o1, o2;
-      {  // column q
-        const double d5 = div_exact(27 * xc.x - 27 * xm1.x - xp1.x + xm2.x, hx, rx);
-        const double d6 = div_exact(27 * qc.x - 27 * ql.y - qc.y + ql.x, hy, ry);
-        const double d7 = div_exact(27 * qp1.x - 27 * qc.x - qp2.x + qm1.x, hx, rx);
-        const double d8 = div_exact(27 * yy.y - 27 * yy.x - yr.x + yl, hy, ry);
-        o1.x = vx.x + el_div_var((d5 + d6) * dt, rh.x);
-        o2.x = vy.x + el_div_var((d7 + d8) * dt, rb.x);
-      }
-      {  // column q+1
-        const double d5 = div_exact(27 * xc.y - 27 * xm1.y - xp1.y + xm2.y, hx, rx);
-        const double d6 = div_exact(27 * qc.y - 27 * qc.x - qr + ql.y, hy, ry);
-        const double d7 = div_exact(27 * qp1.y - 27 * qc.y - qp2.y + qm1.y, hx, rx);
-        const double d8 = div_exact(27 * yr.x - 27 * yy.y - yr.y + yy.x, hy, ry);
-        o1.y = vx.y + el_div_var((d5 + d6) * dt, rh.y);
-        o2.y = vy.y + el_div_var((d7 + d8) * dt, rb.y);
-      }
-      st2(out.vx + c, o1); st2(out.vy + c, o2);
+      auto calc = [&](auto EX) -> bool {  // see el_sigma_fwd_march
+        constexpr bool E = decltype(EX)::value;
+        bool tiny = false;
+        auto DX = [&](double x) { return E ? x / hx : div_core(x, hx, rx, tiny); };
+        auto DY = [&](double x) { return E ? x / hy : div_core(x, hy, ry, tiny); };
+        const double d5 = DX(27 * xc - 27 * xm1 - xp1 + xm2);
+        const double d6 = DY(27 * qc - 27 * q_m1 - q_p1 + q_m2);
+        const double d7 = DX(27 * qp1 - 27 * qc - qp2 + qm1);
+        const double d8 = DY(27 * y_p1 - 27 * y_c - y_p2 + y_m1);
+        out.vx[c] = vx + el_div_var((d5 + d6) * dt, rh);
+        out.vy[c] = vy + el_div_var((d7 + d8) * dt, rb);
+        return tiny;
+      };
+      if (calc(std::false_type{})) calc(std::true_type{});
     }
     qm1 = qc; qc = qp1; qp1 = qp2;
     xm2 = xm1; xm1 = xc; xc = xp1;
@@ -596,13 +580,19 @@ __device__ __forceinline__ void el_vel_fwd_march(const ElGeom& g, const ElCta& d
   }
 }
 
-__global__ void __launch_bounds__(EL_NT, 2)
+__global__ void __launch_bounds__(EL_NT, EL_MINB_FWD)
 el_vel_fwd(ElGeom g, const ElCta* __restrict__ ctas, ElSlot in, ElSlot out, ElMat mt, ElCoef cf, ElPoints src,
            const double* __restrict__ srcv_row, ElPoints rcv, double* __restrict__ rcvv, int rcv_stride, int slot,
            ElFuse f) {
   extern __shared__ __align__(128) unsigned char el_smem[];
   const int bid = el_bid(f);
   const ElCta d = el_cta(ctas, bid);
+#ifdef EL_DEBUG_SKIP_GENERIC  // timing experiments only (wrong results)
+  if (d.kind != 0) return;
+#endif
+#ifdef EL_DEBUG_SKIP_MARCH
+  if (d.kind == 0) return;
+#endif
   bool t_lo, t_hi;
   el_cta_edges(g, f, d, &t_lo, &t_hi);
   el_fuse_wait(f, t_lo, t_hi);
@@ -844,61 +834,50 @@ __device__ __forceinline__ void el_vel_adj_march(const ElGeom& g, const ElCta& d
     }
     return;
   }
-  const int so = 2 + warp * 64 + 2 * lane;
-  const int q = d.c0 + warp * 64 + 2 * lane;
+  const int so = 2 + warp * 32 + lane;
+  const int q = d.c0 + warp * 32 + lane;
   const bool act = q < d.c1;
-  const bool wact = d.c0 + warp * 64 < d.c1;
   const double dt = g.dt, ix = 1.0 / (24 * g.dx), iy = 1.0 / (24 * g.dy);
-  const double hx = g.h24x, hy = g.h24y, rx = g.r24x, ry = g.r24y;
-  const double2 z2 = mk2(0.0, 0.0);
-  auto prod = [dt](double2 v, double2 r) { return mk2(dt * v.x * r.x, dt * v.y * r.y); };
+  const double rx = g.r24x, ry = g.r24y;  // gradient terms: quotients by 24*dx, 24*dy as products (1e-16 relative)
   // windows: A = dt*vbx*rinv rows li-1, li, li+1 (+ li+2) ; B = dt*vby*rbinv rows li-2, li-1, li (+ li+1)
-  double2 Am1 = z2, Ac = z2, Ap1 = z2, Bm2 = z2, Bm1 = z2, Bc = z2;
-  double2 fqm1 = z2, fqc = z2, fqp1 = z2, fsm2 = z2, fsm1 = z2, fsc = z2;  // forward sxy / sxx windows (MATGRAD)
+  double Am1 = 0.0, Ac, Ap1, Bm2 = 0.0, Bm1 = 0.0, Bc;
+  double fqm1 = 0.0, fqc = 0.0, fqp1 = 0.0, fsm2 = 0.0, fsm1 = 0.0, fsc = 0.0;  // forward sxy / sxx windows (MATGRAD)
   if (act) {
     const i64 o1 = (i64)(d.r0 - 1) * ld + q, o2 = (i64)(d.r0 - 2) * ld + q;
-    Am1 = prod(ld2(b.vx + o1), ld2(mt.rinv + o1));
-    Bm2 = prod(ld2(b.vy + o2), ld2(mt.rbinv + o2));
-    Bm1 = prod(ld2(b.vy + o1), ld2(mt.rbinv + o1));
-    if (MATGRAD) { fqm1 = ld2(fwd.sxy + o1); fsm2 = ld2(fwd.sxx + o2); fsm1 = ld2(fwd.sxx + o1); }
+    Am1 = dt * b.vx[o1] * mt.rinv[o1];
+    Bm2 = dt * b.vy[o2] * mt.rbinv[o2];
+    Bm1 = dt * b.vy[o1] * mt.rbinv[o1];
+    if (MATGRAD) { fqm1 = fwd.sxy[o1]; fsm2 = fwd.sxx[o2]; fsm1 = fwd.sxx[o1]; }
   }
   mbar_wait(bars, 0);
-  if (wact) {
-    Ac = prod(ld2(EL_RING(T, 0, 0) + so), ld2(EL_RING(T, 1, 0) + so));
-    Ap1 = prod(ld2(EL_RING(T, 0, 1) + so), ld2(EL_RING(T, 1, 1) + so));
-    Bc = prod(ld2(EL_RING(T, 2, 0) + so), ld2(EL_RING(T, 3, 0) + so));
-    if (MATGRAD) { fqc = ld2(EL_RING(T, 7, 0) + so); fqp1 = ld2(EL_RING(T, 7, 1) + so); fsc = ld2(EL_RING(T, 8, 0) + so); }
-  }
+  Ac = dt * EL_RING(T, 0, 0)[so] * EL_RING(T, 1, 0)[so];
+  Ap1 = dt * EL_RING(T, 0, 1)[so] * EL_RING(T, 1, 1)[so];
+  Bc = dt * EL_RING(T, 2, 0)[so] * EL_RING(T, 3, 0)[so];
+  if (MATGRAD) { fqc = EL_RING(T, 7, 0)[so]; fqp1 = EL_RING(T, 7, 1)[so]; fsc = EL_RING(T, 8, 0)[so]; }
   ElCursor cu;
   cu.init();
   for (int it = 0; it < nrows; it++) {
     const int li = d.r0 + it, bb = it % EL_NB;
     mbar_wait(bars + 1 + bb, (unsigned)(it / EL_NB) & 1u);
-    double2 Ap2 = z2, Bp1 = z2, Ar = z2, Bl = z2, sxx = z2, syy = z2, sxy = z2;
-    double Al = 0.0, Br = 0.0;
-    double2 vxc = z2, ric = z2, vyc = z2, rbc = z2;                       // raw centre values (MATGRAD)
-    double2 fqp2 = z2, fsp1 = z2, fql = z2, fy = z2, fyr = z2, G3 = z2, G4 = z2;
-    double fqr = 0.0, fyl = 0.0;
-    if (wact) {
-      Ap2 = prod(ld2(EL_RING(T, 0, cu.n[2]) + so), ld2(EL_RING(T, 1, cu.n[2]) + so));
-      Bp1 = prod(ld2(EL_RING(T, 2, cu.n[1]) + so), ld2(EL_RING(T, 3, cu.n[1]) + so));
-      const double* va = EL_RING(T, 0, cu.c[2]); const double* ria = EL_RING(T, 1, cu.c[2]);  // centre row of A: q-1, q+2, q+3
-      Al = dt * va[so - 1] * ria[so - 1];
-      Ar = prod(ld2(va + so + 2), ld2(ria + so + 2));
-      const double* vb = EL_RING(T, 2, cu.c[1]); const double* rba = EL_RING(T, 3, cu.c[1]);  // centre row of B: q-2, q-1, q+2
-      Bl = prod(ld2(vb + so - 2), ld2(rba + so - 2));
-      Br = dt * vb[so + 2] * rba[so + 2];
-      sxx = ld2(EL_RING(T, 4, cu.c[0]) + so); syy = ld2(EL_RING(T, 5, cu.c[0]) + so); sxy = ld2(EL_RING(T, 6, cu.c[0]) + so);
-      if (MATGRAD) {
-        vxc = ld2(va + so); ric = ld2(ria + so); vyc = ld2(vb + so); rbc = ld2(rba + so);
-        fqp2 = ld2(EL_RING(T, 7, cu.n[2]) + so);
-        fsp1 = ld2(EL_RING(T, 8, cu.n[1]) + so);
-        const double* cq = EL_RING(T, 7, cu.c[2]);  // centre row of forward sxy: q-2, q-1, q+2
-        fql = ld2(cq + so - 2); fqr = cq[so + 2];
-        const double* cy_ = EL_RING(T, 9, cu.c[0]);  // forward syy: q-1 .. q+3
-        fyl = cy_[so - 1]; fy = ld2(cy_ + so); fyr = ld2(cy_ + so + 2);
-        G3 = ld2(EL_RING(T, 10, cu.c[0]) + so); G4 = ld2(EL_RING(T, 11, cu.c[0]) + so);
-      }
+    const double Ap2 = dt * EL_RING(T, 0, cu.n[2])[so] * EL_RING(T, 1, cu.n[2])[so];
+    const double Bp1 = dt * EL_RING(T, 2, cu.n[1])[so] * EL_RING(T, 3, cu.n[1])[so];
+    const double* va = EL_RING(T, 0, cu.c[2]) + so; const double* ria = EL_RING(T, 1, cu.c[2]) + so;  // centre row of A
+    const double A_m1 = dt * va[-1] * ria[-1], A_p1 = dt * va[1] * ria[1], A_p2 = dt * va[2] * ria[2];
+    const double* vb = EL_RING(T, 2, cu.c[1]) + so; const double* rba = EL_RING(T, 3, cu.c[1]) + so;  // centre row of B
+    const double B_m2 = dt * vb[-2] * rba[-2], B_m1 = dt * vb[-1] * rba[-1], B_p1 = dt * vb[1] * rba[1];
+    double sxx = EL_RING(T, 4, cu.c[0])[so], syy = EL_RING(T, 5, cu.c[0])[so], sxy = EL_RING(T, 6, cu.c[0])[so];
+    double vxc = 0.0, ric = 0.0, vyc = 0.0, rbc = 0.0;  // raw centre values (MATGRAD)
+    double fqp2 = 0.0, fsp1 = 0.0, fq_m2 = 0.0, fq_m1 = 0.0, fq_p1 = 0.0, fy_m1 = 0.0, fy_c = 0.0, fy_p1 = 0.0, fy_p2 = 0.0;
+    double G3 = 0.0, G4 = 0.0;
+    if (MATGRAD) {
+      vxc = va[0]; ric = ria[0]; vyc = vb[0]; rbc = rba[0];
+      fqp2 = EL_RING(T, 7, cu.n[2])[so];
+      fsp1 = EL_RING(T, 8, cu.n[1])[so];
+      const double* cq = EL_RING(T, 7, cu.c[2]) + so;  // centre row of forward sxy
+      fq_m2 = cq[-2]; fq_m1 = cq[-1]; fq_p1 = cq[1];
+      const double* cy_ = EL_RING(T, 9, cu.c[0]) + so;  // forward syy
+      fy_m1 = cy_[-1]; fy_c = cy_[0]; fy_p1 = cy_[1]; fy_p2 = cy_[2];
+      G3 = EL_RING(T, 10, cu.c[0])[so]; G4 = EL_RING(T, 11, cu.c[0])[so];
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bars + 1 + EL_NB + bb);
@@ -906,42 +885,23 @@ __device__ __forceinline__ void el_vel_adj_march(const ElGeom& g, const ElCta& d
       const i64 c = (i64)li * ld + q;
       for (int k = ra; k < rb; k++) {  // stress-type receiver residuals of this slot (GetReceive.cpp:48-97)
         const int fd = rcv.field[k];
-        if (fd >= 2 && (rcv.cell[k] == (int)c || rcv.cell[k] == (int)c + 1)) {
+        if (fd >= 2 && rcv.cell[k] == (int)c) {
           double a = 0.0;
           for (int m = rcv.start[k]; m < rcv.start[k + 1]; m++) a += res[(i64)rcv.perm[m] * res_stride + slot];
-          const bool hi = rcv.cell[k] == (int)c + 1;
-          double2& t = fd == 2 ? sxx : (fd == 3 ? syy : sxy);
-          if (hi) t.y += a; else t.x += a;
+          if (fd == 2) sxx += a; else if (fd == 3) syy += a; else sxy += a;
         }
       }
       // (D-x)^T A -> sxx ; (D-y)^T A -> sxy ; (D+x)^T B -> sxy ; (D+y)^T B -> syy
-      sxx.x += (27 * Ac.x - 27 * Ap1.x - Am1.x + Ap2.x) * ix;
-      sxy.x += (27 * Ac.x - 27 * Ac.y - Al + Ar.x) * iy;
-      sxy.x += (27 * Bm1.x - 27 * Bc.x - Bm2.x + Bp1.x) * ix;
-      syy.x += (27 * Bl.y - 27 * Bc.x - Bl.x + Bc.y) * iy;
-      sxx.y += (27 * Ac.y - 27 * Ap1.y - Am1.y + Ap2.y) * ix;
-      sxy.y += (27 * Ac.y - 27 * Ar.x - Ac.x + Ar.y) * iy;
-      sxy.y += (27 * Bm1.y - 27 * Bc.y - Bm2.y + Bp1.y) * ix;
-      syy.y += (27 * Bc.x - 27 * Bc.y - Bl.y + Br) * iy;
-      st2(bout.sxx + c, sxx); st2(bout.syy + c, syy); st2(bout.sxy + c, sxy);
+      sxx += (27 * Ac - 27 * Ap1 - Am1 + Ap2) * ix;
+      sxy += (27 * Ac - 27 * A_p1 - A_m1 + A_p2) * iy;
+      sxy += (27 * Bm1 - 27 * Bc - Bm2 + Bp1) * ix;
+      syy += (27 * B_m1 - 27 * Bc - B_m2 + B_p1) * iy;
+      bout.sxx[c] = sxx; bout.syy[c] = syy; bout.sxy[c] = sxy;
       if (MATGRAD) {
-        {
-          const double e56 = div_exact(27 * fsc.x - 27 * fsm1.x - fsp1.x + fsm2.x, hx, rx) +
-                             div_exact(27 * fqc.x - 27 * fql.y - fqc.y + fql.x, hy, ry);
-          const double e78 = div_exact(27 * fqp1.x - 27 * fqc.x - fqp2.x + fqm1.x, hx, rx) +
-                             div_exact(27 * fy.y - 27 * fy.x - fyr.x + fyl, hy, ry);
-          G3.x += -(dt * vxc.x) * e56 * (ric.x * ric.x);
-          G4.x += -(dt * vyc.x) * e78 * (rbc.x * rbc.x);
-        }
-        {
-          const double e56 = div_exact(27 * fsc.y - 27 * fsm1.y - fsp1.y + fsm2.y, hx, rx) +
-                             div_exact(27 * fqc.y - 27 * fqc.x - fqr + fql.y, hy, ry);
-          const double e78 = div_exact(27 * fqp1.y - 27 * fqc.y - fqp2.y + fqm1.y, hx, rx) +
-                             div_exact(27 * fyr.x - 27 * fy.y - fyr.y + fy.x, hy, ry);
-          G3.y += -(dt * vxc.y) * e56 * (ric.y * ric.y);
-          G4.y += -(dt * vyc.y) * e78 * (rbc.y * rbc.y);
-        }
-        st2(Gr3 + c, G3); st2(Gr4 + c, G4);
+        const double e56 = (27 * fsc - 27 * fsm1 - fsp1 + fsm2) * rx + (27 * fqc - 27 * fq_m1 - fq_p1 + fq_m2) * ry;
+        const double e78 = (27 * fqp1 - 27 * fqc - fqp2 + fqm1) * rx + (27 * fy_p1 - 27 * fy_c - fy_p2 + fy_m1) * ry;
+        Gr3[c] = G3 + -(dt * vxc) * e56 * (ric * ric);
+        Gr4[c] = G4 + -(dt * vyc) * e78 * (rbc * rbc);
       }
     }
     Am1 = Ac; Ac = Ap1; Ap1 = Ap2;
@@ -952,13 +912,19 @@ __device__ __forceinline__ void el_vel_adj_march(const ElGeom& g, const ElCta& d
 }
 
 template <bool MATGRAD>
-__global__ void __launch_bounds__(EL_NT, MATGRAD ? 1 : 2)
+__global__ void __maxnreg__(MATGRAD ? 112 : 72)
 el_vel_adj(ElGeom g, const ElCta* __restrict__ ctas, ElSlot b, ElSlot bout, ElSlot fwd, ElMat mt, ElCoef cf,
            double* __restrict__ Gr3, double* __restrict__ Gr4, ElPoints rcv, const double* __restrict__ res,
            int res_stride, int slot, ElFuse f) {
   extern __shared__ __align__(128) unsigned char el_smem[];
   const int bid = el_bid(f);
   const ElCta d = el_cta(ctas, bid);
+#ifdef EL_DEBUG_SKIP_GENERIC  // timing experiments only (wrong results)
+  if (d.kind != 0) return;
+#endif
+#ifdef EL_DEBUG_SKIP_MARCH
+  if (d.kind == 0) return;
+#endif
   bool t_lo, t_hi;
   el_cta_edges(g, f, d, &t_lo, &t_hi);
   el_fuse_wait(f, t_lo, t_hi);
@@ -1116,105 +1082,76 @@ __device__ __forceinline__ void el_sigma_adj_march(const ElGeom& g, const ElCta&
     }
     return;
   }
-  const int so = 2 + warp * 64 + 2 * lane;
-  const int q = d.c0 + warp * 64 + 2 * lane;
+  const int so = 2 + warp * 32 + lane;
+  const int q = d.c0 + warp * 32 + lane;
   const bool act = q < d.c1;
-  const bool wact = d.c0 + warp * 64 < d.c1;
   const double dt = g.dt, ix = 1.0 / (24 * g.dx), iy = 1.0 / (24 * g.dy);
-  const double hx = g.h24x, hy = g.h24y, rx = g.r24x, ry = g.r24y;
-  const double2 z2 = mk2(0.0, 0.0);
+  const double rx = g.r24x, ry = g.r24y;  // gradient terms: quotients by 24*dx, 24*dy as products (1e-16 relative)
   // e3 = mub2 * (dt * sbxy) ; e1 = lmb*gx + lamb*gy ; e2 = lmb*gy + lamb*gx with gx = dt*sbxx, gy = dt*sbyy
-  auto e3f = [dt](double2 s, double2 m) { return mk2(m.x * (dt * s.x), m.y * (dt * s.y)); };
-  auto e1f = [dt](double2 sx, double2 sy, double2 lm, double2 l_) {
-    return mk2(lm.x * (dt * sx.x) + l_.x * (dt * sy.x), lm.y * (dt * sx.y) + l_.y * (dt * sy.y));
-  };
+  auto e3f = [dt](double s, double m) { return m * (dt * s); };
+  auto e1f = [dt](double sx, double sy, double lm, double l_) { return lm * (dt * sx) + l_ * (dt * sy); };
   // windows: E3 rows li-1, li, li+1 (+ li+2) ; E1 rows li-2, li-1, li (+ li+1)
-  double2 E3m1 = z2, E3c = z2, E3p1 = z2, E1m2 = z2, E1m1 = z2, E1c = z2;
-  double2 fxm1 = z2, fxc = z2, fxp1 = z2, fym2 = z2, fym1 = z2, fyc = z2;  // forward vx / vy windows (MATGRAD)
+  double E3m1 = 0.0, E3c, E3p1, E1m2 = 0.0, E1m1 = 0.0, E1c;
+  double fxm1 = 0.0, fxc = 0.0, fxp1 = 0.0, fym2 = 0.0, fym1 = 0.0, fyc = 0.0;  // forward vx / vy windows (MATGRAD)
   if (act) {
     const i64 o1 = (i64)(d.r0 - 1) * ld + q, o2 = (i64)(d.r0 - 2) * ld + q;
-    E3m1 = e3f(ld2(b.sxy + o1), ld2(mt.mub2 + o1));
-    E1m2 = e1f(ld2(b.sxx + o2), ld2(b.syy + o2), ld2(mt.lmb + o2), ld2(mt.lamb + o2));
-    E1m1 = e1f(ld2(b.sxx + o1), ld2(b.syy + o1), ld2(mt.lmb + o1), ld2(mt.lamb + o1));
-    if (MATGRAD) { fxm1 = ld2(fwdv.vx + o1); fym2 = ld2(fwdv.vy + o2); fym1 = ld2(fwdv.vy + o1); }
+    E3m1 = e3f(b.sxy[o1], mt.mub2[o1]);
+    E1m2 = e1f(b.sxx[o2], b.syy[o2], mt.lmb[o2], mt.lamb[o2]);
+    E1m1 = e1f(b.sxx[o1], b.syy[o1], mt.lmb[o1], mt.lamb[o1]);
+    if (MATGRAD) { fxm1 = fwdv.vx[o1]; fym2 = fwdv.vy[o2]; fym1 = fwdv.vy[o1]; }
   }
   mbar_wait(bars, 0);
-  if (wact) {
-    E3c = e3f(ld2(EL_RING(T, 0, 0) + so), ld2(EL_RING(T, 1, 0) + so));
-    E3p1 = e3f(ld2(EL_RING(T, 0, 1) + so), ld2(EL_RING(T, 1, 1) + so));
-    E1c = e1f(ld2(EL_RING(T, 2, 0) + so), ld2(EL_RING(T, 3, 0) + so), ld2(EL_RING(T, 4, 0) + so), ld2(EL_RING(T, 5, 0) + so));
-    if (MATGRAD) { fxc = ld2(EL_RING(T, 8, 0) + so); fxp1 = ld2(EL_RING(T, 8, 1) + so); fyc = ld2(EL_RING(T, 9, 0) + so); }
-  }
+  E3c = e3f(EL_RING(T, 0, 0)[so], EL_RING(T, 1, 0)[so]);
+  E3p1 = e3f(EL_RING(T, 0, 1)[so], EL_RING(T, 1, 1)[so]);
+  E1c = e1f(EL_RING(T, 2, 0)[so], EL_RING(T, 3, 0)[so], EL_RING(T, 4, 0)[so], EL_RING(T, 5, 0)[so]);
+  if (MATGRAD) { fxc = EL_RING(T, 8, 0)[so]; fxp1 = EL_RING(T, 8, 1)[so]; fyc = EL_RING(T, 9, 0)[so]; }
   ElCursor cu;
   cu.init();
   for (int it = 0; it < nrows; it++) {
     const int li = d.r0 + it, bb = it % EL_NB;
     mbar_wait(bars + 1 + bb, (unsigned)(it / EL_NB) & 1u);
-    double2 E3p2 = z2, E1p1 = z2, E3l = z2, E2c = z2, E2r = z2, vx = z2, vy = z2;
-    double E3r = 0.0, E2l = 0.0;
-    double2 sxc = z2, syc = z2, sqc = z2;                                   // raw centre sigma_bar (MATGRAD)
-    double2 fxp2 = z2, fyp1 = z2, fxr = z2, fyl = z2, GL = z2, GM1 = z2, GM2 = z2;
-    double fxl = 0.0, fyr = 0.0;
-    if (wact) {
-      E3p2 = e3f(ld2(EL_RING(T, 0, cu.n[2]) + so), ld2(EL_RING(T, 1, cu.n[2]) + so));
-      E1p1 = e1f(ld2(EL_RING(T, 2, cu.n[1]) + so), ld2(EL_RING(T, 3, cu.n[1]) + so), ld2(EL_RING(T, 4, cu.n[1]) + so),
-                 ld2(EL_RING(T, 5, cu.n[1]) + so));
-      const double* sq = EL_RING(T, 0, cu.c[2]); const double* mu = EL_RING(T, 1, cu.c[2]);  // centre row of e3: q-2, q-1, q+2
-      E3l = e3f(ld2(sq + so - 2), ld2(mu + so - 2));
-      E3r = mu[so + 2] * (dt * sq[so + 2]);
-      const double* sx = EL_RING(T, 2, cu.c[1]); const double* sy = EL_RING(T, 3, cu.c[1]);   // centre row of e2: q-1 .. q+3
-      const double* lm = EL_RING(T, 4, cu.c[1]); const double* l_ = EL_RING(T, 5, cu.c[1]);
-      E2l = lm[so - 1] * (dt * sy[so - 1]) + l_[so - 1] * (dt * sx[so - 1]);
-      E2c = e1f(ld2(sy + so), ld2(sx + so), ld2(lm + so), ld2(l_ + so));          // e2 = e1 with gx <-> gy
-      E2r = e1f(ld2(sy + so + 2), ld2(sx + so + 2), ld2(lm + so + 2), ld2(l_ + so + 2));
-      vx = ld2(EL_RING(T, 6, cu.c[0]) + so); vy = ld2(EL_RING(T, 7, cu.c[0]) + so);
-      if (MATGRAD) {
-        sxc = ld2(sx + so); syc = ld2(sy + so); sqc = ld2(sq + so);
-        fxp2 = ld2(EL_RING(T, 8, cu.n[2]) + so);
-        fyp1 = ld2(EL_RING(T, 9, cu.n[1]) + so);
-        const double* cx_ = EL_RING(T, 8, cu.c[2]);  // centre row of forward vx: q-1, q+2, q+3
-        fxl = cx_[so - 1]; fxr = ld2(cx_ + so + 2);
-        const double* cy_ = EL_RING(T, 9, cu.c[1]);  // centre row of forward vy: q-2, q-1, q+2
-        fyl = ld2(cy_ + so - 2); fyr = cy_[so + 2];
-        GL = ld2(EL_RING(T, 10, cu.c[0]) + so); GM1 = ld2(EL_RING(T, 11, cu.c[0]) + so); GM2 = ld2(EL_RING(T, 12, cu.c[0]) + so);
-      }
+    const double E3p2 = e3f(EL_RING(T, 0, cu.n[2])[so], EL_RING(T, 1, cu.n[2])[so]);
+    const double E1p1 = e1f(EL_RING(T, 2, cu.n[1])[so], EL_RING(T, 3, cu.n[1])[so], EL_RING(T, 4, cu.n[1])[so],
+                            EL_RING(T, 5, cu.n[1])[so]);
+    const double* sq = EL_RING(T, 0, cu.c[2]) + so; const double* mu = EL_RING(T, 1, cu.c[2]) + so;  // centre row of e3
+    const double E3_m2 = e3f(sq[-2], mu[-2]), E3_m1 = e3f(sq[-1], mu[-1]), E3_p1 = e3f(sq[1], mu[1]);
+    const double* sx = EL_RING(T, 2, cu.c[1]) + so; const double* sy = EL_RING(T, 3, cu.c[1]) + so;   // centre row of e2
+    const double* lm = EL_RING(T, 4, cu.c[1]) + so; const double* l_ = EL_RING(T, 5, cu.c[1]) + so;
+    // e2 = e1 with gx <-> gy
+    const double E2_m1 = e1f(sy[-1], sx[-1], lm[-1], l_[-1]), E2c = e1f(sy[0], sx[0], lm[0], l_[0]);
+    const double E2_p1 = e1f(sy[1], sx[1], lm[1], l_[1]), E2_p2 = e1f(sy[2], sx[2], lm[2], l_[2]);
+    double vx = EL_RING(T, 6, cu.c[0])[so], vy = EL_RING(T, 7, cu.c[0])[so];
+    double sxc = 0.0, syc = 0.0, sqc = 0.0;  // raw centre sigma_bar (MATGRAD)
+    double fxp2 = 0.0, fyp1 = 0.0, fx_m1 = 0.0, fx_p1 = 0.0, fx_p2 = 0.0, fy_m2 = 0.0, fy_m1 = 0.0, fy_p1 = 0.0;
+    double GL = 0.0, GM1 = 0.0, GM2 = 0.0;
+    if (MATGRAD) {
+      sxc = sx[0]; syc = sy[0]; sqc = sq[0];
+      fxp2 = EL_RING(T, 8, cu.n[2])[so];
+      fyp1 = EL_RING(T, 9, cu.n[1])[so];
+      const double* cx_ = EL_RING(T, 8, cu.c[2]) + so;  // centre row of forward vx
+      fx_m1 = cx_[-1]; fx_p1 = cx_[1]; fx_p2 = cx_[2];
+      const double* cy_ = EL_RING(T, 9, cu.c[1]) + so;  // centre row of forward vy
+      fy_m2 = cy_[-2]; fy_m1 = cy_[-1]; fy_p1 = cy_[1];
+      GL = EL_RING(T, 10, cu.c[0])[so]; GM1 = EL_RING(T, 11, cu.c[0])[so]; GM2 = EL_RING(T, 12, cu.c[0])[so];
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bars + 1 + EL_NB + bb);
     if (act) {
       const i64 c = (i64)li * ld + q;
       // (D+x)^T e1 -> vx ; (D-y)^T e2 -> vy ; (D-x)^T e3 -> vy ; (D+y)^T e3 -> vx
-      vx.x += (27 * E1m1.x - 27 * E1c.x - E1m2.x + E1p1.x) * ix;
-      vy.x += (27 * E2c.x - 27 * E2c.y - E2l + E2r.x) * iy;
-      vy.x += (27 * E3c.x - 27 * E3p1.x - E3m1.x + E3p2.x) * ix;
-      vx.x += (27 * E3l.y - 27 * E3c.x - E3l.x + E3c.y) * iy;
-      vx.y += (27 * E1m1.y - 27 * E1c.y - E1m2.y + E1p1.y) * ix;
-      vy.y += (27 * E2c.y - 27 * E2r.x - E2c.x + E2r.y) * iy;
-      vy.y += (27 * E3c.y - 27 * E3p1.y - E3m1.y + E3p2.y) * ix;
-      vx.y += (27 * E3c.x - 27 * E3c.y - E3l.y + E3r) * iy;
-      st2(bout.vx + c, vx); st2(bout.vy + c, vy);
+      vx += (27 * E1m1 - 27 * E1c - E1m2 + E1p1) * ix;
+      vy += (27 * E2c - 27 * E2_p1 - E2_m1 + E2_p2) * iy;
+      vy += (27 * E3c - 27 * E3p1 - E3m1 + E3p2) * ix;
+      vx += (27 * E3_m1 - 27 * E3c - E3_m2 + E3_p1) * iy;
+      bout.vx[c] = vx; bout.vy[c] = vy;
       if (MATGRAD) {
-        {
-          const double gx = dt * sxc.x, gy = dt * syc.x, gg = dt * sqc.x;
-          const double e1 = div_exact(27 * fxp1.x - 27 * fxc.x - fxp2.x + fxm1.x, hx, rx);
-          const double e2 = div_exact(27 * fyc.x - 27 * fyl.y - fyc.y + fyl.x, hy, ry);
-          const double e34 = div_exact(27 * fyc.x - 27 * fym1.x - fyp1.x + fym2.x, hx, rx) +
-                             div_exact(27 * fxc.y - 27 * fxc.x - fxr.x + fxl, hy, ry);
-          GL.x += (gx + gy) * (e1 + e2);
-          GM1.x += 2 * (gx * e1 + gy * e2);
-          GM2.x += gg * e34;
-        }
-        {
-          const double gx = dt * sxc.y, gy = dt * syc.y, gg = dt * sqc.y;
-          const double e1 = div_exact(27 * fxp1.y - 27 * fxc.y - fxp2.y + fxm1.y, hx, rx);
-          const double e2 = div_exact(27 * fyc.y - 27 * fyc.x - fyr + fyl.y, hy, ry);
-          const double e34 = div_exact(27 * fyc.y - 27 * fym1.y - fyp1.y + fym2.y, hx, rx) +
-                             div_exact(27 * fxr.x - 27 * fxc.y - fxr.y + fxc.x, hy, ry);
-          GL.y += (gx + gy) * (e1 + e2);
-          GM1.y += 2 * (gx * e1 + gy * e2);
-          GM2.y += gg * e34;
-        }
-        st2(Gl + c, GL); st2(Gm1 + c, GM1); st2(Gm2 + c, GM2);
+        const double gx = dt * sxc, gy = dt * syc, gg = dt * sqc;
+        const double e1 = (27 * fxp1 - 27 * fxc - fxp2 + fxm1) * rx;
+        const double e2 = (27 * fyc - 27 * fy_m1 - fy_p1 + fy_m2) * ry;
+        const double e34 = (27 * fyc - 27 * fym1 - fyp1 + fym2) * rx + (27 * fx_p1 - 27 * fxc - fx_p2 + fx_m1) * ry;
+        Gl[c] = GL + (gx + gy) * (e1 + e2);
+        Gm1[c] = GM1 + 2 * (gx * e1 + gy * e2);
+        Gm2[c] = GM2 + gg * e34;
       }
     }
     E3m1 = E3c; E3c = E3p1; E3p1 = E3p2;
@@ -1225,7 +1162,7 @@ __device__ __forceinline__ void el_sigma_adj_march(const ElGeom& g, const ElCta&
 }
 
 template <bool MATGRAD>
-__global__ void __launch_bounds__(EL_NT, 1)
+__global__ void __maxnreg__(MATGRAD ? 112 : 72)
 el_sigma_adj(ElGeom g, const ElCta* __restrict__ ctas, ElSlot b, ElSlot bout, ElSlot fwdv, ElSlot fwdm, ElMat mt,
              ElCoef cf, double* __restrict__ Gl, double* __restrict__ Gm1, double* __restrict__ Gm2, ElPoints rcv,
              const double* __restrict__ res, int res_stride, int slot_prev, ElPoints src,
@@ -1233,6 +1170,12 @@ el_sigma_adj(ElGeom g, const ElCta* __restrict__ ctas, ElSlot b, ElSlot bout, El
   extern __shared__ __align__(128) unsigned char el_smem[];
   const int bid = el_bid(f);
   const ElCta d = el_cta(ctas, bid);
+#ifdef EL_DEBUG_SKIP_GENERIC  // timing experiments only (wrong results)
+  if (d.kind != 0) return;
+#endif
+#ifdef EL_DEBUG_SKIP_MARCH
+  if (d.kind == 0) return;
+#endif
   bool t_lo, t_hi;
   el_cta_edges(g, f, d, &t_lo, &t_hi);
   el_fuse_wait(f, t_lo, t_hi);

@@ -66,6 +66,15 @@ def run_elastic(NX, NY, NSTEP, variant, reps=2, mat=True):
     plan.close()
 
 
+if __name__ == "__main__" and "--elastic-one" in sys.argv:
+    run_elastic(2000, 2000, 12, 1, reps=1)
+    sys.exit(0)
+
+if __name__ == "__main__" and "--elastic-quick" in sys.argv:
+    print("variant", os.environ.get("ADSEIS_LIB_SUFFIX", "(default)"))
+    run_elastic(2000, 2000, 60, 1)
+    sys.exit(0)
+
 if __name__ == "__main__" and "--elastic" in sys.argv:
     run_elastic(500, 500, 200, 0)
     run_elastic(2000, 2000, 60, 1)
