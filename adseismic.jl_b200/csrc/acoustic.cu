@@ -345,12 +345,17 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     P->fast_rows = mr1 - mr0;
     const int nwarpcols = (mc_end - mc0 + AC_WCOLS - 1) / AC_WCOLS;
     t.nct = (nwarpcols + AC_WARPS - 1) / AC_WARPS;
-    // rows per marching CTA: aim at >= 4 CTAs per SM so that every SM has work and the tail is short
+    // rows per marching CTA: the TMA-ring kernels run 2 CTAs per SM, so the marching CTA count is a multiple of
+    // 2 * SMs (whole waves); up to 3 waves for load balance as long as a CTA keeps >= 12 rows to amortise its
+    // pipeline prologue (small slabs of a domain decomposition get exactly one wave)
     int rb = 32;
     if (t.nct > 0 && mr1 > mr0) {
-      const int want_tr = std::max(1, (4 * ctx->sm_count + t.nct - 1) / t.nct);
+      const int per_wave = std::max(1, (2 * ctx->sm_count + t.nct - 1) / t.nct);  // row tiles of one wave
+      const int waves = std::min(3, std::max(1, (mr1 - mr0) / (12 * per_wave)));
+      const int want_tr = per_wave * waves;
       rb = (mr1 - mr0 + want_tr - 1) / want_tr;
-      rb = std::min(64, std::max(AC_U, round_up(rb, AC_U)));  // AC_U is a multiple of AC_UA
+      rb = std::min(128, std::max(AC_U, round_up(rb, AC_FWD_TMA && AC_ADJ_TMA ? 1 : AC_U)));
+      if (getenv("ADSEIS_AC_RB")) rb = std::max(2, atoi(getenv("ADSEIS_AC_RB")));  // tuning experiments
     }
     t.rb = rb;
     t.ntr = (mr1 > mr0) ? (mr1 - mr0 + rb - 1) / rb : 0;

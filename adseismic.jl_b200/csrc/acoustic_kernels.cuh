@@ -62,7 +62,7 @@ struct __align__(128) AcAdjStage {
 #define AC_FWD_TMA 1                        // forward marching CTAs: same TMA row ring
 #endif
 #ifndef AC_MINB_FWD
-#define AC_MINB_FWD (AC_FWD_TMA ? 3 : 2)    // __launch_bounds__ min CTAs/SM, forward
+#define AC_MINB_FWD 2                       // __launch_bounds__ min CTAs/SM, forward (same wave size as the adjoint)
 #endif
 #ifndef AC_NST_FWD
 #define AC_NST_FWD 4

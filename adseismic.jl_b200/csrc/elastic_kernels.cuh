@@ -912,7 +912,8 @@ __device__ __forceinline__ void el_vel_adj_march(const ElGeom& g, const ElCta& d
 }
 
 template <bool MATGRAD>
-__global__ void __maxnreg__(MATGRAD ? 112 : 72)
+// (9 warps per CTA: two CTAs per SM need <= 96 registers, three <= 72 -- the per-scheduler register files hold 5 / 7 warps)
+__global__ void __launch_bounds__(EL_NT, MATGRAD ? 2 : 3)
 el_vel_adj(ElGeom g, const ElCta* __restrict__ ctas, ElSlot b, ElSlot bout, ElSlot fwd, ElMat mt, ElCoef cf,
            double* __restrict__ Gr3, double* __restrict__ Gr4, ElPoints rcv, const double* __restrict__ res,
            int res_stride, int slot, ElFuse f) {
@@ -1162,7 +1163,7 @@ __device__ __forceinline__ void el_sigma_adj_march(const ElGeom& g, const ElCta&
 }
 
 template <bool MATGRAD>
-__global__ void __maxnreg__(MATGRAD ? 112 : 72)
+__global__ void __launch_bounds__(EL_NT, MATGRAD ? 2 : 3)
 el_sigma_adj(ElGeom g, const ElCta* __restrict__ ctas, ElSlot b, ElSlot bout, ElSlot fwdv, ElSlot fwdm, ElMat mt,
              ElCoef cf, double* __restrict__ Gl, double* __restrict__ Gm1, double* __restrict__ Gm2, ElPoints rcv,
              const double* __restrict__ res, int res_stride, int slot_prev, ElPoints src,

@@ -238,7 +238,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        nstep_s = args.cpu_steps or 6
+        nstep_s = args.cpu_steps or 16
         sec, desc = reference_arm(w, args.steps, args.warmup, nstep_s)
         cells = w["NX"] * w["NY"] * (nstep_s - 1)
         val = cells / sec / 1e9
@@ -341,7 +341,7 @@ def main():
                gpu_launches=launches, roofline=roof, loss=loss, loss_e2e=loss_e2e)
     plan.close()
     if not args.no_cpu:
-        nstep_s = args.cpu_steps or 6
+        nstep_s = args.cpu_steps or 16
         out["cpu_baseline"] = cpu_sample_single_thread(w, nstep_s)
     print(json.dumps(out))
 

@@ -34,6 +34,13 @@ if __name__ == "__main__" and "--elastic" not in sys.argv:
         print("variant", os.environ.get("ADSEIS_LIB_SUFFIX", "(default)"))
         run(4096, 4096, 60)
         sys.exit(0)
+    if "--rb" in sys.argv:
+        for nx, ny, nt, rbs in ((512, 4096, 200, (6, 8, 10, 14, 20, 28)), (4096, 4096, 40, (24, 28, 37, 56, 74))):
+            for rb in rbs:
+                os.environ["ADSEIS_AC_RB"] = str(rb)
+                print("rb", rb, end=" ")
+                run(nx, ny, nt, reps=2)
+        sys.exit(0)
     if "--one" in sys.argv:
         run(4096, 4096, 24, reps=1)
         sys.exit(0)
