@@ -640,11 +640,11 @@ static int run_forward_steps(adseis_acoustic_plan* P, i64 base, i64 s_first, i64
   }
   for (i64 s = s_first; s <= s_last; s++) {
     const AcFuse fuse = make_fuse(P, AR_HIST, s - base, AR_PHI, s & 1);
-    ac_fwd_kernel<<<P->nblocks, AC_FWD_THREADS, AC_FWD_SMEM, st>>>(
+    CUDA_TRY(launch_step(ac_fwd_kernel, P->nblocks, AC_FWD_THREADS, AC_FWD_SMEM, st,
         g, P->t, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, P->phi[(s - 1) & 1], P->psi[(s - 1) & 1],
         P->sigx, P->tauy, win_slot(P, base, s), P->phi[s & 1], P->psi[s & 1], P->srcp,
         P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, sample ? P->rcvp : none,
-        (sample && P->nrcv > 0) ? P->rcvv + s * P->nrcv : nullptr, fuse);
+        (sample && P->nrcv > 0) ? P->rcvv + s * P->nrcv : nullptr, fuse));
     LAUNCH_CHECK(P);
   }
   return ADSEIS_OK;
@@ -794,11 +794,11 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
     TRY(span_begin(P, 2, e - (b + 2) + 1));
     for (i64 s = e; s >= b + 2; s--) {
       const AcFuse fuse = make_fuse(P, AR_UB, (s + 2) % 3, AR_PHIB, (s - 1) & 1);
-      ac_adj_kernel<<<P->nblocks, AC_ADJ_THREADS, AC_ADJ_SMEM, st>>>(
+      CUDA_TRY(launch_step(ac_adj_kernel, P->nblocks, AC_ADJ_THREADS, AC_ADJ_SMEM, st,
           g, P->t, P->ub[s % 3], P->ub[(s + 1) % 3], win_slot(P, b, s - 1), P->c2, P->phib[s & 1], P->psib[s & 1],
           P->sigx, P->tauy, P->ub[(s + 2) % 3] /* == (s-1)%3 */, P->phib[(s - 1) & 1], P->psib[(s - 1) & 1], P->G,
           P->rcvp, P->nrcv > 0 ? P->res + (s - 1) * P->nrcv : nullptr, (s - 2 >= 1) ? P->srcp : none,
-          (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr, fuse);
+          (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr, fuse));
       LAUNCH_CHECK(P);
     }
     TRY(span_end(P));

@@ -126,6 +126,7 @@ struct AcFuse {
 };
 
 __device__ __forceinline__ void ac_fuse_wait(const AcFuse& f, bool t_lo, bool t_hi) {
+  pdl_wait();  // (programmatic dependent launch) everything the previous launch wrote is visible from here on
   if (!(t_lo || t_hi)) return;  // CTA-uniform
   if (threadIdx.x == 0) {
     volatile unsigned long long* fl = f.my_flags;
@@ -221,6 +222,7 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
               const double* __restrict__ sigx, const double* __restrict__ tauy, double* __restrict__ u,
               double* __restrict__ phio, double* __restrict__ psio, AcPoints src,
               const double* __restrict__ srcv_row, AcPoints rcv, double* __restrict__ rcvv_row, AcFuse f) {
+  pdl_launch_dependents();
   const int bid = f.perm ? f.perm[blockIdx.x] : blockIdx.x;
   const int ld = g.ld;
   bool t_lo = false, t_hi = false;  // this CTA owns cells of my first / last owned row next to a neighbour
@@ -495,6 +497,7 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
               double* __restrict__ ub0, double* __restrict__ phibo, double* __restrict__ psibo,
               double* __restrict__ G, AcPoints rcv, const double* __restrict__ res_row, AcPoints src,
               double* __restrict__ gsrcv_row, AcFuse f) {
+  pdl_launch_dependents();
   const int bid = f.perm ? f.perm[blockIdx.x] : blockIdx.x;
 #ifdef AC_DEBUG_SKIP_FRAME   // timing experiments only (wrong results)
   if (bid >= t.nmarch) return;

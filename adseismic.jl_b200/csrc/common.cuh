@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -74,6 +75,30 @@ static inline int dev_upload(T** p, const std::vector<T>& h, cudaStream_t s) {
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Programmatic dependent launch (sm_90+): the time-step kernels call griddepcontrol.launch_dependents on entry, so
+// the next step's CTAs are scheduled while the current step drains, run their prologue (CTA table, mbarrier init)
+// and block in griddepcontrol.wait until the current step's memory operations are complete and visible.  Hides the
+// launch gap between the thousands of dependent step launches of a sweep.  ADSEIS_PDL=0 disables it.
+static inline bool adseis_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("ADSEIS_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_step(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st,
+                                      Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = adseis_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------------
 // Point sets: sources and receivers grouped by owning CTA and grid cell, so that the time-step kernels can
 // inject / sample them in their CTA epilogue without atomics and in the reference's sequential order
@@ -140,6 +165,8 @@ static inline void free_point_set(PointSetStorage* st) {
 }
 
 #ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
 // streaming (evict-first) 16-byte accesses for data touched once per time step

@@ -344,9 +344,15 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
     P->box[0] = r0; P->box[1] = r1; P->box[2] = c0; P->box[3] = c1;
     if (r1 > r0) {
       mnct = (c1 - c0 + EL_TCOLS - 1) / EL_TCOLS;
-      // ~6 marching CTAs per SM: whole waves for the kernels that fit 2 and those that fit 3 CTAs per SM
-      const int want_tr = std::max(1, (6 * ctx->sm_count + mnct - 1) / mnct);
-      mrb = std::min(64, std::max(8, (r1 - r0 + want_tr - 1) / want_tr));
+      // marching CTAs per SM: 6 gives whole waves both to the kernels that fit 2 and to those that fit 3 CTAs per
+      // SM; thinner slabs take 3, 2 or 1 per SM so that a CTA keeps >= 16 rows to amortise its pipeline prologue
+      mrb = 8;
+      for (int k : {6, 3, 2, 1}) {
+        const int want_tr = std::max(1, (k * ctx->sm_count + mnct - 1) / mnct);
+        mrb = std::min(64, std::max(8, (r1 - r0 + want_tr - 1) / want_tr));
+        if (mrb >= 16) break;
+      }
+      if (getenv("ADSEIS_EL_RB")) mrb = std::max(2, atoi(getenv("ADSEIS_EL_RB")));  // tuning experiments
       const int ntr = (r1 - r0 + mrb - 1) / mrb;
       for (int tr = 0; tr < ntr; tr++)
         for (int tc = 0; tc < mnct; tc++)
@@ -719,12 +725,12 @@ static int el_step_forward(adseis_elastic_plan* P, i64 s, double* in, double* ou
   const double* prev = (P->nsrc > 0 && s >= 2) ? P->srcv + (s - 2) * P->nsrc : nullptr;
   const i64 widx = (out - P->hist) / P->slot_sz;
   const ElPlaneRef sig_planes[2] = {{EA_HIST, widx, 2}, {EA_HIST, widx, 4}};  // fw3/fw4 difference sxx, sxy along x
-  el_sigma_fwd<<<P->nblocks, EL_NT, el_ring_bytes<ElSigFwdT>(), st>>>(P->g, P->ctas, si, so, mt, cf, P->src.dev, prev, el_make_fuse(P, 2, sig_planes));
+  CUDA_TRY(launch_step(el_sigma_fwd, P->nblocks, EL_NT, el_ring_bytes<ElSigFwdT>(), st, P->g, P->ctas, si, so, mt, cf, P->src.dev, prev, el_make_fuse(P, 2, sig_planes)));
   EL_LAUNCH_CHECK(P);
   const ElPlaneRef vel_planes[2] = {{EA_HIST, widx, 0}, {EA_HIST, widx, 1}};
-  el_vel_fwd<<<P->nblocks, EL_NT, el_ring_bytes<ElVelFwdT>(), st>>>(P->g, P->ctas, si, so, mt, cf, P->src.dev, row, sample ? P->rcv.dev : none,
+  CUDA_TRY(launch_step(el_vel_fwd, P->nblocks, EL_NT, el_ring_bytes<ElVelFwdT>(), st, P->g, P->ctas, si, so, mt, cf, P->src.dev, row, sample ? P->rcv.dev : none,
                                          (sample && P->nrcv > 0) ? P->rcvv : nullptr, (int)(P->p.NSTEP + 1), (int)s,
-                                         el_make_fuse(P, 2, vel_planes));
+                                         el_make_fuse(P, 2, vel_planes)));
   EL_LAUNCH_CHECK(P);
   return ADSEIS_OK;
 }
@@ -863,22 +869,22 @@ ADSEIS_API int adseis_elastic_plan_gradient(adseis_elastic_plan* P, int want_mat
       const double* resp = P->nrcv > 0 ? P->res : nullptr;
       double* grow = (s - 2 >= 0 && P->nsrc > 0 && s >= 2) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr;
       if (mat) {
-        el_vel_adj<true><<<P->nblocks, EL_NT, el_ring_bytes<ElVelAdjT<true>>(), st>>>(g, P->ctas, bi, bo, fs, mt, cf, P->Gr3, P->Gr4, P->rcv.dev, resp, stride, (int)s,
-                                                     el_make_fuse(P, 3, sb_planes));
+        CUDA_TRY(launch_step(el_vel_adj<true>, P->nblocks, EL_NT, el_ring_bytes<ElVelAdjT<true>>(), st, g, P->ctas, bi, bo, fs, mt, cf, P->Gr3, P->Gr4, P->rcv.dev, resp, stride, (int)s,
+                                                     el_make_fuse(P, 3, sb_planes)));
         EL_LAUNCH_CHECK(P);
-        el_sigma_adj<true><<<P->nblocks, EL_NT, el_ring_bytes<ElSigAdjT<true>>(), st>>>(g, P->ctas, bi, bo, fp, fs, mt, cf, P->Gl, P->Gm1, P->Gm2,
+        CUDA_TRY(launch_step(el_sigma_adj<true>, P->nblocks, EL_NT, el_ring_bytes<ElSigAdjT<true>>(), st, g, P->ctas, bi, bo, fp, fs, mt, cf, P->Gl, P->Gm1, P->Gm2,
                                                        s >= 2 ? P->rcv.dev : none, s >= 2 ? resp : nullptr, stride,
                                                        (int)(s - 1), s >= 2 ? P->src.dev : none, grow,
-                                                       el_make_fuse(P, 2, vb_planes));
+                                                       el_make_fuse(P, 2, vb_planes)));
         EL_LAUNCH_CHECK(P);
       } else {
-        el_vel_adj<false><<<P->nblocks, EL_NT, el_ring_bytes<ElVelAdjT<false>>(), st>>>(g, P->ctas, bi, bo, zero, mt, cf, nullptr, nullptr, P->rcv.dev, resp, stride,
-                                                      (int)s, el_make_fuse(P, 3, sb_planes));
+        CUDA_TRY(launch_step(el_vel_adj<false>, P->nblocks, EL_NT, el_ring_bytes<ElVelAdjT<false>>(), st, g, P->ctas, bi, bo, zero, mt, cf, nullptr, nullptr, P->rcv.dev, resp, stride,
+                                                      (int)s, el_make_fuse(P, 3, sb_planes)));
         EL_LAUNCH_CHECK(P);
-        el_sigma_adj<false><<<P->nblocks, EL_NT, el_ring_bytes<ElSigAdjT<false>>(), st>>>(g, P->ctas, bi, bo, zero, zero, mt, cf, nullptr, nullptr, nullptr,
+        CUDA_TRY(launch_step(el_sigma_adj<false>, P->nblocks, EL_NT, el_ring_bytes<ElSigAdjT<false>>(), st, g, P->ctas, bi, bo, zero, zero, mt, cf, nullptr, nullptr, nullptr,
                                                         s >= 2 ? P->rcv.dev : none, s >= 2 ? resp : nullptr, stride,
                                                         (int)(s - 1), s >= 2 ? P->src.dev : none, grow,
-                                                        el_make_fuse(P, 2, vb_planes));
+                                                        el_make_fuse(P, 2, vb_planes)));
         EL_LAUNCH_CHECK(P);
       }
     }

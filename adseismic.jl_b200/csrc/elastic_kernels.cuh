@@ -134,6 +134,7 @@ __device__ __forceinline__ void el_cta_edges(const ElGeom& g, const ElFuse& f, c
 }
 
 __device__ __forceinline__ void el_fuse_wait(const ElFuse& f, bool t_lo, bool t_hi) {
+  pdl_wait();  // (programmatic dependent launch) everything the previous launch wrote is visible from here on
   if (!(t_lo || t_hi)) return;  // CTA-uniform
   if (threadIdx.x == 0) {
     volatile unsigned long long* fl = f.my_flags;
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__(EL_NT, EL_MINB_FWD)
 el_sigma_fwd(ElGeom g, const ElCta* __restrict__ ctas, ElSlot in, ElSlot out, ElMat mt, ElCoef cf, ElPoints src,
              const double* __restrict__ srcv_prev, ElFuse f) {
   extern __shared__ __align__(128) unsigned char el_smem[];
+  pdl_launch_dependents();
   const int bid = el_bid(f);
   const ElCta d = el_cta(ctas, bid);
 #ifdef EL_DEBUG_SKIP_GENERIC  // timing experiments only (wrong results)
@@ -585,6 +587,7 @@ el_vel_fwd(ElGeom g, const ElCta* __restrict__ ctas, ElSlot in, ElSlot out, ElMa
            const double* __restrict__ srcv_row, ElPoints rcv, double* __restrict__ rcvv, int rcv_stride, int slot,
            ElFuse f) {
   extern __shared__ __align__(128) unsigned char el_smem[];
+  pdl_launch_dependents();
   const int bid = el_bid(f);
   const ElCta d = el_cta(ctas, bid);
 #ifdef EL_DEBUG_SKIP_GENERIC  // timing experiments only (wrong results)
@@ -918,6 +921,7 @@ el_vel_adj(ElGeom g, const ElCta* __restrict__ ctas, ElSlot b, ElSlot bout, ElSl
            double* __restrict__ Gr3, double* __restrict__ Gr4, ElPoints rcv, const double* __restrict__ res,
            int res_stride, int slot, ElFuse f) {
   extern __shared__ __align__(128) unsigned char el_smem[];
+  pdl_launch_dependents();
   const int bid = el_bid(f);
   const ElCta d = el_cta(ctas, bid);
 #ifdef EL_DEBUG_SKIP_GENERIC  // timing experiments only (wrong results)
@@ -1169,6 +1173,7 @@ el_sigma_adj(ElGeom g, const ElCta* __restrict__ ctas, ElSlot b, ElSlot bout, El
              const double* __restrict__ res, int res_stride, int slot_prev, ElPoints src,
              double* __restrict__ gsrcv_row, ElFuse f) {
   extern __shared__ __align__(128) unsigned char el_smem[];
+  pdl_launch_dependents();
   const int bid = el_bid(f);
   const ElCta d = el_cta(ctas, bid);
 #ifdef EL_DEBUG_SKIP_GENERIC  // timing experiments only (wrong results)
