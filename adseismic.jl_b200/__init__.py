@@ -14,6 +14,7 @@ from . import elastic as _el
 from .elastic import (ElasticPlan, ElasticPropagator, ElasticPropagatorSolver, compute_PML_Params, elastic_forward,
                       elastic_misfit_grad)
 from .utils import Gauss, Ricker, compute_lame_parameters
+from . import io
 
 
 def SimulatedObservation_(prop, rcv):
@@ -23,6 +24,13 @@ def SimulatedObservation_(prop, rcv):
         rcv.rcvv = elastic_forward(prop.param, prop.src, prop.rho, prop.lam, prop.mu, rcv, False, prop.ctx)[0]
         return rcv.rcvv
     return _ac.SimulatedObservation_(prop, rcv)
+
+
+def __getattr__(name):
+    if name == "fwi":      # needs torch: imported on first use
+        import importlib
+        return importlib.import_module(__name__ + ".fwi")
+    raise AttributeError(name)
 
 
 def build(force=False, verbose=False):

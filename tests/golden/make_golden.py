@@ -90,6 +90,33 @@ def elastic_case(name, variant, NX, NY, NSTEP, seed):
     print(name, "loss", B["loss"])
 
 
+def marmousi_case(name, nstep=400, shot=3):
+    """The reference's own model fixture (examples/nn_fwi/models/marmousi2-model-true.mat: 202 x 68 padded cells, 8
+    shots, 183 receivers; the FWI scripts run it with AcousticPropagatorSolver, examples/nn_fwi/FWI_inversion.jl): one
+    shot, the first `nstep` of its 1678 time steps, through the reference's C++ op bodies; observed data from the
+    smooth starting model of the same directory, exactly the misfit the inversion scripts start from."""
+    import adseis_b200 as A
+    d = "/root/reference/examples/nn_fwi/models/"
+    param, vp_true = A.io.load_acoustic_model(d + "marmousi2-model-true.mat")
+    _, vp_smooth = A.io.load_acoustic_model(d + "marmousi2-model-smooth.mat")
+    src = A.io.load_acoustic_source(d + "marmousi2-model-true.mat")[shot]
+    rcv = A.io.load_acoustic_receiver(d + "marmousi2-model-true.mat")[shot]
+    NX, NY, dx, dy, dt = param.NX, param.NY, param.DELTAX, param.DELTAY, param.DELTAT
+    vp_ref = float(vp_true.mean())
+    srcv = np.ascontiguousarray(src.srcv[:nstep])
+    sig, tau = po.acoustic_pml(NX, NY, dx, dy, npml=param.NPOINTS_PML, vp_ref=vp_ref)
+    _, obs = po.acoustic_forward(NX, NY, nstep, dt, dx, dy, sig, tau, vp_true, src.srci, src.srcj, srcv, rcv.rcvi,
+                                 rcv.rcvj, which="ref")
+    u, rcvv = po.acoustic_forward(NX, NY, nstep, dt, dx, dy, sig, tau, vp_smooth, src.srci, src.srcj, srcv, rcv.rcvi,
+                                  rcv.rcvj, which="ref")
+    loss, gc, gs = po.acoustic_misfit_grad(NX, NY, nstep, dt, dx, dy, sig, tau, vp_smooth, src.srci, src.srcj,
+                                           rcv.rcvi, rcv.rcvj, obs, u, which="ref")
+    np.savez_compressed(os.path.join(HERE, name), NX=NX, NY=NY, NSTEP=nstep, dx=dx, dy=dy, dt=dt,
+                        npml=param.NPOINTS_PML, vp_ref=vp_ref, c=vp_smooth, srci=src.srci, srcj=src.srcj, srcv=srcv,
+                        rcvi=rcv.rcvi, rcvj=rcv.rcvj, obs=obs, rcvv=rcvv, loss=loss, grad_c=gc, grad_srcv=gs)
+    print(name, "loss", loss, "|grad_c|max", np.abs(gc).max(), "|rcvv|max", np.abs(rcvv).max())
+
+
 if __name__ == "__main__":
     assert po.has_ref(), "oracle/_ref is not built: run `make -C oracle` where /root/reference exists"
     acoustic_step_case("acoustic_step_gradtest.npz", 233)
@@ -97,3 +124,4 @@ if __name__ == "__main__":
     acoustic_case("acoustic_nopml_y.npz", 33, 45, 60, 8.0, 12.0, 1e-3, 5, 2500.0, 99, use=(True, True, False, False))
     elastic_case("elastic_S.npz", 0, 26, 22, 30, 7)
     elastic_case("elastic_M.npz", 1, 26, 22, 30, 8)
+    marmousi_case("acoustic_marmousi2_shot3.npz")
