@@ -18,6 +18,13 @@ def _layered(shape, v0, v1, rng):
     return (v0 + (v1 - v0) * np.floor(z * 4) / 4) * (1 + 0.02 * rng.random(shape))
 
 
+def _exactly_scaled(r, r1, k):
+    """r == k r1 bit for bit; the numerical precursor ahead of the wavefront underflows into the denormal range,
+    where scaling is not exact -- there only the magnitude is checked."""
+    big = np.abs(r1) > 1e-280
+    return np.array_equal(r[big], k * r1[big]) and np.all(np.abs(r[~big] - k * r1[~big]) < 1e-270)
+
+
 def _acoustic_plan(A, ctx, NX, NY, NSTEP, nrcv, hist=0):
     p = A.AcousticPropagatorParams(NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=10.0, DELTAY=10.0, DELTAT=1e-3, vp_ref=2500.0)
     srci, srcj = np.array([NX // 2, NX // 3]), np.array([NY // 2, 40])
@@ -40,7 +47,7 @@ def test_acoustic_fullsize_properties(A, ctx, grid):
     assert np.abs(r1).max() > 0
     plan.set_srcv(4.0 * srcv)
     plan.forward()
-    assert np.array_equal(plan.rcvv(), 4.0 * r1)                              # exact linearity
+    assert _exactly_scaled(plan.rcvv(), r1, 4.0)                              # exact linearity
     # adjoint identity
     plan.set_srcv(srcv); plan.set_obs(np.zeros_like(r1))
     plan.gradient()
@@ -102,7 +109,7 @@ def test_elastic_fullsize_properties(A, ctx, variant):
     assert np.abs(r1).max() > 0
     plan.set_srcv(2.0 * srcv)
     plan.forward()
-    assert np.array_equal(plan.rcvv(), 2.0 * r1)
+    assert _exactly_scaled(plan.rcvv(), r1, 2.0)
     plan.set_srcv(srcv); plan.set_obs(np.zeros_like(r1))
     plan.gradient(False)                                  # source-time-function gradient: no tape at all
     L, gs = plan.loss(), plan.grad_srcv()
