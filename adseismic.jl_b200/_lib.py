@@ -169,6 +169,7 @@ class Context:
         check(lib.adseis_ctx_create(int(device), C.byref(h)))
         self.handle = h
         self.lib = lib
+        track(self)
 
     def sync(self):
         check(self.lib.adseis_ctx_sync(self.handle))
@@ -209,6 +210,27 @@ class Context:
 
 
 _default_ctx = None
+_live = None      # weak set of plans / contexts, closed in order (plans first) at interpreter exit
+
+
+def track(obj):
+    """Plans and contexts register here so that interpreter shutdown closes plans before their contexts, while the
+    CUDA runtime is still alive (finalisers run in arbitrary order otherwise)."""
+    global _live
+    if _live is None:
+        import atexit
+        import weakref
+        _live = weakref.WeakSet()
+
+        def _close_all():
+            objs = list(_live)
+            for o in sorted(objs, key=lambda o: isinstance(o, Context)):
+                try:
+                    o.close()
+                except Exception:
+                    pass
+        atexit.register(_close_all)
+    _live.add(obj)
 
 
 def default_context():

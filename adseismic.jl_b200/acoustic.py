@@ -46,6 +46,7 @@ class AcousticPlan:
                                                    pi(self.srcj), self.nrcv, pi(self.rcvi), pi(self.rcvj),
                                                    int(hist_bytes_budget), C.byref(h)))
         self.handle = h
+        _lib.track(self)
 
     # -- inputs (numpy arrays, torch CUDA tensors or raw device addresses) --
     def set_model(self, c):

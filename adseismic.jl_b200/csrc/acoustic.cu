@@ -244,7 +244,9 @@ ADSEIS_API int adseis_acoustic_plan_destroy(adseis_acoustic_plan* P) {
   cudaFree(P->srcv); cudaFree(P->rcvv); cudaFree(P->obs); cudaFree(P->res); cudaFree(P->loss);
   cudaFree(P->G); cudaFree(P->gradc); cudaFree(P->gradsrcv);
   for (cudaEvent_t e : P->ev_pool) cudaEventDestroy(e);
+  adseis_ctx* ctx = P->ctx;
   delete P;
+  adseis_ctx_release_plan(ctx);
   return ADSEIS_OK;
 }
 
@@ -278,6 +280,7 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
   cudaStream_t st = ctx->stream;
   adseis_acoustic_plan* P = new adseis_acoustic_plan();
   P->ctx = ctx;
+  ctx->plans++;
   P->p = *p;
   const int H = (int)p->NX + 2, W = (int)p->NY + 2;
   if (slab) P->slab = *slab; else { P->slab.rank = 0; P->slab.nranks = 1; P->slab.row0 = 0; P->slab.row1 = H; }
@@ -285,6 +288,7 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
   if (!(sl.nranks >= 1 && sl.rank >= 0 && sl.rank < sl.nranks && sl.row0 >= 0 && sl.row1 <= H && sl.row0 < sl.row1 &&
         (sl.rank > 0 || sl.row0 == 0) && (sl.rank < sl.nranks - 1 || sl.row1 == H))) {
     delete P;
+    ctx->plans--;
     adseis_set_error("acoustic_plan_create: inconsistent slab {rank %d/%d rows [%lld,%lld)}", sl.rank, sl.nranks,
                      (long long)sl.row0, (long long)sl.row1);
     return ADSEIS_EINVAL;
@@ -318,7 +322,7 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
   // PML profiles and the PML-free box
   std::vector<double> sx(H), ty(W);
   int rc = adseis_acoustic_pml_profiles(p, sx.data(), ty.data());
-  if (rc) { delete P; return rc; }
+  if (rc) { adseis_acoustic_plan_destroy(P); return rc; }
   auto box = [](const std::vector<double>& v, int n, int* a, int* b) {  // maximal zero run inside 1..n
     int lo = 1;
     while (lo <= n && v[lo] != 0.0) lo++;

@@ -50,7 +50,10 @@ struct adseis_ctx {
   cudaStream_t stream;
   cudaEvent_t ev0, ev1;
   i64 launches;
+  int plans;    // live plans bound to this context
+  bool zombie;  // adseis_ctx_destroy was called while plans were alive: destruction happens with the last plan
 };
+void adseis_ctx_release_plan(adseis_ctx* ctx);  // ctx.cu: called by every plan destructor (last statement)
 
 // RAII-free tiny device buffer helper (plans free explicitly in destroy)
 template <typename T>

@@ -53,15 +53,27 @@ ADSEIS_API int adseis_ctx_create(int device, adseis_ctx** out) {
   return ADSEIS_OK;
 }
 
-ADSEIS_API int adseis_ctx_destroy(adseis_ctx* ctx) {
-  if (!ctx) return ADSEIS_OK;
+static void ctx_free(adseis_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+
+// A context outlives its plans: destroying it while plans are alive (garbage-collected host languages finalise in
+// arbitrary order) only marks it; the last plan's destructor frees it.
+ADSEIS_API int adseis_ctx_destroy(adseis_ctx* ctx) {
+  if (!ctx) return ADSEIS_OK;
+  if (ctx->plans > 0) { ctx->zombie = true; return ADSEIS_OK; }
+  ctx_free(ctx);
   return ADSEIS_OK;
+}
+
+void adseis_ctx_release_plan(adseis_ctx* ctx) {
+  if (!ctx) return;
+  if (--ctx->plans <= 0 && ctx->zombie) ctx_free(ctx);
 }
 
 ADSEIS_API int adseis_ctx_sync(adseis_ctx* ctx) {

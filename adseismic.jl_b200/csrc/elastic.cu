@@ -180,7 +180,9 @@ ADSEIS_API int adseis_elastic_plan_destroy(adseis_elastic_plan* P) {
   for (double* c : P->ckpt) cudaFree(c);
   cudaFree(P->rcv_owned);
   free_points(&P->src); free_points(&P->rcv);
+  adseis_ctx* ctx = P->ctx;
   delete P;
+  adseis_ctx_release_plan(ctx);
   return ADSEIS_OK;
 }
 
@@ -230,6 +232,7 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
   cudaStream_t st = ctx->stream;
   adseis_elastic_plan* P = new adseis_elastic_plan();
   P->ctx = ctx;
+  ctx->plans++;
   P->p = *p;
   const int NX = (int)p->NX, NY = (int)p->NY;
   ElGeom& g = P->g;
@@ -258,6 +261,7 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
     adseis_set_error("elastic_plan_create: inconsistent slab {rank %d/%d rows [%lld,%lld)} for %d internal rows",
                      sl.rank, sl.nranks, (long long)sl.row0, (long long)sl.row1, g.H);
     delete P;
+    ctx->plans--;
     return ADSEIS_EINVAL;
   }
   const int halo_lo = sl.rank > 0 ? EL_HALO : 0, halo_hi = sl.rank < sl.nranks - 1 ? EL_HALO : 0;

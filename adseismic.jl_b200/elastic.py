@@ -45,6 +45,7 @@ class ElasticPlan:
                                                   pi(self.rcvj), pi(self.rcvtype), int(hist_bytes_budget),
                                                   C.byref(h)))
         self.handle = h
+        _lib.track(self)
 
     def set_model(self, rho, lam, mu):
         arrs = []

@@ -133,26 +133,43 @@ def variable_source(param, x, y, v, sigma=None):
 
 
 def LBFGS_(loss_fn, params, max_iter=50, callback=None, history_size=10, tolerance_grad=1e-12,
-           tolerance_change=1e-14):
+           tolerance_change=1e-14, max_linesearch=20):
     """LBFGS!(sess, loss, grads, vars; callback) (src/Optim.jl:135-193): minimise `loss_fn()` (a closure returning a
-    differentiable torch scalar) over `params` with L-BFGS + strong-Wolfe line search; returns the list of losses
-    (one per outer iteration).  callback(params, iteration, loss) as in the reference."""
+    differentiable torch scalar) over `params` with L-BFGS + strong-Wolfe line search; returns the list of losses:
+    losses[0] at the starting point, losses[k] after outer iteration k.  callback(params, iteration, loss) after every
+    iteration as in the reference.  Every loss/gradient evaluation is one forward+adjoint sweep of the CUDA library."""
     params = list(params)
-    opt = torch.optim.LBFGS(params, lr=1.0, max_iter=1, history_size=history_size, line_search_fn="strong_wolfe",
-                            tolerance_grad=tolerance_grad, tolerance_change=tolerance_change)
-    losses = []
+    opt = torch.optim.LBFGS(params, lr=1.0, max_iter=1, max_eval=max_linesearch + 1, history_size=history_size,
+                            line_search_fn="strong_wolfe", tolerance_grad=tolerance_grad,
+                            tolerance_change=tolerance_change)
+    seen = {}          # parameter fingerprint -> loss, for the points the line search has evaluated
+
+    def key():
+        return hash(tuple(p.detach().cpu().numpy().tobytes() for p in params))
 
     def closure():
         opt.zero_grad()
         loss = loss_fn()
         loss.backward()
+        seen[key()] = float(loss.detach())
         return loss
 
+    def current():
+        k = key()
+        if k not in seen:
+            with torch.enable_grad():
+                closure()
+        return seen[k]
+
+    losses = []
     for it in range(max_iter):
-        loss = opt.step(closure)
-        losses.append(float(loss))
+        seen.clear()
+        l0 = float(opt.step(closure))        # returns the loss at the START of the step
+        if not losses:
+            losses.append(l0)
+        losses.append(current())             # the accepted point was evaluated by the line search
         if callback is not None:
             callback(params, it, losses[-1])
-        if len(losses) > 1 and abs(losses[-2] - losses[-1]) <= tolerance_change * max(1.0, abs(losses[-1])):
+        if abs(losses[-2] - losses[-1]) <= tolerance_change * max(1.0, abs(losses[-1])):
             break
     return losses
