@@ -137,6 +137,8 @@ struct adseis_acoustic_plan {
   // adjoint state
   double *ub[3] = {nullptr, nullptr, nullptr}, *phib[2] = {nullptr, nullptr}, *psib[2] = {nullptr, nullptr};
   double *G = nullptr, *gradc = nullptr, *gradsrcv = nullptr;
+  double* ut[2] = {nullptr, nullptr};  // PropagatorKernel=0: utilde planes (adjoint of the pre-injection outputs)
+  bool k0_corr = false;                // ... and some source touches a cell whose phi/psi coefficient is non-zero
   bool have_model = false, have_srcv = false, have_obs = false, have_grad = false, have_fwd = false;
   // slab decomposition (nranks > 1): arena, neighbours
   double* arena = nullptr;
@@ -242,7 +244,7 @@ ADSEIS_API int adseis_acoustic_plan_destroy(adseis_acoustic_plan* P) {
   free_point_set(&P->src); free_point_set(&P->rcv);
   cudaFree(P->rcv_owned);
   cudaFree(P->srcv); cudaFree(P->rcvv); cudaFree(P->obs); cudaFree(P->res); cudaFree(P->loss);
-  cudaFree(P->G); cudaFree(P->gradc); cudaFree(P->gradsrcv);
+  cudaFree(P->G); cudaFree(P->gradc); cudaFree(P->gradsrcv); cudaFree(P->ut[0]); cudaFree(P->ut[1]);
   for (cudaEvent_t e : P->ev_pool) cudaEventDestroy(e);
   adseis_ctx* ctx = P->ctx;
   delete P;
@@ -257,9 +259,9 @@ static int validate_params(const adseis_acoustic_params* p) {
   REQUIRE((p->NX + 2) * (p->NY + 18) < 2147483647LL, "acoustic: grid too large for 32-bit cell offsets");
   REQUIRE(p->DELTAX > 0 && p->DELTAY > 0 && p->DELTAT > 0, "acoustic: DELTAX/DELTAY/DELTAT must be > 0");
   REQUIRE(p->NPOINTS_PML >= 1 && p->Rcoef > 0 && p->vp_ref > 0, "acoustic: bad PML parameters");
-  REQUIRE(p->PropagatorKernel == 1,
-          "acoustic: PropagatorKernel=%d not supported; this library implements the custom-op scheme (1)",
-          p->PropagatorKernel);
+  REQUIRE(p->PropagatorKernel >= 0 && p->PropagatorKernel <= 2,
+          "acoustic: PropagatorKernel=%d not supported (0 = TF-op scheme, Core.jl:528-549; 1 = custom-op scheme; "
+          "2 is numerically identical to 1)", p->PropagatorKernel);
   return ADSEIS_OK;
 }
 
@@ -273,15 +275,24 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
   REQUIRE(nsrc >= 0 && nrcv >= 0 && (nsrc == 0 || (srci && srcj)) && (nrcv == 0 || (rcvi && rcvj)),
           "acoustic_plan_create: bad source/receiver arrays");
   CUDA_TRY(cudaSetDevice(ctx->device));
-  if (AC_FWD_SMEM > 0)
-    CUDA_TRY(cudaFuncSetAttribute(ac_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_FWD_SMEM));
-  if (AC_ADJ_SMEM > 0)
-    CUDA_TRY(cudaFuncSetAttribute(ac_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_ADJ_SMEM));
+  if (AC_FWD_SMEM > 0) {
+    CUDA_TRY(cudaFuncSetAttribute(ac_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_FWD_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(ac_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_FWD_SMEM));
+  }
+  if (AC_ADJ_SMEM > 0) {
+    CUDA_TRY(cudaFuncSetAttribute(ac_adj_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_ADJ_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(ac_adj_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_ADJ_SMEM));
+  }
+  REQUIRE(p->PropagatorKernel != 0 || !slab || slab->nranks <= 1,
+          "acoustic_plan_create: PropagatorKernel=0 is implemented for single-GPU plans (and shot parallelism); slab "
+          "decomposition needs PropagatorKernel=1");
   cudaStream_t st = ctx->stream;
   adseis_acoustic_plan* P = new adseis_acoustic_plan();
   P->ctx = ctx;
   ctx->plans++;
   P->p = *p;
+  if (P->p.PropagatorKernel == 2) P->p.PropagatorKernel = 1;  // Core.jl:504-525 == the custom op without the op
+  p = &P->p;
   const int H = (int)p->NX + 2, W = (int)p->NY + 2;
   if (slab) P->slab = *slab; else { P->slab.rank = 0; P->slab.nranks = 1; P->slab.row0 = 0; P->slab.row1 = H; }
   const adseis_slab& sl = P->slab;
@@ -337,7 +348,9 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
   box(ty, (int)p->NY, &ja, &jb);
   {
     // fast region = box shrunk by one cell: every stencil neighbour is PML-free, interior, and has phi=psi=0
-    const int fi0 = ia + 1, fi1 = ib - 1, fj0 = ja + 1, fj1 = jb - 1;
+    // (PropagatorKernel=0: by two cells -- the adjoint of a neighbour's u' collects phibar/psibar of ITS neighbours)
+    const int shrink = p->PropagatorKernel == 0 ? 2 : 1;
+    const int fi0 = ia + shrink, fi1 = ib - shrink, fj0 = ja + shrink, fj1 = jb - shrink;
     AcTiling& t = P->t;
     memset(&t, 0, sizeof(t));
     // marched local rows: owned rows whose global index lies in [fi0, fi1]
@@ -459,6 +472,12 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     build_point_set(own, cells, gid, none, P->nblocks, &h);
     return upload_point_set(h, dst, st);
   };
+  if (p->PropagatorKernel == 0)
+    for (i64 k = 0; k < nsrc && !P->k0_corr; k++) {
+      const i64 gi = srci[k] + ioff, gj = srcj[k] + ioff;
+      auto coef = [&](i64 i, i64 j) { return i >= 1 && i <= H - 2 && j >= 1 && j <= W - 2 && sx[i] != ty[j]; };
+      P->k0_corr = coef(gi - 1, gj) || coef(gi + 1, gj) || coef(gi, gj - 1) || coef(gi, gj + 1);
+    }
   std::vector<unsigned char> owned;
   PTRY(build(nsrc, srci, srcj, &P->src, nullptr, "source"));
   PTRY(build(nrcv, rcvi, rcvj, &P->rcv, &owned, "receiver"));
@@ -644,7 +663,8 @@ static int run_forward_steps(adseis_acoustic_plan* P, i64 base, i64 s_first, i64
   }
   for (i64 s = s_first; s <= s_last; s++) {
     const AcFuse fuse = make_fuse(P, AR_HIST, s - base, AR_PHI, s & 1);
-    CUDA_TRY(launch_step(ac_fwd_kernel, P->nblocks, AC_FWD_THREADS, AC_FWD_SMEM, st,
+    CUDA_TRY(launch_step(P->p.PropagatorKernel == 0 ? ac_fwd_kernel<0> : ac_fwd_kernel<1>, P->nblocks, AC_FWD_THREADS,
+                         AC_FWD_SMEM, st,
         g, P->t, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, P->phi[(s - 1) & 1], P->psi[(s - 1) & 1],
         P->sigx, P->tauy, win_slot(P, base, s), P->phi[s & 1], P->psi[s & 1], P->srcp,
         P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, sample ? P->rcvp : none,
@@ -726,6 +746,8 @@ static int ensure_adjoint_state(adseis_acoustic_plan* P) {
     for (int k = 0; k < 3; k++) TRY(dev_alloc_zero(&P->ub[k], n, st));
     for (int k = 0; k < 2; k++) { TRY(dev_alloc_zero(&P->phib[k], n, st)); TRY(dev_alloc_zero(&P->psib[k], n, st)); }
   }
+  if (P->p.PropagatorKernel == 0)
+    for (int k = 0; k < 2; k++) TRY(dev_alloc_zero(&P->ut[k], n, st));
   TRY(dev_alloc_zero(&P->G, n, st));
   TRY(dev_alloc_zero(&P->gradc, (size_t)P->model_elems, st));
   TRY(dev_alloc_zero(&P->gradsrcv, (size_t)(P->p.NSTEP * P->nsrc), st));
@@ -755,6 +777,7 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
   for (int k = 0; k < 3; k++) CUDA_TRY(cudaMemsetAsync(P->ub[k], 0, pb, st));
   for (int k = 0; k < 2; k++) { CUDA_TRY(cudaMemsetAsync(P->phib[k], 0, pb, st)); CUDA_TRY(cudaMemsetAsync(P->psib[k], 0, pb, st)); }
   CUDA_TRY(cudaMemsetAsync(P->G, 0, pb, st));
+  for (int k = 0; k < 2; k++) if (P->ut[k]) CUDA_TRY(cudaMemsetAsync(P->ut[k], 0, pb, st));
   if (P->nsrc > 0) CUDA_TRY(cudaMemsetAsync(P->gradsrcv, 0, (size_t)(NSTEP * P->nsrc) * 8, st));
   TRY(halo_exchange(P, 0, nullptr, nullptr));
   // ubar[NSTEP] = receiver term only; grad_srcv row NSTEP-1
@@ -798,11 +821,22 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
     TRY(span_begin(P, 2, e - (b + 2) + 1));
     for (i64 s = e; s >= b + 2; s--) {
       const AcFuse fuse = make_fuse(P, AR_UB, (s + 2) % 3, AR_PHIB, (s - 1) & 1);
-      CUDA_TRY(launch_step(ac_adj_kernel, P->nblocks, AC_ADJ_THREADS, AC_ADJ_SMEM, st,
+      AcK0 k0{};
+      if (P->p.PropagatorKernel == 0) {
+        k0.wnew = win_slot(P, b, s); k0.ut_in = P->ut[(s + 1) & 1]; k0.ut_out = P->ut[s & 1];
+        if (P->k0_corr && P->src.nu > 0) {
+          k_ac_k0_src_corr<<<(P->src.nu + 127) / 128, 128, 0, st>>>(g, P->src.cell, P->src.start, P->src.perm, P->src.nu,
+                                                                    P->srcv + (s - 1) * P->nsrc, P->phib[s & 1],
+                                                                    P->psib[s & 1], P->sigx, P->tauy, P->G);
+          LAUNCH_CHECK(P);
+        }
+      }
+      CUDA_TRY(launch_step(P->p.PropagatorKernel == 0 ? ac_adj_kernel<0> : ac_adj_kernel<1>, P->nblocks, AC_ADJ_THREADS,
+                           AC_ADJ_SMEM, st,
           g, P->t, P->ub[s % 3], P->ub[(s + 1) % 3], win_slot(P, b, s - 1), P->c2, P->phib[s & 1], P->psib[s & 1],
           P->sigx, P->tauy, P->ub[(s + 2) % 3] /* == (s-1)%3 */, P->phib[(s - 1) & 1], P->psib[(s - 1) & 1], P->G,
           P->rcvp, P->nrcv > 0 ? P->res + (s - 1) * P->nrcv : nullptr, (s - 2 >= 1) ? P->srcp : none,
-          (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr, fuse));
+          (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr, fuse, k0));
       LAUNCH_CHECK(P);
     }
     TRY(span_end(P));

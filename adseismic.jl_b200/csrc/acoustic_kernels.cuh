@@ -178,6 +178,55 @@ __device__ __forceinline__ void ac_fwd_general_cell(const AcGeom& g, int li, int
   psio[IJ] = (1. - dt * ta) * psi[IJ] + div_exact(dt * c * (sg - ta) / 2.0, g.hy, g.rhy) * (w[IJp] - w[IJn]);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// PropagatorKernel = 0 (src/Core.jl:528-549; MPI twin src/MPIAcoustic.jl:212-246): phi', psi' are driven by the NEW
+// wavefield u' (before this step's source injection).  Only frame cells carry phi/psi, and a frame cell recomputes
+// u' of its four neighbours from the launch's read-only inputs with the very expression their owner CTA uses -- the
+// values are bit-identical to the stored ones, no second pass and no inter-CTA dependency is needed.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ac_uprime(const AcGeom& g, int gi, int j, i64 IJ, const double* __restrict__ w,
+                                            const double* __restrict__ wold, const double* __restrict__ c2,
+                                            const double* __restrict__ phi, const double* __restrict__ psi,
+                                            const double* __restrict__ sigx, const double* __restrict__ tauy) {
+  if (gi < 1 || gi > g.H - 2 || j < 1 || j > g.W - 2) return 0.0;  // ring: scatter_nd onto the interior
+  const double sg = sigx[gi], ta = tauy[j], c = c2[IJ], dt = g.dt;
+  const double v = (2 - sg * ta * dt * dt - g.kx2 * c - g.ky2 * c) * w[IJ] +
+                   c * g.rx * g.rx * (w[IJ + g.ld] + w[IJ - g.ld]) +
+                   c * g.ry * g.ry * (w[IJ + 1] + w[IJ - 1]) +
+                   g.px * (phi[IJ + g.ld] - phi[IJ - g.ld]) +
+                   g.py * (psi[IJ + 1] - psi[IJ - 1]) -
+                   (1 - (sg + ta) * dt / 2) * wold[IJ];
+  return (v == 0.0) ? v : v / (1 + (sg + ta) / 2 * dt);
+}
+
+__device__ __noinline__ void ac_fwd_general_cell_k0(const AcGeom& g, int li, int j, const double* __restrict__ w,
+                                                    const double* __restrict__ wold, const double* __restrict__ c2,
+                                                    const double* __restrict__ phi, const double* __restrict__ psi,
+                                                    const double* __restrict__ sigx, const double* __restrict__ tauy,
+                                                    double* __restrict__ u, double* __restrict__ phio,
+                                                    double* __restrict__ psio) {
+  const int gi = g.goff + li;
+  const i64 IJ = (i64)li * g.ld + j;
+  if (j >= g.W) { u[IJ] = 0.0; return; }
+  if (gi == 0 || gi == g.H - 1 || j == 0 || j == g.W - 1) {
+    u[IJ] = 0.0; phio[IJ] = 0.0; psio[IJ] = 0.0;
+    return;
+  }
+  const double sg = sigx[gi], ta = tauy[j], c = c2[IJ], dt = g.dt;
+  u[IJ] = ac_uprime(g, gi, j, IJ, w, wold, c2, phi, psi, sigx, tauy);
+  const double a = div_exact(dt * c * (ta - sg) / 2.0, g.hx, g.rhx);
+  const double b = div_exact(dt * c * (sg - ta) / 2.0, g.hy, g.rhy);
+  double dux = 0.0, duy = 0.0;
+  if (a != 0.0)
+    dux = ac_uprime(g, gi + 1, j, IJ + g.ld, w, wold, c2, phi, psi, sigx, tauy) -
+          ac_uprime(g, gi - 1, j, IJ - g.ld, w, wold, c2, phi, psi, sigx, tauy);
+  if (b != 0.0)
+    duy = ac_uprime(g, gi, j + 1, IJ + 1, w, wold, c2, phi, psi, sigx, tauy) -
+          ac_uprime(g, gi, j - 1, IJ - 1, w, wold, c2, phi, psi, sigx, tauy);
+  phio[IJ] = (1. - dt * sg) * phi[IJ] + a * dux;
+  psio[IJ] = (1. - dt * ta) * psi[IJ] + b * duy;
+}
+
 // CTA epilogue shared by both kernels: add `scale * val[perm]` into field[cell] for the injected points this CTA
 // owns (sequentially per cell, in original point order), then sample field[cell]*scale into out[perm].
 __device__ __forceinline__ void ac_cta_epilogue(int bid, double* __restrict__ field, const AcPoints& inj,
@@ -216,6 +265,7 @@ __device__ __forceinline__ void ac_frame_locate(const AcTiling& t, int fb, int* 
 // ------------------------------------------------------------------------------------------------------------
 // forward kernel
 // ------------------------------------------------------------------------------------------------------------
+template <int PK>  // PropagatorKernel: 1 = custom-op scheme (phi, psi from the old wavefield), 0 = TF-op scheme
 __global__ void __launch_bounds__(AC_FWD_THREADS, AC_MINB_FWD)
 ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* __restrict__ wold,
               const double* __restrict__ c2, const double* __restrict__ phi, const double* __restrict__ psi,
@@ -241,7 +291,8 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
       const int idx = idx0 + k * AC_THREADS + threadIdx.x;
       if (idx < ncell && threadIdx.x < AC_THREADS) {
         const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
-        ac_fwd_general_cell(g, li, j, w, wold, c2, phi, psi, sigx, tauy, u, phio, psio);
+        if constexpr (PK == 0) ac_fwd_general_cell_k0(g, li, j, w, wold, c2, phi, psi, sigx, tauy, u, phio, psio);
+        else ac_fwd_general_cell(g, li, j, w, wold, c2, phi, psi, sigx, tauy, u, phio, psio);
       }
     }
   } else {
@@ -488,15 +539,138 @@ __device__ __forceinline__ void ac_adj_general_cell(const AcGeom& g, int li, int
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// adjoint, general cell, PropagatorKernel = 0 (transpose of Core.jl:528-549 as tf.gradients builds it).  With
+//   a_R = dt c_R (tau_R - sigma_R) / (2 hx),  b_R = dt c_R (sigma_R - tau_R) / (2 hy)   (interior R)
+// the adjoint of the pre-injection output u'_s is
+//   utilde_s[Q] = ubar_s[Q] + a_{Q-ex} phibar_s[Q-ex] - a_{Q+ex} phibar_s[Q+ex] + b_{Q-ey} psibar_s[Q-ey] - b_{Q+ey} psibar_s[Q+ey]
+// and g_s = utilde_s / D replaces ubar_s / D everywhere; w receives no phibar / psibar terms; the c-gradient's
+// phibar / psibar terms use u'_s (here: the stored post-injection u[s]; the injected part is removed by
+// k_ac_k0_src_corr).  utilde_s of the frame cells is kept in a side plane for the wold-term of the next launch
+// (inside the marching box utilde == ubar).
+// ------------------------------------------------------------------------------------------------------------
+struct AcK0 {
+  const double* wnew;   // u[s] (post-injection), history slot s
+  const double* ut_in;  // utilde_{s+1} (frame cells)
+  double* ut_out;       // utilde_s
+};
+
+__device__ __forceinline__ bool ac_interior(const AcGeom& g, int gi, int j) {
+  return gi >= 1 && gi <= g.H - 2 && j >= 1 && j <= g.W - 2;
+}
+
+__device__ __forceinline__ double ac_utilde(const AcGeom& g, int gi, int j, i64 Q, const double* __restrict__ ub1,
+                                            const double* __restrict__ c2, const double* __restrict__ phib,
+                                            const double* __restrict__ psib, const double* __restrict__ sigx,
+                                            const double* __restrict__ tauy, double kx, double ky) {
+  double v = ub1[Q];
+  if (ac_interior(g, gi - 1, j)) v += c2[Q - g.ld] * (tauy[j] - sigx[gi - 1]) * kx * phib[Q - g.ld];
+  if (ac_interior(g, gi + 1, j)) v -= c2[Q + g.ld] * (tauy[j] - sigx[gi + 1]) * kx * phib[Q + g.ld];
+  if (ac_interior(g, gi, j - 1)) v += c2[Q - 1] * (sigx[gi] - tauy[j - 1]) * ky * psib[Q - 1];
+  if (ac_interior(g, gi, j + 1)) v -= c2[Q + 1] * (sigx[gi] - tauy[j + 1]) * ky * psib[Q + 1];
+  return v;
+}
+
+__device__ __noinline__ void ac_adj_general_cell_k0(const AcGeom& g, int li, int j, const double* __restrict__ ub1,
+                                                    const double* __restrict__ wf, const double* __restrict__ c2,
+                                                    const double* __restrict__ phib, const double* __restrict__ psib,
+                                                    const double* __restrict__ sigx, const double* __restrict__ tauy,
+                                                    double* __restrict__ ub0, double* __restrict__ phibo,
+                                                    double* __restrict__ psibo, double* __restrict__ G, AcK0 k0) {
+  const int gi = g.goff + li;
+  const i64 IJ = (i64)li * g.ld + j;
+  if (j >= g.W) { ub0[IJ] = 0.0; return; }
+  const double dt = g.dt;
+  const double kx = dt * 0.5 * g.rhx, ky = dt * 0.5 * g.rhy;
+  const bool intP = ac_interior(g, gi, j);
+  double acc = 0.0, gP = 0.0, gxm = 0.0, gxp = 0.0, gym = 0.0, gyp = 0.0;
+  if (intP) {
+    const double ut = ac_utilde(g, gi, j, IJ, ub1, c2, phib, psib, sigx, tauy, kx, ky);
+    k0.ut_out[IJ] = ut;
+    gP = ut * (1.0 / (1 + (sigx[gi] + tauy[j]) / 2 * dt));
+    acc = (2 - sigx[gi] * tauy[j] * dt * dt - g.kx2 * c2[IJ] - g.ky2 * c2[IJ]) * gP;
+  }
+  if (ac_interior(g, gi - 1, j)) {
+    gxm = ac_utilde(g, gi - 1, j, IJ - g.ld, ub1, c2, phib, psib, sigx, tauy, kx, ky) *
+          (1.0 / (1 + (sigx[gi - 1] + tauy[j]) / 2 * dt));
+    acc += c2[IJ - g.ld] * g.rx * g.rx * gxm;
+  }
+  if (ac_interior(g, gi + 1, j)) {
+    gxp = ac_utilde(g, gi + 1, j, IJ + g.ld, ub1, c2, phib, psib, sigx, tauy, kx, ky) *
+          (1.0 / (1 + (sigx[gi + 1] + tauy[j]) / 2 * dt));
+    acc += c2[IJ + g.ld] * g.rx * g.rx * gxp;
+  }
+  if (ac_interior(g, gi, j - 1)) {
+    gym = ac_utilde(g, gi, j - 1, IJ - 1, ub1, c2, phib, psib, sigx, tauy, kx, ky) *
+          (1.0 / (1 + (sigx[gi] + tauy[j - 1]) / 2 * dt));
+    acc += c2[IJ - 1] * g.ry * g.ry * gym;
+  }
+  if (ac_interior(g, gi, j + 1)) {
+    gyp = ac_utilde(g, gi, j + 1, IJ + 1, ub1, c2, phib, psib, sigx, tauy, kx, ky) *
+          (1.0 / (1 + (sigx[gi] + tauy[j + 1]) / 2 * dt));
+    acc += c2[IJ + 1] * g.ry * g.ry * gyp;
+  }
+  if (intP) {
+    const double sg = sigx[gi], ta = tauy[j], pb = phib[IJ], qb = psib[IJ];
+    acc += -(1 - (sg + ta) * dt / 2) * (k0.ut_in[IJ] * (1.0 / (1 + (sg + ta) / 2 * dt)));  // grad_wold of step s+1
+    phibo[IJ] = (1. - dt * sg) * pb + g.px * (gxm - gxp);
+    psibo[IJ] = (1. - dt * ta) * qb + g.py * (gym - gyp);
+    const double* un = k0.wnew;
+    const double cb = ((-g.kx2 - g.ky2) * wf[IJ] + g.rx * g.rx * (wf[IJ + g.ld] + wf[IJ - g.ld]) +
+                       g.ry * g.ry * (wf[IJ + 1] + wf[IJ - 1])) * gP +
+                      (ta - sg) * kx * (un[IJ + g.ld] - un[IJ - g.ld]) * pb + (sg - ta) * ky * (un[IJ + 1] - un[IJ - 1]) * qb;
+    G[IJ] = G[IJ] + cb;
+  }
+  ub0[IJ] = acc;
+}
+
+// PropagatorKernel = 0: remove the injected part of u[s] from the c-gradient's phibar / psibar terms (they are
+// defined on the pre-injection u'_s).  One thread per unique source cell S with v = sum of its srcv[s-1, .] dt^2:
+//   G[S-ex] -= kxc(S-ex) v phibar_s[S-ex],  G[S+ex] += kxc(S+ex) v phibar_s[S+ex],  same in y with psibar_s,
+//   kxc(P) = dt (tau_P - sigma_P) / (2 hx), kyc(P) = dt (sigma_P - tau_P) / (2 hy), interior P only.
+// Runs between two adjoint launches on the same stream (plain launch: fully ordered); fp64 atomics because several
+// sources may share a neighbour.
+__global__ void k_ac_k0_src_corr(AcGeom g, const int* __restrict__ cell, const int* __restrict__ start,
+                                 const int* __restrict__ perm, int nu, const double* __restrict__ srcv_row,
+                                 const double* __restrict__ phib, const double* __restrict__ psib,
+                                 const double* __restrict__ sigx, const double* __restrict__ tauy,
+                                 double* __restrict__ G) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nu) return;
+  double v = 0.0;
+  for (int m = start[k]; m < start[k + 1]; m++) v += srcv_row[perm[m]] * g.dt2;
+  if (v == 0.0) return;
+  const int li = cell[k] / g.ld, j = cell[k] % g.ld, gi = g.goff + li;
+  const i64 S = cell[k];
+  const double kx = g.dt * 0.5 * g.rhx, ky = g.dt * 0.5 * g.rhy;
+  if (ac_interior(g, gi - 1, j)) {
+    const double cf = (tauy[j] - sigx[gi - 1]) * kx;
+    if (cf != 0.0) atomicAdd(&G[S - g.ld], -(cf * v * phib[S - g.ld]));
+  }
+  if (ac_interior(g, gi + 1, j)) {
+    const double cf = (tauy[j] - sigx[gi + 1]) * kx;
+    if (cf != 0.0) atomicAdd(&G[S + g.ld], cf * v * phib[S + g.ld]);
+  }
+  if (ac_interior(g, gi, j - 1)) {
+    const double cf = (sigx[gi] - tauy[j - 1]) * ky;
+    if (cf != 0.0) atomicAdd(&G[S - 1], -(cf * v * psib[S - 1]));
+  }
+  if (ac_interior(g, gi, j + 1)) {
+    const double cf = (sigx[gi] - tauy[j + 1]) * ky;
+    if (cf != 0.0) atomicAdd(&G[S + 1], cf * v * psib[S + 1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // adjoint kernel: ub0 = ubar[s-1] from ub1 = ubar[s], ub2 = ubar[s+1], wf = u[s-1]
 // ------------------------------------------------------------------------------------------------------------
+template <int PK>
 __global__ void __launch_bounds__(AC_ADJ_THREADS, AC_MINB_ADJ)
 ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double* __restrict__ ub2,
               const double* __restrict__ wf, const double* __restrict__ c2, const double* __restrict__ phib,
               const double* __restrict__ psib, const double* __restrict__ sigx, const double* __restrict__ tauy,
               double* __restrict__ ub0, double* __restrict__ phibo, double* __restrict__ psibo,
               double* __restrict__ G, AcPoints rcv, const double* __restrict__ res_row, AcPoints src,
-              double* __restrict__ gsrcv_row, AcFuse f) {
+              double* __restrict__ gsrcv_row, AcFuse f, AcK0 k0) {
   pdl_launch_dependents();
   const int bid = f.perm ? f.perm[blockIdx.x] : blockIdx.x;
 #ifdef AC_DEBUG_SKIP_FRAME   // timing experiments only (wrong results)
@@ -524,7 +698,8 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
       const int idx = idx0 + k * AC_THREADS + threadIdx.x;
       if (idx < ncell && threadIdx.x < AC_THREADS) {
         const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
-        ac_adj_general_cell(g, li, j, ub1, ub2, wf, c2, phib, psib, sigx, tauy, ub0, phibo, psibo, G);
+        if constexpr (PK == 0) ac_adj_general_cell_k0(g, li, j, ub1, wf, c2, phib, psib, sigx, tauy, ub0, phibo, psibo, G, k0);
+        else ac_adj_general_cell(g, li, j, ub1, ub2, wf, c2, phib, psib, sigx, tauy, ub0, phibo, psibo, G);
       }
     }
   } else {

@@ -340,7 +340,7 @@ def bench_domain_decomposed(A, w, args, rank, world, local_rank):
     init_process_group("nccl")
     dist = _dist()
     ctx = A.Context(local_rank)
-    p = A.AcousticPropagatorParams(NX=w["NX"], NY=w["NY"], NSTEP=w["NSTEP"], DELTAX=w["DELTAX"], DELTAY=w["DELTAY"],
+    p = A.AcousticPropagatorParams(PropagatorKernel=1, NX=w["NX"], NY=w["NY"], NSTEP=w["NSTEP"], DELTAX=w["DELTAX"], DELTAY=w["DELTAY"],
                                    DELTAT=w["DELTAT"], Rcoef=w["Rcoef"], vp_ref=w["vp_ref"],
                                    NPOINTS_PML=w["NPOINTS_PML"], mpi_convention=True)
     srcv_np = (A.Ricker(p, 100.0, 500.0) * 1e6).reshape(-1, 1)

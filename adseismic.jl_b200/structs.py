@@ -12,8 +12,9 @@ from . import _lib
 
 @dataclass
 class AcousticPropagatorParams:
-    """src/Struct.jl:82-121.  `PropagatorKernel` keeps the reference's meaning; this library implements scheme 1
-    (the custom-op scheme, phi/psi updated from the OLD wavefield); the default is therefore 1, not 0."""
+    """src/Struct.jl:82-121, same defaults.  `PropagatorKernel` keeps the reference's meaning: 0 = the TF-op scheme
+    (phi, psi driven by the NEW wavefield, Core.jl:528-549), 1 = the custom-op scheme (phi, psi from the OLD
+    wavefield, AcousticOneStepCpu.h), 2 = its op-free twin (numerically scheme 1).  Slab decomposition needs 1."""
     NX: int = 101
     NY: int = 641
     NSTEP: int = 2000 * 2
@@ -33,7 +34,7 @@ class AcousticPropagatorParams:
     Σx: Optional[np.ndarray] = None
     Σy: Optional[np.ndarray] = None
     IT_DISPLAY: int = 0
-    PropagatorKernel: int = 1
+    PropagatorKernel: int = 0
     mpi_convention: bool = False  # True: MPIAcousticPropagatorParams inputs (src/MPIAcoustic.jl:3-49)
 
     def to_c(self):

@@ -68,7 +68,8 @@ typedef struct {
   int64_t NPOINTS_PML;
   double Rcoef, vp_ref;
   int32_t mpi_convention;   /* 0: AcousticPropagatorSolver inputs; 1: MPIAcousticPropagatorSolver inputs */
-  int32_t PropagatorKernel; /* must be 1 (custom-op scheme: phi/psi from the OLD wavefield, Core.jl:580-591) */
+  int32_t PropagatorKernel; /* 0: TF-op scheme, phi/psi from the NEW wavefield (Core.jl:528-549; single-GPU plans);
+                               1: custom-op scheme, phi/psi from the OLD wavefield (AcousticOneStepCpu.h); 2 == 1 */
 } adseis_acoustic_params;
 
 /* Slab of a 1-D domain decomposition along i (rows).  Global padded rows [0, NX+2) are split into `nranks`

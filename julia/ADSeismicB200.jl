@@ -67,7 +67,7 @@ end
     NPOINTS_PML::Int64 = 12; NPOWER::Int64 = 2
     Rcoef::Float64 = 0.001; vp_ref::Float64 = 1000.
     IT_DISPLAY::Int64 = 0
-    PropagatorKernel::Int64 = 1      # the custom-op scheme is the one implemented
+    PropagatorKernel::Int64 = 0      # as src/Struct.jl:120 (0: TF-op scheme, 1|2: custom-op scheme; slabs need 1)
     mpi_convention::Bool = false     # true: MPIAcousticPropagatorParams inputs
 end
 toC(p::AcousticPropagatorParams) = CAcousticParams(p.NX, p.NY, p.NSTEP, p.DELTAX, p.DELTAY, p.DELTAT,

@@ -132,9 +132,22 @@ def acoustic_step_bwd(gu, gphio, gpsio, w, sigma, tau, c2, dt, hx, hy, NX, NY, w
 
 
 def acoustic_forward(NX, NY, NSTEP, dt, hx, hy, sigma, tau, c, srci, srcj, srcv, rcvi, rcvj, mpi_convention=False,
-                     which="oracle"):
-    """-> (u_hist[(NSTEP+1), NX+2, NY+2], rcvv[(NSTEP+1), nrcv])"""
+                     which="oracle", kernel=1):
+    """-> (u_hist[(NSTEP+1), NX+2, NY+2], rcvv[(NSTEP+1), nrcv]); kernel=0 (PropagatorKernel=0, oracle only) returns
+    (u_hist, upre_hist, rcvv) -- upre_hist holds every step's pre-injection output."""
     N = (NX + 2) * (NY + 2)
+    if kernel == 0:
+        assert which == "oracle"
+        srci, psi_ = _i(srci); srcj, psj_ = _i(srcj); rcvi, pri_ = _i(rcvi); rcvj, prj_ = _i(rcvj)
+        srcv = np.ascontiguousarray(srcv, dtype=np.float64)
+        assert srcv.shape[0] >= NSTEP and srcv.shape[1] == len(srci)
+        u, up = np.empty((NSTEP + 1) * N), np.empty((NSTEP + 1) * N)
+        rcvv = np.empty((NSTEP + 1, len(rcvi)))
+        lib().orc_acoustic_forward_k0(_i64(NX), _i64(NY), _i64(NSTEP), C.c_double(dt), C.c_double(hx), C.c_double(hy),
+                                      _d(sigma)[1], _d(tau)[1], _d(c)[1], C.c_int(int(mpi_convention)),
+                                      _i64(len(srci)), psi_, psj_, srcv.ctypes.data_as(_dp), _i64(len(rcvi)), pri_,
+                                      prj_, u.ctypes.data_as(_dp), up.ctypes.data_as(_dp), rcvv.ctypes.data_as(_dp))
+        return u.reshape(NSTEP + 1, NX + 2, NY + 2), up.reshape(NSTEP + 1, NX + 2, NY + 2), rcvv
     srci, psi_ = _i(srci)
     srcj, psj_ = _i(srcj)
     rcvi, pri_ = _i(rcvi)
@@ -158,9 +171,23 @@ def acoustic_forward(NX, NY, NSTEP, dt, hx, hy, sigma, tau, c, srci, srcj, srcv,
 
 
 def acoustic_misfit_grad(NX, NY, NSTEP, dt, hx, hy, sigma, tau, c, srci, srcj, rcvi, rcvj, obs, u_hist,
-                         mpi_convention=False, which="oracle"):
-    """-> (loss, grad_c[NX+2, NY+2], grad_srcv[NSTEP, nsrc])"""
+                         mpi_convention=False, which="oracle", upre_hist=None):
+    """-> (loss, grad_c[NX+2, NY+2], grad_srcv[NSTEP, nsrc]); with upre_hist: the PropagatorKernel=0 reverse sweep."""
     N = (NX + 2) * (NY + 2)
+    if upre_hist is not None:
+        assert which == "oracle"
+        srci, psi_ = _i(srci); srcj, psj_ = _i(srcj); rcvi, pri_ = _i(rcvi); rcvj, prj_ = _i(rcvj)
+        loss, gc, gs = C.c_double(0.0), np.empty(N), np.empty((NSTEP, len(srci)))
+        obs = np.ascontiguousarray(obs, dtype=np.float64)
+        u_hist = np.ascontiguousarray(u_hist, dtype=np.float64)
+        upre_hist = np.ascontiguousarray(upre_hist, dtype=np.float64)
+        lib().orc_acoustic_misfit_grad_k0(_i64(NX), _i64(NY), _i64(NSTEP), C.c_double(dt), C.c_double(hx),
+                                          C.c_double(hy), _d(sigma)[1], _d(tau)[1], _d(c)[1],
+                                          C.c_int(int(mpi_convention)), _i64(len(srci)), psi_, psj_, _i64(len(rcvi)),
+                                          pri_, prj_, obs.ctypes.data_as(_dp), u_hist.ctypes.data_as(_dp),
+                                          upre_hist.ctypes.data_as(_dp), C.byref(loss), gc.ctypes.data_as(_dp),
+                                          gs.ctypes.data_as(_dp))
+        return loss.value, gc.reshape(NX + 2, NY + 2), gs
     srci, psi_ = _i(srci)
     srcj, psj_ = _i(srcj)
     rcvi, pri_ = _i(rcvi)

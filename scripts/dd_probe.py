@@ -35,7 +35,7 @@ for name, fn in (("forward", dd.forward), ("grad srcv", lambda: dd.gradient(Fals
 dd.close()
 
 NXa = int(os.environ.get("PNA", "4096"))
-pa = A.AcousticPropagatorParams(NX=NXa, NY=NXa, NSTEP=NSTEP, DELTAX=10.0, DELTAY=10.0, DELTAT=0.05, Rcoef=0.2,
+pa = A.AcousticPropagatorParams(PropagatorKernel=1, NX=NXa, NY=NXa, NSTEP=NSTEP, DELTAX=10.0, DELTAY=10.0, DELTAT=0.05, Rcoef=0.2,
                                 vp_ref=1000.0, mpi_convention=True)
 c2 = np.full((NXa, NXa), 1000.0)
 rj = np.arange(20, NXa - 19); ri = np.full(len(rj), NXa // 5)

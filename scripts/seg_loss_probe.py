@@ -3,7 +3,7 @@ sys.path.insert(0, "/root/repo")
 import adseis_b200 as A
 ctx = A.default_context()
 NX=NY=int(os.environ.get("PN","1024")); NSTEP=int(os.environ.get("PT","1500"))
-p = A.AcousticPropagatorParams(NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=10.0, DELTAY=10.0, DELTAT=0.05, Rcoef=0.2, vp_ref=1000.0, mpi_convention=True)
+p = A.AcousticPropagatorParams(PropagatorKernel=1, NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=10.0, DELTAY=10.0, DELTAT=0.05, Rcoef=0.2, vp_ref=1000.0, mpi_convention=True)
 c2 = np.full((NX, NY), 1000.0); c2[NX//2-NX//8:NX//2+NX//8, NY//2-NY//8:NY//2+NY//8]=2000.0
 srcv = (A.Ricker(p, 100.0, 500.0)*1e6).reshape(-1, 1)
 rcvj = np.arange(20, NY - 19); rcvi = np.full(len(rcvj), NX // 5)

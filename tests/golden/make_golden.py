@@ -90,6 +90,37 @@ def elastic_case(name, variant, NX, NY, NSTEP, seed):
     print(name, "loss", B["loss"])
 
 
+def acoustic_kernel0_case(name, NX, NY, NSTEP, seed):
+    """PropagatorKernel=0 (src/Core.jl:528-549): golden values from the torch-autograd restatement of the reference's
+    gather / scatter_nd graph (oracle/torch_acoustic.py), which stands in for tf.gradients."""
+    import torch
+    from oracle import torch_acoustic as ta
+    rng = np.random.default_rng(seed)
+    dx, dy, dt, npml, vp_ref = 10.0, 8.0, 1e-3, 6, 2500.0
+    sig, tau = po.acoustic_pml(NX, NY, dx, dy, npml=npml, vp_ref=vp_ref)
+    c = vp_ref * (1 + 0.1 * rng.random((NX + 2, NY + 2)))
+    # interior source, two sources inside the absorbing frame on neighbouring cells, one on the ring, one in a corner
+    srci = np.array([NX // 2, 3, 4, 1, NX - 1], dtype=np.int64)
+    srcj = np.array([NY // 2, 5, 5, NY // 3, NY], dtype=np.int64)
+    srcv = np.stack([po.ricker(NSTEP, 6.0 + k, 10.0 + k, 1e6) for k in range(5)], 1)
+    rcvi = rng.integers(1, NX + 3, 24)
+    rcvj = rng.integers(1, NY + 3, 24)
+    ct = torch.tensor(c.reshape(-1), requires_grad=True)
+    st = torch.tensor(srcv, requires_grad=True)
+    with torch.no_grad():
+        _, r0 = ta.acoustic_loss(0, NX, NY, NSTEP, dt, dx, dy, sig, tau, ct, srci, srcj, st, rcvi, rcvj,
+                                 np.zeros((NSTEP + 1, 24)))
+    r0 = r0.numpy()
+    obs = 0.7 * r0 + 0.01 * np.abs(r0).max() * rng.standard_normal(r0.shape)
+    L, rt = ta.acoustic_loss(0, NX, NY, NSTEP, dt, dx, dy, sig, tau, ct, srci, srcj, st, rcvi, rcvj, obs)
+    L.backward()
+    np.savez_compressed(os.path.join(HERE, name), NX=NX, NY=NY, NSTEP=NSTEP, dx=dx, dy=dy, dt=dt, npml=npml,
+                        vp_ref=vp_ref, c=c, srci=srci, srcj=srcj, srcv=srcv, rcvi=rcvi, rcvj=rcvj, obs=obs,
+                        rcvv=rt.detach().numpy(), loss=float(L.detach()), grad_c=ct.grad.numpy().reshape(NX + 2, NY + 2),
+                        grad_srcv=st.grad.numpy()[:NSTEP])
+    print(name, "loss", float(L.detach()), "|grad_c|max", np.abs(ct.grad.numpy()).max())
+
+
 def marmousi_case(name, nstep=400, shot=3):
     """The reference's own model fixture (examples/nn_fwi/models/marmousi2-model-true.mat: 202 x 68 padded cells, 8
     shots, 183 receivers; the FWI scripts run it with AcousticPropagatorSolver, examples/nn_fwi/FWI_inversion.jl): one
@@ -125,3 +156,4 @@ if __name__ == "__main__":
     elastic_case("elastic_S.npz", 0, 26, 22, 30, 7)
     elastic_case("elastic_M.npz", 1, 26, 22, 30, 8)
     marmousi_case("acoustic_marmousi2_shot3.npz")
+    acoustic_kernel0_case("acoustic_kernel0.npz", 30, 37, 60, 17)

@@ -42,7 +42,7 @@ def main():
     u0, r0 = po.acoustic_forward(NX, NY, NSTEP, dt, dx, dx, sig, tau, c, srci, srcj, srcv, rcvi, rcvj)
     obs = 0.7 * r0 + 0.02 * np.abs(r0).max() * rng.standard_normal(r0.shape)
     L0, g0, s0 = po.acoustic_misfit_grad(NX, NY, NSTEP, dt, dx, dx, sig, tau, c, srci, srcj, rcvi, rcvj, obs, u0)
-    p = A.AcousticPropagatorParams(NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dx, DELTAT=dt, vp_ref=vp,
+    p = A.AcousticPropagatorParams(PropagatorKernel=1, NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dx, DELTAT=dt, vp_ref=vp,
                                    NPOINTS_PML=8)
     for slots in (None, 14):          # full history, then a 14-snapshot window (checkpointed reverse sweep)
         dd = parallel.DomainDecomposedAcoustic(p, srci, srcj, rcvi, rcvj, ctx=ctx, hist_slots=slots)
@@ -126,7 +126,7 @@ def main():
     NX, NY, NSTEP = 60, 300, 40
     sig, tau = po.acoustic_pml(NX, NY, dx, dx, npml=8, vp_ref=vp)
     c = vp * (1 + 0.1 * rng.random((NX + 2, NY + 2)))
-    p = A.AcousticPropagatorParams(NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dx, DELTAT=dt, vp_ref=vp,
+    p = A.AcousticPropagatorParams(PropagatorKernel=1, NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dx, DELTAT=dt, vp_ref=vp,
                                    NPOINTS_PML=8)
     srcs, rcvs, Rs, Ltot, gtot = [], [], [], 0.0, 0.0
     for k in range(nshots):

@@ -13,7 +13,7 @@ TOL = 1e-10
 
 def _params(A, G):
     use = [bool(x) for x in G["use"]]
-    return A.AcousticPropagatorParams(NX=int(G["NX"]), NY=int(G["NY"]), NSTEP=int(G["NSTEP"]), DELTAX=float(G["dx"]),
+    return A.AcousticPropagatorParams(PropagatorKernel=1, NX=int(G["NX"]), NY=int(G["NY"]), NSTEP=int(G["NSTEP"]), DELTAX=float(G["dx"]),
                                       DELTAY=float(G["dy"]), DELTAT=float(G["dt"]), NPOINTS_PML=int(G["npml"]),
                                       vp_ref=float(G["vp_ref"]), USE_PML_XMIN=use[0], USE_PML_XMAX=use[1],
                                       USE_PML_YMIN=use[2], USE_PML_YMAX=use[3])
@@ -59,7 +59,7 @@ def test_vs_oracle_random(A, ctx, po, shape):
     srci[0], srcj[0] = 1, NY // 2           # a source on the ring row
     rcvi[:2], rcvj[:2] = srci[1], srcj[1]   # duplicate receivers on a source cell
     u0, r0 = po.acoustic_forward(NX, NY, NSTEP, dt, dx, dy, sig, tau, c, srci, srcj, srcv, rcvi, rcvj)
-    p = A.AcousticPropagatorParams(NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dy, DELTAT=dt, vp_ref=vp)
+    p = A.AcousticPropagatorParams(PropagatorKernel=1, NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dy, DELTAT=dt, vp_ref=vp)
     src, rcv = A.AcousticSource(srci, srcj, srcv), A.AcousticReceiver(rcvi, rcvj)
     plan = A.AcousticPlan(p, srci, srcj, rcvi, rcvj, ctx=ctx)
     assert plan.info()["fast_rows"] > 0
@@ -85,7 +85,7 @@ def test_checkpointed_gradient_equals_full_history(A, ctx, po):
     rng = np.random.default_rng(77)
     NX, NY, NSTEP, dx, dt, vp = 90, 600, 75, 10.0, 1e-3, 2000.0
     sig, tau, c, srci, srcj, srcv, rcvi, rcvj = _case(po, rng, NX, NY, NSTEP, dx, dx, dt, 10, vp)
-    p = A.AcousticPropagatorParams(NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dx, DELTAT=dt, vp_ref=vp,
+    p = A.AcousticPropagatorParams(PropagatorKernel=1, NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dx, DELTAT=dt, vp_ref=vp,
                                    NPOINTS_PML=10)
     u0, r0 = po.acoustic_forward(NX, NY, NSTEP, dt, dx, dx, sig, tau, c, srci, srcj, srcv, rcvi, rcvj)
     obs = 0.5 * r0
@@ -123,7 +123,7 @@ def test_mpi_convention(A, ctx, po):
     obs = 0.9 * r0
     L0, g0, s0 = po.acoustic_misfit_grad(NX, NY, NSTEP, dt, dx, dx, sig, tau, c2p, srci, srcj, rcvi, rcvj, obs, u0,
                                          mpi_convention=True)
-    p = A.AcousticPropagatorParams(NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dx, DELTAT=dt, vp_ref=1000.0,
+    p = A.AcousticPropagatorParams(PropagatorKernel=1, NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dx, DELTAT=dt, vp_ref=1000.0,
                                    Rcoef=0.2, mpi_convention=True)
     R = A.acoustic_misfit_grad(p, A.AcousticSource(srci, srcj, srcv), c2, A.AcousticReceiver(rcvi, rcvj), obs, ctx=ctx)
     assert np.array_equal(R["rcvv"], r0)
@@ -150,9 +150,12 @@ def test_op_level_step(A, ctx, po):
 
 
 def test_errors_are_reported(A, ctx):
-    p = A.AcousticPropagatorParams(NX=50, NY=50, NSTEP=10, PropagatorKernel=0)
+    p = A.AcousticPropagatorParams(NX=50, NY=50, NSTEP=10, PropagatorKernel=3)
     with pytest.raises(A.AdseisError):
         A.AcousticPlan(p, [5], [5], [6], [6], ctx=ctx)
+    with pytest.raises(A.AdseisError):     # PropagatorKernel=0 has no slab decomposition
+        A.AcousticPlan(A.AcousticPropagatorParams(NX=50, NY=50, NSTEP=10, PropagatorKernel=0), [5], [5], [6], [6],
+                       ctx=ctx, slab=(0, 2, 0, 26))
     p = A.AcousticPropagatorParams(NX=50, NY=50, NSTEP=10)
     with pytest.raises(A.AdseisError):
         A.AcousticPlan(p, [500], [5], [6], [6], ctx=ctx)       # source outside the grid
@@ -161,3 +164,59 @@ def test_errors_are_reported(A, ctx):
         plan.forward()                                          # no model yet
     with pytest.raises(A.AdseisError):
         plan.set_srcv(np.zeros((3, 1)))                         # too few rows
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PropagatorKernel = 0 (phi, psi driven by the new wavefield; src/Core.jl:528-549).  The reference computes this
+# scheme with TF element-wise kernels, not with the C++ op, so parity is to fp64 round-off (1e-10 bar), not bit-exact.
+# ---------------------------------------------------------------------------------------------------------------
+def test_kernel0_golden(A, ctx):
+    G = golden("acoustic_kernel0.npz")
+    p = A.AcousticPropagatorParams(NX=int(G["NX"]), NY=int(G["NY"]), NSTEP=int(G["NSTEP"]), DELTAX=float(G["dx"]),
+                                   DELTAY=float(G["dy"]), DELTAT=float(G["dt"]), NPOINTS_PML=int(G["npml"]),
+                                   vp_ref=float(G["vp_ref"]))
+    assert p.PropagatorKernel == 0                                   # the reference's default (src/Struct.jl:120)
+    src, rcv = A.AcousticSource(G["srci"], G["srcj"], G["srcv"]), A.AcousticReceiver(G["rcvi"], G["rcvj"])
+    R = A.acoustic_misfit_grad(p, src, G["c"], rcv, G["obs"], ctx=ctx)
+    assert relerr(R["rcvv"], G["rcvv"]) < 1e-12
+    assert abs(R["loss"] - float(G["loss"])) / float(G["loss"]) < 1e-12
+    assert relerr(R["grad_c"], G["grad_c"]) < TOL and relerr(R["grad_srcv"], G["grad_srcv"]) < TOL
+
+
+@pytest.mark.parametrize("shape,mpi", [((150, 700, 60), False), ((90, 1100, 50), True), ((64, 80, 70), False)])
+def test_kernel0_vs_oracle(A, ctx, po, shape, mpi):
+    """Marching box + frame, sources inside the absorbing frame / next to each other / on the ring (their injected
+    part must not leak into the phi/psi-driven terms), both input conventions, checkpoint segments."""
+    NX, NY, NSTEP = shape
+    rng = np.random.default_rng(NX + NY)
+    dx, dy, dt, vp = 10.0, 8.0, 1e-3, 2500.0
+    sig, tau, c, srci, srcj, srcv, rcvi, rcvj = _case(po, rng, NX, NY, NSTEP, dx, dy, dt, 12, vp, nsrc=5)
+    srci[0], srcj[0] = 1, NY // 2            # ring row
+    srci[1], srcj[1] = 4, 6                  # inside the corner of the absorbing frame
+    srci[2], srcj[2] = 5, 6                  # its neighbour
+    srci[3], srcj[3] = NX // 2, NY - 2       # inside the y-max strip
+    off = 1 if mpi else 0                    # MPI convention: 1-based into the UNPADDED grid
+    cc = c * c if mpi else c
+    u0, up0, r0 = po.acoustic_forward(NX, NY, NSTEP, dt, dx, dy, sig, tau, cc, srci - off, srcj - off, srcv, rcvi - off,
+                                      rcvj - off, mpi_convention=mpi, kernel=0)
+    obs = 0.7 * r0 + 0.02 * np.abs(r0).max() * rng.standard_normal(r0.shape)
+    L0, gc0, gs0 = po.acoustic_misfit_grad(NX, NY, NSTEP, dt, dx, dy, sig, tau, cc, srci - off, srcj - off, rcvi - off,
+                                           rcvj - off, obs, u0, mpi_convention=mpi, upre_hist=up0)
+    p = A.AcousticPropagatorParams(NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dy, DELTAT=dt, vp_ref=vp,
+                                   PropagatorKernel=0, mpi_convention=mpi)
+    model = cc[1:-1, 1:-1] if mpi else cc
+    want_gc = gc0[1:-1, 1:-1] if mpi else gc0
+    out = []
+    for hist in (0, 9):
+        plan = A.AcousticPlan(p, srci - off, srcj - off, rcvi - off, rcvj - off, ctx=ctx,
+                              hist_bytes_budget=hist * (NX + 2) * ((NY + 2 + 15) // 16 * 16) * 8)
+        plan.set_model(np.ascontiguousarray(model)); plan.set_srcv(srcv); plan.set_obs(obs)
+        plan.gradient()
+        assert relerr(plan.rcvv(), r0) < 1e-12
+        assert abs(plan.loss() - L0) / L0 < 1e-12
+        assert relerr(plan.grad_c(), want_gc) < TOL
+        assert relerr(plan.grad_srcv(), gs0) < TOL
+        out.append((plan.loss(), plan.grad_c(), plan.info()))
+        plan.close()
+    assert out[1][2]["segments"] > 1
+    assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])

@@ -26,7 +26,7 @@ def _exactly_scaled(r, r1, k):
 
 
 def _acoustic_plan(A, ctx, NX, NY, NSTEP, nrcv, hist=0):
-    p = A.AcousticPropagatorParams(NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=10.0, DELTAY=10.0, DELTAT=1e-3, vp_ref=2500.0)
+    p = A.AcousticPropagatorParams(PropagatorKernel=1, NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=10.0, DELTAY=10.0, DELTAT=1e-3, vp_ref=2500.0)
     srci, srcj = np.array([NX // 2, NX // 3]), np.array([NY // 2, 40])
     rcvi = np.linspace(20, NX - 20, nrcv).astype(np.int64)
     rcvj = np.full(nrcv, NY // 2 + 30)

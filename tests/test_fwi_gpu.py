@@ -12,7 +12,7 @@ TOL = 1e-10
 
 def _marmousi(A):
     G = golden("acoustic_marmousi2_shot3.npz")
-    p = A.AcousticPropagatorParams(NX=int(G["NX"]), NY=int(G["NY"]), NSTEP=int(G["NSTEP"]), DELTAX=float(G["dx"]),
+    p = A.AcousticPropagatorParams(PropagatorKernel=1, NX=int(G["NX"]), NY=int(G["NY"]), NSTEP=int(G["NSTEP"]), DELTAX=float(G["dx"]),
                                    DELTAY=float(G["dy"]), DELTAT=float(G["dt"]), NPOINTS_PML=int(G["npml"]),
                                    vp_ref=float(G["vp_ref"]))
     return G, p

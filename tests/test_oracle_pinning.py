@@ -207,3 +207,66 @@ def test_block_decomposed_ref_gradient_matches_oracle(po):
                                       mpi_convention=True)
     assert abs(L - Lb) / L < 1e-14
     assert relerr(gb, g[1:-1, 1:-1]) < 1e-13 and relerr(sb, s) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PropagatorKernel = 0 (src/Core.jl:528-549): pinned by a torch-autograd restatement of the reference's graph
+# ---------------------------------------------------------------------------------------------------------------
+def _k0_run(po, G):
+    NX, NY, NSTEP = int(G["NX"]), int(G["NY"]), int(G["NSTEP"])
+    dx, dy, dt = float(G["dx"]), float(G["dy"]), float(G["dt"])
+    sig, tau = po.acoustic_pml(NX, NY, dx, dy, npml=int(G["npml"]), vp_ref=float(G["vp_ref"]))
+    u, up, r = po.acoustic_forward(NX, NY, NSTEP, dt, dx, dy, sig, tau, G["c"], G["srci"], G["srcj"], G["srcv"],
+                                   G["rcvi"], G["rcvj"], kernel=0)
+    L, gc, gs = po.acoustic_misfit_grad(NX, NY, NSTEP, dt, dx, dy, sig, tau, G["c"], G["srci"], G["srcj"], G["rcvi"],
+                                        G["rcvj"], G["obs"], u, upre_hist=up)
+    return r, L, gc, gs
+
+
+def test_acoustic_kernel0_oracle_vs_golden(po):
+    G = golden("acoustic_kernel0.npz")
+    r, L, gc, gs = _k0_run(po, G)
+    assert relerr(r, G["rcvv"]) < 1e-13
+    assert abs(L - float(G["loss"])) / float(G["loss"]) < 1e-13
+    assert relerr(gc, G["grad_c"]) < 1e-12 and relerr(gs, G["grad_srcv"]) < 1e-12
+
+
+@pytest.mark.parametrize("kernel", [0, 2])
+def test_acoustic_torch_restatement_live(po, kernel):
+    """kernel=2 (acoustic_one_step_customop_ref, Core.jl:504-525) ties the torch restatement to the C++ op bodies'
+    oracle; kernel=0 ties the hand-derived scheme-0 reverse sweep to autograd of the same restatement."""
+    import torch
+    from oracle import torch_acoustic as ta
+    rng = np.random.default_rng(11)
+    NX, NY, NSTEP, dx, dy, dt = 22, 27, 40, 10.0, 8.0, 1e-3
+    sig, tau = po.acoustic_pml(NX, NY, dx, dy, npml=5, vp_ref=2500.0)
+    c = 2500 * (1 + 0.1 * rng.random((NX + 2, NY + 2)))
+    srci, srcj = np.array([11, 3, 4, 20]), np.array([13, 5, 5, 26])
+    srcv = np.stack([po.ricker(NSTEP, 6.0 + k, 10.0 + k, 1e6) for k in range(4)], 1)
+    rcvi, rcvj = rng.integers(1, NX + 3, 20), rng.integers(1, NY + 3, 20)
+    if kernel == 0:
+        u, up, r = po.acoustic_forward(NX, NY, NSTEP, dt, dx, dy, sig, tau, c, srci, srcj, srcv, rcvi, rcvj, kernel=0)
+    else:
+        u, r = po.acoustic_forward(NX, NY, NSTEP, dt, dx, dy, sig, tau, c, srci, srcj, srcv, rcvi, rcvj)
+        up = None
+    obs = 0.7 * r + 0.01 * np.abs(r).max() * rng.standard_normal(r.shape)
+    L0, gc, gs = po.acoustic_misfit_grad(NX, NY, NSTEP, dt, dx, dy, sig, tau, c, srci, srcj, rcvi, rcvj, obs, u,
+                                         upre_hist=up)
+    ct, st = torch.tensor(c.reshape(-1), requires_grad=True), torch.tensor(srcv, requires_grad=True)
+    L, rt = ta.acoustic_loss(kernel, NX, NY, NSTEP, dt, dx, dy, sig, tau, ct, srci, srcj, st, rcvi, rcvj, obs)
+    L.backward()
+    assert relerr(rt.detach().numpy(), r) < 1e-13 and abs(float(L.detach()) - L0) / L0 < 1e-13
+    assert relerr(ct.grad.numpy().reshape(NX + 2, NY + 2), gc) < 1e-12
+    assert relerr(st.grad.numpy()[:NSTEP], gs) < 1e-12
+
+
+def test_acoustic_kernel0_differs_from_kernel1(po):
+    """The two schemes are different discretisations of the PML memory variables: equal outside PML influence only."""
+    G = golden("acoustic_kernel0.npz")
+    NX, NY, NSTEP = int(G["NX"]), int(G["NY"]), int(G["NSTEP"])
+    dx, dy, dt = float(G["dx"]), float(G["dy"]), float(G["dt"])
+    sig, tau = po.acoustic_pml(NX, NY, dx, dy, npml=int(G["npml"]), vp_ref=float(G["vp_ref"]))
+    _, r1 = po.acoustic_forward(NX, NY, NSTEP, dt, dx, dy, sig, tau, G["c"], G["srci"], G["srcj"], G["srcv"], G["rcvi"],
+                                G["rcvj"])
+    d = relerr(r1, G["rcvv"])
+    assert 1e-8 < d < 0.5
