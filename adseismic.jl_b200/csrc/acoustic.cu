@@ -362,20 +362,37 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     P->fast_rows = mr1 - mr0;
     const int nwarpcols = (mc_end - mc0 + AC_WCOLS - 1) / AC_WCOLS;
     t.nct = (nwarpcols + AC_WARPS - 1) / AC_WARPS;
-    // rows per marching CTA: the TMA-ring kernels run 2 CTAs per SM, so the marching CTA count is a multiple of
-    // 2 * SMs (whole waves); up to 3 waves for load balance as long as a CTA keeps >= 12 rows to amortise its
+    // thin edge tiles (slab plans): one row next to each neighbour, when that row is a marched row
+    if (halo_lo && mr0 == P->own0 && mr1 - mr0 >= 8) t.elo = 1;
+    if (halo_hi && mr1 == P->own1 && mr1 - mr0 >= 8) t.ehi = 1;
+    // rows per marching CTA: the TMA-ring kernels run 2 CTAs per SM, and all CTAs of a launch should be resident at
+    // once in whole waves (a CTA that has to wait for a slot ends the launch late): marching + frame CTAs fill
+    // 1..3 waves of 2 * SMs, up to 3 waves for load balance as long as a CTA keeps >= 12 rows to amortise its
     // pipeline prologue (small slabs of a domain decomposition get exactly one wave)
+    int nframe_est = 0;
+    {
+      const i64 fc[4] = {(i64)(mr0 - P->own0) * g.W, (i64)(P->own1 - mr1) * g.W, (i64)(mr1 - mr0) * mc0,
+                         (i64)(mr1 - mr0) * (g.W - mc_end)};
+      for (int k = 0; k < 4; k++) nframe_est += (int)((fc[k] + AC_FRAME_CELLS - 1) / AC_FRAME_CELLS);
+    }
     int rb = 32;
-    if (t.nct > 0 && mr1 > mr0) {
-      const int per_wave = std::max(1, (2 * ctx->sm_count + t.nct - 1) / t.nct);  // row tiles of one wave
-      const int waves = std::min(3, std::max(1, (mr1 - mr0) / (12 * per_wave)));
-      const int want_tr = per_wave * waves;
-      rb = (mr1 - mr0 + want_tr - 1) / want_tr;
-      rb = std::min(128, std::max(AC_U, round_up(rb, AC_FWD_TMA && AC_ADJ_TMA ? 1 : AC_U)));
+    const int nedge = (t.elo ? 1 : 0) + (t.ehi ? 1 : 0);
+    const int mid = mr1 - mr0 - t.elo - t.ehi;
+    if (t.nct > 0 && mid > 0) {
+      const int slots = 2 * ctx->sm_count;
+      const int per_wave = std::max(1, (slots + t.nct - 1) / t.nct);  // row tiles of one wave
+      const int waves = std::min(3, std::max(1, mid / (12 * per_wave)));
+      int want_tr = per_wave * waves;
+      if (waves == 1) {  // one wave: every CTA of the launch (marching, thin edge and frame CTAs) gets a slot at once
+        want_tr = (slots - nframe_est) / t.nct - nedge;
+        if (want_tr < 1) want_tr = std::max(1, per_wave - nedge);
+      }
+      rb = (mid + want_tr - 1) / want_tr;
+      rb = std::min(128, std::max(2, rb));
       if (getenv("ADSEIS_AC_RB")) rb = std::max(2, atoi(getenv("ADSEIS_AC_RB")));  // tuning experiments
     }
     t.rb = rb;
-    t.ntr = (mr1 > mr0) ? (mr1 - mr0 + rb - 1) / rb : 0;
+    t.ntr = (mr1 > mr0) ? nedge + (mid + rb - 1) / rb : 0;
     t.nmarch = t.nct * t.ntr;
     // frame rectangles: rows above / below the marched rows (all columns), columns left / right of the marched ones
     auto add_rect = [&](int r0, int r1, int c0, int c1) {
@@ -405,7 +422,9 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     for (int b = 0; b < P->nblocks; b++) {
       int rlo, rhi;
       if (b < t.nmarch) {
-        rlo = t.mr0 + (b / t.nct) * t.rb; rhi = std::min(t.mr1, rlo + t.rb) - 1;
+        int a0, a1;
+        ac_row_tile(t, b / t.nct, &a0, &a1);
+        rlo = a0; rhi = a1 - 1;
       } else {
         int fb = b - t.nmarch, r = 0;
         for (int k = 1; k < t.nrect; k++) if (fb >= t.rblk[k]) r = k;
@@ -446,7 +465,7 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
   auto owner_cta = [&](int li, int j) -> int {
     const AcTiling& t = P->t;
     if (li >= t.mr0 && li < t.mr1 && j >= t.mc0 && j < t.mc_end)
-      return ((li - t.mr0) / t.rb) * t.nct + (j - t.mc0) / AC_TILE_COLS;
+      return ac_row_tile_of(t, li) * t.nct + (j - t.mc0) / AC_TILE_COLS;
     for (int k = 0; k < t.nrect; k++)
       if (li >= t.rr0[k] && li < t.rr1[k] && j >= t.rc0[k] && j < t.rc1[k])
         return t.nmarch + t.rblk[k] + (int)(((i64)(li - t.rr0[k]) * (t.rc1[k] - t.rc0[k]) + (j - t.rc0[k])) / AC_FRAME_CELLS);
@@ -663,7 +682,7 @@ static int run_forward_steps(adseis_acoustic_plan* P, i64 base, i64 s_first, i64
   }
   for (i64 s = s_first; s <= s_last; s++) {
     const AcFuse fuse = make_fuse(P, AR_HIST, s - base, AR_PHI, s & 1);
-    CUDA_TRY(launch_step(P->p.PropagatorKernel == 0 ? ac_fwd_kernel<0> : ac_fwd_kernel<1>, P->nblocks, AC_FWD_THREADS,
+    CUDA_TRY(launch_step(P->arena == nullptr || getenv("ADSEIS_PDL_SLAB") != nullptr, P->p.PropagatorKernel == 0 ? ac_fwd_kernel<0> : ac_fwd_kernel<1>, P->nblocks, AC_FWD_THREADS,
                          AC_FWD_SMEM, st,
         g, P->t, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, P->phi[(s - 1) & 1], P->psi[(s - 1) & 1],
         P->sigx, P->tauy, win_slot(P, base, s), P->phi[s & 1], P->psi[s & 1], P->srcp,
@@ -831,7 +850,7 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
           LAUNCH_CHECK(P);
         }
       }
-      CUDA_TRY(launch_step(P->p.PropagatorKernel == 0 ? ac_adj_kernel<0> : ac_adj_kernel<1>, P->nblocks, AC_ADJ_THREADS,
+      CUDA_TRY(launch_step(P->arena == nullptr || getenv("ADSEIS_PDL_SLAB") != nullptr, P->p.PropagatorKernel == 0 ? ac_adj_kernel<0> : ac_adj_kernel<1>, P->nblocks, AC_ADJ_THREADS,
                            AC_ADJ_SMEM, st,
           g, P->t, P->ub[s % 3], P->ub[(s + 1) % 3], win_slot(P, b, s - 1), P->c2, P->phib[s & 1], P->psib[s & 1],
           P->sigx, P->tauy, P->ub[(s + 2) % 3] /* == (s-1)%3 */, P->phib[(s - 1) & 1], P->psib[(s - 1) & 1], P->G,

@@ -92,13 +92,31 @@ struct AcGeom {
 struct AcTiling {
   int mr0, mr1;       // marched local rows [mr0, mr1)
   int mc0, mc_end;    // marched columns [mc0, mc_end), mc0 % 16 == 0, both even
-  int rb;             // rows per marching CTA (multiple of AC_U)
+  int rb;             // rows per marching CTA (uniform tiles of the middle rows)
+  int elo, ehi;       // slab plans: rows of the thin first / last row tile next to a neighbour (0 = none)
   int nct, ntr;       // marching column tiles / row tiles; marching CTA id = tr*nct + ct
   int nmarch;         // nct*ntr
   int nrect;          // frame rectangles (local rows [rr0,rr1) x columns [rc0,rc1))
   int rr0[4], rr1[4], rc0[4], rc1[4];
   int rblk[5];        // CTA-id prefix of the rectangles, relative to nmarch
 };
+
+// Row tile tr of the marched rows -> [r0, r1).  Slab plans put a thin tile on the rows next to a neighbour: those CTAs
+// are launched first and finish within a couple of microseconds, so the halo rows they push travel over NVLink while
+// the rest of the (single-wave) launch is still streaming, instead of leaving at the very end of it.
+__host__ __device__ __forceinline__ void ac_row_tile(const AcTiling& t, int tr, int* r0, int* r1) {
+  const int m0 = t.mr0 + t.elo, m1 = t.mr1 - t.ehi;  // uniform middle
+  if (t.elo && tr == 0) { *r0 = t.mr0; *r1 = m0; return; }
+  const int a = m0 + (tr - (t.elo ? 1 : 0)) * t.rb;
+  if (a >= m1) { *r0 = m1; *r1 = t.mr1; return; }
+  *r0 = a; *r1 = (a + t.rb < m1) ? a + t.rb : m1;
+}
+__host__ __device__ __forceinline__ int ac_row_tile_of(const AcTiling& t, int li) {
+  const int m0 = t.mr0 + t.elo, m1 = t.mr1 - t.ehi;
+  if (li < m0) return 0;
+  if (li >= m1) return (t.elo ? 1 : 0) + (m1 - m0 + t.rb - 1) / t.rb;
+  return (t.elo ? 1 : 0) + (li - m0) / t.rb;
+}
 
 // Per-CTA point lists: points (sources or receivers) owned by CTA b are entries [blk[b], blk[b+1]) of the
 // unique-cell arrays; start/perm give the original point indices on each cell (see PointSet in common.cuh).
@@ -298,8 +316,8 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
   } else {
     // ---------------- marching CTA ----------------
     const int ct = bid % t.nct, tr = bid / t.nct;
-    const int r0 = t.mr0 + tr * t.rb;
-    const int r1 = min(t.mr1, r0 + t.rb);
+    int r0, r1;
+    ac_row_tile(t, tr, &r0, &r1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c0 = t.mc0 + ct * AC_TILE_COLS;
     const int jb = c0 + warp * AC_WCOLS;
@@ -704,8 +722,8 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
     }
   } else {
     const int ct = bid % t.nct, tr = bid / t.nct;
-    const int r0 = t.mr0 + tr * t.rb;
-    const int r1 = min(t.mr1, r0 + t.rb);
+    int r0, r1;
+    ac_row_tile(t, tr, &r0, &r1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c0 = t.mc0 + ct * AC_TILE_COLS;
     const int jb = c0 + warp * AC_WCOLS;

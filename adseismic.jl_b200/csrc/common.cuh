@@ -81,7 +81,9 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // Programmatic dependent launch (sm_90+): the time-step kernels call griddepcontrol.launch_dependents on entry, so
 // the next step's CTAs are scheduled while the current step drains, run their prologue (CTA table, mbarrier init)
 // and block in griddepcontrol.wait until the current step's memory operations are complete and visible.  Hides the
-// launch gap between the thousands of dependent step launches of a sweep.  ADSEIS_PDL=0 disables it.
+// launch gap between the thousands of dependent step launches of a sweep.  ADSEIS_PDL=0 disables it.  Slab plans
+// launch without it (`pdl` = false): measured on 2 and 8 B200s, early-resident CTAs of the next step make the
+// single-wave slab launches 10-25 % slower (forward 16.5 -> 22.2 us on a 512 x 4096 slab).
 static inline bool adseis_pdl_enabled() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("ADSEIS_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
@@ -89,15 +91,15 @@ static inline bool adseis_pdl_enabled() {
 }
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_step(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st,
-                                      Args&&... args) {
+static inline cudaError_t launch_step(bool pdl, void (*kernel)(KArgs...), int grid, int block, size_t smem,
+                                      cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
   cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = adseis_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = (pdl && adseis_pdl_enabled()) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 #endif

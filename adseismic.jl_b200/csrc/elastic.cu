@@ -2,6 +2,7 @@
 // Reference behaviour restated: src/Core.jl:31-228 (variant 0), src/MPIElastic.jl:374-682 on the global grid
 // (variant 1), CPML coefficients src/Core.jl:231-407, receivers src/Core.jl:701-712 + ReceiveOps/GetReceive.cpp,
 // sources SourceOps/AddSource.cpp, misfit src/Utils.jl:308; adjoint = SURVEY Appendix B.
+#include <algorithm>
 #include <map>
 
 #include "elastic_kernels.cuh"
@@ -329,6 +330,7 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
   struct Rect { int r0, r1, c0, c1, base, ntc, tw, th; };
   std::vector<Rect> rects;
   int mrb = 0, mnct = 0;  // marching tile rows / column tiles
+  std::vector<int> mrt;   // marching row-tile boundaries (local rows), ascending
   {
     // box: inside the update regions of fw1..fw4, CPML-free, and 2 cells away from anything that is not
     int bp0 = 0, bp1 = g.H - 1, bq0 = 0, bq1 = g.W - 1;  // inclusive, global
@@ -357,11 +359,19 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
         if (mrb >= 16) break;
       }
       if (getenv("ADSEIS_EL_RB")) mrb = std::max(2, atoi(getenv("ADSEIS_EL_RB")));  // tuning experiments
-      const int ntr = (r1 - r0 + mrb - 1) / mrb;
-      for (int tr = 0; tr < ntr; tr++)
+      // slab plans: the EL_HALO rows next to a neighbour form thin row tiles of their own -- launched first, done
+      // within a couple of microseconds, so the halo rows they push cross NVLink while the rest of the (single-wave)
+      // launch is still streaming instead of leaving at its very end
+      const int thin_lo = (halo_lo && r0 == g.own0 && r1 - r0 >= 6 * EL_HALO) ? EL_HALO : 0;
+      const int thin_hi = (halo_hi && r1 == g.own1 && r1 - r0 >= 6 * EL_HALO) ? EL_HALO : 0;
+      mrt.push_back(r0);
+      if (thin_lo) mrt.push_back(r0 + thin_lo);
+      for (int a = r0 + thin_lo + mrb; a < r1 - thin_hi; a += mrb) mrt.push_back(a);
+      if (thin_hi) mrt.push_back(r1 - thin_hi);
+      mrt.push_back(r1);
+      for (size_t tr = 0; tr + 1 < mrt.size(); tr++)
         for (int tc = 0; tc < mnct; tc++)
-          ctas.push_back(ElCta{0, r0 + tr * mrb, std::min(r1, r0 + (tr + 1) * mrb), c0 + tc * EL_TCOLS,
-                               std::min(c1, c0 + (tc + 1) * EL_TCOLS), 0, 0, 0});
+          ctas.push_back(ElCta{0, mrt[tr], mrt[tr + 1], c0 + tc * EL_TCOLS, std::min(c1, c0 + (tc + 1) * EL_TCOLS), 0, 0, 0});
     }
     P->nmarch = (int)ctas.size();
     auto add_rect = [&](int rr0, int rr1, int cc0, int cc1) {
@@ -412,7 +422,7 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
   }
   auto owner_cta = [&](int li, int q) -> int {
     if (li >= P->box[0] && li < P->box[1] && q >= P->box[2] && q < P->box[3])
-      return ((li - P->box[0]) / mrb) * mnct + (q - P->box[2]) / EL_TCOLS;
+      return (int)(std::upper_bound(mrt.begin(), mrt.end(), li) - mrt.begin() - 1) * mnct + (q - P->box[2]) / EL_TCOLS;
     for (const Rect& R : rects)
       if (li >= R.r0 && li < R.r1 && q >= R.c0 && q < R.c1)
         return R.base + ((li - R.r0) / R.th) * R.ntc + (q - R.c0) / R.tw;
@@ -729,10 +739,10 @@ static int el_step_forward(adseis_elastic_plan* P, i64 s, double* in, double* ou
   const double* prev = (P->nsrc > 0 && s >= 2) ? P->srcv + (s - 2) * P->nsrc : nullptr;
   const i64 widx = (out - P->hist) / P->slot_sz;
   const ElPlaneRef sig_planes[2] = {{EA_HIST, widx, 2}, {EA_HIST, widx, 4}};  // fw3/fw4 difference sxx, sxy along x
-  CUDA_TRY(launch_step(el_sigma_fwd, P->nblocks, EL_NT, el_ring_bytes<ElSigFwdT>(), st, P->g, P->ctas, si, so, mt, cf, P->src.dev, prev, el_make_fuse(P, 2, sig_planes)));
+  CUDA_TRY(launch_step(P->arena == nullptr || getenv("ADSEIS_PDL_SLAB") != nullptr, el_sigma_fwd, P->nblocks, EL_NT, el_ring_bytes<ElSigFwdT>(), st, P->g, P->ctas, si, so, mt, cf, P->src.dev, prev, el_make_fuse(P, 2, sig_planes)));
   EL_LAUNCH_CHECK(P);
   const ElPlaneRef vel_planes[2] = {{EA_HIST, widx, 0}, {EA_HIST, widx, 1}};
-  CUDA_TRY(launch_step(el_vel_fwd, P->nblocks, EL_NT, el_ring_bytes<ElVelFwdT>(), st, P->g, P->ctas, si, so, mt, cf, P->src.dev, row, sample ? P->rcv.dev : none,
+  CUDA_TRY(launch_step(P->arena == nullptr || getenv("ADSEIS_PDL_SLAB") != nullptr, el_vel_fwd, P->nblocks, EL_NT, el_ring_bytes<ElVelFwdT>(), st, P->g, P->ctas, si, so, mt, cf, P->src.dev, row, sample ? P->rcv.dev : none,
                                          (sample && P->nrcv > 0) ? P->rcvv : nullptr, (int)(P->p.NSTEP + 1), (int)s,
                                          el_make_fuse(P, 2, vel_planes)));
   EL_LAUNCH_CHECK(P);
@@ -873,19 +883,19 @@ ADSEIS_API int adseis_elastic_plan_gradient(adseis_elastic_plan* P, int want_mat
       const double* resp = P->nrcv > 0 ? P->res : nullptr;
       double* grow = (s - 2 >= 0 && P->nsrc > 0 && s >= 2) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr;
       if (mat) {
-        CUDA_TRY(launch_step(el_vel_adj<true>, P->nblocks, EL_NT, el_ring_bytes<ElVelAdjT<true>>(), st, g, P->ctas, bi, bo, fs, mt, cf, P->Gr3, P->Gr4, P->rcv.dev, resp, stride, (int)s,
+        CUDA_TRY(launch_step(P->arena == nullptr || getenv("ADSEIS_PDL_SLAB") != nullptr, el_vel_adj<true>, P->nblocks, EL_NT, el_ring_bytes<ElVelAdjT<true>>(), st, g, P->ctas, bi, bo, fs, mt, cf, P->Gr3, P->Gr4, P->rcv.dev, resp, stride, (int)s,
                                                      el_make_fuse(P, 3, sb_planes)));
         EL_LAUNCH_CHECK(P);
-        CUDA_TRY(launch_step(el_sigma_adj<true>, P->nblocks, EL_NT, el_ring_bytes<ElSigAdjT<true>>(), st, g, P->ctas, bi, bo, fp, fs, mt, cf, P->Gl, P->Gm1, P->Gm2,
+        CUDA_TRY(launch_step(P->arena == nullptr || getenv("ADSEIS_PDL_SLAB") != nullptr, el_sigma_adj<true>, P->nblocks, EL_NT, el_ring_bytes<ElSigAdjT<true>>(), st, g, P->ctas, bi, bo, fp, fs, mt, cf, P->Gl, P->Gm1, P->Gm2,
                                                        s >= 2 ? P->rcv.dev : none, s >= 2 ? resp : nullptr, stride,
                                                        (int)(s - 1), s >= 2 ? P->src.dev : none, grow,
                                                        el_make_fuse(P, 2, vb_planes)));
         EL_LAUNCH_CHECK(P);
       } else {
-        CUDA_TRY(launch_step(el_vel_adj<false>, P->nblocks, EL_NT, el_ring_bytes<ElVelAdjT<false>>(), st, g, P->ctas, bi, bo, zero, mt, cf, nullptr, nullptr, P->rcv.dev, resp, stride,
+        CUDA_TRY(launch_step(P->arena == nullptr || getenv("ADSEIS_PDL_SLAB") != nullptr, el_vel_adj<false>, P->nblocks, EL_NT, el_ring_bytes<ElVelAdjT<false>>(), st, g, P->ctas, bi, bo, zero, mt, cf, nullptr, nullptr, P->rcv.dev, resp, stride,
                                                       (int)s, el_make_fuse(P, 3, sb_planes)));
         EL_LAUNCH_CHECK(P);
-        CUDA_TRY(launch_step(el_sigma_adj<false>, P->nblocks, EL_NT, el_ring_bytes<ElSigAdjT<false>>(), st, g, P->ctas, bi, bo, zero, zero, mt, cf, nullptr, nullptr, nullptr,
+        CUDA_TRY(launch_step(P->arena == nullptr || getenv("ADSEIS_PDL_SLAB") != nullptr, el_sigma_adj<false>, P->nblocks, EL_NT, el_ring_bytes<ElSigAdjT<false>>(), st, g, P->ctas, bi, bo, zero, zero, mt, cf, nullptr, nullptr, nullptr,
                                                         s >= 2 ? P->rcv.dev : none, s >= 2 ? resp : nullptr, stride,
                                                         (int)(s - 1), s >= 2 ? P->src.dev : none, grow,
                                                         el_make_fuse(P, 2, vb_planes)));

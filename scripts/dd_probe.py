@@ -18,7 +18,7 @@ def timed(fn, reps=2):
     return parallel.all_reduce_scalar(min(ts), "max")
 
 
-NX = NY = int(os.environ.get("PN", "2000")); NSTEP = int(os.environ.get("PT", "60"))
+NX = int(os.environ.get("PN", "2000")); NY = int(os.environ.get("PNY", str(NX))); NSTEP = int(os.environ.get("PT", "60"))
 p = A.ElasticPropagatorParams(NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=1.0, DELTAY=1.0, DELTAT=5e-5, vp_ref=3300.0, variant=1)
 rho = np.full((NX, NY), 2800.0); vp = np.full((NX, NY), 3300.0); vs = vp / 1.732
 lam, mu, rho = A.compute_lame_parameters(vp, vs, rho)
@@ -35,6 +35,8 @@ for name, fn in (("forward", dd.forward), ("grad srcv", lambda: dd.gradient(Fals
 dd.close()
 
 NXa = int(os.environ.get("PNA", "4096"))
+if NXa == 0:
+    dist.barrier(); dist.destroy_process_group(); sys.exit(0)
 pa = A.AcousticPropagatorParams(PropagatorKernel=1, NX=NXa, NY=NXa, NSTEP=NSTEP, DELTAX=10.0, DELTAY=10.0, DELTAT=0.05, Rcoef=0.2,
                                 vp_ref=1000.0, mpi_convention=True)
 c2 = np.full((NXa, NXa), 1000.0)
