@@ -215,13 +215,17 @@ static int plan_segments(adseis_acoustic_plan* P, size_t budget_bytes, bool coun
     }
     P->win = best;
   }
+  // The LAST segment is never replayed (its snapshots are still in the window when the reverse sweep starts), so
+  // it is the one that gets the full window; the remainder goes to the first segment.
   P->seg_b.clear(); P->seg_e.clear();
-  i64 b = 0;
+  const i64 per = P->win - 2;                                   // new steps per full segment
+  const i64 nseg = std::max<i64>(1, (NSTEP - 1 + per - 1) / per);
+  i64 b = 0, e = std::min(NSTEP, 1 + (NSTEP - 1) - (nseg - 1) * per);
   while (true) {
-    i64 e = std::min(b + P->win - 1, NSTEP);
     P->seg_b.push_back(b); P->seg_e.push_back(e);
     if (e >= NSTEP) break;
     b = e - 1;
+    e = std::min(b + P->win - 1, NSTEP);
   }
   return ADSEIS_OK;
 }

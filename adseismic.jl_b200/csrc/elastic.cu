@@ -200,13 +200,16 @@ static int el_validate(const adseis_elastic_params* p) {
 
 // segments over slots 0..NSTEP with a window of `win` slots; consecutive segments share one slot
 static void el_make_segments(adseis_elastic_plan* P) {
+  // the last segment is never replayed: it gets the full window, the remainder goes to the first segment
   P->seg_b.clear(); P->seg_e.clear();
-  i64 b = 0;
+  const i64 NSTEP = P->p.NSTEP, per = P->win - 1;  // new slots per full segment
+  const i64 nseg = std::max<i64>(1, (NSTEP + per - 1) / per);
+  i64 b = 0, e = std::min(NSTEP, NSTEP - (nseg - 1) * per);
   while (true) {
-    i64 e = std::min(b + P->win - 1, (i64)P->p.NSTEP);
     P->seg_b.push_back(b); P->seg_e.push_back(e);
-    if (e >= P->p.NSTEP) break;
+    if (e >= NSTEP) break;
     b = e;
+    e = std::min(b + P->win - 1, NSTEP);
   }
 }
 

@@ -53,6 +53,9 @@
 #define EL_PF 2                     // row bundles in flight beyond the one being consumed
 #endif
 #define EL_NB (EL_PF + 1)           // bundle barriers
+#ifndef EL_LATE_RELEASE
+#define EL_LATE_RELEASE 1           // adjoint marching loops: release a ring bundle after the row's arithmetic (the loads need not
+#endif                              // all be live at once: no spills at 96 registers) instead of right after its loads
 #define EL_HALO 2                   // slab decomposition: halo rows per interior side
 #ifndef EL_MINB_FWD
 #define EL_MINB_FWD 3                // forward kernels: CTAs per SM the register allocation aims at
@@ -281,6 +284,11 @@ struct ElCursor {
     }
   }
 };
+
+// Adjoint arithmetic (compared with the reference at 1e-10, not bit for bit) uses fused multiply-adds explicitly -- the
+// library is compiled with -fmad=false for the forward kernels -- and the 4th-order stencil as 27 (a - b) + (c - d).
+__device__ __forceinline__ double el_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ double el_st4(double a, double b, double c, double d) { return __fma_rn(27.0, a - b, c - d); }
 
 // x / r with the zero numerators of the quiet zone kept off the divide's slow path
 __device__ __forceinline__ double el_div_var(double x, double r) { return x == 0.0 ? x : x / r; }
@@ -840,34 +848,35 @@ __device__ __forceinline__ void el_vel_adj_march(const ElGeom& g, const ElCta& d
   const int so = 2 + warp * 32 + lane;
   const int q = d.c0 + warp * 32 + lane;
   const bool act = q < d.c1;
-  const double dt = g.dt, ix = 1.0 / (24 * g.dx), iy = 1.0 / (24 * g.dy);
+  const double dt = g.dt, dtix = dt * (1.0 / (24 * g.dx)), dtiy = dt * (1.0 / (24 * g.dy));
   const double rx = g.r24x, ry = g.r24y;  // gradient terms: quotients by 24*dx, 24*dy as products (1e-16 relative)
-  // windows: A = dt*vbx*rinv rows li-1, li, li+1 (+ li+2) ; B = dt*vby*rbinv rows li-2, li-1, li (+ li+1)
+  // windows: A = vbx*rinv rows li-1, li, li+1 (+ li+2) ; B = vby*rbinv rows li-2, li-1, li (+ li+1); dt is folded
+  // into the stencil weights dtix, dtiy
   double Am1 = 0.0, Ac, Ap1, Bm2 = 0.0, Bm1 = 0.0, Bc;
   double fqm1 = 0.0, fqc = 0.0, fqp1 = 0.0, fsm2 = 0.0, fsm1 = 0.0, fsc = 0.0;  // forward sxy / sxx windows (MATGRAD)
   if (act) {
     const i64 o1 = (i64)(d.r0 - 1) * ld + q, o2 = (i64)(d.r0 - 2) * ld + q;
-    Am1 = dt * b.vx[o1] * mt.rinv[o1];
-    Bm2 = dt * b.vy[o2] * mt.rbinv[o2];
-    Bm1 = dt * b.vy[o1] * mt.rbinv[o1];
+    Am1 = b.vx[o1] * mt.rinv[o1];
+    Bm2 = b.vy[o2] * mt.rbinv[o2];
+    Bm1 = b.vy[o1] * mt.rbinv[o1];
     if (MATGRAD) { fqm1 = fwd.sxy[o1]; fsm2 = fwd.sxx[o2]; fsm1 = fwd.sxx[o1]; }
   }
   mbar_wait(bars, 0);
-  Ac = dt * EL_RING(T, 0, 0)[so] * EL_RING(T, 1, 0)[so];
-  Ap1 = dt * EL_RING(T, 0, 1)[so] * EL_RING(T, 1, 1)[so];
-  Bc = dt * EL_RING(T, 2, 0)[so] * EL_RING(T, 3, 0)[so];
+  Ac = EL_RING(T, 0, 0)[so] * EL_RING(T, 1, 0)[so];
+  Ap1 = EL_RING(T, 0, 1)[so] * EL_RING(T, 1, 1)[so];
+  Bc = EL_RING(T, 2, 0)[so] * EL_RING(T, 3, 0)[so];
   if (MATGRAD) { fqc = EL_RING(T, 7, 0)[so]; fqp1 = EL_RING(T, 7, 1)[so]; fsc = EL_RING(T, 8, 0)[so]; }
   ElCursor cu;
   cu.init();
   for (int it = 0; it < nrows; it++) {
     const int li = d.r0 + it, bb = it % EL_NB;
     mbar_wait(bars + 1 + bb, (unsigned)(it / EL_NB) & 1u);
-    const double Ap2 = dt * EL_RING(T, 0, cu.n[2])[so] * EL_RING(T, 1, cu.n[2])[so];
-    const double Bp1 = dt * EL_RING(T, 2, cu.n[1])[so] * EL_RING(T, 3, cu.n[1])[so];
+    const double Ap2 = EL_RING(T, 0, cu.n[2])[so] * EL_RING(T, 1, cu.n[2])[so];
+    const double Bp1 = EL_RING(T, 2, cu.n[1])[so] * EL_RING(T, 3, cu.n[1])[so];
     const double* va = EL_RING(T, 0, cu.c[2]) + so; const double* ria = EL_RING(T, 1, cu.c[2]) + so;  // centre row of A
-    const double A_m1 = dt * va[-1] * ria[-1], A_p1 = dt * va[1] * ria[1], A_p2 = dt * va[2] * ria[2];
+    const double A_m1 = va[-1] * ria[-1], A_p1 = va[1] * ria[1], A_p2 = va[2] * ria[2];
     const double* vb = EL_RING(T, 2, cu.c[1]) + so; const double* rba = EL_RING(T, 3, cu.c[1]) + so;  // centre row of B
-    const double B_m2 = dt * vb[-2] * rba[-2], B_m1 = dt * vb[-1] * rba[-1], B_p1 = dt * vb[1] * rba[1];
+    const double B_m2 = vb[-2] * rba[-2], B_m1 = vb[-1] * rba[-1], B_p1 = vb[1] * rba[1];
     double sxx = EL_RING(T, 4, cu.c[0])[so], syy = EL_RING(T, 5, cu.c[0])[so], sxy = EL_RING(T, 6, cu.c[0])[so];
     double vxc = 0.0, ric = 0.0, vyc = 0.0, rbc = 0.0;  // raw centre values (MATGRAD)
     double fqp2 = 0.0, fsp1 = 0.0, fq_m2 = 0.0, fq_m1 = 0.0, fq_p1 = 0.0, fy_m1 = 0.0, fy_c = 0.0, fy_p1 = 0.0, fy_p2 = 0.0;
@@ -882,31 +891,30 @@ __device__ __forceinline__ void el_vel_adj_march(const ElGeom& g, const ElCta& d
       fy_m1 = cy_[-1]; fy_c = cy_[0]; fy_p1 = cy_[1]; fy_p2 = cy_[2];
       G3 = EL_RING(T, 10, cu.c[0])[so]; G4 = EL_RING(T, 11, cu.c[0])[so];
     }
+#if !EL_LATE_RELEASE
     __syncwarp();
     if (lane == 0) mbar_arrive(bars + 1 + EL_NB + bb);
+#endif
     if (act) {
       const i64 c = (i64)li * ld + q;
-      for (int k = ra; k < rb; k++) {  // stress-type receiver residuals of this slot (GetReceive.cpp:48-97)
-        const int fd = rcv.field[k];
-        if (fd >= 2 && rcv.cell[k] == (int)c) {
-          double a = 0.0;
-          for (int m = rcv.start[k]; m < rcv.start[k + 1]; m++) a += res[(i64)rcv.perm[m] * res_stride + slot];
-          if (fd == 2) sxx += a; else if (fd == 3) syy += a; else sxy += a;
-        }
-      }
+      // (stress-type receiver residuals of this slot are added by the kernel after the march: addition commutes)
       // (D-x)^T A -> sxx ; (D-y)^T A -> sxy ; (D+x)^T B -> sxy ; (D+y)^T B -> syy
-      sxx += (27 * Ac - 27 * Ap1 - Am1 + Ap2) * ix;
-      sxy += (27 * Ac - 27 * A_p1 - A_m1 + A_p2) * iy;
-      sxy += (27 * Bm1 - 27 * Bc - Bm2 + Bp1) * ix;
-      syy += (27 * B_m1 - 27 * Bc - B_m2 + B_p1) * iy;
+      sxx = el_fma(el_st4(Ac, Ap1, Ap2, Am1), dtix, sxx);
+      sxy = el_fma(el_st4(Ac, A_p1, A_p2, A_m1), dtiy, sxy);
+      sxy = el_fma(el_st4(Bm1, Bc, Bp1, Bm2), dtix, sxy);
+      syy = el_fma(el_st4(B_m1, Bc, B_p1, B_m2), dtiy, syy);
       bout.sxx[c] = sxx; bout.syy[c] = syy; bout.sxy[c] = sxy;
       if (MATGRAD) {
-        const double e56 = (27 * fsc - 27 * fsm1 - fsp1 + fsm2) * rx + (27 * fqc - 27 * fq_m1 - fq_p1 + fq_m2) * ry;
-        const double e78 = (27 * fqp1 - 27 * fqc - fqp2 + fqm1) * rx + (27 * fy_p1 - 27 * fy_c - fy_p2 + fy_m1) * ry;
-        Gr3[c] = G3 + -(dt * vxc) * e56 * (ric * ric);
-        Gr4[c] = G4 + -(dt * vyc) * e78 * (rbc * rbc);
+        const double e56 = el_fma(el_st4(fsc, fsm1, fsm2, fsp1), rx, el_st4(fqc, fq_m1, fq_m2, fq_p1) * ry);
+        const double e78 = el_fma(el_st4(fqp1, fqc, fqm1, fqp2), rx, el_st4(fy_p1, fy_c, fy_m1, fy_p2) * ry);
+        Gr3[c] = el_fma(-(dt * vxc) * (ric * ric), e56, G3);
+        Gr4[c] = el_fma(-(dt * vyc) * (rbc * rbc), e78, G4);
       }
     }
+#if EL_LATE_RELEASE
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + 1 + EL_NB + bb);
+#endif
     Am1 = Ac; Ac = Ap1; Ap1 = Ap2;
     Bm2 = Bm1; Bm1 = Bc; Bc = Bp1;
     if (MATGRAD) { fqm1 = fqc; fqc = fqp1; fqp1 = fqp2; fsm2 = fsm1; fsm1 = fsc; fsc = fsp1; }
@@ -939,6 +947,17 @@ el_vel_adj(ElGeom g, const ElCta* __restrict__ ctas, ElSlot b, ElSlot bout, ElSl
     double* ring = reinterpret_cast<double*>(el_smem + 64);
     el_vel_adj_march<MATGRAD>(g, d, b, bout, fwd, mt, Gr3, Gr4, rcv, ra, rb, res, res_stride, slot, ring,
                               reinterpret_cast<unsigned long long*>(el_smem));
+    if (rb > ra) {  // CTA-uniform: stress-type receiver residuals of this slot (GetReceive.cpp:48-97) on my cells
+      __syncthreads();
+      for (int k = ra + threadIdx.x; k < rb; k += blockDim.x) {
+        const int fd = rcv.field[k];
+        if (fd >= 2) {
+          double a = 0.0;
+          for (int m = rcv.start[k]; m < rcv.start[k + 1]; m++) a += res[(i64)rcv.perm[m] * res_stride + slot];
+          el_field(bout, fd)[rcv.cell[k]] += a;
+        }
+      }
+    }
   } else if (threadIdx.x < EL_BX * EL_BY) {
     const int q = d.c0 + (threadIdx.x & ((1 << d.ltw) - 1));
     if (q < d.c1)
@@ -1090,11 +1109,11 @@ __device__ __forceinline__ void el_sigma_adj_march(const ElGeom& g, const ElCta&
   const int so = 2 + warp * 32 + lane;
   const int q = d.c0 + warp * 32 + lane;
   const bool act = q < d.c1;
-  const double dt = g.dt, ix = 1.0 / (24 * g.dx), iy = 1.0 / (24 * g.dy);
+  const double dt = g.dt, dtix = dt * (1.0 / (24 * g.dx)), dtiy = dt * (1.0 / (24 * g.dy));
   const double rx = g.r24x, ry = g.r24y;  // gradient terms: quotients by 24*dx, 24*dy as products (1e-16 relative)
-  // e3 = mub2 * (dt * sbxy) ; e1 = lmb*gx + lamb*gy ; e2 = lmb*gy + lamb*gx with gx = dt*sbxx, gy = dt*sbyy
-  auto e3f = [dt](double s, double m) { return m * (dt * s); };
-  auto e1f = [dt](double sx, double sy, double lm, double l_) { return lm * (dt * sx) + l_ * (dt * sy); };
+  // e3 = mub2 * sbxy ; e1 = lmb*sbxx + lamb*sbyy ; e2 = lmb*sbyy + lamb*sbxx ; dt is folded into dtix, dtiy
+  auto e3f = [](double s, double m) { return m * s; };
+  auto e1f = [](double sx, double sy, double lm, double l_) { return el_fma(lm, sx, l_ * sy); };
   // windows: E3 rows li-1, li, li+1 (+ li+2) ; E1 rows li-2, li-1, li (+ li+1)
   double E3m1 = 0.0, E3c, E3p1, E1m2 = 0.0, E1m1 = 0.0, E1c;
   double fxm1 = 0.0, fxc = 0.0, fxp1 = 0.0, fym2 = 0.0, fym1 = 0.0, fyc = 0.0;  // forward vx / vy windows (MATGRAD)
@@ -1139,26 +1158,32 @@ __device__ __forceinline__ void el_sigma_adj_march(const ElGeom& g, const ElCta&
       fy_m2 = cy_[-2]; fy_m1 = cy_[-1]; fy_p1 = cy_[1];
       GL = EL_RING(T, 10, cu.c[0])[so]; GM1 = EL_RING(T, 11, cu.c[0])[so]; GM2 = EL_RING(T, 12, cu.c[0])[so];
     }
+#if !EL_LATE_RELEASE
     __syncwarp();
     if (lane == 0) mbar_arrive(bars + 1 + EL_NB + bb);
+#endif
     if (act) {
       const i64 c = (i64)li * ld + q;
       // (D+x)^T e1 -> vx ; (D-y)^T e2 -> vy ; (D-x)^T e3 -> vy ; (D+y)^T e3 -> vx
-      vx += (27 * E1m1 - 27 * E1c - E1m2 + E1p1) * ix;
-      vy += (27 * E2c - 27 * E2_p1 - E2_m1 + E2_p2) * iy;
-      vy += (27 * E3c - 27 * E3p1 - E3m1 + E3p2) * ix;
-      vx += (27 * E3_m1 - 27 * E3c - E3_m2 + E3_p1) * iy;
+      vx = el_fma(el_st4(E1m1, E1c, E1p1, E1m2), dtix, vx);
+      vy = el_fma(el_st4(E2c, E2_p1, E2_p2, E2_m1), dtiy, vy);
+      vy = el_fma(el_st4(E3c, E3p1, E3p2, E3m1), dtix, vy);
+      vx = el_fma(el_st4(E3_m1, E3c, E3_p1, E3_m2), dtiy, vx);
       bout.vx[c] = vx; bout.vy[c] = vy;
       if (MATGRAD) {
         const double gx = dt * sxc, gy = dt * syc, gg = dt * sqc;
-        const double e1 = (27 * fxp1 - 27 * fxc - fxp2 + fxm1) * rx;
-        const double e2 = (27 * fyc - 27 * fy_m1 - fy_p1 + fy_m2) * ry;
-        const double e34 = (27 * fyc - 27 * fym1 - fyp1 + fym2) * rx + (27 * fx_p1 - 27 * fxc - fx_p2 + fx_m1) * ry;
-        Gl[c] = GL + (gx + gy) * (e1 + e2);
-        Gm1[c] = GM1 + 2 * (gx * e1 + gy * e2);
-        Gm2[c] = GM2 + gg * e34;
+        const double e1 = el_st4(fxp1, fxc, fxm1, fxp2) * rx;
+        const double e2 = el_st4(fyc, fy_m1, fy_m2, fy_p1) * ry;
+        const double e34 = el_fma(el_st4(fyc, fym1, fym2, fyp1), rx, el_st4(fx_p1, fxc, fx_m1, fx_p2) * ry);
+        Gl[c] = el_fma(gx + gy, e1 + e2, GL);
+        Gm1[c] = el_fma(2.0, el_fma(gx, e1, gy * e2), GM1);
+        Gm2[c] = el_fma(gg, e34, GM2);
       }
     }
+#if EL_LATE_RELEASE
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + 1 + EL_NB + bb);
+#endif
     E3m1 = E3c; E3c = E3p1; E3p1 = E3p2;
     E1m2 = E1m1; E1m1 = E1c; E1c = E1p1;
     if (MATGRAD) { fxm1 = fxc; fxc = fxp1; fxp1 = fxp2; fym2 = fym1; fym1 = fyc; fyc = fyp1; }

@@ -135,8 +135,11 @@ def measured_peaks():
 def ncu_traffic(kernel):
     """dram bytes per launch of `kernel` from the committed ncu --set full summary (profiles/), or None."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
-        return d["kernels"][kernel]["dram_bytes_per_launch"]
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))["kernels"]
+        for k in (kernel + "<1>", kernel):        # the step kernels are templates on PropagatorKernel (1 = custom-op scheme)
+            if k in d:
+                return d[k]["dram_bytes_per_launch"]
+        return None
     except Exception:
         return None
 

@@ -37,7 +37,10 @@ def load(rep):
     idx = {h: i for i, h in enumerate(hdr)}
     res = []
     for r in rows[2:]:
-        d = {"kernel": r[idx["Kernel Name"]].split("(")[0]}
+        name = r[idx["Kernel Name"]].split("(")[0].strip()
+        if name.startswith("void "):
+            name = name[5:]
+        d = {"kernel": name.replace("(bool)", "")}   # e.g. ac_adj_kernel<1>, el_vel_adj<1>
         for k, name in KEYS.items():
             if k in idx and r[idx[k]] != "":
                 v = float(r[idx[k]].replace(",", ""))

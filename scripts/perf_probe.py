@@ -29,7 +29,7 @@ def run(NX, NY, NSTEP, reps=3, budget=0):
                info["hist_slots"], info["segments"]), flush=True)
     plan.close()
 
-if __name__ == "__main__" and "--elastic" not in sys.argv:
+if __name__ == "__main__" and not any(a.startswith("--elastic") for a in sys.argv):
     if "--quick" in sys.argv:
         print("variant", os.environ.get("ADSEIS_LIB_SUFFIX", "(default)"))
         run(4096, 4096, 60)
@@ -80,6 +80,7 @@ if __name__ == "__main__" and "--elastic-one" in sys.argv:
 if __name__ == "__main__" and "--elastic-quick" in sys.argv:
     print("variant", os.environ.get("ADSEIS_LIB_SUFFIX", "(default)"))
     run_elastic(2000, 2000, 60, 1)
+    run_elastic(2000, 2000, 60, 1, mat=False)
     sys.exit(0)
 
 if __name__ == "__main__" and "--elastic" in sys.argv:
