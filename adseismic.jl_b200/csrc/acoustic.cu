@@ -508,7 +508,7 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
   if (P->rcv.nu > 0) P->rcvp = AcPoints{P->rcv.blk, P->rcv.cell, P->rcv.start, P->rcv.perm};
   PTRY(dev_upload(&P->rcv_owned, owned, st));
   PTRY(dev_alloc_zero(&P->rcvv, (size_t)((p->NSTEP + 1) * nrcv), st));
-  PTRY(dev_alloc_zero(&P->loss, 1, st));
+  PTRY(dev_alloc_zero(&P->loss, 1 + RL_BLOCKS, st));
 
   // adjoint state is allocated lazily (first gradient); history sizing now
   size_t free_b = 0, total_b = 0;
@@ -794,7 +794,9 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
   P->last_segments = (i64)nseg;
   // ---- misfit and adjoint sources
   const i64 nr = (NSTEP + 1) * P->nrcv;
-  k_residual_loss<<<1, 1024, 0, st>>>(P->rcvv, P->obs, P->rcv_owned, (int)std::max<i64>(P->nrcv, 1), 1, nr, P->res, P->loss);
+  k_residual_partial<<<RL_BLOCKS, 256, 0, st>>>(P->rcvv, P->obs, P->rcv_owned, (int)std::max<i64>(P->nrcv, 1), 1, nr, P->res, P->loss);
+  LAUNCH_CHECK(P);
+  k_residual_final<<<1, RL_BLOCKS, 0, st>>>(P->loss);
   LAUNCH_CHECK(P);
   // ---- reverse sweep
   for (int k = 0; k < 3; k++) CUDA_TRY(cudaMemsetAsync(P->ub[k], 0, pb, st));

@@ -483,7 +483,7 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
   for (const Pt& t : rp) owned[t.gid] = 1;
   EPTRY(dev_upload(&P->rcv_owned, owned, st));
   EPTRY(dev_alloc_zero(&P->rcvv, (size_t)((p->NSTEP + 1) * nrcv), st));
-  EPTRY(dev_alloc_zero(&P->loss, 1, st));
+  EPTRY(dev_alloc_zero(&P->loss, 1 + RL_BLOCKS, st));
 
   // history window
   size_t free_b = 0, total_b = 0;
@@ -835,8 +835,9 @@ ADSEIS_API int adseis_elastic_plan_gradient(adseis_elastic_plan* P, int want_mat
   const size_t nseg = mat ? P->seg_b.size() : 1;
   P->last_segments = (i64)nseg;
   const i64 nr = (NSTEP + 1) * P->nrcv;
-  k_residual_loss<<<1, 1024, 0, st>>>(P->rcvv, P->obs, P->rcv_owned, (int)std::max<i64>(P->nrcv, 1), 0, nr, P->res,
-                                      P->loss);
+  k_residual_partial<<<RL_BLOCKS, 256, 0, st>>>(P->rcvv, P->obs, P->rcv_owned, (int)std::max<i64>(P->nrcv, 1), 0, nr,
+                                               P->res, P->loss);
+  k_residual_final<<<1, RL_BLOCKS, 0, st>>>(P->loss);
   EL_LAUNCH_CHECK(P);
   // ---- reverse sweep ----
   const size_t msz = (size_t)(4 * g.xm_sz + 4 * g.ym_sz);
