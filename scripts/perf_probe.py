@@ -6,7 +6,7 @@ import adseis_b200 as A
 
 def run(NX, NY, NSTEP, reps=3, budget=0):
     ctx = A.default_context()
-    p = A.AcousticPropagatorParams(PropagatorKernel=1, NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=10.0, DELTAY=10.0, DELTAT=0.05, Rcoef=0.2,
+    p = A.AcousticPropagatorParams(PropagatorKernel=int(os.environ.get('PK', '1')), NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=10.0, DELTAY=10.0, DELTAT=0.05, Rcoef=0.2,
                                    vp_ref=1000.0, mpi_convention=True)
     c2 = np.full((NX, NY), 1000.0); c2[NX//2-NX//8:NX//2+NX//8, NY//2-NY//8:NY//2+NY//8] = 2000.0
     srcv = A.Ricker(p, 100.0, 500.0).reshape(-1, 1)
