@@ -353,14 +353,18 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
     P->box[0] = r0; P->box[1] = r1; P->box[2] = c0; P->box[3] = c1;
     if (r1 > r0) {
       mnct = (c1 - c0 + EL_TCOLS - 1) / EL_TCOLS;
-      // marching CTAs per SM: 6 gives whole waves both to the kernels that fit 2 and to those that fit 3 CTAs per
-      // SM; thinner slabs take 3, 2 or 1 per SM so that a CTA keeps >= 16 rows to amortise its pipeline prologue
-      mrb = 8;
-      for (int k : {6, 3, 2, 1}) {
+      // marching CTAs per SM: 6 (else 3) gives whole waves both to the kernels that fit 2 and to those that fit 3
+      // CTAs per SM, as long as a CTA keeps >= 12 rows to amortise its pipeline prologue.  Thinner slabs: a marching
+      // CTA streams its rows at a latency-bound ~2.5 us per row (ring depth), so the launch needs ALL slots busy --
+      // about one CTA per slot (3 per SM), at least 4 rows each (measured on 250 x 2000 slabs: 13-row tiles 62.9 us
+      // per forward step, 4..6-row tiles 36..40 us)
+      mrb = 0;
+      for (int k : {6, 3}) {
         const int want_tr = std::max(1, (k * ctx->sm_count + mnct - 1) / mnct);
-        mrb = std::min(64, std::max(8, (r1 - r0 + want_tr - 1) / want_tr));
-        if (mrb >= 16) break;
+        const int r = (r1 - r0 + want_tr - 1) / want_tr;
+        if (r >= 12) { mrb = std::min(64, r); break; }
       }
+      if (!mrb) mrb = std::min(64, std::max(4, ((r1 - r0) * mnct + 3 * ctx->sm_count - 1) / (3 * ctx->sm_count)));
       if (getenv("ADSEIS_EL_RB")) mrb = std::max(2, atoi(getenv("ADSEIS_EL_RB")));  // tuning experiments
       // slab plans: the EL_HALO rows next to a neighbour form thin row tiles of their own -- launched first, done
       // within a couple of microseconds, so the halo rows they push cross NVLink while the rest of the (single-wave)
@@ -377,11 +381,15 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
           ctas.push_back(ElCta{0, mrt[tr], mrt[tr + 1], c0 + tc * EL_TCOLS, std::min(c1, c0 + (tc + 1) * EL_TCOLS), 0, 0, 0});
     }
     P->nmarch = (int)ctas.size();
+    // cells per thread of a generic CTA: 4 on large grids (fewer CTAs); 1 on slabs / small grids, where the launch
+    // is a single wave and its duration is the latency chain of the longest CTA
+    int gen_cpt = (sl.nranks > 1 || (i64)g.Hl * g.W < (i64)1500 * 1500) ? 1 : 4;
+    if (getenv("ADSEIS_EL_CPT")) gen_cpt = std::max(1, atoi(getenv("ADSEIS_EL_CPT")));
     auto add_rect = [&](int rr0, int rr1, int cc0, int cc1) {
       if (rr1 <= rr0 || cc1 <= cc0) return;
       // narrow strips get tall tiles (16 x 64, 32 x 32), wide rectangles 64 x 16: 256 threads x 4 cells each
       const int ltw = (cc1 - cc0 <= 16) ? 4 : ((cc1 - cc0 <= 32) ? 5 : 6);
-      const int tw = 1 << ltw, th = 4 * ((EL_BX * EL_BY) >> ltw);
+      const int tw = 1 << ltw, th = gen_cpt * ((EL_BX * EL_BY) >> ltw);
       Rect R{rr0, rr1, cc0, cc1, (int)ctas.size(), (cc1 - cc0 + tw - 1) / tw, tw, th};
       for (int a = rr0; a < rr1; a += th)
         for (int b = cc0; b < cc1; b += tw)

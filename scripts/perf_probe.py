@@ -41,6 +41,13 @@ if __name__ == "__main__" and not any(a.startswith("--elastic") for a in sys.arg
                 print("rb", rb, end=" ")
                 run(nx, ny, nt, reps=2)
         sys.exit(0)
+    if "--pk" in sys.argv:
+        for pk in ("1", "0"):
+            os.environ["PK"] = pk
+            print("PropagatorKernel", pk)
+            run(4096, 4096, 60, reps=2)
+            run(401, 133, 600, reps=2)
+        sys.exit(0)
     if "--one" in sys.argv:
         run(4096, 4096, 24, reps=1)
         sys.exit(0)
