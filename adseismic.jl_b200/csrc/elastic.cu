@@ -354,7 +354,8 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
     if (r1 > r0) {
       mnct = (c1 - c0 + EL_TCOLS - 1) / EL_TCOLS;
       // marching CTAs per SM: 6 (else 3) gives whole waves both to the kernels that fit 2 and to those that fit 3
-      // CTAs per SM, as long as a CTA keeps >= 12 rows to amortise its pipeline prologue.  Thinner slabs: a marching
+      // CTAs per SM, as long as a CTA keeps >= 8 rows to amortise its pipeline prologue (1000 x 2000 slab: 9-row tiles
+      // 77 us per forward step, 18-row tiles 105 us).  Thinner slabs: a marching
       // CTA streams its rows at a latency-bound ~2.5 us per row (ring depth), so the launch needs ALL slots busy --
       // about one CTA per slot (3 per SM), at least 4 rows each (measured on 250 x 2000 slabs: 13-row tiles 62.9 us
       // per forward step, 4..6-row tiles 36..40 us)
@@ -362,7 +363,7 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
       for (int k : {6, 3}) {
         const int want_tr = std::max(1, (k * ctx->sm_count + mnct - 1) / mnct);
         const int r = (r1 - r0 + want_tr - 1) / want_tr;
-        if (r >= 12) { mrb = std::min(64, r); break; }
+        if (r >= 8) { mrb = std::min(64, r); break; }
       }
       if (!mrb) mrb = std::min(64, std::max(4, ((r1 - r0) * mnct + 3 * ctx->sm_count - 1) / (3 * ctx->sm_count)));
       if (getenv("ADSEIS_EL_RB")) mrb = std::max(2, atoi(getenv("ADSEIS_EL_RB")));  // tuning experiments
