@@ -206,7 +206,8 @@ __device__ __forceinline__ double ac_uprime(const AcGeom& g, int gi, int j, i64 
                                             const double* __restrict__ wold, const double* __restrict__ c2,
                                             const double* __restrict__ phi, const double* __restrict__ psi,
                                             const double* __restrict__ sigx, const double* __restrict__ tauy) {
-  if (gi < 1 || gi > g.H - 2 || j < 1 || j > g.W - 2) return 0.0;  // ring: scatter_nd onto the interior
+  // (gi, j) must be an interior cell: callers clamp ring neighbours onto the centre cell and discard the value, so
+  // that the loads of all five evaluations of a frame cell can be issued together (no branches in between)
   const double sg = sigx[gi], ta = tauy[j], c = c2[IJ], dt = g.dt;
   const double v = (2 - sg * ta * dt * dt - g.kx2 * c - g.ky2 * c) * w[IJ] +
                    c * g.rx * g.rx * (w[IJ + g.ld] + w[IJ - g.ld]) +
@@ -217,12 +218,12 @@ __device__ __forceinline__ double ac_uprime(const AcGeom& g, int gi, int j, i64 
   return (v == 0.0) ? v : v / (1 + (sg + ta) / 2 * dt);
 }
 
-__device__ __noinline__ void ac_fwd_general_cell_k0(const AcGeom& g, int li, int j, const double* __restrict__ w,
-                                                    const double* __restrict__ wold, const double* __restrict__ c2,
-                                                    const double* __restrict__ phi, const double* __restrict__ psi,
-                                                    const double* __restrict__ sigx, const double* __restrict__ tauy,
-                                                    double* __restrict__ u, double* __restrict__ phio,
-                                                    double* __restrict__ psio) {
+__device__ __forceinline__ void ac_fwd_general_cell_k0(const AcGeom& g, int li, int j, const double* __restrict__ w,
+                                                       const double* __restrict__ wold, const double* __restrict__ c2,
+                                                       const double* __restrict__ phi, const double* __restrict__ psi,
+                                                       const double* __restrict__ sigx, const double* __restrict__ tauy,
+                                                       double* __restrict__ u, double* __restrict__ phio,
+                                                       double* __restrict__ psio) {
   const int gi = g.goff + li;
   const i64 IJ = (i64)li * g.ld + j;
   if (j >= g.W) { u[IJ] = 0.0; return; }
@@ -231,18 +232,18 @@ __device__ __noinline__ void ac_fwd_general_cell_k0(const AcGeom& g, int li, int
     return;
   }
   const double sg = sigx[gi], ta = tauy[j], c = c2[IJ], dt = g.dt;
-  u[IJ] = ac_uprime(g, gi, j, IJ, w, wold, c2, phi, psi, sigx, tauy);
+  // u' is zero on the ring (scatter_nd onto the interior): ring neighbours are evaluated on the centre cell, then dropped
+  const bool vxm = gi - 1 >= 1, vxp = gi + 1 <= g.H - 2, vym = j - 1 >= 1, vyp = j + 1 <= g.W - 2;
+  const double uP = ac_uprime(g, gi, j, IJ, w, wold, c2, phi, psi, sigx, tauy);
+  const double uxp = ac_uprime(g, vxp ? gi + 1 : gi, j, vxp ? IJ + g.ld : IJ, w, wold, c2, phi, psi, sigx, tauy);
+  const double uxm = ac_uprime(g, vxm ? gi - 1 : gi, j, vxm ? IJ - g.ld : IJ, w, wold, c2, phi, psi, sigx, tauy);
+  const double uyp = ac_uprime(g, gi, vyp ? j + 1 : j, vyp ? IJ + 1 : IJ, w, wold, c2, phi, psi, sigx, tauy);
+  const double uym = ac_uprime(g, gi, vym ? j - 1 : j, vym ? IJ - 1 : IJ, w, wold, c2, phi, psi, sigx, tauy);
+  u[IJ] = uP;
   const double a = div_exact(dt * c * (ta - sg) / 2.0, g.hx, g.rhx);
   const double b = div_exact(dt * c * (sg - ta) / 2.0, g.hy, g.rhy);
-  double dux = 0.0, duy = 0.0;
-  if (a != 0.0)
-    dux = ac_uprime(g, gi + 1, j, IJ + g.ld, w, wold, c2, phi, psi, sigx, tauy) -
-          ac_uprime(g, gi - 1, j, IJ - g.ld, w, wold, c2, phi, psi, sigx, tauy);
-  if (b != 0.0)
-    duy = ac_uprime(g, gi, j + 1, IJ + 1, w, wold, c2, phi, psi, sigx, tauy) -
-          ac_uprime(g, gi, j - 1, IJ - 1, w, wold, c2, phi, psi, sigx, tauy);
-  phio[IJ] = (1. - dt * sg) * phi[IJ] + a * dux;
-  psio[IJ] = (1. - dt * ta) * psi[IJ] + b * duy;
+  phio[IJ] = (1. - dt * sg) * phi[IJ] + a * ((vxp ? uxp : 0.0) - (vxm ? uxm : 0.0));
+  psio[IJ] = (1. - dt * ta) * psi[IJ] + b * ((vyp ? uyp : 0.0) - (vym ? uym : 0.0));
 }
 
 // CTA epilogue shared by both kernels: add `scale * val[perm]` into field[cell] for the injected points this CTA
@@ -580,56 +581,67 @@ __device__ __forceinline__ double ac_utilde(const AcGeom& g, int gi, int j, i64 
                                             const double* __restrict__ c2, const double* __restrict__ phib,
                                             const double* __restrict__ psib, const double* __restrict__ sigx,
                                             const double* __restrict__ tauy, double kx, double ky) {
+  // (gi, j) must be interior.  Branch-free: ring neighbours are read at Q itself and their term is dropped, so the
+  // loads of the five evaluations of a frame cell can be issued together.
+  const bool vxm = gi - 1 >= 1, vxp = gi + 1 <= g.H - 2, vym = j - 1 >= 1, vyp = j + 1 <= g.W - 2;
+  const i64 Rxm = vxm ? Q - g.ld : Q, Rxp = vxp ? Q + g.ld : Q, Rym = vym ? Q - 1 : Q, Ryp = vyp ? Q + 1 : Q;
+  const double sg = sigx[gi], ta = tauy[j];
+  const double sgm = sigx[vxm ? gi - 1 : gi], sgp = sigx[vxp ? gi + 1 : gi];
+  const double tam = tauy[vym ? j - 1 : j], tap = tauy[vyp ? j + 1 : j];
+  const double txm = c2[Rxm] * (ta - sgm) * kx * phib[Rxm], txp = c2[Rxp] * (ta - sgp) * kx * phib[Rxp];
+  const double tym = c2[Rym] * (sg - tam) * ky * psib[Rym], typ = c2[Ryp] * (sg - tap) * ky * psib[Ryp];
   double v = ub1[Q];
-  if (ac_interior(g, gi - 1, j)) v += c2[Q - g.ld] * (tauy[j] - sigx[gi - 1]) * kx * phib[Q - g.ld];
-  if (ac_interior(g, gi + 1, j)) v -= c2[Q + g.ld] * (tauy[j] - sigx[gi + 1]) * kx * phib[Q + g.ld];
-  if (ac_interior(g, gi, j - 1)) v += c2[Q - 1] * (sigx[gi] - tauy[j - 1]) * ky * psib[Q - 1];
-  if (ac_interior(g, gi, j + 1)) v -= c2[Q + 1] * (sigx[gi] - tauy[j + 1]) * ky * psib[Q + 1];
+  v += vxm ? txm : 0.0;
+  v -= vxp ? txp : 0.0;
+  v += vym ? tym : 0.0;
+  v -= vyp ? typ : 0.0;
   return v;
 }
 
-__device__ __noinline__ void ac_adj_general_cell_k0(const AcGeom& g, int li, int j, const double* __restrict__ ub1,
-                                                    const double* __restrict__ wf, const double* __restrict__ c2,
-                                                    const double* __restrict__ phib, const double* __restrict__ psib,
-                                                    const double* __restrict__ sigx, const double* __restrict__ tauy,
-                                                    double* __restrict__ ub0, double* __restrict__ phibo,
-                                                    double* __restrict__ psibo, double* __restrict__ G, AcK0 k0) {
+__device__ __forceinline__ void ac_adj_general_cell_k0(const AcGeom& g, int li, int j, const double* __restrict__ ub1,
+                                                       const double* __restrict__ wf, const double* __restrict__ c2,
+                                                       const double* __restrict__ phib, const double* __restrict__ psib,
+                                                       const double* __restrict__ sigx, const double* __restrict__ tauy,
+                                                       double* __restrict__ ub0, double* __restrict__ phibo,
+                                                       double* __restrict__ psibo, double* __restrict__ G, AcK0 k0) {
   const int gi = g.goff + li;
   const i64 IJ = (i64)li * g.ld + j;
   if (j >= g.W) { ub0[IJ] = 0.0; return; }
   const double dt = g.dt;
   const double kx = dt * 0.5 * g.rhx, ky = dt * 0.5 * g.rhy;
-  const bool intP = ac_interior(g, gi, j);
-  double acc = 0.0, gP = 0.0, gxm = 0.0, gxp = 0.0, gym = 0.0, gyp = 0.0;
-  if (intP) {
-    const double ut = ac_utilde(g, gi, j, IJ, ub1, c2, phib, psib, sigx, tauy, kx, ky);
-    k0.ut_out[IJ] = ut;
-    gP = ut * (1.0 / (1 + (sigx[gi] + tauy[j]) / 2 * dt));
-    acc = (2 - sigx[gi] * tauy[j] * dt * dt - g.kx2 * c2[IJ] - g.ky2 * c2[IJ]) * gP;
-  }
-  if (ac_interior(g, gi - 1, j)) {
-    gxm = ac_utilde(g, gi - 1, j, IJ - g.ld, ub1, c2, phib, psib, sigx, tauy, kx, ky) *
-          (1.0 / (1 + (sigx[gi - 1] + tauy[j]) / 2 * dt));
-    acc += c2[IJ - g.ld] * g.rx * g.rx * gxm;
-  }
-  if (ac_interior(g, gi + 1, j)) {
-    gxp = ac_utilde(g, gi + 1, j, IJ + g.ld, ub1, c2, phib, psib, sigx, tauy, kx, ky) *
-          (1.0 / (1 + (sigx[gi + 1] + tauy[j]) / 2 * dt));
-    acc += c2[IJ + g.ld] * g.rx * g.rx * gxp;
-  }
-  if (ac_interior(g, gi, j - 1)) {
-    gym = ac_utilde(g, gi, j - 1, IJ - 1, ub1, c2, phib, psib, sigx, tauy, kx, ky) *
-          (1.0 / (1 + (sigx[gi] + tauy[j - 1]) / 2 * dt));
-    acc += c2[IJ - 1] * g.ry * g.ry * gym;
-  }
-  if (ac_interior(g, gi, j + 1)) {
-    gyp = ac_utilde(g, gi, j + 1, IJ + 1, ub1, c2, phib, psib, sigx, tauy, kx, ky) *
-          (1.0 / (1 + (sigx[gi] + tauy[j + 1]) / 2 * dt));
-    acc += c2[IJ + 1] * g.ry * g.ry * gyp;
-  }
+  const bool colok = (j >= 1 && j <= g.W - 2), rowok = (gi >= 1 && gi <= g.H - 2);
+  const bool intP = rowok && colok;
+  const bool vxm = colok && gi - 1 >= 1 && gi - 1 <= g.H - 2;  // Q = P - e_x is an interior cell
+  const bool vxp = colok && gi + 1 >= 1 && gi + 1 <= g.H - 2;
+  const bool vym = rowok && j - 1 >= 1 && j - 1 <= g.W - 2;
+  const bool vyp = rowok && j + 1 >= 1 && j + 1 <= g.W - 2;
+  // every evaluation runs on an interior cell: invalid ones are redirected to a valid one and dropped.  A ring cell P
+  // has at most one interior neighbour; `safe` is that neighbour (or P itself when P is interior).
+  const int sgi = intP ? gi : (vxm ? gi - 1 : (vxp ? gi + 1 : gi)), sj = intP ? j : (vym ? j - 1 : (vyp ? j + 1 : j));
+  const bool any = intP || vxm || vxp || vym || vyp;
+  if (!any) { ub0[IJ] = 0.0; return; }  // ring corners: no interior neighbour at all
+  const i64 S = IJ + (i64)(sgi - gi) * g.ld + (sj - j);
+  auto gof = [&](bool ok, int qi, int qj, i64 Q) -> double {
+    const int ei = ok ? qi : sgi, ej = ok ? qj : sj;
+    const i64 E = ok ? Q : S;
+    const double ut = ac_utilde(g, ei, ej, E, ub1, c2, phib, psib, sigx, tauy, kx, ky);
+    return ok ? ut * (1.0 / (1 + (sigx[ei] + tauy[ej]) / 2 * dt)) : 0.0;
+  };
+  const double utP = ac_utilde(g, sgi, sj, S, ub1, c2, phib, psib, sigx, tauy, kx, ky);  // == utilde[P] when intP
+  const double gxm = gof(vxm, gi - 1, j, IJ - g.ld), gxp = gof(vxp, gi + 1, j, IJ + g.ld);
+  const double gym = gof(vym, gi, j - 1, IJ - 1), gyp = gof(vyp, gi, j + 1, IJ + 1);
+  double acc = 0.0;
+  acc += vxm ? c2[IJ - g.ld] * g.rx * g.rx * gxm : 0.0;
+  acc += vxp ? c2[IJ + g.ld] * g.rx * g.rx * gxp : 0.0;
+  acc += vym ? c2[IJ - 1] * g.ry * g.ry * gym : 0.0;
+  acc += vyp ? c2[IJ + 1] * g.ry * g.ry * gyp : 0.0;
   if (intP) {
     const double sg = sigx[gi], ta = tauy[j], pb = phib[IJ], qb = psib[IJ];
-    acc += -(1 - (sg + ta) * dt / 2) * (k0.ut_in[IJ] * (1.0 / (1 + (sg + ta) / 2 * dt)));  // grad_wold of step s+1
+    const double rD = 1.0 / (1 + (sg + ta) / 2 * dt);
+    const double gP = utP * rD;
+    k0.ut_out[IJ] = utP;
+    acc += (2 - sg * ta * dt * dt - g.kx2 * c2[IJ] - g.ky2 * c2[IJ]) * gP;
+    acc += -(1 - (sg + ta) * dt / 2) * (k0.ut_in[IJ] * rD);  // grad_wold of step s+1
     phibo[IJ] = (1. - dt * sg) * pb + g.px * (gxm - gxp);
     psibo[IJ] = (1. - dt * ta) * qb + g.py * (gym - gyp);
     const double* un = k0.wnew;
