@@ -135,8 +135,10 @@ def compute_loss_and_grads_GPU(param, srcs, rcvs, Rs, c, ctx=None, plan_cache=No
         plan.set_obs(Rs[k])
         plan.gradient()
         loss += plan.loss()
-        plan.grad_c(out=gtmp)      # device -> device
+        plan.grad_c(out=gtmp)      # device -> device on the context's stream, synchronised on return
         gsum += gtmp
+        if on_gpu:                 # torch's stream must be done with gtmp before the next shot overwrites it
+            torch.cuda.current_stream().synchronize()
         rcv.rcvv = plan.rcvv()
         if plan_cache is None:
             plan.close()
