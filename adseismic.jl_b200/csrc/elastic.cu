@@ -360,7 +360,16 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
       // about one CTA per slot (3 per SM), at least 4 rows each (measured on 250 x 2000 slabs: 13-row tiles 62.9 us
       // per forward step, 4..6-row tiles 36..40 us)
       mrb = 0;
+      if (sl.nranks == 1) {
+        // one GPU: if ONE wave of 2 CTAs per SM covers the box with 24..64 rows per CTA, take exactly that -- every
+        // CTA is resident from the start and pays one pipeline prologue (2000^2: 54-row tiles, forward 126 -> 117,
+        // material gradient 402 -> 367 us/step against 18-row tiles; wave quantisation matters: 33..41 rows lose)
+        const int tiles = std::max(1, 2 * ctx->sm_count / mnct);
+        const int r = (r1 - r0 + tiles - 1) / tiles;
+        if (r >= 24 && r <= 64) mrb = r;
+      }
       for (int k : {6, 3}) {
+        if (mrb) break;
         const int want_tr = std::max(1, (k * ctx->sm_count + mnct - 1) / mnct);
         const int r = (r1 - r0 + want_tr - 1) / want_tr;
         if (r >= 8) { mrb = std::min(64, r); break; }

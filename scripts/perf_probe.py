@@ -80,6 +80,16 @@ def run_elastic(NX, NY, NSTEP, variant, reps=2, mat=True):
     plan.close()
 
 
+if __name__ == "__main__" and "--elastic-rb" in sys.argv:
+    for rb in sys.argv[sys.argv.index("--elastic-rb") + 1].split(","):
+        os.environ["ADSEIS_EL_RB"] = rb
+        print("EL_RB", rb)
+        if "--big" in sys.argv:
+            run_elastic(4096, 4096, 16, 0, reps=2)
+        else:
+            run_elastic(2000, 2000, 40, 1, reps=2)
+    sys.exit(0)
+
 if __name__ == "__main__" and "--elastic-one" in sys.argv:
     run_elastic(2000, 2000, 12, 1, reps=1)
     sys.exit(0)
