@@ -9,11 +9,13 @@
 //                      + receiver-residual injection into ubar[s-1] + grad_srcv sampling
 //
 // Work decomposition (HBM-bound fp64 stencil, no tensor cores).  The grid of one launch holds two kinds of CTAs:
-//   * MARCHING CTAs cover the PML-free box.  A warp owns 64 consecutive columns (one double2 per lane, 512 B per
-//     row -> whole 128 B lines) and marches down `rb` rows keeping the 3-row stencil window in registers;
-//     left/right neighbours come from warp shuffles, the two warp-edge values from one predicated 8-byte load
-//     that hits L1/L2.  Every element is requested from DRAM once per step: 32 B/cell forward (w, wold, c^2 in,
-//     u out), 56 B/cell adjoint.  Loads of AC_U rows are issued back to back before their arithmetic.
+//   * MARCHING CTAs cover the PML-free box.  A CTA owns a 512-column tile and marches down `rb` rows.  One producer
+//     warp streams a row of every input plane per iteration into a shared-memory ring with TMA bulk copies
+//     (cp.async.bulk, one 4-KB copy per plane and row, mbarrier full/empty handshake, 8 / 4 rows in flight); the
+//     eight consumer warps own 64 consecutive columns each (one double2 per lane), keep the 3-row stencil window
+//     in registers, take left/right neighbours from warp shuffles and the two warp-edge values from the ring.
+//     Every element is requested from DRAM once per step: 32 B/cell forward (w, wold, c^2 in, u out), 56 B/cell
+//     adjoint.
 //   * FRAME CTAs cover everything else (absorbing frame, ring, pitch padding) one cell per thread-iteration with
 //     the full reference expression (phi/psi traffic, sigma/tau profiles, the fp64 divide).  The frame is ~1 % of
 //     a 4096^2 grid, so it is mapped for parallelism, not reuse.
@@ -28,26 +30,17 @@
 #define AC_THREADS (AC_WARPS * 32)
 #define AC_WCOLS 64                         // columns per warp
 #define AC_TILE_COLS (AC_WARPS * AC_WCOLS)  // columns per marching CTA
-#ifndef AC_U
-#define AC_U 4                              // forward: rows whose loads are issued together
-#endif
-#ifndef AC_UA
-#define AC_UA 1                             // adjoint: rows whose loads are issued together (occupancy beats unrolling here)
-#endif
 #ifndef AC_FRAME_CPT
 #define AC_FRAME_CPT 4                      // frame cells per thread
 #endif
 #define AC_FRAME_CELLS (AC_THREADS * AC_FRAME_CPT)
-#ifndef AC_ADJ_TMA
-#define AC_ADJ_TMA 1                        // adjoint marching CTAs stage their rows through shared memory by TMA bulk copies
-#endif
 #ifndef AC_NST_ADJ
 #define AC_NST_ADJ 4                        // adjoint: ring depth (rows of the CTA tile in flight)
 #endif
 #ifndef AC_MINB_ADJ
-#define AC_MINB_ADJ (AC_ADJ_TMA ? 2 : 3)    // __launch_bounds__ min CTAs/SM, adjoint (TMA: bounded by shared memory)
+#define AC_MINB_ADJ 2                       // __launch_bounds__ min CTAs/SM, adjoint (bounded by shared memory)
 #endif
-#define AC_ADJ_THREADS (AC_THREADS + 32 * AC_ADJ_TMA)  // + one producer warp
+#define AC_ADJ_THREADS (AC_THREADS + 32)    // + one producer warp
 #define AC_HCOLS (AC_TILE_COLS + 4)         // staged columns of an array with y-neighbours: 16-byte halo on each side
 
 // One ring stage of an adjoint marching CTA: row `li` of its 512-column tile (iteration li - r0).  Filled by five
@@ -58,22 +51,19 @@ struct __align__(128) AcAdjStage {
   double ub1[AC_HCOLS], c2[AC_HCOLS], wf[AC_HCOLS];  // row li+1, columns c0-2 .. c0+513
   double ub2[AC_TILE_COLS], G[AC_TILE_COLS];         // row li,   columns c0   .. c0+511
 };
-#ifndef AC_FWD_TMA
-#define AC_FWD_TMA 1                        // forward marching CTAs: same TMA row ring
-#endif
 #ifndef AC_MINB_FWD
 #define AC_MINB_FWD 2                       // __launch_bounds__ min CTAs/SM, forward (same wave size as the adjoint)
 #endif
 #ifndef AC_NST_FWD
 #define AC_NST_FWD 8   // power of two (slot = it % depth); 8 x 12.4 KB x 2 CTAs = 198 KB: 94.7 -> 92.1 us at 4096^2 vs depth 4
 #endif
-#define AC_FWD_THREADS (AC_THREADS + 32 * AC_FWD_TMA)
+#define AC_FWD_THREADS (AC_THREADS + 32)
 struct __align__(128) AcFwdStage {
   double w[AC_HCOLS];                                // row li+1, columns c0-2 .. c0+513
   double wold[AC_TILE_COLS], c2[AC_TILE_COLS];       // row li
 };
-#define AC_FWD_SMEM (AC_FWD_TMA ? (int)(AC_NST_FWD * (sizeof(AcFwdStage) + 16)) : 0)
-#define AC_ADJ_SMEM (AC_ADJ_TMA ? (int)(AC_NST_ADJ * (sizeof(AcAdjStage) + 16)) : 0)
+#define AC_FWD_SMEM ((int)(AC_NST_FWD * (sizeof(AcFwdStage) + 16)))
+#define AC_ADJ_SMEM ((int)(AC_NST_ADJ * (sizeof(AcAdjStage) + 16)))
 
 struct AcGeom {
   int H, W;    // global padded rows (NX+2) and columns (NY+2)
@@ -328,7 +318,6 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
     t_lo = f.has_lo && r0 <= f.own0 && f.own0 < r1;
     t_hi = f.has_hi && r0 <= f.own_last && f.own_last < r1;
     ac_fuse_wait(f, t_lo, t_hi);
-#if AC_FWD_TMA
     extern __shared__ __align__(128) unsigned char ac_smem[];
     AcFwdStage* stg = reinterpret_cast<AcFwdStage*>(ac_smem);
     unsigned long long* full = reinterpret_cast<unsigned long long*>(ac_smem + AC_NST_FWD * sizeof(AcFwdStage));
@@ -407,59 +396,6 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
         }
       }
     }
-#else
-    if (jb < t.mc_end) {
-      const double2 z2 = make_double2(0.0, 0.0);
-      const double kx2 = g.kx2, ky2 = g.ky2, rx = g.rx, ry = g.ry;
-      double2 wm = ldok ? ld2(w + (i64)(r0 - 1) * ld + j) : z2;  // r0 >= 1: the box never contains row 0
-      double2 wc = ldok ? ld2(w + (i64)r0 * ld + j) : z2;
-      for (int rbase = r0; rbase < r1; rbase += AC_U) {
-        double2 wn[AC_U], wo[AC_U], cc[AC_U];
-        double we[AC_U];
-#pragma unroll
-        for (int k = 0; k < AC_U; k++) {
-          const int li = rbase + k;
-          wn[k] = z2; wo[k] = z2; cc[k] = z2; we[k] = 0.0;
-          if (li < r1) {
-            const i64 ro = (i64)li * ld;
-            if (ldok) wn[k] = ld2(w + ro + ld + j);  // li+1 <= Hl-1: the box never contains the last row
-            if (act) {
-              wo[k] = ld2_stream(wold + ro + j);
-              cc[k] = ld2(c2 + ro + j);
-              if (lane == 0) we[k] = w[ro + jb - 1];
-              if (lane == 31) we[k] = w[ro + jb + AC_WCOLS];
-            }
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < AC_U; k++) {
-          const int li = rbase + k;
-          if (li < r1) {
-            double lft = __shfl_up_sync(0xffffffffu, wc.y, 1);
-            double rgt = __shfl_down_sync(0xffffffffu, wc.x, 1);
-            if (lane == 0) lft = we[k];
-            if (lane == 31) rgt = we[k];
-            if (act) {
-              double2 o;
-              {
-                const double c = cc[k].x;
-                o.x = (2 - kx2 * c - ky2 * c) * wc.x + c * rx * rx * (wn[k].x + wm.x) + c * ry * ry * (wc.y + lft) -
-                      wo[k].x;
-              }
-              {
-                const double c = cc[k].y;
-                o.y = (2 - kx2 * c - ky2 * c) * wc.y + c * rx * rx * (wn[k].y + wm.y) + c * ry * ry * (rgt + wc.x) -
-                      wo[k].y;
-              }
-              st2(u + (i64)li * ld + j, o);
-            }
-            wm = wc;
-            wc = wn[k];
-          }
-        }
-      }
-    }
-#endif
   }
   ac_cta_epilogue(bid, u, src, srcv_row, g.dt2, rcv, rcvv_row, 1.0);
   if (t_lo || t_hi) {  // push my piece of the new edge row(s) into the neighbours' halo rows, then publish
@@ -745,7 +681,6 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
     t_lo = f.has_lo && r0 <= f.own0 && f.own0 < r1;
     t_hi = f.has_hi && r0 <= f.own_last && f.own_last < r1;
     ac_fuse_wait(f, t_lo, t_hi);
-#if AC_ADJ_TMA
     extern __shared__ __align__(128) unsigned char ac_smem[];
     AcAdjStage* stg = reinterpret_cast<AcAdjStage*>(ac_smem);
     unsigned long long* full = reinterpret_cast<unsigned long long*>(ac_smem + AC_NST_ADJ * sizeof(AcAdjStage));
@@ -844,79 +779,6 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
         }
       }
     }
-#else
-    if (jb < t.mc_end) {
-      const double2 z2 = make_double2(0.0, 0.0);
-      const double rx2 = g.rx * g.rx, ry2 = g.ry * g.ry, kk = -g.kx2 - g.ky2, kx2 = g.kx2, ky2 = g.ky2;
-      // register windows: cg = c^2 * ubar[s] (D == 1 and no ring cell within one cell of the box), w = u[s-1]
-      double2 cgm = z2, cgc = z2, wm = z2, wc = z2, gc = z2, ccen = z2;
-      if (ldok) {
-        i64 ro = (i64)(r0 - 1) * ld + j;
-        const double2 c_ = ld2(c2 + ro), u_ = ld2(ub1 + ro);
-        cgm = make_double2(c_.x * u_.x, c_.y * u_.y);
-        wm = ld2(wf + ro);
-        ro += ld;
-        ccen = ld2(c2 + ro);
-        gc = ld2(ub1 + ro);
-        cgc = make_double2(ccen.x * gc.x, ccen.y * gc.y);
-        wc = ld2(wf + ro);
-      }
-      for (int rbase = r0; rbase < r1; rbase += AC_UA) {
-        double2 un[AC_UA], cn[AC_UA], wn[AC_UA], u2[AC_UA], Gr[AC_UA];
-        double ecg[AC_UA], ew[AC_UA];
-#pragma unroll
-        for (int k = 0; k < AC_UA; k++) {
-          const int li = rbase + k;
-          un[k] = z2; cn[k] = z2; wn[k] = z2; u2[k] = z2; Gr[k] = z2; ecg[k] = 0.0; ew[k] = 0.0;
-          if (li < r1) {
-            const i64 ro = (i64)li * ld;
-            if (ldok) {
-              un[k] = ld2(ub1 + ro + ld + j);
-              cn[k] = ld2(c2 + ro + ld + j);
-              wn[k] = ld2(wf + ro + ld + j);
-            }
-            if (act) {
-              u2[k] = ld2_stream(ub2 + ro + j);
-              Gr[k] = ld2_stream(G + ro + j);
-              if (lane == 0) { ecg[k] = c2[ro + jb - 1] * ub1[ro + jb - 1]; ew[k] = wf[ro + jb - 1]; }
-              if (lane == 31) { ecg[k] = c2[ro + jb + AC_WCOLS] * ub1[ro + jb + AC_WCOLS]; ew[k] = wf[ro + jb + AC_WCOLS]; }
-            }
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < AC_UA; k++) {
-          const int li = rbase + k;
-          if (li < r1) {
-            const double2 cgp = make_double2(cn[k].x * un[k].x, cn[k].y * un[k].y);
-            double cgl = __shfl_up_sync(0xffffffffu, cgc.y, 1);
-            double cgr = __shfl_down_sync(0xffffffffu, cgc.x, 1);
-            double wl = __shfl_up_sync(0xffffffffu, wc.y, 1);
-            double wr = __shfl_down_sync(0xffffffffu, wc.x, 1);
-            if (lane == 0) { cgl = ecg[k]; wl = ew[k]; }
-            if (lane == 31) { cgr = ecg[k]; wr = ew[k]; }
-            if (act) {
-              double2 o, Go;
-              {
-                const double c = ccen.x, gg = gc.x;
-                o.x = (2 - kx2 * c - ky2 * c) * gg + rx2 * (cgp.x + cgm.x) + ry2 * (cgc.y + cgl) - u2[k].x;
-                Go.x = Gr[k].x + (kk * wc.x + rx2 * (wn[k].x + wm.x) + ry2 * (wc.y + wl)) * gg;
-              }
-              {
-                const double c = ccen.y, gg = gc.y;
-                o.y = (2 - kx2 * c - ky2 * c) * gg + rx2 * (cgp.y + cgm.y) + ry2 * (cgr + cgc.x) - u2[k].y;
-                Go.y = Gr[k].y + (kk * wc.y + rx2 * (wn[k].y + wm.y) + ry2 * (wr + wc.x)) * gg;
-              }
-              st2(ub0 + (i64)li * ld + j, o);
-              st2(G + (i64)li * ld + j, Go);
-            }
-            cgm = cgc; cgc = cgp;
-            wm = wc; wc = wn[k];
-            gc = un[k]; ccen = cn[k];
-          }
-        }
-      }
-    }
-#endif
   }
   ac_cta_epilogue(bid, ub0, rcv, res_row, 1.0, src, gsrcv_row, g.dt2);
   if (t_lo || t_hi) {
