@@ -164,7 +164,7 @@ def LBFGS_(loss_fn, params, max_iter=50, callback=None, history_size=10, toleran
     losses = []
     for it in range(max_iter):
         seen.clear()
-        l0 = float(opt.step(closure))        # returns the loss at the START of the step
+        l0 = float(opt.step(closure).detach())   # returns the loss at the START of the step
         if not losses:
             losses.append(l0)
         losses.append(current())             # the accepted point was evaluated by the line search

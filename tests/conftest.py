@@ -40,5 +40,8 @@ def golden(name):
 def relerr(a, b):
     import numpy as np
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if b.size == 0:
+        return 0.0
     d = np.abs(b).max()
     return float(np.abs(a - b).max() / d) if d > 0 else float(np.abs(a - b).max())
