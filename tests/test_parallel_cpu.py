@@ -176,3 +176,19 @@ def test_elastic_slab_partition_and_ownership():
             pi = rng.integers(lo, hi + 1, 200)
             own = np.stack([parallel.elastic_owned_points(p, pi, b0, b1) for b0, b1 in bounds])
             assert np.all(own.sum(0) == 1)
+
+
+def test_plan_window_budget():
+    """The slab window chosen on the host (parallel.plan_window) obeys the budget the C side checks: W snapshots +
+    4 checkpoint planes per extra segment fit, W is maximal, and the whole tape is kept when it fits."""
+    from adseis_b200.parallel import plan_window
+    assert plan_window(5000, 6000) == 5001 and plan_window(50, 51) == 51
+    for NSTEP, slots in ((5000, 2700), (5000, 1390), (1000, 150), (60, 30), (200, 120)):
+        W = plan_window(NSTEP, slots)
+        nseg = -(-(NSTEP - 1) // (W - 2))
+        assert 6 <= W <= slots and W + 4 * (nseg - 1) <= slots
+        if W + 1 <= slots:                         # a larger window would not fit
+            nseg1 = -(-(NSTEP - 1) // (W - 1))
+            assert W + 1 + 4 * (nseg1 - 1) > slots
+    with pytest.raises(MemoryError):
+        plan_window(1000, 5)
