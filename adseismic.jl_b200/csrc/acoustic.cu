@@ -686,7 +686,7 @@ static int run_forward_steps(adseis_acoustic_plan* P, i64 base, i64 s_first, i64
   }
   for (i64 s = s_first; s <= s_last; s++) {
     const AcFuse fuse = make_fuse(P, AR_HIST, s - base, AR_PHI, s & 1);
-    CUDA_TRY(launch_step(P->arena == nullptr || getenv("ADSEIS_PDL_SLAB") != nullptr, P->p.PropagatorKernel == 0 ? ac_fwd_kernel<0> : ac_fwd_kernel<1>, P->nblocks, AC_FWD_THREADS,
+    CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), P->p.PropagatorKernel == 0 ? ac_fwd_kernel<0> : ac_fwd_kernel<1>, P->nblocks, AC_FWD_THREADS,
                          AC_FWD_SMEM, st,
         g, P->t, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, P->phi[(s - 1) & 1], P->psi[(s - 1) & 1],
         P->sigx, P->tauy, win_slot(P, base, s), P->phi[s & 1], P->psi[s & 1], P->srcp,
@@ -856,7 +856,7 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
           LAUNCH_CHECK(P);
         }
       }
-      CUDA_TRY(launch_step(P->arena == nullptr || getenv("ADSEIS_PDL_SLAB") != nullptr, P->p.PropagatorKernel == 0 ? ac_adj_kernel<0> : ac_adj_kernel<1>, P->nblocks, AC_ADJ_THREADS,
+      CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), P->p.PropagatorKernel == 0 ? ac_adj_kernel<0> : ac_adj_kernel<1>, P->nblocks, AC_ADJ_THREADS,
                            AC_ADJ_SMEM, st,
           g, P->t, P->ub[s % 3], P->ub[(s + 1) % 3], win_slot(P, b, s - 1), P->c2, P->phib[s & 1], P->psib[s & 1],
           P->sigx, P->tauy, P->ub[(s + 2) % 3] /* == (s-1)%3 */, P->phib[(s - 1) & 1], P->psib[(s - 1) & 1], P->G,

@@ -89,6 +89,11 @@ static inline bool adseis_pdl_enabled() {
   if (on < 0) { const char* e = getenv("ADSEIS_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
   return on != 0;
 }
+static inline bool adseis_pdl_slab() {  // ADSEIS_PDL_SLAB=1: tuning experiments (PDL on slab plans too)
+  static int on = -1;
+  if (on < 0) on = getenv("ADSEIS_PDL_SLAB") != nullptr ? 1 : 0;
+  return on != 0;
+}
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_step(bool pdl, void (*kernel)(KArgs...), int grid, int block, size_t smem,

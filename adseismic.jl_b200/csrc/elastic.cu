@@ -760,10 +760,10 @@ static int el_step_forward(adseis_elastic_plan* P, i64 s, double* in, double* ou
   const double* prev = (P->nsrc > 0 && s >= 2) ? P->srcv + (s - 2) * P->nsrc : nullptr;
   const i64 widx = (out - P->hist) / P->slot_sz;
   const ElPlaneRef sig_planes[2] = {{EA_HIST, widx, 2}, {EA_HIST, widx, 4}};  // fw3/fw4 difference sxx, sxy along x
-  CUDA_TRY(launch_step(P->arena == nullptr || getenv("ADSEIS_PDL_SLAB") != nullptr, el_sigma_fwd, P->nblocks, EL_NT, el_ring_bytes<ElSigFwdT>(), st, P->g, P->ctas, si, so, mt, cf, P->src.dev, prev, el_make_fuse(P, 2, sig_planes)));
+  CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), el_sigma_fwd, P->nblocks, EL_NT, el_ring_bytes<ElSigFwdT>(), st, P->g, P->ctas, si, so, mt, cf, P->src.dev, prev, el_make_fuse(P, 2, sig_planes)));
   EL_LAUNCH_CHECK(P);
   const ElPlaneRef vel_planes[2] = {{EA_HIST, widx, 0}, {EA_HIST, widx, 1}};
-  CUDA_TRY(launch_step(P->arena == nullptr || getenv("ADSEIS_PDL_SLAB") != nullptr, el_vel_fwd, P->nblocks, EL_NT, el_ring_bytes<ElVelFwdT>(), st, P->g, P->ctas, si, so, mt, cf, P->src.dev, row, sample ? P->rcv.dev : none,
+  CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), el_vel_fwd, P->nblocks, EL_NT, el_ring_bytes<ElVelFwdT>(), st, P->g, P->ctas, si, so, mt, cf, P->src.dev, row, sample ? P->rcv.dev : none,
                                          (sample && P->nrcv > 0) ? P->rcvv : nullptr, (int)(P->p.NSTEP + 1), (int)s,
                                          el_make_fuse(P, 2, vel_planes)));
   EL_LAUNCH_CHECK(P);
@@ -905,19 +905,19 @@ ADSEIS_API int adseis_elastic_plan_gradient(adseis_elastic_plan* P, int want_mat
       const double* resp = P->nrcv > 0 ? P->res : nullptr;
       double* grow = (s - 2 >= 0 && P->nsrc > 0 && s >= 2) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr;
       if (mat) {
-        CUDA_TRY(launch_step(P->arena == nullptr || getenv("ADSEIS_PDL_SLAB") != nullptr, el_vel_adj<true>, P->nblocks, EL_NT, el_ring_bytes<ElVelAdjT<true>>(), st, g, P->ctas, bi, bo, fs, mt, cf, P->Gr3, P->Gr4, P->rcv.dev, resp, stride, (int)s,
+        CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), el_vel_adj<true>, P->nblocks, EL_NT, el_ring_bytes<ElVelAdjT<true>>(), st, g, P->ctas, bi, bo, fs, mt, cf, P->Gr3, P->Gr4, P->rcv.dev, resp, stride, (int)s,
                                                      el_make_fuse(P, 3, sb_planes)));
         EL_LAUNCH_CHECK(P);
-        CUDA_TRY(launch_step(P->arena == nullptr || getenv("ADSEIS_PDL_SLAB") != nullptr, el_sigma_adj<true>, P->nblocks, EL_NT, el_ring_bytes<ElSigAdjT<true>>(), st, g, P->ctas, bi, bo, fp, fs, mt, cf, P->Gl, P->Gm1, P->Gm2,
+        CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), el_sigma_adj<true>, P->nblocks, EL_NT, el_ring_bytes<ElSigAdjT<true>>(), st, g, P->ctas, bi, bo, fp, fs, mt, cf, P->Gl, P->Gm1, P->Gm2,
                                                        s >= 2 ? P->rcv.dev : none, s >= 2 ? resp : nullptr, stride,
                                                        (int)(s - 1), s >= 2 ? P->src.dev : none, grow,
                                                        el_make_fuse(P, 2, vb_planes)));
         EL_LAUNCH_CHECK(P);
       } else {
-        CUDA_TRY(launch_step(P->arena == nullptr || getenv("ADSEIS_PDL_SLAB") != nullptr, el_vel_adj<false>, P->nblocks, EL_NT, el_ring_bytes<ElVelAdjT<false>>(), st, g, P->ctas, bi, bo, zero, mt, cf, nullptr, nullptr, P->rcv.dev, resp, stride,
+        CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), el_vel_adj<false>, P->nblocks, EL_NT, el_ring_bytes<ElVelAdjT<false>>(), st, g, P->ctas, bi, bo, zero, mt, cf, nullptr, nullptr, P->rcv.dev, resp, stride,
                                                       (int)s, el_make_fuse(P, 3, sb_planes)));
         EL_LAUNCH_CHECK(P);
-        CUDA_TRY(launch_step(P->arena == nullptr || getenv("ADSEIS_PDL_SLAB") != nullptr, el_sigma_adj<false>, P->nblocks, EL_NT, el_ring_bytes<ElSigAdjT<false>>(), st, g, P->ctas, bi, bo, zero, zero, mt, cf, nullptr, nullptr, nullptr,
+        CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), el_sigma_adj<false>, P->nblocks, EL_NT, el_ring_bytes<ElSigAdjT<false>>(), st, g, P->ctas, bi, bo, zero, zero, mt, cf, nullptr, nullptr, nullptr,
                                                         s >= 2 ? P->rcv.dev : none, s >= 2 ? resp : nullptr, stride,
                                                         (int)(s - 1), s >= 2 ? P->src.dev : none, grow,
                                                         el_make_fuse(P, 2, vb_planes)));
