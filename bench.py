@@ -228,6 +228,9 @@ def main():
     ap.add_argument("--nstep", type=int, default=5000)
     ap.add_argument("--cpu-steps", type=int, default=0, help="time steps of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--hist-slots", type=int, default=0,
+                    help="force a history window of this many snapshots (profiling: reproduces the checkpoint/replay "
+                         "mix of the full workload at a small --nstep); 0 = as many as fit")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -272,7 +275,9 @@ def main():
                                    DELTAT=w["DELTAT"], Rcoef=w["Rcoef"], vp_ref=w["vp_ref"],
                                    NPOINTS_PML=w["NPOINTS_PML"], mpi_convention=True)
     srcv_np = (A.Ricker(p, 100.0, 500.0) * 1e6).reshape(-1, 1)
-    plan = A.AcousticPlan(p, w["srci"], w["srcj"], w["rcvi"], w["rcvj"], ctx=ctx)
+    pitch = (w["NY"] + 2 + 15) // 16 * 16
+    plan = A.AcousticPlan(p, w["srci"], w["srcj"], w["rcvi"], w["rcvj"], ctx=ctx,
+                          hist_bytes_budget=args.hist_slots * (w["NX"] + 2) * pitch * 8)
     nrcv = len(w["rcvi"])
 
     # pinned host buffers (the e2e leg copies from / to these)
