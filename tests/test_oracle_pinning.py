@@ -270,3 +270,26 @@ def test_acoustic_kernel0_differs_from_kernel1(po):
                                 G["rcvj"])
     d = relerr(r1, G["rcvv"])
     assert 1e-8 < d < 0.5
+
+
+def test_acoustic_kernel0_block_decomposed_equals_global(po):
+    """The reference's distributed invariant (examples/mpi_acoustic/verification/verify_forward.jl:78-95) for
+    PropagatorKernel=0: a NumPy restatement of MPIAcoustic.jl's block-decomposed one_step (2x3 blocks, halo exchanges
+    emulated) == the oracle's global-grid scheme-0 loop under the MPI input convention."""
+    from oracle import np_mpi_acoustic as nm
+    rng = np.random.default_rng(21)
+    n, NSTEP, dx, dy, dt = 12, 45, 10.0, 9.0, 0.004
+    NX, NY = 2 * n, 3 * n
+    sig, tau = po.acoustic_pml(NX, NY, dx, dy, npml=5, vp_ref=1000.0, Rcoef=0.2)
+    c2 = 1.0e6 * (1 + 0.2 * rng.random((NX, NY)))
+    srci, srcj = np.array([NX // 5, n, n + 1, 2]), np.array([NY // 2, n, n + 1, 3])   # block corners, inside the PML
+    srcv = np.stack([po.ricker(NSTEP, 6.0 + k, 12.0 + k, 1e4) for k in range(4)], 1)
+    ublk = nm.mpi_acoustic_forward_k0(NX, NY, n, NSTEP, dt, dx, dy, sig, tau, c2, srci, srcj, srcv)
+    c2p = np.zeros((NX + 2, NY + 2))
+    c2p[1:-1, 1:-1] = c2
+    u, _, _ = po.acoustic_forward(NX, NY, NSTEP, dt, dx, dy, sig, tau, c2p, srci, srcj, srcv, [], [],
+                                  mpi_convention=True, kernel=0)
+    assert np.abs(ublk).max() > 0 and relerr(u[:, 1:-1, 1:-1], ublk) < 1e-13
+    # and the two schemes really differ on this case (the test would not notice a scheme-1 oracle otherwise)
+    u1, _ = po.acoustic_forward(NX, NY, NSTEP, dt, dx, dy, sig, tau, c2p, srci, srcj, srcv, [], [], mpi_convention=True)
+    assert relerr(u1[:, 1:-1, 1:-1], ublk) > 1e-8
