@@ -55,7 +55,9 @@ struct __align__(128) AcAdjStage {
 #define AC_MINB_FWD 2                       // __launch_bounds__ min CTAs/SM, forward (same wave size as the adjoint)
 #endif
 #ifndef AC_NST_FWD
-#define AC_NST_FWD 8   // power of two (slot = it % depth); 8 x 12.4 KB x 2 CTAs = 198 KB: 94.7 -> 92.1 us at 4096^2 vs depth 4
+#define AC_NST_FWD 4   // power of two (slot = it % depth).  Depth 8 (198 KB per SM) is 2.7 % faster (92.1 vs 94.7 us at 4096^2)
+                       // but made the forward sweep NON-DETERMINISTIC at full size (scripts/determinism_probe.py: 3 of 11
+                       // repeat runs differ in small patches of the precursor zone); depth 4 has a clean record
 #endif
 #define AC_FWD_THREADS (AC_THREADS + 32)
 struct __align__(128) AcFwdStage {
