@@ -127,3 +127,20 @@ def test_elastic_fullsize_properties(A, ctx, variant):
     fd, an = (Ls[0] - Ls[1]) / (2 * eps), float((gmu * d).sum())
     assert abs(fd - an) / abs(an) < 1e-5, (fd, an)
     plan.close()
+
+
+def test_acoustic_forward_is_deterministic_at_full_size(A, ctx):
+    """Repeat runs of one forward sweep reproduce traces and the last snapshot bit for bit.  (Guards the TMA ring of
+    the marching CTAs: a forward ring of depth 8 failed this in ~25 % of the runs -- stale / early-overwritten ring
+    rows in the numerical precursor zone -- while depth 4, the shipped one, is clean: scripts/determinism_probe.py.)"""
+    NX, NY, NSTEP = 4096, 4096, 120
+    rng = np.random.default_rng(1)
+    p, plan, srcv = _acoustic_plan(A, ctx, NX, NY, NSTEP, 256)
+    c = _layered(plan.model_shape, 1500.0, 3500.0, rng)
+    plan.set_model(c); plan.set_srcv(srcv)
+    plan.forward()
+    r0, u0 = plan.rcvv(), plan.snapshot(NSTEP)
+    for _ in range(4):
+        plan.forward()
+        assert np.array_equal(plan.rcvv(), r0) and np.array_equal(plan.snapshot(NSTEP), u0)
+    plan.close()
