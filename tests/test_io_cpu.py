@@ -84,6 +84,76 @@ def test_parameterisation_helpers(A):
     assert srcv.shape == (4, 8 * 7) and len(srci) == 56
     k = int(np.argmax(srcv[0].detach().numpy()))
     assert (srci[k], srcj[k]) == (4, 3)                 # the blob peaks at x = (srci-1) dx = 30, y = 20
-    assert float(srcv[0, k]) == pytest.approx(1 / (2 * np.pi))
+    assert float(srcv[0, k].detach()) == pytest.approx(1 / (2 * np.pi))
     srcv.sum().backward()
     assert xs.grad is not None
+
+
+class _QuadraticPlan:
+    """Stand-in for AcousticPlan / ElasticPlan in CPU tests of the autograd wiring: loss = sum w (c - c*)^2 (+ a term in
+    srcv), gradients analytic.  (The real plans need a GPU; tests/test_fwi_gpu.py covers them.)"""
+
+    def __init__(self, target, weight, nstep=5, nsrc=2):
+        self.t, self.w = np.asarray(target, dtype=np.float64), np.asarray(weight, dtype=np.float64)
+        self.model_shape, self.nstep, self.nsrc = self.t.shape, nstep, nsrc
+        self.c, self.s, self.calls = None, np.zeros((nstep, nsrc)), 0
+
+        class _Ctx:
+            def sync(self_inner):
+                pass
+        self.ctx = _Ctx()
+
+    def set_model(self, *arrs):
+        self.c = sum(np.array(a, dtype=np.float64).reshape(self.model_shape) for a in arrs)
+
+    def set_srcv(self, s, rows=None):
+        self.s = np.array(s, dtype=np.float64)[:self.nstep]
+
+    def gradient(self, material_grads=True):
+        self.calls += 1
+
+    def loss(self):
+        return float((self.w * (self.c - self.t) ** 2).sum() + 0.5 * (self.s ** 2).sum())
+
+    def grad_c(self, out=None):
+        g = 2 * self.w * (self.c - self.t)
+        if out is not None:
+            out[...] = g
+        return g
+
+    grad_rho = grad_lambda = grad_mu = lambda self: 2 * self.w * (self.c - self.t)
+
+    def grad_srcv(self):
+        return self.s.copy()
+
+
+def test_autograd_wiring_and_lbfgs_on_cpu(A):
+    import torch
+    fwi = A.fwi
+    rng = np.random.default_rng(8)
+    target, weight = 2000 + 500 * rng.random((6, 5)), 0.5 + rng.random((6, 5))
+    plan = _QuadraticPlan(target, weight)
+    mask = np.ones((6, 5)); mask[:, 0] = 0
+    x0 = np.full((6, 5), 2100.0)
+    vp = fwi.ConstantOrVariable(x0, trainable=True, mask=mask)
+    srcv = torch.tensor(rng.standard_normal((7, 2)), requires_grad=True)      # 7 rows, the plan uses 5
+    loss = fwi.acoustic_misfit(plan, vp(), srcv)
+    (2.0 * loss).backward()
+    want = 2.0 * 2 * weight * (x0 - target) * mask * x0.mean()
+    assert np.allclose(vp.x_.grad.numpy(), want, rtol=1e-13)
+    g = srcv.grad.numpy()
+    assert np.allclose(g[:5], 2.0 * srcv.detach().numpy()[:5], rtol=1e-14) and not g[5:].any()
+    # L-BFGS drives the masked quadratic to its minimum; unmasked column stays at the start value
+    vp2 = fwi.ConstantOrVariable(x0, trainable=True, mask=mask)
+    plan = _QuadraticPlan(target, weight)        # fresh: no source term
+    losses = fwi.LBFGS_(lambda: fwi.acoustic_misfit(plan, vp2()), vp2.parameters(), max_iter=40)
+    out = vp2().detach().numpy()
+    assert losses[-1] < 1e-12 * losses[0] + float((weight[:, 0] * (x0[:, 0] - target[:, 0]) ** 2).sum()) * (1 + 1e-9)
+    assert np.allclose(out[:, 1:], target[:, 1:], rtol=1e-5) and np.allclose(out[:, 0], x0[:, 0], rtol=1e-15)
+    assert all(b <= a * (1 + 1e-12) for a, b in zip(losses, losses[1:]))
+    # elastic wrapper: three material tensors, gradients routed to each
+    rho, lam, mu = (torch.tensor(rng.random((6, 5)) * 700, requires_grad=True) for _ in range(3))
+    fwi.elastic_misfit(plan, rho, lam, mu).backward()
+    gsum = 2 * weight * ((rho + lam + mu).detach().numpy() - target)
+    for t in (rho, lam, mu):
+        assert np.allclose(t.grad.numpy(), gsum, rtol=1e-13)
