@@ -293,3 +293,28 @@ def test_acoustic_kernel0_block_decomposed_equals_global(po):
     # and the two schemes really differ on this case (the test would not notice a scheme-1 oracle otherwise)
     u1, _ = po.acoustic_forward(NX, NY, NSTEP, dt, dx, dy, sig, tau, c2p, srci, srcj, srcv, [], [], mpi_convention=True)
     assert relerr(u1[:, 1:-1, 1:-1], ublk) > 1e-8
+
+
+def test_acoustic_kernel0_gradient_fd(po):
+    """The reference's own gradient test strategy (finite-difference convergence, deps/CustomOps/*/gradtest.jl) applied
+    to the hand-derived PropagatorKernel=0 reverse sweep: sources inside the absorbing frame, so the injected-source
+    handling of the phibar / psibar terms is exercised."""
+    rng = np.random.default_rng(31)
+    NX, NY, NSTEP, dx, dt = 24, 30, 50, 10.0, 1e-3
+    sig, tau = po.acoustic_pml(NX, NY, dx, dx, npml=6, vp_ref=2500.0)
+    c = 2500.0 * (1 + 0.1 * rng.random((NX + 2, NY + 2)))
+    srci, srcj = np.array([12, 3, 4]), np.array([15, 4, 4])
+    srcv = np.stack([po.ricker(NSTEP, 6.0 + k, 10.0 + k, 1e6) for k in range(3)], 1)
+    rcvi, rcvj = rng.integers(2, NX + 1, 12), rng.integers(2, NY + 1, 12)
+
+    def fwd(c_, s_):
+        return po.acoustic_forward(NX, NY, NSTEP, dt, dx, dx, sig, tau, c_, srci, srcj, s_, rcvi, rcvj, kernel=0)
+
+    u, up, r = fwd(c, srcv)
+    obs = 0.8 * r + 0.01 * np.abs(r).max() * rng.standard_normal(r.shape)
+    loss, gc, gs = po.acoustic_misfit_grad(NX, NY, NSTEP, dt, dx, dx, sig, tau, c, srci, srcj, rcvi, rcvj, obs, u,
+                                           upre_hist=up)
+    L = lambda c_, s_=srcv: ((fwd(c_, s_)[2] - obs) ** 2).sum()
+    assert abs(L(c) - loss) <= 1e-12 * loss
+    _fd_check(L, gc, c, rng.standard_normal(c.shape), [1e-2, 1e-3, 1e-4], 1e-7)
+    _fd_check(lambda s: L(c, s), gs, srcv, rng.standard_normal(srcv.shape) * 1e5, [1e-2, 1e-3], 1e-8)
