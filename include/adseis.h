@@ -43,6 +43,8 @@ const char* adseis_last_error(void);
 int adseis_device_count(int* n);
 /* device < 0: use the current device.  Creates one compute stream (non-blocking). */
 int adseis_ctx_create(int device, adseis_ctx** out);
+/* A context outlives its plans: destroying it while plans are alive (finalisers of a garbage-collected host language
+ * run in any order) only marks it, and the last plan's destructor frees it. */
 int adseis_ctx_destroy(adseis_ctx* ctx);
 int adseis_ctx_sync(adseis_ctx* ctx);
 /* cudaStream_t of the ctx (as void*), so a host framework can order its own work against ours. */
