@@ -24,21 +24,38 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compile if needed.  Safe under torchrun: ranks serialise on a file lock, the compiler writes to a temporary
+    file and the result is moved into place atomically, so no rank can dlopen a half-written library.  A tuning
+    variant (ADSEIS_LIB_SUFFIX set) that already exists is never rebuilt implicitly: its flags are not recorded."""
+    if not force and os.environ.get("ADSEIS_LIB_SUFFIX") and os.path.exists(LIB):
+        return LIB
     if not force and not needs_build():
         return LIB
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    extra = os.environ.get("ADSEIS_NVCC_EXTRA", "").split()
-    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    env = dict(os.environ)
-    env.pop("CC", None), env.pop("CXX", None)
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
-    log = os.path.join(HERE, "build.log")
-    with open(log, "w") as f:
-        f.write(" ".join(cmd) + "\n" + r.stdout)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed (see %s)" % log)
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():      # another rank built it while we waited
+                return LIB
+            nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+            extra = os.environ.get("ADSEIS_NVCC_EXTRA", "").split()
+            tmp = "%s.tmp.%d" % (LIB, os.getpid())
+            cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+            env = dict(os.environ)
+            env.pop("CC", None), env.pop("CXX", None)
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+            log = os.path.join(HERE, "build.log")
+            with open(log, "w") as f:
+                f.write(" ".join(cmd) + "\n" + r.stdout)
+            if verbose or r.returncode != 0:
+                sys.stderr.write(r.stdout)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed (see %s)" % log)
+            os.replace(tmp, LIB)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

@@ -1117,3 +1117,15 @@ ADSEIS_API int adseis_acoustic_misfit_grad(adseis_ctx* ctx, const adseis_acousti
   adseis_acoustic_plan_destroy(P);
   return rc;
 }
+
+#ifdef AC_RING_DEBUG
+// debug builds only: copy out (and reset) the ring mismatch records of ac_fwd_kernel; returns the count
+extern "C" __attribute__((visibility("default"))) int adseis_debug_ring(double* out /* 64*12 */) {
+  unsigned n = 0, z = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_ring_dbg_n, sizeof(n));
+  cudaMemcpyFromSymbol(out, g_ring_dbg, sizeof(double) * 64 * 12);
+  cudaMemcpyToSymbol(g_ring_dbg_n, &z, sizeof(z));
+  return (int)n;
+}
+#endif

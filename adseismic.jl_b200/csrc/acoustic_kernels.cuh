@@ -42,13 +42,22 @@
 #endif
 #define AC_ADJ_THREADS (AC_THREADS + 32)    // + one producer warp
 #define AC_HCOLS (AC_TILE_COLS + 4)         // staged columns of an array with y-neighbours: 16-byte halo on each side
+// Shared-memory footprint of a halo'd stage row.  Padded to a multiple of 128 bytes so that no two bulk copies in
+// flight ever write into the same 128-byte shared-memory line (the copy of a 516-double row would otherwise end 32
+// bytes into the line the next array's copy starts in).  -DADSEIS_NO_SMEM_PAD restores the packed round-1 layout for
+// the A/B determinism experiment (scripts/ring_race_ab.sh).
+#ifdef ADSEIS_NO_SMEM_PAD
+#define AC_HPAD AC_HCOLS
+#else
+#define AC_HPAD ((AC_HCOLS + 15) / 16 * 16)
+#endif
 
 // One ring stage of an adjoint marching CTA: row `li` of its 512-column tile (iteration li - r0).  Filled by five
 // 4-KB bulk copies (one UBLKCP per array: the TMA unit retires ~one op per 45 cycles whatever its size, so the
 // copies must be CTA-wide, not per warp), completion on the stage's `full` mbarrier; the eight consumer warps
 // release it through the `empty` mbarrier.
 struct __align__(128) AcAdjStage {
-  double ub1[AC_HCOLS], c2[AC_HCOLS], wf[AC_HCOLS];  // row li+1, columns c0-2 .. c0+513
+  double ub1[AC_HPAD], c2[AC_HPAD], wf[AC_HPAD];     // row li+1, columns c0-2 .. c0+513
   double ub2[AC_TILE_COLS], G[AC_TILE_COLS];         // row li,   columns c0   .. c0+511
 };
 #ifndef AC_MINB_FWD
@@ -61,11 +70,21 @@ struct __align__(128) AcAdjStage {
 #endif
 #define AC_FWD_THREADS (AC_THREADS + 32)
 struct __align__(128) AcFwdStage {
-  double w[AC_HCOLS];                                // row li+1, columns c0-2 .. c0+513
+  double w[AC_HPAD];                                 // row li+1, columns c0-2 .. c0+513
   double wold[AC_TILE_COLS], c2[AC_TILE_COLS];       // row li
 };
-#define AC_FWD_SMEM ((int)(AC_NST_FWD * (sizeof(AcFwdStage) + 16)))
+#ifndef AC_FWD_SMEM_EXTRA
+#define AC_FWD_SMEM_EXTRA 0                 // experiments: unused shared memory (lowers the CTAs per SM)
+#endif
+#define AC_FWD_SMEM ((int)(AC_NST_FWD * (sizeof(AcFwdStage) + 16)) + AC_FWD_SMEM_EXTRA)
 #define AC_ADJ_SMEM ((int)(AC_NST_ADJ * (sizeof(AcAdjStage) + 16)))
+
+#ifdef AC_RING_DEBUG
+// Debug build only (scripts/ring_race_ab.sh): every consumer lane re-reads its ring data straight from global memory
+// and records mismatches -- tells "stage read before the copy landed" (old row) from "overwritten early" (later row).
+__device__ unsigned int g_ring_dbg_n;
+__device__ double g_ring_dbg[64 * 12];
+#endif
 
 struct AcGeom {
   int H, W;    // global padded rows (NX+2) and columns (NY+2)
@@ -338,7 +357,7 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
         const unsigned cbytes = (unsigned)min(AC_TILE_COLS, ld - c0) * 8u;
         for (int it = 0; it < nrows; it++) {
           const int sidx = it % AC_NST_FWD;
-          if (it >= AC_NST_FWD) mbar_wait(empty + sidx, (unsigned)(it / AC_NST_FWD - 1) & 1u);
+          if (it >= AC_NST_FWD) { mbar_wait(empty + sidx, (unsigned)(it / AC_NST_FWD - 1) & 1u); ring_refill_fence(); }
           AcFwdStage& s = stg[sidx];
           const i64 ro = (i64)(r0 + it) * ld + c0;
           mbar_arrive_expect_tx(full + sidx, hbytes + 2u * cbytes);
@@ -373,6 +392,29 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
           if (lane == 0) we_n = s.w[so - 1];
           if (lane == 31) we_n = s.w[so + 2];
         }
+#ifdef AC_RING_DEBUG
+        if (wact && ldok) {
+          const i64 gro = (i64)li * ld + j;
+          const double2 gn = ld2(w + gro + ld), go = ld2(wold + gro), gc2 = ld2(c2 + gro);
+          const bool bad_w = __double_as_longlong(gn.x) != __double_as_longlong(wn.x) || __double_as_longlong(gn.y) != __double_as_longlong(wn.y);
+          const bool bad_o = __double_as_longlong(go.x) != __double_as_longlong(wo.x) || __double_as_longlong(go.y) != __double_as_longlong(wo.y);
+          const bool bad_c = __double_as_longlong(gc2.x) != __double_as_longlong(cc.x) || __double_as_longlong(gc2.y) != __double_as_longlong(cc.y);
+          if (bad_w || bad_o || bad_c) {
+            const unsigned k = atomicAdd(&g_ring_dbg_n, 1u);
+            if (k < 64) {
+              double* r = g_ring_dbg + k * 12;
+              r[0] = bid; r[1] = it; r[2] = nrows; r[3] = warp * 32 + lane; r[4] = li; r[5] = j;
+              r[6] = (bad_w ? 1 : 0) + (bad_o ? 2 : 0) + (bad_c ? 4 : 0);
+              const double* arr = bad_w ? w + ld : (bad_o ? wold : c2);
+              r[7] = bad_w ? wn.x : (bad_o ? wo.x : cc.x);              // what the stage held
+              r[8] = arr[gro];                                          // what it should hold
+              r[9] = (it >= AC_NST_FWD) ? arr[gro - (i64)AC_NST_FWD * ld] : -1.0;             // the row AC_NST_FWD iterations earlier
+              r[10] = (it + AC_NST_FWD < nrows) ? arr[gro + (i64)AC_NST_FWD * ld] : -1.0;      // ... later
+              r[11] = (double)clock64();
+            }
+          }
+        }
+#endif
         __syncwarp();  // every lane has read the stage
         if (lane == 0) mbar_arrive(empty + sidx);
         if (wact) {
@@ -701,7 +743,7 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
         const unsigned cbytes = (unsigned)min(AC_TILE_COLS, ld - c0) * 8u;
         for (int it = 0; it < nrows; it++) {
           const int sidx = it % AC_NST_ADJ;
-          if (it >= AC_NST_ADJ) mbar_wait(empty + sidx, (unsigned)(it / AC_NST_ADJ - 1) & 1u);
+          if (it >= AC_NST_ADJ) { mbar_wait(empty + sidx, (unsigned)(it / AC_NST_ADJ - 1) & 1u); ring_refill_fence(); }
           AcAdjStage& s = stg[sidx];
           const i64 ro = (i64)(r0 + it) * ld + c0;
           mbar_arrive_expect_tx(full + sidx, 3u * hbytes + 2u * cbytes);

@@ -242,6 +242,19 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
   } while (!ok);
 }
+// Cross-proxy write-after-read fence of the TMA rings.  The consumers read a ring stage with ordinary (generic-proxy)
+// shared-memory loads and release it through the `empty` mbarrier; the producer then refills the stage with
+// cp.async.bulk, which writes through the ASYNC proxy.  mbarrier release/acquire orders generic-proxy accesses only,
+// so the refill needs a proxy fence between the producer's acquire of `empty` and the bulk copies -- without it a
+// refill can overtake a consumer's still-pending loads of the previous row.  Measured on B200 (round 2,
+// profiles/r02_ring_race.md): without the fence the forward sweep at 2 CTAs/SM is non-deterministic in ~10 % of
+// 120-step runs at 4096^2 (ring depth 8, and depth 4 padded to the same shared-memory footprint); with it, clean.
+// -DADSEIS_NO_RING_FENCE rebuilds the unfenced round-1 behaviour for that A/B experiment.
+__device__ __forceinline__ void ring_refill_fence() {
+#ifndef ADSEIS_NO_RING_FENCE
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
 // bytes: multiple of 16; src and dst 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

@@ -48,7 +48,13 @@
 #define EL_MW 8                     // marching CTA: consumer warps (32 columns each, one column per lane)
 #define EL_NT (EL_MW * 32 + 32)     // threads per CTA: consumers + one producer warp (generic tiles use the first 256)
 #define EL_TCOLS (EL_MW * 32)       // marching CTA: columns
-#define EL_RC (EL_TCOLS + 4)        // ring row: tile columns + a 2-column (16-byte) halo on each side
+// ring row stride: tile columns + a 2-column (16-byte) halo on each side, padded to a multiple of 128 bytes so that
+// bulk copies into neighbouring ring rows never share a 128-byte shared-memory line (see AC_HPAD)
+#ifdef ADSEIS_NO_SMEM_PAD
+#define EL_RC (EL_TCOLS + 4)
+#else
+#define EL_RC ((EL_TCOLS + 4 + 15) / 16 * 16)
+#endif
 #ifndef EL_PF
 #define EL_PF 2                     // row bundles in flight beyond the one being consumed
 #endif
@@ -256,7 +262,7 @@ __device__ __forceinline__ void el_produce(const double* const* sp, double* ring
   int sl[3] = {0, 1 % el_depth(1), 2 % el_depth(2)};  // slot of row it+L for L = 0,1,2
   for (int it = 0; it < nrows; it++) {
     const int b = it % EL_NB;
-    if (it >= EL_NB) mbar_wait(bars + 1 + EL_NB + b, (unsigned)(it / EL_NB - 1) & 1u);
+    if (it >= EL_NB) { mbar_wait(bars + 1 + EL_NB + b, (unsigned)(it / EL_NB - 1) & 1u); ring_refill_fence(); }
     mbar_arrive_expect_tx(bars + 1 + b, (unsigned)T::NS * bytes);
 #pragma unroll
     for (int s = 0; s < T::NS; s++) {

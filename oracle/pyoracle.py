@@ -302,3 +302,91 @@ def elastic_misfit_grad(variant, NX, NY, NSTEP, dt, dx, dy, ax, bx, ay, by, rho,
                                   gr.ctypes.data_as(_dp), gl.ctypes.data_as(_dp), gm.ctypes.data_as(_dp),
                                   gs.ctypes.data_as(_dp))
     return dict(loss=loss.value, rcvv=rcvv, grad_rho=gr, grad_lam=gl, grad_mu=gm, grad_srcv=gs)
+
+
+def ref_elastic(variant, NX, NY, NSTEP, dt, dx, dy, ax, bx, ay, by, rho, lam, mu, srci, srcj, srctype, srcv, rcvi, rcvj,
+                rcvtype, obs=None, want_grad=True, want_hist=False, block=None):
+    """The reference's elastic graph recorded and differentiated op by op with ITS OWN gather / scatter_add /
+    scatter_nd / add_source / get_receive bodies (oracle/ref_graph.inc).  variant 0 = src/Core.jl (S), 1 =
+    src/MPIElastic.jl (M) on `block` = (n1, n2)-cell blocks (default: one block) with emulated halo exchanges.
+    -> dict(loss, rcvv[nrcv, NSTEP+1], hist[5, NSTEP+1, H, W] | None, grad_rho, grad_lam, grad_mu [H, W], grad_srcv)"""
+    H, W = elastic_dims(variant, NX, NY)
+    srci, p1 = _i(srci); srcj, p2 = _i(srcj); srctype, p3 = _i(srctype)
+    rcvi, p4 = _i(rcvi); rcvj, p5 = _i(rcvj); rcvtype, p6 = _i(rcvtype)
+    srcv = np.ascontiguousarray(np.asarray(srcv, dtype=np.float64)[:NSTEP])
+    nsrc, nrcv = len(srci), len(rcvi)
+    assert srcv.shape == (NSTEP, nsrc)
+    loss = C.c_double(0.0)
+    rcvv = np.zeros((nrcv, NSTEP + 1))
+    hist = np.zeros((5, NSTEP + 1, H, W)) if want_hist else None
+    gr, gl, gm, gs = np.zeros((H, W)), np.zeros((H, W)), np.zeros((H, W)), np.zeros((NSTEP, nsrc))
+    obs_p = None
+    if obs is not None:
+        obs = np.ascontiguousarray(obs, dtype=np.float64)
+        assert obs.shape == rcvv.shape
+        obs_p = obs.ctypes.data_as(_dp)
+    common = [C.c_double(dt), C.c_double(dx), C.c_double(dy), _d(ax)[1], _d(bx)[1], _d(ay)[1], _d(by)[1], _d(rho)[1],
+              _d(lam)[1], _d(mu)[1], _i64(nsrc), p1, p2, p3, srcv.ctypes.data_as(_dp), _i64(nrcv), p4, p5, p6, obs_p,
+              C.c_int(int(want_grad and obs is not None)), C.byref(loss), rcvv.ctypes.data_as(_dp),
+              hist.ctypes.data_as(_dp) if want_hist else None, gr.ctypes.data_as(_dp), gl.ctypes.data_as(_dp),
+              gm.ctypes.data_as(_dp), gs.ctypes.data_as(_dp)]
+    if variant == 0:
+        ref_lib().ref_drv_elastic_S(_i64(NX), _i64(NY), _i64(NSTEP), *common)
+    else:
+        n1, n2 = block or (NX, NY)
+        assert NX % n1 == 0 and NY % n2 == 0
+        ref_lib().ref_drv_elastic_M(_i64(NX), _i64(NY), _i64(n1), _i64(n2), _i64(NSTEP), *common)
+    return dict(loss=loss.value, rcvv=rcvv, hist=hist, grad_rho=gr, grad_lam=gl, grad_mu=gm, grad_srcv=gs)
+
+
+def ref_acoustic_graph(kernel, NX, NY, NSTEP, dt, hx, hy, sigma, tau, c, srci, srcj, srcv, rcvi, rcvj, obs=None,
+                       want_grad=True, want_hist=False):
+    """AcousticPropagatorSolver as a graph over the reference's own gather / scatter_nd / scatter_add op bodies,
+    differentiated with their backward bodies (oracle/ref_graph.inc).  kernel 0 = `one_step` (Core.jl:528-549),
+    2 = `acoustic_one_step_customop_ref` (:504-525).  -> dict(loss, rcvv, u, grad_c, grad_srcv)"""
+    N = (NX + 2) * (NY + 2)
+    srci, p1 = _i(srci); srcj, p2 = _i(srcj); rcvi, p3 = _i(rcvi); rcvj, p4 = _i(rcvj)
+    nsrc, nrcv = len(srci), len(rcvi)
+    srcv = np.ascontiguousarray(np.asarray(srcv, dtype=np.float64)[:NSTEP]).reshape(NSTEP, nsrc)
+    loss = C.c_double(0.0)
+    rcvv = np.zeros((NSTEP + 1, nrcv))
+    u = np.zeros((NSTEP + 1, NX + 2, NY + 2)) if want_hist else None
+    gc, gs = np.zeros((NX + 2, NY + 2)), np.zeros((NSTEP, nsrc))
+    obs_p = None
+    if obs is not None:
+        obs = np.ascontiguousarray(obs, dtype=np.float64)
+        obs_p = obs.ctypes.data_as(_dp)
+    ref_lib().ref_drv_acoustic_graph(C.c_int(kernel), _i64(NX), _i64(NY), _i64(NSTEP), C.c_double(dt), C.c_double(hx),
+                                     C.c_double(hy), _d(sigma)[1], _d(tau)[1], _d(c)[1], _i64(nsrc), p1, p2,
+                                     srcv.ctypes.data_as(_dp), _i64(nrcv), p3, p4, obs_p,
+                                     C.c_int(int(want_grad and obs is not None)), C.byref(loss),
+                                     rcvv.ctypes.data_as(_dp), u.ctypes.data_as(_dp) if want_hist else None,
+                                     gc.ctypes.data_as(_dp), gs.ctypes.data_as(_dp))
+    return dict(loss=loss.value, rcvv=rcvv, u=u, grad_c=gc, grad_srcv=gs)
+
+
+def ref_mpi_acoustic_graph(kernel, NX, NY, block, NSTEP, dt, hx, hy, sigma, tau, c2g, srci, srcj, srcv, rcvi, rcvj,
+                           obs=None, want_grad=True, want_hist=False):
+    """MPIAcousticPropagatorSolver (src/MPIAcoustic.jl) on Mb x Nb blocks of block=(n1, n2) cells held in one process
+    (mpi_halo_exchange emulated), as a graph over the reference's op bodies.  Global unpadded grid; c2g = c^2.
+    -> dict(loss, rcvv, u[(NSTEP+1), NX, NY], grad_c2[NX, NY], grad_srcv)"""
+    n1, n2 = block
+    assert NX % n1 == 0 and NY % n2 == 0
+    srci, p1 = _i(srci); srcj, p2 = _i(srcj); rcvi, p3 = _i(rcvi); rcvj, p4 = _i(rcvj)
+    nsrc, nrcv = len(srci), len(rcvi)
+    srcv = np.ascontiguousarray(np.asarray(srcv, dtype=np.float64)[:NSTEP]).reshape(NSTEP, nsrc)
+    loss = C.c_double(0.0)
+    rcvv = np.zeros((NSTEP + 1, nrcv))
+    u = np.zeros((NSTEP + 1, NX, NY)) if want_hist else None
+    gc, gs = np.zeros((NX, NY)), np.zeros((NSTEP, nsrc))
+    obs_p = None
+    if obs is not None:
+        obs = np.ascontiguousarray(obs, dtype=np.float64)
+        obs_p = obs.ctypes.data_as(_dp)
+    ref_lib().ref_drv_mpi_acoustic_graph(C.c_int(kernel), _i64(NX), _i64(NY), _i64(n1), _i64(n2), _i64(NSTEP),
+                                         C.c_double(dt), C.c_double(hx), C.c_double(hy), _d(sigma)[1], _d(tau)[1],
+                                         _d(c2g)[1], _i64(nsrc), p1, p2, srcv.ctypes.data_as(_dp), _i64(nrcv), p3, p4,
+                                         obs_p, C.c_int(int(want_grad and obs is not None)), C.byref(loss),
+                                         rcvv.ctypes.data_as(_dp), u.ctypes.data_as(_dp) if want_hist else None,
+                                         gc.ctypes.data_as(_dp), gs.ctypes.data_as(_dp))
+    return dict(loss=loss.value, rcvv=rcvv, u=u, grad_c2=gc, grad_srcv=gs)

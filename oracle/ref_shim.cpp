@@ -13,7 +13,10 @@
 // those bodies in the order the reference's Julia graph builders do (src/Core.jl:562-620 for the
 // acoustic loop, src/Core.jl:31-228 for the elastic loop, src/MPIAcoustic.jl:251-404 for the block
 // decomposed loop).  The drivers are what bench.py times as the "reference" CPU arm and what the
-// C oracle (oracle/oracle.c) is pinned against in tests/test_oracle_vs_ref.py.
+// C oracle (oracle/oracle.c) is pinned against in tests/test_oracle_pinning.py.  The elastic solvers and the acoustic
+// PropagatorKernel=0 scheme are TensorFlow graphs over the reference's gather / scatter / add_source / get_receive
+// ops; their drivers live in ref_graph.inc (#included at the end), which records and differentiates those graphs
+// with the reference's own forward AND backward op bodies.
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -393,3 +396,5 @@ API int ref_max_threads(void) {
   return 1;
 #endif
 }
+
+#include "ref_graph.inc"

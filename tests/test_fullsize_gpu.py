@@ -130,9 +130,10 @@ def test_elastic_fullsize_properties(A, ctx, variant):
 
 
 def test_acoustic_forward_is_deterministic_at_full_size(A, ctx):
-    """Repeat runs of one forward sweep reproduce traces and the last snapshot bit for bit.  (Guards the TMA ring of
-    the marching CTAs: a forward ring of depth 8 failed this in ~25 % of the runs -- stale / early-overwritten ring
-    rows in the numerical precursor zone -- while depth 4, the shipped one, is clean: scripts/determinism_probe.py.)"""
+    """Repeat runs of one forward sweep reproduce traces and the last snapshot bit for bit.  Guards the TMA ring of
+    the marching CTAs: without the generic->async proxy fence before a stage refill (ring_refill_fence, common.cuh) a
+    refill could overtake a consumer's pending loads at 2 CTAs/SM -- 10 % to 100 % of such runs differed
+    (profiles/r02_ring_race.md); with it 0 of 249."""
     NX, NY, NSTEP = 4096, 4096, 120
     rng = np.random.default_rng(1)
     p, plan, srcv = _acoustic_plan(A, ctx, NX, NY, NSTEP, 256)
@@ -140,7 +141,65 @@ def test_acoustic_forward_is_deterministic_at_full_size(A, ctx):
     plan.set_model(c); plan.set_srcv(srcv)
     plan.forward()
     r0, u0 = plan.rcvv(), plan.snapshot(NSTEP)
-    for _ in range(4):
+    for _ in range(8):
         plan.forward()
         assert np.array_equal(plan.rcvv(), r0) and np.array_equal(plan.snapshot(NSTEP), u0)
+    plan.close()
+
+
+def test_acoustic_gradient_is_deterministic_at_full_size(A, ctx):
+    """The reverse sweep (ac_adj_kernel's five-plane ring, 2 CTAs/SM) reproduces loss and both gradients bit for bit."""
+    NX, NY, NSTEP = 4096, 4096, 80
+    rng = np.random.default_rng(4)
+    p, plan, srcv = _acoustic_plan(A, ctx, NX, NY, NSTEP, 256)
+    c = _layered(plan.model_shape, 1500.0, 3500.0, rng)
+    plan.set_model(c); plan.set_srcv(srcv)
+    plan.forward()
+    plan.set_obs(0.7 * plan.rcvv())
+    plan.gradient()
+    L0, g0, s0 = plan.loss(), plan.grad_c(), plan.grad_srcv()
+    assert np.abs(g0).max() > 0
+    for _ in range(6):
+        plan.gradient()
+        assert plan.loss() == L0 and np.array_equal(plan.grad_c(), g0) and np.array_equal(plan.grad_srcv(), s0)
+    plan.close()
+
+
+@pytest.mark.parametrize("variant", [1, 0])
+def test_elastic_is_deterministic_at_full_size(A, ctx, variant):
+    """el_sigma_fwd / el_vel_fwd (fields) and el_vel_adj / el_sigma_adj (source-only and material gradients) on the C5
+    grid: repeat runs are bit-identical (same TMA ring protocol as the acoustic kernels, 2-3 CTAs/SM)."""
+    NX = NY = 2000
+    NSTEP = 40
+    rng = np.random.default_rng(5)
+    p = A.ElasticPropagatorParams(NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=10.0, DELTAY=10.0, DELTAT=1e-3, vp_ref=3000.0,
+                                  f0=10.0, variant=variant)
+    shape = p.model_shape()
+    vp = _layered(shape, 2500.0, 3500.0, rng)
+    vs, rho = vp / 1.732, np.full(shape, 2500.0) * (1 + 0.02 * rng.random(shape))
+    lam, mu = rho * (vp * vp - 2 * vs * vs), rho * vs * vs
+    srci, srcj, srctype = np.array([1000, 700, 1200]), np.array([1000, 900, 1100]), np.array([2, 0, 4])
+    srcv = np.stack([A.Ricker(p, 20.0 + k, 30.0, 1e6) for k in range(3)], 1)[:NSTEP]
+    nrcv = 96
+    rcvi, rcvj, rcvtype = np.linspace(900, 1100, nrcv).astype(np.int64), np.full(nrcv, 1010), np.arange(nrcv) % 5
+    plan = A.ElasticPlan(p, srci, srcj, srctype, rcvi, rcvj, rcvtype, ctx=ctx)
+    plan.set_model(rho, lam, mu); plan.set_srcv(srcv)
+    plan.forward()
+    r0, f0 = plan.rcvv(), [plan.snapshot(f, NSTEP) for f in (0, 4)]
+    plan.set_obs(0.5 * r0)
+    plan.gradient(True)
+    ref = (plan.loss(), plan.grad_srcv(), plan.grad_rho(), plan.grad_lambda(), plan.grad_mu())
+    assert np.abs(ref[4]).max() > 0
+    for _ in range(4):
+        plan.forward()
+        assert np.array_equal(plan.rcvv(), r0)
+        assert all(np.array_equal(plan.snapshot(f, NSTEP), x) for f, x in zip((0, 4), f0))
+        plan.gradient(True)
+        got = (plan.loss(), plan.grad_srcv(), plan.grad_rho(), plan.grad_lambda(), plan.grad_mu())
+        assert got[0] == ref[0] and all(np.array_equal(a, b) for a, b in zip(got[1:], ref[1:]))
+    plan.gradient(False)
+    s1 = plan.grad_srcv()
+    for _ in range(3):
+        plan.gradient(False)
+        assert np.array_equal(plan.grad_srcv(), s1)
     plan.close()
