@@ -15,6 +15,7 @@ from .elastic import (ElasticPlan, ElasticPropagator, ElasticPropagatorSolver, c
                       elastic_misfit_grad)
 from .utils import Gauss, Ricker, compute_lame_parameters
 from . import io
+from . import workloads
 
 
 def SimulatedObservation_(prop, rcv):

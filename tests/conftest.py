@@ -45,3 +45,10 @@ def relerr(a, b):
         return 0.0
     d = np.abs(b).max()
     return float(np.abs(a - b).max() / d) if d > 0 else float(np.abs(a - b).max())
+
+
+def on_both_records():
+    """Decorator for CPU-only tests that must ALSO appear on the GPU box's `-m gpu` record (the chain
+    CUDA -> oracle.c -> reference op bodies is then closed in one run): the test is collected twice, once plain
+    (runs under -m "not gpu") and once carrying the gpu marker."""
+    return pytest.mark.parametrize("record", ["cpu", pytest.param("gpubox", marks=pytest.mark.gpu)])

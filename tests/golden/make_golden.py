@@ -4,9 +4,12 @@ The reference ships no golden vectors and cannot run here (Julia + ADCME + Tenso
 vectors are produced by the strongest stand-ins available:
   acoustic_*.npz : the reference's OWN C++ op bodies (AcousticOneStepCpu.h, ScatterAddOps.h) driven in the order of
                    src/Core.jl:562-620 by oracle/ref_shim.cpp (oracle/_ref/libadseis_ref.so)
-  elastic_*.npz  : a literal PyTorch restatement of the reference's elastic op graph (src/Core.jl:31-228,
-                   src/MPIElastic.jl:374-645) differentiated by torch.autograd (oracle/torch_elastic.py), which plays
-                   the role tf.gradients plays in the reference
+  elastic_*.npz, acoustic_kernel0.npz : the reference's elastic / PropagatorKernel=0 TensorFlow graphs
+                   (src/Core.jl:31-228, 528-620; src/MPIElastic.jl:374-645) recorded op by op and executed /
+                   differentiated with the reference's OWN gather, scatter_add, scatter_nd, add_source and get_receive
+                   bodies (oracle/ref_graph.inc -> oracle/_ref/libadseis_ref.so); only the element-wise fp64
+                   arithmetic in between is restated.  (Round 1 generated them from torch restatements,
+                   oracle/torch_*.py, which are kept as an independent cross-check.)
 Usage: python tests/golden/make_golden.py
 """
 import os
@@ -57,7 +60,6 @@ def acoustic_step_case(name, seed):
 
 
 def elastic_case(name, variant, NX, NY, NSTEP, seed):
-    from oracle import torch_elastic as te
     rng = np.random.default_rng(seed)
     dx = dy = 1.0
     dt = 1e-4
@@ -80,8 +82,8 @@ def elastic_case(name, variant, NX, NY, NSTEP, seed):
     r0, _ = po.elastic_forward(variant, NX, NY, NSTEP, dt, dx, dy, ax, bx, ay, by, rho, lam, mu, srci, srcj, srctype,
                                srcv, rcvi, rcvj, rcvtype)
     obs = r0 * (1 + 0.2 * rng.standard_normal(r0.shape)) + 0.05 * np.abs(r0).max() * rng.standard_normal(r0.shape)
-    B = te.elastic_misfit_grad(variant, NX, NY, NSTEP, dt, dx, dy, ax, bx, ay, by, rho, lam, mu, srci, srcj, srctype,
-                               srcv, rcvi, rcvj, rcvtype, obs)
+    B = po.ref_elastic(variant, NX, NY, NSTEP, dt, dx, dy, ax, bx, ay, by, rho, lam, mu, srci, srcj, srctype, srcv,
+                       rcvi, rcvj, rcvtype, obs)
     np.savez_compressed(os.path.join(HERE, name), variant=variant, NX=NX, NY=NY, NSTEP=NSTEP, dx=dx, dy=dy, dt=dt,
                         npml=5, vp_ref=3300., alpha_max=np.pi * 15, ax=ax, bx=bx, ay=ay, by=by, rho=rho, lam=lam,
                         mu=mu, srci=srci, srcj=srcj, srctype=srctype, srcv=srcv, rcvi=rcvi, rcvj=rcvj, rcvtype=rcvtype,
@@ -91,10 +93,8 @@ def elastic_case(name, variant, NX, NY, NSTEP, seed):
 
 
 def acoustic_kernel0_case(name, NX, NY, NSTEP, seed):
-    """PropagatorKernel=0 (src/Core.jl:528-549): golden values from the torch-autograd restatement of the reference's
-    gather / scatter_nd graph (oracle/torch_acoustic.py), which stands in for tf.gradients."""
-    import torch
-    from oracle import torch_acoustic as ta
+    """PropagatorKernel=0 (src/Core.jl:528-549): golden values from the graph over the reference's own gather /
+    scatter_nd / scatter_add op bodies (oracle/ref_graph.inc)."""
     rng = np.random.default_rng(seed)
     dx, dy, dt, npml, vp_ref = 10.0, 8.0, 1e-3, 6, 2500.0
     sig, tau = po.acoustic_pml(NX, NY, dx, dy, npml=npml, vp_ref=vp_ref)
@@ -105,20 +105,13 @@ def acoustic_kernel0_case(name, NX, NY, NSTEP, seed):
     srcv = np.stack([po.ricker(NSTEP, 6.0 + k, 10.0 + k, 1e6) for k in range(5)], 1)
     rcvi = rng.integers(1, NX + 3, 24)
     rcvj = rng.integers(1, NY + 3, 24)
-    ct = torch.tensor(c.reshape(-1), requires_grad=True)
-    st = torch.tensor(srcv, requires_grad=True)
-    with torch.no_grad():
-        _, r0 = ta.acoustic_loss(0, NX, NY, NSTEP, dt, dx, dy, sig, tau, ct, srci, srcj, st, rcvi, rcvj,
-                                 np.zeros((NSTEP + 1, 24)))
-    r0 = r0.numpy()
+    r0 = po.ref_acoustic_graph(0, NX, NY, NSTEP, dt, dx, dy, sig, tau, c, srci, srcj, srcv, rcvi, rcvj)["rcvv"]
     obs = 0.7 * r0 + 0.01 * np.abs(r0).max() * rng.standard_normal(r0.shape)
-    L, rt = ta.acoustic_loss(0, NX, NY, NSTEP, dt, dx, dy, sig, tau, ct, srci, srcj, st, rcvi, rcvj, obs)
-    L.backward()
+    R = po.ref_acoustic_graph(0, NX, NY, NSTEP, dt, dx, dy, sig, tau, c, srci, srcj, srcv, rcvi, rcvj, obs)
     np.savez_compressed(os.path.join(HERE, name), NX=NX, NY=NY, NSTEP=NSTEP, dx=dx, dy=dy, dt=dt, npml=npml,
                         vp_ref=vp_ref, c=c, srci=srci, srcj=srcj, srcv=srcv, rcvi=rcvi, rcvj=rcvj, obs=obs,
-                        rcvv=rt.detach().numpy(), loss=float(L.detach()), grad_c=ct.grad.numpy().reshape(NX + 2, NY + 2),
-                        grad_srcv=st.grad.numpy()[:NSTEP])
-    print(name, "loss", float(L.detach()), "|grad_c|max", np.abs(ct.grad.numpy()).max())
+                        rcvv=R["rcvv"], loss=R["loss"], grad_c=R["grad_c"], grad_srcv=R["grad_srcv"])
+    print(name, "loss", R["loss"], "|grad_c|max", np.abs(R["grad_c"]).max())
 
 
 def marmousi_case(name, nstep=400, shot=3):
