@@ -19,6 +19,7 @@ vp = C.c_void_p
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, ECOMM = 0, -1, -2, -3, -4, -5
 GET_RCVV, GET_LOSS, GET_GRAD_C, GET_GRAD_SRCV, GET_GRAD_RHO, GET_GRAD_LAMBDA, GET_GRAD_MU = 1, 2, 3, 4, 5, 6, 7
+GET_GRAD_C_OWNED = 8
 IPC_HANDLE_BYTES = 64
 
 
@@ -66,6 +67,7 @@ SIGNATURES = {
     "adseis_elastic_slab_partition": (C.c_int, [_PE, C.c_int32, C.c_int32, _PS]),
     "adseis_acoustic_plan_create": (C.c_int, [vp, _PA, _PS, i64, ip, ip, i64, ip, ip, C.c_size_t, C.POINTER(vp)]),
     "adseis_acoustic_plan_destroy": (C.c_int, [vp]),
+    "adseis_acoustic_plan_set_points": (C.c_int, [vp, i64, ip, ip, i64, ip, ip]),
     "adseis_acoustic_plan_set_model": (C.c_int, [vp, vp, C.c_int]),
     "adseis_acoustic_plan_set_srcv": (C.c_int, [vp, vp, i64, C.c_int]),
     "adseis_acoustic_plan_set_obs": (C.c_int, [vp, vp, C.c_int]),

@@ -48,6 +48,15 @@ class AcousticPlan:
         self.handle = h
         _lib.track(self)
 
+    def set_points(self, srci, srcj, rcvi, rcvj):
+        """Replace sources and receivers (next shot, same grid): the device state -- history window, checkpoints,
+        model -- is kept.  set_srcv / set_obs must follow."""
+        self.srci, self.srcj = _lib.as_i64(srci), _lib.as_i64(srcj)
+        self.rcvi, self.rcvj = _lib.as_i64(rcvi), _lib.as_i64(rcvj)
+        self.nsrc, self.nrcv = len(self.srci), len(self.rcvi)
+        check(self.lib.adseis_acoustic_plan_set_points(self.handle, self.nsrc, pi(self.srci), pi(self.srcj), self.nrcv,
+                                                       pi(self.rcvi), pi(self.rcvj)))
+
     # -- inputs (numpy arrays, torch CUDA tensors or raw device addresses) --
     def set_model(self, c):
         on_dev = int(not isinstance(c, np.ndarray))
@@ -98,6 +107,22 @@ class AcousticPlan:
 
     def grad_c(self, out=None):
         return self._get(_lib.GET_GRAD_C, self.model_shape, out)
+
+    def owned_model_rows(self):
+        """(first, count): rows of the caller's model array this plan's slab owns (the whole model on one GPU)."""
+        nrows = self.model_shape[0]
+        sl = getattr(self, "_slab", None)
+        if sl is None:
+            return 0, nrows
+        if self.param.mpi_convention:
+            r0, r1 = max(int(sl.row0), 1), min(int(sl.row1), self.param.NX + 1)
+            return r0 - 1, max(r1 - r0, 0)
+        return int(sl.row0), int(sl.row1) - int(sl.row0)
+
+    def grad_c_owned(self, out=None):
+        """Only the gradient rows this slab owns (contiguous), for sharded optimisers: (first_row, rows x cols)."""
+        first, cnt = self.owned_model_rows()
+        return first, self._get(_lib.GET_GRAD_C_OWNED, (cnt, self.model_shape[1]), out)
 
     def grad_srcv(self, out=None):
         return self._get(_lib.GET_GRAD_SRCV, (self.param.NSTEP, self.nsrc), out)

@@ -269,6 +269,91 @@ static int validate_params(const adseis_acoustic_params* p) {
   return ADSEIS_OK;
 }
 
+// Sources / receivers of a plan: keep the points whose padded row is owned (MPIAcoustic.jl:71-78, 98-104), group them
+// by owner CTA (per-CTA CSR lists, see PointSet in common.cuh) and size the per-point buffers.  Called by plan_create
+// and by adseis_acoustic_plan_set_points (one plan per GPU serves all shots of a multi-shot gradient).
+static int plan_build_points(adseis_acoustic_plan* P, int64_t nsrc, const int64_t* srci, const int64_t* srcj,
+                             int64_t nrcv, const int64_t* rcvi, const int64_t* rcvj) {
+  const adseis_acoustic_params* p = &P->p;
+  const AcGeom& g = P->g;
+  const adseis_slab& sl = P->slab;
+  cudaStream_t st = P->ctx->stream;
+  const int H = g.H, W = g.W;
+  std::vector<double> sx(H), ty(W);
+  TRY(adseis_acoustic_pml_profiles(p, sx.data(), ty.data()));
+  free_point_set(&P->src); free_point_set(&P->rcv);
+  P->srcp = AcPoints{}; P->rcvp = AcPoints{};
+  cudaFree(P->rcv_owned); P->rcv_owned = nullptr;
+  cudaFree(P->rcvv); P->rcvv = nullptr;
+  cudaFree(P->obs); P->obs = nullptr;
+  cudaFree(P->res); P->res = nullptr;
+  cudaFree(P->srcv); P->srcv = nullptr; P->srcv_rows = 0;
+  cudaFree(P->gradsrcv); P->gradsrcv = nullptr;
+  P->have_srcv = P->have_obs = P->have_fwd = P->have_grad = false;
+  P->k0_corr = false;
+  P->nsrc = nsrc; P->nrcv = nrcv;
+  const int ioff = p->mpi_convention ? 0 : -1;  // 1-based padded -> 0-based padded ; 1-based unpadded -> padded
+  auto owner_cta = [&](int li, int j) -> int {
+    const AcTiling& t = P->t;
+    if (li >= t.mr0 && li < t.mr1 && j >= t.mc0 && j < t.mc_end)
+      return ac_row_tile_of(t, li) * t.nct + (j - t.mc0) / AC_TILE_COLS;
+    for (int k = 0; k < t.nrect; k++)
+      if (li >= t.rr0[k] && li < t.rr1[k] && j >= t.rc0[k] && j < t.rc1[k])
+        return t.nmarch + t.rblk[k] + (int)(((i64)(li - t.rr0[k]) * (t.rc1[k] - t.rc0[k]) + (j - t.rc0[k])) / AC_FRAME_CELLS);
+    return -1;
+  };
+  auto build = [&](i64 n, const int64_t* pi, const int64_t* pj, PointSetStorage* dst, std::vector<unsigned char>* owned,
+                   const char* what) -> int {
+    std::vector<int> own, cells, gid, none;
+    if (owned) owned->assign((size_t)n, 0);
+    for (i64 k = 0; k < n; k++) {
+      i64 gi = pi[k] + ioff, gj = pj[k] + ioff;
+      REQUIRE(gi >= 0 && gi < H && gj >= 0 && gj < W, "acoustic plan: %s %lld at (%lld,%lld) is outside the grid",
+              what, (long long)k, (long long)pi[k], (long long)pj[k]);
+      if (gi >= sl.row0 && gi < sl.row1) {
+        const int li = (int)(gi - g.goff);
+        const int o = owner_cta(li, (int)gj);
+        REQUIRE(o >= 0, "acoustic plan: internal error: cell (%d,%d) has no owner CTA", li, (int)gj);
+        own.push_back(o); cells.push_back(li * g.ld + (int)gj); gid.push_back((int)k);
+        if (owned) (*owned)[k] = 1;
+      }
+    }
+    PointSetHost h;
+    build_point_set(own, cells, gid, none, P->nblocks, &h);
+    return upload_point_set(h, dst, st);
+  };
+  if (p->PropagatorKernel == 0)
+    for (i64 k = 0; k < nsrc && !P->k0_corr; k++) {
+      const i64 gi = srci[k] + ioff, gj = srcj[k] + ioff;
+      auto coef = [&](i64 i, i64 j) { return i >= 1 && i <= H - 2 && j >= 1 && j <= W - 2 && sx[i] != ty[j]; };
+      P->k0_corr = coef(gi - 1, gj) || coef(gi + 1, gj) || coef(gi, gj - 1) || coef(gi, gj + 1);
+    }
+  std::vector<unsigned char> owned;
+  TRY(build(nsrc, srci, srcj, &P->src, nullptr, "source"));
+  TRY(build(nrcv, rcvi, rcvj, &P->rcv, &owned, "receiver"));
+  if (P->src.nu > 0) P->srcp = AcPoints{P->src.blk, P->src.cell, P->src.start, P->src.perm};
+  if (P->rcv.nu > 0) P->rcvp = AcPoints{P->rcv.blk, P->rcv.cell, P->rcv.start, P->rcv.perm};
+  TRY(dev_upload(&P->rcv_owned, owned, st));
+  TRY(dev_alloc_zero(&P->rcvv, (size_t)((p->NSTEP + 1) * nrcv), st));
+  if (P->G) TRY(dev_alloc_zero(&P->gradsrcv, (size_t)(p->NSTEP * nsrc), st));  // adjoint state already exists
+  return ADSEIS_OK;
+}
+
+// Replace the sources and receivers of a plan (a new shot on the same grid): the device state -- history window,
+// checkpoints, adjoint planes, model -- is kept, so a multi-shot gradient (compute_loss_and_grads_GPU,
+// src/Utils.jl:300-332) runs on ONE plan per GPU instead of one 100-GB history allocation per shot.
+// set_srcv / set_obs must be called again afterwards.
+ADSEIS_API int adseis_acoustic_plan_set_points(adseis_acoustic_plan* P, int64_t nsrc, const int64_t* srci,
+                                               const int64_t* srcj, int64_t nrcv, const int64_t* rcvi,
+                                               const int64_t* rcvj) {
+  REQUIRE(P, "acoustic_plan_set_points: null plan");
+  REQUIRE(nsrc >= 0 && nrcv >= 0 && (nsrc == 0 || (srci && srcj)) && (nrcv == 0 || (rcvi && rcvj)),
+          "acoustic_plan_set_points: bad source/receiver arrays");
+  CUDA_TRY(cudaSetDevice(P->ctx->device));
+  CUDA_TRY(cudaStreamSynchronize(P->ctx->stream));
+  return plan_build_points(P, nsrc, srci, srcj, nrcv, rcvi, rcvj);
+}
+
 ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acoustic_params* p, const adseis_slab* slab,
                                            int64_t nsrc, const int64_t* srci, const int64_t* srcj, int64_t nrcv,
                                            const int64_t* rcvi, const int64_t* rcvj, size_t hist_bytes_budget,
@@ -333,6 +418,15 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
       adseis_acoustic_plan_destroy(P);               \
       return _r;                                     \
     }                                                \
+  } while (0)
+#define PCUDA(expr)                                                                              \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      adseis_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));   \
+      adseis_acoustic_plan_destroy(P);                                                          \
+      return (_e == cudaErrorMemoryAllocation) ? ADSEIS_ENOMEM : ADSEIS_ECUDA;                  \
+    }                                                                                           \
   } while (0)
   // PML profiles and the PML-free box
   std::vector<double> sx(H), ty(W);
@@ -463,56 +557,12 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
       PTRY(dev_alloc_zero(&P->psi[k], (size_t)g.plane, st));
     }
 
-  // sources / receivers: keep the points whose padded row is owned (MPIAcoustic.jl:71-78, 98-104)
-  P->nsrc = nsrc; P->nrcv = nrcv;
-  const int ioff = p->mpi_convention ? 0 : -1;  // 1-based padded -> 0-based padded ; 1-based unpadded -> padded
-  auto owner_cta = [&](int li, int j) -> int {
-    const AcTiling& t = P->t;
-    if (li >= t.mr0 && li < t.mr1 && j >= t.mc0 && j < t.mc_end)
-      return ac_row_tile_of(t, li) * t.nct + (j - t.mc0) / AC_TILE_COLS;
-    for (int k = 0; k < t.nrect; k++)
-      if (li >= t.rr0[k] && li < t.rr1[k] && j >= t.rc0[k] && j < t.rc1[k])
-        return t.nmarch + t.rblk[k] + (int)(((i64)(li - t.rr0[k]) * (t.rc1[k] - t.rc0[k]) + (j - t.rc0[k])) / AC_FRAME_CELLS);
-    return -1;
-  };
-  auto build = [&](i64 n, const int64_t* pi, const int64_t* pj, PointSetStorage* dst, std::vector<unsigned char>* owned,
-                   const char* what) -> int {
-    std::vector<int> own, cells, gid, none;
-    if (owned) owned->assign((size_t)n, 0);
-    for (i64 k = 0; k < n; k++) {
-      i64 gi = pi[k] + ioff, gj = pj[k] + ioff;
-      REQUIRE(gi >= 0 && gi < H && gj >= 0 && gj < W, "acoustic_plan_create: %s %lld at (%lld,%lld) is outside the grid",
-              what, (long long)k, (long long)pi[k], (long long)pj[k]);
-      if (gi >= sl.row0 && gi < sl.row1) {
-        const int li = (int)(gi - g.goff);
-        const int o = owner_cta(li, (int)gj);
-        REQUIRE(o >= 0, "acoustic_plan_create: internal error: cell (%d,%d) has no owner CTA", li, (int)gj);
-        own.push_back(o); cells.push_back(li * g.ld + (int)gj); gid.push_back((int)k);
-        if (owned) (*owned)[k] = 1;
-      }
-    }
-    PointSetHost h;
-    build_point_set(own, cells, gid, none, P->nblocks, &h);
-    return upload_point_set(h, dst, st);
-  };
-  if (p->PropagatorKernel == 0)
-    for (i64 k = 0; k < nsrc && !P->k0_corr; k++) {
-      const i64 gi = srci[k] + ioff, gj = srcj[k] + ioff;
-      auto coef = [&](i64 i, i64 j) { return i >= 1 && i <= H - 2 && j >= 1 && j <= W - 2 && sx[i] != ty[j]; };
-      P->k0_corr = coef(gi - 1, gj) || coef(gi + 1, gj) || coef(gi, gj - 1) || coef(gi, gj + 1);
-    }
-  std::vector<unsigned char> owned;
-  PTRY(build(nsrc, srci, srcj, &P->src, nullptr, "source"));
-  PTRY(build(nrcv, rcvi, rcvj, &P->rcv, &owned, "receiver"));
-  if (P->src.nu > 0) P->srcp = AcPoints{P->src.blk, P->src.cell, P->src.start, P->src.perm};
-  if (P->rcv.nu > 0) P->rcvp = AcPoints{P->rcv.blk, P->rcv.cell, P->rcv.start, P->rcv.perm};
-  PTRY(dev_upload(&P->rcv_owned, owned, st));
-  PTRY(dev_alloc_zero(&P->rcvv, (size_t)((p->NSTEP + 1) * nrcv), st));
+  PTRY(plan_build_points(P, nsrc, srci, srcj, nrcv, rcvi, rcvj));
   PTRY(dev_alloc_zero(&P->loss, 1 + RL_BLOCKS, st));
 
   // adjoint state is allocated lazily (first gradient); history sizing now
   size_t free_b = 0, total_b = 0;
-  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  PCUDA(cudaMemGetInfo(&free_b, &total_b));
   const size_t plane_bytes = (size_t)g.plane * sizeof(double);
   // reserve: adjoint state (3 ubar + 2 phib + 2 psib + G + gradc) + slack
   const size_t reserve = 10 * plane_bytes + (size_t)(2 * (p->NSTEP + 1) * nrcv + 2 * p->NSTEP * nsrc) * 8 + (512u << 20);
@@ -556,14 +606,14 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
       adseis_acoustic_plan_destroy(P);
       return ADSEIS_ENOMEM;
     }
-    CUDA_TRY(cudaMemsetAsync(P->arena, 0, P->arena_bytes, st));
-    CUDA_TRY(cudaMemcpyAsync(P->arena, &d, sizeof(d), cudaMemcpyHostToDevice, st));
+    PCUDA(cudaMemsetAsync(P->arena, 0, P->arena_bytes, st));
+    PCUDA(cudaMemcpyAsync(P->arena, &d, sizeof(d), cudaMemcpyHostToDevice, st));
     char* base = (char*)P->arena;
     P->hist = (double*)(base + d.off_hist);
     for (int k = 0; k < 2; k++) { P->phi[k] = (double*)(base + d.off_phi[k]); P->psi[k] = (double*)(base + d.off_psi[k]); }
     for (int k = 0; k < 3; k++) P->ub[k] = (double*)(base + d.off_ub[k]);
     for (int k = 0; k < 2; k++) { P->phib[k] = (double*)(base + d.off_phib[k]); P->psib[k] = (double*)(base + d.off_psib[k]); }
-    CUDA_TRY(cudaStreamSynchronize(st));
+    PCUDA(cudaStreamSynchronize(st));
   }
   for (size_t k = 1; k < P->seg_b.size(); k++) {
     double* c = nullptr;
@@ -762,7 +812,10 @@ ADSEIS_API int adseis_acoustic_plan_forward(adseis_acoustic_plan* P) {
 }
 
 static int ensure_adjoint_state(adseis_acoustic_plan* P) {
-  if (P->G) return ADSEIS_OK;
+  if (P->G) {
+    if (!P->gradsrcv) TRY(dev_alloc_zero(&P->gradsrcv, (size_t)(P->p.NSTEP * P->nsrc), P->ctx->stream));
+    return ADSEIS_OK;
+  }
   const size_t n = (size_t)P->g.plane;
   cudaStream_t st = P->ctx->stream;
   if (!P->arena) {
@@ -891,6 +944,15 @@ ADSEIS_API int adseis_acoustic_plan_get(adseis_acoustic_plan* P, int what, doubl
     case ADSEIS_GET_LOSS: src = P->loss; n = 1; break;
     case ADSEIS_GET_GRAD_C: src = P->gradc; n = (size_t)P->model_elems; break;
     case ADSEIS_GET_GRAD_SRCV: src = P->gradsrcv; n = (size_t)(P->p.NSTEP * P->nsrc); break;
+    case ADSEIS_GET_GRAD_C_OWNED: {
+      const i64 H = P->g.H, W = P->g.W;
+      if (P->p.mpi_convention) {
+        const i64 r0 = std::max<i64>(P->slab.row0, 1), r1 = std::min<i64>(P->slab.row1, H - 1);
+        src = P->gradc + (r0 - 1) * (W - 2); n = (size_t)(std::max<i64>(r1 - r0, 0) * (W - 2));
+      } else {
+        src = P->gradc + P->slab.row0 * W; n = (size_t)((P->slab.row1 - P->slab.row0) * W);
+      }
+    } break;
     default: adseis_set_error("acoustic_plan_get: unknown item %d", what); return ADSEIS_EINVAL;
   }
   if (what != ADSEIS_GET_RCVV && !P->have_grad) {

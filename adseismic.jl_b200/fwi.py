@@ -17,6 +17,10 @@ def _handoff(t):
 
 
 class _AcousticMisfit(torch.autograd.Function):
+    """The gradients are computed by the same sweep as the loss, so forward() copies them out of the plan right away:
+    a plan that is re-evaluated before backward() runs (several shots or loss terms on one plan, a line-search probe)
+    cannot leak the gradient of a later evaluation into this one."""
+
     @staticmethod
     def forward(ctx, c, srcv, plan):
         cc = c.detach().contiguous().to(torch.float64)
@@ -25,22 +29,26 @@ class _AcousticMisfit(torch.autograd.Function):
             ss = srcv.detach().contiguous().to(torch.float64)
             plan.set_srcv(_handoff(ss), rows=ss.shape[0])
         plan.gradient()
-        ctx.plan, ctx.c_like, ctx.s_like = plan, c, srcv
-        return torch.tensor(plan.loss(), dtype=torch.float64, device=c.device)
-
-    @staticmethod
-    def backward(ctx, gout):
-        plan, c, srcv = ctx.plan, ctx.c_like, ctx.s_like
-        gc = gs = None
+        ctx.gc = ctx.gs = None
         if ctx.needs_input_grad[0]:
             buf = torch.empty(plan.model_shape, dtype=torch.float64, device=c.device)
             plan.grad_c(out=buf if buf.is_cuda else buf.numpy())
             plan.ctx.sync()
-            gc = (gout * buf).reshape(c.shape).to(c.dtype)
+            ctx.gc = buf
         if srcv is not None and ctx.needs_input_grad[1]:
-            g = torch.from_numpy(plan.grad_srcv()).to(srcv.device)
+            ctx.gs = torch.from_numpy(plan.grad_srcv()).to(srcv.device)
+        ctx.c_like, ctx.s_like = c, srcv
+        return torch.tensor(plan.loss(), dtype=torch.float64, device=c.device)
+
+    @staticmethod
+    def backward(ctx, gout):
+        c, srcv = ctx.c_like, ctx.s_like
+        gc = gs = None
+        if ctx.needs_input_grad[0] and ctx.gc is not None:
+            gc = (gout * ctx.gc).reshape(c.shape).to(c.dtype)
+        if srcv is not None and ctx.needs_input_grad[1] and ctx.gs is not None:
             gs = torch.zeros_like(srcv)
-            gs[:g.shape[0]] = gout * g          # rows >= NSTEP of srcv never enter the simulation
+            gs[:ctx.gs.shape[0]] = gout * ctx.gs          # rows >= NSTEP of srcv never enter the simulation
         return gc, gs, None
 
 
@@ -59,25 +67,29 @@ class _ElasticMisfit(torch.autograd.Function):
         if srcv is not None:
             ss = srcv.detach().contiguous().to(torch.float64)
             plan.set_srcv(_handoff(ss), rows=ss.shape[0])
-        ctx.mat = any(t.requires_grad for t in (rho, lam, mu))
-        plan.gradient(ctx.mat)
-        ctx.plan, ctx.like, ctx.s_like = plan, (rho, lam, mu), srcv
+        mat = any(ctx.needs_input_grad[:3])
+        plan.gradient(mat)
+        ctx.g = [None, None, None]
+        if mat:                                   # copied out now: see _AcousticMisfit
+            for k, (t, fn) in enumerate(zip((rho, lam, mu), (plan.grad_rho, plan.grad_lambda, plan.grad_mu))):
+                if ctx.needs_input_grad[k]:
+                    ctx.g[k] = torch.from_numpy(fn()).to(t.device)
+        ctx.gs = torch.from_numpy(plan.grad_srcv()).to(srcv.device) if (srcv is not None and ctx.needs_input_grad[3]) else None
+        ctx.like, ctx.s_like = (rho, lam, mu), srcv
         return torch.tensor(plan.loss(), dtype=torch.float64, device=rho.device)
 
     @staticmethod
     def backward(ctx, gout):
-        plan, srcv = ctx.plan, ctx.s_like
+        srcv = ctx.s_like
         out = [None, None, None]
-        if ctx.mat:
-            for k, fn in enumerate((plan.grad_rho, plan.grad_lambda, plan.grad_mu)):
-                if ctx.needs_input_grad[k]:
-                    t = ctx.like[k]
-                    out[k] = (gout * torch.from_numpy(fn()).to(t.device)).reshape(t.shape).to(t.dtype)
+        for k in range(3):
+            if ctx.needs_input_grad[k] and ctx.g[k] is not None:
+                t = ctx.like[k]
+                out[k] = (gout * ctx.g[k]).reshape(t.shape).to(t.dtype)
         gs = None
-        if srcv is not None and ctx.needs_input_grad[3]:
-            g = torch.from_numpy(plan.grad_srcv()).to(srcv.device)
+        if srcv is not None and ctx.needs_input_grad[3] and ctx.gs is not None:
             gs = torch.zeros_like(srcv)
-            gs[:g.shape[0]] = gout * g
+            gs[:ctx.gs.shape[0]] = gout * ctx.gs
         return out[0], out[1], out[2], gs, None
 
 

@@ -105,54 +105,140 @@ def all_reduce_scalar(x, op="sum", device=None):
 # ------------------------------------------------------------------------------------------------------------
 # shot parallelism
 # ------------------------------------------------------------------------------------------------------------
-def compute_loss_and_grads_GPU(param, srcs, rcvs, Rs, c, ctx=None, plan_cache=None):
-    """compute_loss_and_grads_GPU (src/Utils.jl:300-332) for the acoustic solver: sum over shots of
-    sum((rcvv-Rs)^2) and its gradient w.r.t. the velocity model `c`.  Shots are dealt to the ranks of the current
-    process group with the reference's round-robin rule; the per-rank partial sums are all-reduced, so every rank
-    returns the full (loss, grad).  Works single-process too.  Returns (loss: float, grad: np.ndarray)."""
-    import torch
+def _shot_context(n):
     dist = _dist()
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
+    return rank, world, shot_assignment(n, world)[rank]
+
+
+class ShotPlanCache:
+    """One device-resident plan per GPU, re-pointed at every shot (adseis_acoustic_plan_set_points): the history
+    window / checkpoints / adjoint planes are allocated once per inversion instead of once per shot.  Keep one
+    instance across the L-BFGS iterations of an FWI run; close() it at the end."""
+
+    def __init__(self, hist_bytes_budget=0):
+        self.plan, self.key, self.budget = None, None, hist_bytes_budget
+
+    def acoustic(self, param, src, rcv, ctx):
+        key = ("ac", param.NX, param.NY, param.NSTEP, param.DELTAX, param.DELTAY, param.DELTAT, param.PropagatorKernel,
+               param.mpi_convention, param.NPOINTS_PML, param.Rcoef, param.vp_ref)
+        if self.plan is None or self.key != key:
+            self.close()
+            self.plan = AcousticPlan(param, src.srci, src.srcj, rcv.rcvi, rcv.rcvj, ctx=ctx,
+                                     hist_bytes_budget=self.budget)
+            self.key = key
+        else:
+            self.plan.set_points(src.srci, src.srcj, rcv.rcvi, rcv.rcvj)
+        return self.plan
+
+    def close(self):
+        if self.plan is not None:
+            self.plan.close()
+        self.plan, self.key = None, None
+
+
+def compute_loss_and_grads_GPU(param, srcs, rcvs, Rs, model, ctx=None, plan_cache=None, material_grads=True):
+    """compute_loss_and_grads_GPU (src/Utils.jl:300-332): sum over shots of sum((rcvv-Rs)^2) and its gradient w.r.t. the
+    model.  Acoustic (`srcs` of AcousticSource, `model` = velocity c) or elastic (`srcs` of ElasticSource, `model` =
+    (rho, lambda, mu) -> gradient tuple in the same order).  Shots are dealt to the ranks of the current process group
+    with the reference's round-robin rule (shot k, 1-based, on device k % n_gpu); the per-rank partial sums are
+    all-reduced over NCCL, so every rank returns the full (loss, grad).  Works single-process too.
+    `plan_cache`: a ShotPlanCache kept by the caller across calls (FWI iterations)."""
+    import torch
+    from .structs import ElasticSource
+    rank, world, jobs = _shot_context(len(srcs))
     ctx = ctx or _lib.default_context()
-    jobs = shot_assignment(len(srcs), world)[rank]
-    shape = (param.NX, param.NY) if param.mpi_convention else (param.NX + 2, param.NY + 2)
     on_gpu = torch.cuda.is_available()
     dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
-    gsum = torch.zeros(shape, dtype=torch.float64, device=dev)
+    elastic = len(srcs) > 0 and isinstance(srcs[0], ElasticSource)
+    own_cache = plan_cache is None
+    cache = plan_cache if plan_cache is not None else ShotPlanCache()
+    shape = param.model_shape() if elastic else ((param.NX, param.NY) if param.mpi_convention else (param.NX + 2, param.NY + 2))
+    ngrad = 3 if elastic else 1
+    gsum = [torch.zeros(shape, dtype=torch.float64, device=dev) for _ in range(ngrad)]
     gtmp = torch.empty(shape, dtype=torch.float64, device=dev)
     loss = 0.0
     for k in jobs:
         src, rcv = srcs[k], rcvs[k]
-        key = (k,)
-        plan = plan_cache.get(key) if plan_cache is not None else None
-        if plan is None:
-            plan = AcousticPlan(param, src.srci, src.srcj, rcv.rcvi, rcv.rcvj, ctx=ctx)
-            if plan_cache is not None:
-                plan_cache[key] = plan
-        plan.set_model(c)
+        if elastic:
+            plan = ElasticPlan(param, src.srci, src.srcj, src.srctype, rcv.rcvi, rcv.rcvj, rcv.rcvtype, ctx=ctx,
+                               hist_bytes_budget=cache.budget)
+            plan.set_model(*model)
+        else:
+            plan = cache.acoustic(param, src, rcv, ctx)
+            plan.set_model(model)
         plan.set_srcv(src.srcv)
         plan.set_obs(Rs[k])
-        plan.gradient()
+        if elastic:
+            plan.gradient(material_grads)
+            getters = (plan.grad_rho, plan.grad_lambda, plan.grad_mu) if material_grads else ()
+        else:
+            plan.gradient()
+            getters = (plan.grad_c,)
         loss += plan.loss()
-        plan.grad_c(out=gtmp)      # device -> device on the context's stream, synchronised on return
-        gsum += gtmp
-        if on_gpu:                 # torch's stream must be done with gtmp before the next shot overwrites it
-            torch.cuda.current_stream().synchronize()
+        for g, get in zip(gsum, getters):
+            get(out=gtmp)          # device -> device on the context's stream, synchronised on return
+            g += gtmp
+            if on_gpu:             # torch's stream must be done with gtmp before it is overwritten
+                torch.cuda.current_stream().synchronize()
         rcv.rcvv = plan.rcvv()
-        if plan_cache is None:
+        if elastic:
             plan.close()
-    all_reduce_sum_(gsum)          # NCCL over NVLink: the reference sums per-GPU gradients on the host
+    if own_cache:
+        cache.close()
+    for g in gsum:
+        all_reduce_sum_(g)         # NCCL over NVLink: the reference sums per-GPU gradients on the host
     loss = all_reduce_scalar(loss, "sum", device=dev)
-    return loss, gsum.cpu().numpy()
+    out = [g.cpu().numpy() for g in gsum]
+    return loss, (tuple(out) if elastic else out[0])
+
+
+def compute_forward_GPU(param, srcs, rcvs, model, ctx=None, plan_cache=None):
+    """compute_forward_GPU (src/Utils.jl:574-600): simulated observations of every shot, shots dealt round-robin to the
+    ranks; returns the list Rs (every rank gets all of it; rcvs[k].rcvv is filled too)."""
+    from .structs import ElasticSource
+    from .elastic import elastic_forward
+    rank, world, jobs = _shot_context(len(srcs))
+    ctx = ctx or _lib.default_context()
+    elastic = len(srcs) > 0 and isinstance(srcs[0], ElasticSource)
+    own_cache = plan_cache is None
+    cache = plan_cache if plan_cache is not None else ShotPlanCache()
+    mine = {}
+    for k in jobs:
+        src, rcv = srcs[k], rcvs[k]
+        if elastic:
+            mine[k] = elastic_forward(param, src, *model, rcv, ctx=ctx)[0]
+        else:
+            plan = cache.acoustic(param, src, rcv, ctx)
+            plan.set_model(model)
+            plan.set_srcv(src.srcv)
+            plan.forward()
+            mine[k] = plan.rcvv()
+    if own_cache:
+        cache.close()
+    dist = _dist()
+    parts = [mine]
+    if dist.is_initialized() and world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+    Rs = [None] * len(srcs)
+    for part in parts:
+        for k, v in part.items():
+            Rs[k] = v
+    for k, rcv in enumerate(rcvs):
+        rcv.rcvv = Rs[k]
+    return Rs
 
 
 # ------------------------------------------------------------------------------------------------------------
 # domain decomposition (acoustic)
 # ------------------------------------------------------------------------------------------------------------
 class DomainDecomposedAcoustic:
-    """One slab of the acoustic solver per rank of the current process group.  Inputs are always the GLOBAL arrays
-    (every rank passes the same model / srcv / obs; each keeps what it owns), results are reduced on request."""
+    """One slab of the acoustic solver per rank of the current process group.  The model is always the GLOBAL array
+    (each rank uploads only its rows).  Sources and receivers are given globally; each rank keeps the ones whose row it
+    owns (MPIAcoustic.jl:71-78, 98-104), so srcv / obs / traces travel between host and device only on the owning
+    rank; results are reduced on request."""
 
     def __init__(self, param, srci, srcj, rcvi, rcvj, ctx=None, hist_slots=None):
         import torch
@@ -164,23 +250,27 @@ class DomainDecomposedAcoustic:
         self.geo = slab_geometry(param.NX, param.NY, self.world, self.rank)
         self.dev = torch.device("cuda", torch.cuda.current_device())
         plane_bytes = self.geo["Hl"] * self.geo["ld"] * 8
-        nsrc, nrcv = len(np.atleast_1d(srci)), len(np.atleast_1d(rcvi))
+        srci, srcj, rcvi, rcvj = (np.atleast_1d(np.asarray(x, dtype=np.int64)) for x in (srci, srcj, rcvi, rcvj))
+        self.nsrc, self.nrcv = len(srci), len(rcvi)
+        self.smask = owned_points(srci, self.geo["row0"], self.geo["row1"], param.mpi_convention)
+        self.rmask = owned_points(rcvi, self.geo["row0"], self.geo["row1"], param.mpi_convention)
         if self.world == 1:
             self.plan = AcousticPlan(param, srci, srcj, rcvi, rcvj, ctx=self.ctx)
             return
+        nsrc, nrcv = int(self.smask.sum()), int(self.rmask.sum())
         if hist_slots is None:
             free_b, _ = self.ctx.mem_info()
-            model_bytes = (param.NX + 2) * (param.NY + 2) * 8
-            # adjoint accumulators, checkpoints of the C side, full-size gradient buffers, torch / NCCL workspaces
-            reserve = (16 * plane_bytes + 6 * model_bytes + (4 * (param.NSTEP + 1) * nrcv + 2 * param.NSTEP * nsrc) * 8
-                       + (6 << 30))
+            own_model_bytes = (self.geo["row1"] - self.geo["row0"]) * (param.NY + 2) * 8
+            # adjoint accumulators, checkpoints of the C side, gradient buffers, torch / NCCL workspaces
+            reserve = (16 * plane_bytes + 6 * own_model_bytes + (param.NX + 2) * (param.NY + 2) * 8 +
+                       (4 * (param.NSTEP + 1) * nrcv + 2 * param.NSTEP * nsrc) * 8 + (6 << 30))
             slots = max(0, free_b - reserve) // plane_bytes
             W = plan_window(param.NSTEP, slots)
             hist_slots = int(all_reduce_scalar(W, "min", device=self.dev))   # every rank must use the same window
         self.hist_slots = hist_slots
         slab = (self.rank, self.world, self.geo["row0"], self.geo["row1"])
-        self.plan = AcousticPlan(param, srci, srcj, rcvi, rcvj, ctx=self.ctx, slab=slab,
-                                 hist_bytes_budget=hist_slots * plane_bytes)
+        self.plan = AcousticPlan(param, srci[self.smask], srcj[self.smask], rcvi[self.rmask], rcvj[self.rmask],
+                                 ctx=self.ctx, slab=slab, hist_bytes_budget=hist_slots * plane_bytes)
         handles = [None] * self.world
         dist.all_gather_object(handles, self.plan.ipc_export())
         lo = handles[self.rank - 1] if self.rank > 0 else None
@@ -188,14 +278,19 @@ class DomainDecomposedAcoustic:
         self.plan.ipc_connect(lo, hi)
         dist.barrier()
 
+    def _cols(self, a, mask):
+        if self.world == 1:
+            return a
+        return np.ascontiguousarray(np.asarray(a)[:, mask])
+
     def set_model(self, c):
         self.plan.set_model(c)
 
     def set_srcv(self, srcv):
-        self.plan.set_srcv(srcv)
+        self.plan.set_srcv(self._cols(srcv, self.smask))
 
     def set_obs(self, obs):
-        self.plan.set_obs(obs)
+        self.plan.set_obs(self._cols(obs, self.rmask))
 
     def forward(self):
         self.plan.forward()
@@ -206,24 +301,34 @@ class DomainDecomposedAcoustic:
     def loss(self):
         return all_reduce_scalar(self.plan.loss(), "sum", device=self.dev)
 
-    def rcvv(self):
+    def _scatter_cols(self, a, mask, n):
         import torch
-        t = torch.from_numpy(self.plan.rcvv()).to(self.dev)
-        return all_reduce_sum_(t).cpu().numpy()   # every receiver is owned by exactly one slab, the others hold 0
+        if self.world == 1:
+            return a
+        full = np.zeros((a.shape[0], n))
+        full[:, mask] = a
+        return all_reduce_sum_(torch.from_numpy(full).to(self.dev)).cpu().numpy()   # every point has exactly one owner
+
+    def rcvv(self):
+        return self._scatter_cols(self.plan.rcvv(), self.rmask, self.nrcv)
 
     def grad_c(self, reduce=True):
         import torch
         shape = self.plan.model_shape
-        t = torch.empty(shape, dtype=torch.float64, device=self.dev)
-        self.plan.grad_c(out=t)                   # own rows filled, the rest zero
+        t = torch.zeros(shape, dtype=torch.float64, device=self.dev)
+        first, cnt = self.plan.owned_model_rows()
+        if cnt > 0:
+            self.plan.grad_c_owned(out=t[first:first + cnt])      # device -> device, own rows only
         if reduce:
             all_reduce_sum_(t)
         return t
 
+    def grad_c_owned(self, out=None):
+        """(first_row, rows): this rank's shard of the model gradient (no collective)."""
+        return self.plan.grad_c_owned(out=out)
+
     def grad_srcv(self):
-        import torch
-        t = torch.from_numpy(self.plan.grad_srcv()).to(self.dev)
-        return all_reduce_sum_(t).cpu().numpy()
+        return self._scatter_cols(self.plan.grad_srcv(), self.smask, self.nsrc)
 
     def close(self):
         self.plan.close()
@@ -334,25 +439,21 @@ class DomainDecomposedElastic:
 
 def bench_domain_decomposed(A, w, args, rank, world, local_rank):
     """bench.py at N > 1: the C4 workload slab-partitioned over the ranks (strong scaling).  Returns the JSON dict
-    (meaningful on rank 0)."""
-    import json
+    (meaningful on rank 0) plus the context under "_ctx" for the extra workloads."""
     import time
     import torch
     import bench as B
     init_process_group("nccl")
     dist = _dist()
     ctx = A.Context(local_rank)
-    p = A.AcousticPropagatorParams(PropagatorKernel=1, NX=w["NX"], NY=w["NY"], NSTEP=w["NSTEP"], DELTAX=w["DELTAX"], DELTAY=w["DELTAY"],
-                                   DELTAT=w["DELTAT"], Rcoef=w["Rcoef"], vp_ref=w["vp_ref"],
-                                   NPOINTS_PML=w["NPOINTS_PML"], mpi_convention=True)
-    srcv_np = (A.Ricker(p, 100.0, 500.0) * 1e6).reshape(-1, 1)
-    dd = DomainDecomposedAcoustic(p, w["srci"], w["srcj"], w["rcvi"], w["rcvj"], ctx=ctx)
-    nrcv = len(w["rcvi"])
+    p, sh = w["param"], w["shots"][0]
+    dd = DomainDecomposedAcoustic(p, sh["srci"], sh["srcj"], sh["rcvi"], sh["rcvj"], ctx=ctx)
+    nrcv = len(sh["rcvi"])
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    h_c2, h_srcv = pin(w["c2"]), pin(srcv_np)
-    dd.set_model(w["c2_background"]); dd.set_srcv(srcv_np); dd.forward()
-    h_obs = pin(dd.rcvv())
-    dd.set_model(h_c2.numpy()); dd.set_srcv(h_srcv.numpy()); dd.set_obs(h_obs.numpy())
+    h_c2, h_srcv = pin(w["model"]), pin(dd._cols(sh["srcv"], dd.smask))
+    dd.set_model(w["model_obs"]); dd.set_srcv(sh["srcv"]); dd.forward()
+    h_obs = pin(dd.plan.rcvv())                     # this rank's receivers only
+    dd.plan.set_model(h_c2.numpy()); dd.plan.set_srcv(h_srcv.numpy()); dd.plan.set_obs(h_obs.numpy())
     for _ in range(args.warmup):
         dd.gradient()
     ctx.sync(); dist.barrier()
@@ -370,41 +471,101 @@ def bench_domain_decomposed(A, w, args, rank, world, local_rank):
     tm, info = dd.plan.timings(), dd.plan.info()
     loss = dd.loss()
     sec = ms / 1e3 / args.steps
-    cells = w["NX"] * w["NY"] * (w["NSTEP"] - 1)
-    # e2e: host model / srcv / obs in, loss + (sharded) gradient rows out, every step
-    rows = dd.geo["row1"] - dd.geo["row0"]
-    h_grad = torch.empty((w["NX"], w["NY"]), dtype=torch.float64).pin_memory()
+    cells = p.NX * p.NY * (p.NSTEP - 1)
+    # e2e: host model rows / owned srcv / owned obs in, loss + this rank's gradient rows out, every step
+    first, cnt = dd.plan.owned_model_rows()
+    h_grad = torch.empty((cnt, dd.plan.model_shape[1]), dtype=torch.float64).pin_memory()
     ctx.sync(); dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        dd.set_model(h_c2.numpy()); dd.set_srcv(h_srcv.numpy()); dd.set_obs(h_obs.numpy())
+        dd.plan.set_model(h_c2.numpy()); dd.plan.set_srcv(h_srcv.numpy()); dd.plan.set_obs(h_obs.numpy())
         dd.gradient()
         loss_e2e = dd.loss()
-        dd.plan.grad_c(out=h_grad.numpy())
+        dd.plan.grad_c_owned(out=h_grad.numpy())
     ctx.sync(); dist.barrier()
     sec_e2e = all_reduce_scalar(time.perf_counter() - t0, "max", device=dd.dev) / args.steps
     clk = clocks.stop() if rank == 0 else None
+    # gradient fingerprint (must not depend on N): sum and sum of squares over the shards
+    g = h_grad.numpy().astype(np.longdouble)
+    gsum = all_reduce_scalar(float(g.sum()), "sum", device=dd.dev)
+    gsq = all_reduce_scalar(float((g * g).sum()), "sum", device=dd.dev)
+    h2d_mine = (cnt * dd.plan.model_shape[1] + h_srcv.numel() + h_obs.numel()) * 8
+    h2d = all_reduce_scalar(h2d_mine, "sum", device=dd.dev)
+    d2h = all_reduce_scalar(h_grad.numel() * 8 + 8, "sum", device=dd.dev)
     peak, peak_src = B.measured_peaks()
-    # per-GPU algorithmic bytes of the dominant kernel: this rank's rows
-    frac_rows = rows / float(w["NX"] + 2)
-    ab = B.algorithmic_bytes(w)
+    rows = dd.geo["row1"] - dd.geo["row0"]
+    frac_rows = rows / float(p.NX + 2)
+    ab = A.workloads.algorithmic_bytes(w)
     adj_us = tm["adjoint_ms"] * 1e3 / max(tm["adjoint_launches"], 1)
-    achieved = ab["adjoint"] * frac_rows / (adj_us * 1e-6) / 1e9
-    roof = dict(bound="hbm", kernel="ac_adj_kernel (+ halo exchange, per GPU, rank 0)", achieved=achieved, peak=peak,
-                unit="GB/s", frac=achieved / peak, traffic=None, peak_source=peak_src,
-                bytes_per_launch=ab["adjoint"] * frac_rows, us_per_launch=adj_us,
-                note="launch duration includes the per-step peer halo exchange that follows every kernel")
-    cfg = dict(workload=w["name"], grid=[w["NX"], w["NY"]], nstep=w["NSTEP"], shots=1, dx=w["DELTAX"], dt=w["DELTAT"],
-               npml=w["NPOINTS_PML"], nrcv=nrcv, parallelism="slab domain decomposition x%d (NVLink peer halo rows)" % world,
+    fwd_us = (tm["forward_ms"] + tm["recompute_ms"]) * 1e3 / max(tm["forward_launches"] + tm["recompute_launches"], 1)
+    roof = B.roof_entry("ac_adj_kernel (+ fused halo exchange, per GPU, rank 0)", ab["adjoint"] * frac_rows, adj_us, peak,
+                        peak_src, share=tm["adjoint_ms"] / (ms / args.steps),
+                        note="launch duration includes the in-kernel peer halo push / wait of every step")
+    roof["other_kernels"] = dict(ac_fwd_kernel=B.roof_entry("ac_fwd_kernel (+ fused halo exchange)", ab["forward"] * frac_rows,
+                                                            fwd_us, peak, peak_src))
+    whole = (ab["forward"] + ab["adjoint"]) * (p.NSTEP - 1) / sec / 1e9 / world
+    roof["whole_gradient"] = dict(achieved=whole, frac=whole / peak, unit="GB/s per GPU")
+    cfg = dict(workload=w["name"], grid=[p.NX, p.NY], nstep=p.NSTEP, shots=1, dx=p.DELTAX, dt=p.DELTAT,
+               npml=p.NPOINTS_PML, nrcv=nrcv, parallelism="slab domain decomposition x%d (NVLink peer halo rows)" % world,
                history_slots=info["hist_slots"], segments=info["segments"],
                recomputed_forward_steps=info["recomputed_steps"],
                l2_policy="working set far exceeds L2; no explicit flush")
     out = dict(metric=B.METRIC, value=cells / sec / 1e9, unit=B.UNIT, n_gpus=world, steps=args.steps,
                warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None,
                dtype="f64", data="synthetic", config=cfg, clocks=clk,
-               e2e=dict(value=cells / sec_e2e / 1e9, unit=B.UNIT,
-                        h2d_bytes_per_step=(h_c2.numel() + h_srcv.numel() + h_obs.numel()) * 8 * world,
-                        d2h_bytes_per_step=(h_grad.numel() * 8 + 8) * world, ms_per_step=sec_e2e * 1e3),
-               gpu_launches=launches * world, roofline=roof, loss=loss, loss_e2e=loss_e2e)
+               e2e=dict(value=cells / sec_e2e / 1e9, unit=B.UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                        ms_per_step=sec_e2e * 1e3,
+                        note="every rank moves only the model rows, source columns, trace columns and gradient rows it owns"),
+               gpu_launches=launches * world, roofline=roof, loss=loss, loss_e2e=loss_e2e, grad_checksum=[gsum, gsq])
     dd.close()
+    out["_ctx"] = ctx
     return out
+
+
+def bench_elastic_domain_decomposed(A, w, steps, warmup, rank, world, ctx):
+    """C5 at N > 1: elastic variant M, slab-decomposed; source-time-function gradient and material gradient."""
+    import torch
+    import bench as B
+    dist = _dist()
+    p, sh = w["param"], w["shots"][0]
+    dd = DomainDecomposedElastic(p, sh["srci"], sh["srcj"], sh["srctype"], sh["rcvi"], sh["rcvj"], sh["rcvtype"], ctx=ctx)
+    dd.set_model(*w["model_obs"]); dd.set_srcv(sh["srcv"]); dd.forward()
+    obs = dd.rcvv()
+    dd.set_model(*w["model"]); dd.set_obs(obs)
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        ctx.sync(); dist.barrier()
+        l0 = ctx.launch_count()
+        ctx.timer_start()
+        for _ in range(steps):
+            fn()
+        ms = ctx.timer_stop_ms() / steps
+        dist.barrier()
+        return all_reduce_scalar(ms, "max", device=dd.dev), (ctx.launch_count() - l0) // steps
+
+    ms_f, _ = timed(dd.forward)
+    ms_s, _ = timed(lambda: dd.gradient(False))
+    ms_m, l_m = timed(lambda: dd.gradient(True))
+    info = dd.plan.info()
+    loss = dd.loss()
+    gl = dd.plan.grad_lambda().astype(np.longdouble)
+    gsum = all_reduce_scalar(float(gl.sum()), "sum", device=dd.dev)
+    gsq = all_reduce_scalar(float((gl * gl).sum()), "sum", device=dd.dev)
+    dd.close()
+    peak, peak_src = B.measured_peaks()
+    ab = A.workloads.algorithmic_bytes(w)
+    n, replay = p.NSTEP, info["recomputed_steps"]
+    cells = p.NX * p.NY * n
+    fwd_us, adj_mat_us = ms_f * 1e3 / n, (ms_m - ms_f * (1 + replay / n)) * 1e3 / n
+    roof = B.roof_entry("el_vel_adj<1> + el_sigma_adj<1> (+ fused halo pushes), per GPU", ab["adjoint"] / world, adj_mat_us,
+                        peak, peak_src)
+    roof["other_kernels"] = {"forward step": B.roof_entry("el_sigma_fwd + el_vel_fwd", ab["forward"] / world, fwd_us, peak, peak_src)}
+    return dict(workload=w["name"], metric=B.METRIC, unit=B.UNIT, value=cells / (ms_m * 1e-3) / 1e9, ms_per_step=ms_m,
+                value_forward_only=cells / (ms_f * 1e-3) / 1e9, value_source_gradient=cells / (ms_s * 1e-3) / 1e9,
+                n_gpus=world, scaling="strong", gpu_launches=int(l_m) * world, roofline=roof, loss=loss,
+                grad_checksum=[gsum, gsq],
+                config=dict(grid=[p.NX, p.NY], nstep=n, variant="M", history_slots=info["hist_slots"],
+                            segments=info["segments"], recomputed_forward_steps=replay,
+                            parallelism="slab domain decomposition x%d" % world))

@@ -102,6 +102,11 @@ int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acoustic_params* p
                                 const int64_t* rcvi, const int64_t* rcvj, size_t hist_bytes_budget,
                                 adseis_acoustic_plan** out);
 int adseis_acoustic_plan_destroy(adseis_acoustic_plan* plan);
+/* Replace the plan's sources and receivers (the next shot on the same grid and model): the device state is kept, so a
+ * multi-shot gradient -- compute_loss_and_grads_GPU / compute_forward_GPU, src/Utils.jl:300-332, 574-600 -- runs on
+ * one plan per GPU.  Invalidates srcv / obs / results: call set_srcv (and set_obs) again. */
+int adseis_acoustic_plan_set_points(adseis_acoustic_plan* plan, int64_t nsrc, const int64_t* srci,
+                                    const int64_t* srcj, int64_t nrcv, const int64_t* rcvi, const int64_t* rcvj);
 
 /* c: velocity, (NX+2)*(NY+2) [mpi_convention=0] or c^2, NX*NY [mpi_convention=1]; ALWAYS the global array
  * (a slab plan copies its rows).  on_device!=0: `c` is a device pointer on the plan's GPU. */
@@ -120,6 +125,9 @@ int adseis_acoustic_plan_gradient(adseis_acoustic_plan* plan);
 #define ADSEIS_GET_LOSS 2      /* 1 */
 #define ADSEIS_GET_GRAD_C 3    /* same shape as the model passed to set_model; slab plans fill their rows, rest 0 */
 #define ADSEIS_GET_GRAD_SRCV 4 /* NSTEP*nsrc ; slab plans: columns of sources owned elsewhere are 0 */
+#define ADSEIS_GET_GRAD_C_OWNED 8 /* slab plans: only the model rows this slab owns, contiguous (the rows
+                                   * [max(row0,1)-1, min(row1,NX+1)-1) of an NX x NY model under mpi_convention, rows
+                                   * [row0,row1) of the padded model otherwise): what a sharded optimiser needs back */
 /* Synchronises the ctx stream, then copies result `what` to dst (host, or device when to_device!=0). */
 int adseis_acoustic_plan_get(adseis_acoustic_plan* plan, int what, double* dst, int to_device);
 /* Copy wavefield snapshot `slot` (0..NSTEP) in the caller's layout ((NX+2)*(NY+2), or NX*NY under

@@ -140,8 +140,41 @@ def main():
         srcs.append(A.AcousticSource(si, sj, sv)); rcvs.append(A.AcousticReceiver(ri, rj)); Rs.append(ob)
     L, g = parallel.compute_loss_and_grads_GPU(p, srcs, rcvs, Rs, c, ctx=ctx)
     assert abs(L - Ltot) / Ltot < 1e-12 and relerr(g, gtot) < 1e-10
+    # one plan per GPU re-pointed at every shot (adseis_acoustic_plan_set_points), reused across evaluations
+    cache = parallel.ShotPlanCache()
+    R2 = parallel.compute_forward_GPU(p, srcs, rcvs, c, ctx=ctx, plan_cache=cache)       # compute_forward_GPU, Utils.jl:574-600
+    assert all(np.array_equal(R2[k], 2.0 * Rs[k]) for k in range(nshots))               # obs were 0.5 * traces
+    for _ in range(2):
+        L2, g2 = parallel.compute_loss_and_grads_GPU(p, srcs, rcvs, Rs, c, ctx=ctx, plan_cache=cache)
+        assert L2 == L and np.array_equal(g2, g)
+    cache.close()
+    # elastic sources through the same entry point (the reference's signature takes ElasticSource too, Utils.jl:300)
+    NXe, NYe, NSe = 50, 64, 24
+    axe, bxe = po.elastic_cpml_1d(NXe, 1.0, 1e-4, npml=6, vp_ref=3300.0, alpha_max=np.pi * 15)
+    aye, bye = po.elastic_cpml_1d(NYe, 1.0, 1e-4, npml=6, vp_ref=3300.0, alpha_max=np.pi * 15)
+    rng3 = np.random.default_rng(5)
+    rho = 2800.0 * (1 + 0.1 * rng3.random((NXe + 2, NYe + 2)))
+    vpe = 3000.0 * (1 + 0.1 * rng3.random((NXe + 2, NYe + 2)))
+    mu, lam = rho * (vpe / 1.732) ** 2, rho * (vpe ** 2 - 2 * (vpe / 1.732) ** 2)
+    pe = A.ElasticPropagatorParams(NX=NXe, NY=NYe, NSTEP=NSe, DELTAX=1.0, DELTAY=1.0, DELTAT=1e-4, NPOINTS_PML=6,
+                                   vp_ref=3300.0, ALPHA_MAX_PML=np.pi * 15, variant=0)
+    es, er, eR, eL, eg = [], [], [], 0.0, [0.0, 0.0, 0.0]
+    for k in range(3):
+        si, sj, ty = np.array([12 + 9 * k]), np.array([20 + 10 * k]), np.array([k])
+        sv = po.ricker(NSe, 5.0, 8.0, 1e4).reshape(-1, 1)
+        ri, rj, rt = np.arange(8, 44, 3), np.full(12, 30), np.arange(12) % 5
+        a = (0, NXe, NYe, NSe, 1e-4, 1.0, 1.0, axe, bxe, aye, bye, rho, lam, mu, si, sj, ty, sv, ri, rj, rt)
+        r0e, _ = po.elastic_forward(*a)
+        O = po.elastic_misfit_grad(*a, 0.5 * r0e)
+        eL += O["loss"]
+        for q, key in enumerate(("grad_rho", "grad_lam", "grad_mu")):
+            eg[q] = eg[q] + O[key]
+        es.append(A.ElasticSource(si, sj, ty, sv)); er.append(A.ElasticReceiver(ri, rj, rt)); eR.append(0.5 * r0e)
+    Le, ge = parallel.compute_loss_and_grads_GPU(pe, es, er, eR, (rho, lam, mu), ctx=ctx)
+    assert abs(Le - eL) / eL < 1e-12 and all(relerr(ge[q], eg[q]) < 1e-10 for q in range(3))
     if rank == 0:
-        print("shot-parallel x%d ok: loss rel %.1e grad rel %.1e" % (world, abs(L - Ltot) / Ltot, relerr(g, gtot)), flush=True)
+        print("shot-parallel x%d ok: loss rel %.1e grad rel %.1e; plan reuse and elastic shots ok" %
+              (world, abs(L - Ltot) / Ltot, relerr(g, gtot)), flush=True)
     import torch.distributed as dist
     dist.barrier()
     dist.destroy_process_group()
