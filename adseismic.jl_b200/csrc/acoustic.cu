@@ -115,6 +115,14 @@ struct adseis_acoustic_plan {
   AcGeom g;
   AcTiling t;
   int nblocks = 0;   // CTAs per time-step launch
+  // temporal blocking (two forward steps per launch; single-GPU plans with a large enough PML-free box):
+  //   t2 = marching-only tiling of the box shrunk by two cells, tf = frame-only tiling of everything else
+  bool tb = false;
+  AcTiling t2{}, tf{};
+  int nblocks2 = 0, nblocksf = 0;
+  int box_i0 = 0, box_i1 = -1, box_j0 = 0, box_j1 = -1;  // PML-free box (global padded indices, inclusive)
+  PointSetStorage srcF, rcvF, srcM, rcvM, srcH;          // points by owner under tf (frame) / t2 (box) / t2 + rim
+  AcPoints srcFp{}, rcvFp{}, srcMp{}, rcvMp{}, srcHp{};
   int fast_rows = 0; // rows of the PML-free box owned by this GPU
   int own0, own1;  // owned local rows [own0, own1)
   i64 model_elems; // elements of the caller's model array
@@ -246,6 +254,8 @@ ADSEIS_API int adseis_acoustic_plan_destroy(adseis_acoustic_plan* P) {
   }
   for (double* c : P->ckpt) cudaFree(c);
   free_point_set(&P->src); free_point_set(&P->rcv);
+  free_point_set(&P->srcF); free_point_set(&P->rcvF); free_point_set(&P->srcM); free_point_set(&P->rcvM);
+  free_point_set(&P->srcH);
   cudaFree(P->rcv_owned);
   cudaFree(P->srcv); cudaFree(P->rcvv); cudaFree(P->obs); cudaFree(P->res); cudaFree(P->loss);
   cudaFree(P->G); cudaFree(P->gradc); cudaFree(P->gradsrcv); cudaFree(P->ut[0]); cudaFree(P->ut[1]);
@@ -267,6 +277,61 @@ static int validate_params(const adseis_acoustic_params* p) {
           "acoustic: PropagatorKernel=%d not supported (0 = TF-op scheme, Core.jl:528-549; 1 = custom-op scheme; "
           "2 is numerically identical to 1)", p->PropagatorKernel);
   return ADSEIS_OK;
+}
+
+// Temporal blocking: tilings of the two-step forward path (see ac_fwd2_kernel).  Single-GPU plans only; the marched box
+// is the PML-free box shrunk by TWO cells so that the one-cell rim of every tile is made of plain interior cells.
+static void build_tb_tilings(adseis_acoustic_plan* P) {
+  P->tb = false;
+  const char* e = getenv("ADSEIS_AC_TB");
+  if (e && e[0] == '0') return;
+  if (P->slab.nranks != 1) return;
+  const AcGeom& g = P->g;
+  const int fi0 = P->box_i0 + 2, fi1 = P->box_i1 - 2, fj0 = P->box_j0 + 2, fj1 = P->box_j1 - 2;
+  const int mr0 = std::max(P->own0, fi0 - g.goff), mr1 = std::min(P->own1, fi1 + 1 - g.goff);
+  const int mc0 = round_up(std::max(fj0, 1), 16);
+  const int mc_end = mc0 + 2 * ((fj1 + 1 - mc0) / 2);
+  if (mr1 - mr0 < 8 || mc_end - mc0 < 32) return;
+  AcTiling& t = P->t2;
+  memset(&t, 0, sizeof(t));
+  t.mr0 = mr0; t.mr1 = mr1; t.mc0 = mc0; t.mc_end = mc_end;
+  const int nwarpcols = (mc_end - mc0 + AC_WCOLS - 1) / AC_WCOLS;
+  t.nct = (nwarpcols + AC_WARPS - 1) / AC_WARPS;
+  const int rows = mr1 - mr0;
+  {
+    // whole waves of 2 CTAs per SM, up to 3 waves while a CTA keeps >= 16 rows (two of its rows are rim overhead)
+    const int slots = 2 * P->ctx->sm_count;
+    const int per_wave = std::max(1, slots / t.nct);
+    const int waves = std::min(3, std::max(1, rows / (16 * per_wave)));
+    const int want_tr = per_wave * waves;
+    int rb = (rows + want_tr - 1) / want_tr;
+    rb = std::min(256, std::max(4, rb));
+    if (getenv("ADSEIS_AC_RB2")) rb = std::max(2, atoi(getenv("ADSEIS_AC_RB2")));
+    t.rb = rb;
+  }
+  t.ntr = (rows + t.rb - 1) / t.rb;
+  t.nmarch = t.nct * t.ntr;
+  P->nblocks2 = t.nmarch;
+  // frame-only tiling: everything outside [mr0, mr1) x [mc0, mc_end)
+  AcTiling& f = P->tf;
+  memset(&f, 0, sizeof(f));
+  f.mr0 = f.mr1 = P->own0;  // no marched rows
+  f.rb = 1;
+  auto add_rect = [&](int r0, int r1, int c0, int c1) {
+    if (r1 <= r0 || c1 <= c0) return;
+    const int k = f.nrect++;
+    f.rr0[k] = r0; f.rr1[k] = r1; f.rc0[k] = c0; f.rc1[k] = c1;
+    const i64 cells = (i64)(r1 - r0) * (c1 - c0);
+    f.rblk[k + 1] = f.rblk[k] + (int)((cells + AC_FRAME_CELLS - 1) / AC_FRAME_CELLS);
+  };
+  f.rblk[0] = 0;
+  add_rect(P->own0, mr0, 0, g.W);
+  add_rect(mr1, P->own1, 0, g.W);
+  add_rect(mr0, mr1, 0, mc0);
+  add_rect(mr0, mr1, mc_end, g.W);
+  for (int k = f.nrect; k < 4; k++) { f.rblk[k + 1] = f.rblk[f.nrect]; f.rr0[k] = f.rr1[k] = f.rc0[k] = 0; f.rc1[k] = 1; }
+  P->nblocksf = f.rblk[f.nrect];
+  P->tb = true;
 }
 
 // Sources / receivers of a plan: keep the points whose padded row is owned (MPIAcoustic.jl:71-78, 98-104), group them
@@ -336,6 +401,62 @@ static int plan_build_points(adseis_acoustic_plan* P, int64_t nsrc, const int64_
   TRY(dev_upload(&P->rcv_owned, owned, st));
   TRY(dev_alloc_zero(&P->rcvv, (size_t)((p->NSTEP + 1) * nrcv), st));
   if (P->G) TRY(dev_alloc_zero(&P->gradsrcv, (size_t)(p->NSTEP * nsrc), st));  // adjoint state already exists
+  // two-step path: the same points grouped by owner under the frame-only tiling (frame points), under the box tiling
+  // (box points), and -- sources only -- under every box tile whose one-cell rim contains them (injection into the
+  // tile's private copy of the intermediate time level)
+  free_point_set(&P->srcF); free_point_set(&P->rcvF); free_point_set(&P->srcM); free_point_set(&P->rcvM);
+  free_point_set(&P->srcH);
+  P->srcFp = P->rcvFp = P->srcMp = P->rcvMp = P->srcHp = AcPoints{};
+  if (P->tb) {
+    const AcTiling &t2 = P->t2, &tf = P->tf;
+    auto in_box = [&](int li, int j) { return li >= t2.mr0 && li < t2.mr1 && j >= t2.mc0 && j < t2.mc_end; };
+    auto owner_f = [&](int li, int j) -> int {
+      for (int k = 0; k < tf.nrect; k++)
+        if (li >= tf.rr0[k] && li < tf.rr1[k] && j >= tf.rc0[k] && j < tf.rc1[k])
+          return tf.rblk[k] + (int)(((i64)(li - tf.rr0[k]) * (tf.rc1[k] - tf.rc0[k]) + (j - tf.rc0[k])) / AC_FRAME_CELLS);
+      return -1;
+    };
+    auto build2 = [&](i64 n, const int64_t* pi, const int64_t* pj, int mode, int nblk, PointSetStorage* dst) -> int {
+      std::vector<int> own, cells, gid, none;
+      for (i64 k = 0; k < n; k++) {
+        const i64 gi = pi[k] + ioff, gj = pj[k] + ioff;
+        const int li = (int)(gi - g.goff), j = (int)gj;
+        if (mode == 0) {          // frame
+          if (in_box(li, j)) continue;
+          const int o = owner_f(li, j);
+          REQUIRE(o >= 0, "acoustic plan: internal error: frame cell (%d,%d) has no owner CTA", li, j);
+          own.push_back(o); cells.push_back(li * g.ld + j); gid.push_back((int)k);
+        } else if (mode == 1) {   // box
+          if (!in_box(li, j)) continue;
+          own.push_back(ac_row_tile_of(t2, li) * t2.nct + (j - t2.mc0) / AC_TILE_COLS);
+          cells.push_back(li * g.ld + j); gid.push_back((int)k);
+        } else {                  // every box tile whose (tile + rim) holds the cell
+          if (li < t2.mr0 - 1 || li > t2.mr1 || j < t2.mc0 - 1 || j > t2.mc_end) continue;
+          for (int tr = 0; tr < t2.ntr; tr++) {
+            int r0, r1;
+            ac_row_tile(t2, tr, &r0, &r1);
+            if (li < r0 - 1 || li > r1) continue;
+            for (int ct = 0; ct < t2.nct; ct++) {
+              const int c0 = t2.mc0 + ct * AC_TILE_COLS, c1 = std::min(c0 + AC_TILE_COLS, t2.mc_end);
+              if (j < c0 - 1 || j > c1) continue;
+              own.push_back(tr * t2.nct + ct); cells.push_back(li * g.ld + j); gid.push_back((int)k);
+            }
+          }
+        }
+      }
+      PointSetHost h;
+      build_point_set(own, cells, gid, none, nblk, &h);
+      return upload_point_set(h, dst, st);
+    };
+    TRY(build2(nsrc, srci, srcj, 0, P->nblocksf, &P->srcF));
+    TRY(build2(nrcv, rcvi, rcvj, 0, P->nblocksf, &P->rcvF));
+    TRY(build2(nsrc, srci, srcj, 1, P->nblocks2, &P->srcM));
+    TRY(build2(nrcv, rcvi, rcvj, 1, P->nblocks2, &P->rcvM));
+    TRY(build2(nsrc, srci, srcj, 2, P->nblocks2, &P->srcH));
+    auto view = [](const PointSetStorage& q) { return q.nu > 0 ? AcPoints{q.blk, q.cell, q.start, q.perm} : AcPoints{}; };
+    P->srcFp = view(P->srcF); P->rcvFp = view(P->rcvF); P->srcMp = view(P->srcM); P->rcvMp = view(P->rcvM);
+    P->srcHp = view(P->srcH);
+  }
   return ADSEIS_OK;
 }
 
@@ -368,6 +489,7 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     CUDA_TRY(cudaFuncSetAttribute(ac_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_FWD_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(ac_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_FWD_SMEM));
   }
+  CUDA_TRY(cudaFuncSetAttribute(ac_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_FWD2_SMEM));
   if (AC_ADJ_SMEM > 0) {
     CUDA_TRY(cudaFuncSetAttribute(ac_adj_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_ADJ_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(ac_adj_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_ADJ_SMEM));
@@ -444,6 +566,7 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
   int ia, ib, ja, jb;
   box(sx, (int)p->NX, &ia, &ib);
   box(ty, (int)p->NY, &ja, &jb);
+  P->box_i0 = ia; P->box_i1 = ib; P->box_j0 = ja; P->box_j1 = jb;
   {
     // fast region = box shrunk by one cell: every stencil neighbour is PML-free, interior, and has phi=psi=0
     // (PropagatorKernel=0: by two cells -- the adjoint of a neighbour's u' collects phibar/psibar of ITS neighbours)
@@ -547,6 +670,7 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     PTRY(dev_upload(&P->perm, order, st));
   }
 
+  build_tb_tilings(P);
   PTRY(dev_upload(&P->sigx, sx, st));
   PTRY(dev_upload(&P->tauy, ty, st));
   PTRY(dev_alloc_zero(&P->c2, (size_t)g.plane, st));
@@ -726,6 +850,26 @@ static AcFuse make_fuse(adseis_acoustic_plan* P, int arr_u, i64 idx_u, int arr_p
   return f;
 }
 
+// one forward step s (slot s from slots s-1, s-2) with the one-step kernel; `frame_only`: only the cells outside the
+// two-step box (tiling tf) -- the box cells of that slot are written by ac_fwd2_kernel
+static int launch_forward_step(adseis_acoustic_plan* P, i64 base, i64 s, bool sample, bool frame_only) {
+  const AcGeom& g = P->g;
+  cudaStream_t st = P->ctx->stream;
+  AcPoints none{};
+  AcFuse fuse;
+  if (frame_only) memset(&fuse, 0, sizeof(fuse));
+  else fuse = make_fuse(P, AR_HIST, s - base, AR_PHI, s & 1);
+  const AcPoints srcp = frame_only ? P->srcFp : P->srcp, rcvp = frame_only ? P->rcvFp : P->rcvp;
+  CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), P->p.PropagatorKernel == 0 ? ac_fwd_kernel<0> : ac_fwd_kernel<1>,
+                       frame_only ? P->nblocksf : P->nblocks, AC_FWD_THREADS, frame_only ? 0 : AC_FWD_SMEM, st,
+      g, frame_only ? P->tf : P->t, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, P->phi[(s - 1) & 1],
+      P->psi[(s - 1) & 1], P->sigx, P->tauy, win_slot(P, base, s), P->phi[s & 1], P->psi[s & 1], srcp,
+      P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, sample ? rcvp : none,
+      (sample && P->nrcv > 0) ? P->rcvv + s * P->nrcv : nullptr, fuse));
+  LAUNCH_CHECK(P);
+  return ADSEIS_OK;
+}
+
 static int run_forward_steps(adseis_acoustic_plan* P, i64 base, i64 s_first, i64 s_last, bool sample) {
   const AcGeom& g = P->g;
   cudaStream_t st = P->ctx->stream;
@@ -734,16 +878,23 @@ static int run_forward_steps(adseis_acoustic_plan* P, i64 base, i64 s_first, i64
     adseis_set_error("acoustic slab plan: adseis_acoustic_plan_ipc_connect has not been called");
     return ADSEIS_ESTATE;
   }
-  for (i64 s = s_first; s <= s_last; s++) {
-    const AcFuse fuse = make_fuse(P, AR_HIST, s - base, AR_PHI, s & 1);
-    CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), P->p.PropagatorKernel == 0 ? ac_fwd_kernel<0> : ac_fwd_kernel<1>, P->nblocks, AC_FWD_THREADS,
-                         AC_FWD_SMEM, st,
-        g, P->t, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, P->phi[(s - 1) & 1], P->psi[(s - 1) & 1],
-        P->sigx, P->tauy, win_slot(P, base, s), P->phi[s & 1], P->psi[s & 1], P->srcp,
-        P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, sample ? P->rcvp : none,
-        (sample && P->nrcv > 0) ? P->rcvv + s * P->nrcv : nullptr, fuse));
-    LAUNCH_CHECK(P);
+  i64 s = s_first;
+  if (P->tb) {
+    // pairs of steps (s, s+1): frame of s, box of s and s+1 in one launch, frame of s+1.  The box launch reads time
+    // levels s-1 and s-2 only; the second frame launch reads the box cells of slot s next to the frame.
+    for (; s + 1 <= s_last; s += 2) {
+      TRY(launch_forward_step(P, base, s, sample, true));
+      CUDA_TRY(launch_step(true, ac_fwd2_kernel, P->nblocks2, AC_FWD_THREADS, AC_FWD2_SMEM, st,
+          g, P->t2, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, win_slot(P, base, s), win_slot(P, base, s + 1),
+          P->srcHp, P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, P->srcMp,
+          P->nsrc > 0 ? P->srcv + s * P->nsrc : nullptr, sample ? P->rcvMp : none,
+          (sample && P->nrcv > 0) ? P->rcvv + s * P->nrcv : nullptr,
+          (sample && P->nrcv > 0) ? P->rcvv + (s + 1) * P->nrcv : nullptr));
+      LAUNCH_CHECK(P);
+      TRY(launch_forward_step(P, base, s + 1, sample, true));
+    }
   }
+  for (; s <= s_last; s++) TRY(launch_forward_step(P, base, s, sample, false));
   return ADSEIS_OK;
 }
 

@@ -849,3 +849,163 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
     ac_fuse_signal(f, t_lo, t_hi);
   }
 }
+
+// ============================================================================================================
+// TWO time steps per launch (temporal blocking), marching CTAs only.
+//
+// A marching CTA already holds the rows it needs in shared memory / registers, so it can apply the update twice
+// before anything goes back to HBM: u[s+1] = Step(u[s], u[s-1]) is computed on the tile plus a one-cell rim, kept in
+// a three-row register window, and u[s+2] = Step(u[s+1], u[s]) follows one row behind.  HBM traffic per cell and
+// pair of steps: read u[s], u[s-1], c^2, write u[s+1], u[s+2] = 40 B, i.e. 20 B per cell-step instead of 32 B (both
+// snapshots are still written: the reverse sweep needs every time level).  The rim values are recomputed by each
+// tile with the same expression (bit-identical to the owner's), so tiles stay independent: no inter-CTA exchange.
+// The marched box is the PML-free box shrunk by TWO cells (t2), so that every rim cell is itself a plain interior
+// cell (sigma = tau = 0, phi = psi = 0): the launch depends on time levels s and s-1 only.  Everything outside the
+// box (absorbing frame, ring, rim) is advanced one step at a time by frame-only launches of ac_fwd_kernel.
+// Sources inside (tile + rim) are injected into the register copy of u[s+1] before it is used; injection into
+// u[s+2] and receiver sampling of both levels happen in the CTA epilogue as in the one-step kernel.
+// Lane layout as in ac_fwd_kernel (8 consumer warps x 64 columns, one double2 per lane); lanes 0 and 31 also carry
+// the warp's rim column of u[s+1], computed from a 3-row window of that column.
+// ============================================================================================================
+#ifndef AC_NST_FWD2
+#define AC_NST_FWD2 6
+#endif
+struct __align__(128) AcFwd2Stage {
+  double w[AC_HPAD];      // u[s]   row q+1, columns c0-2 .. c0+513
+  double wold[AC_HPAD];   // u[s-1] row q
+  double c2[AC_HPAD];     // c^2    row q
+};
+#define AC_FWD2_SMEM ((int)(AC_NST_FWD2 * (sizeof(AcFwd2Stage) + 16)))
+
+__device__ __forceinline__ double ac_int_cell(double c, double kx2, double ky2, double rx, double ry, double wc,
+                                              double wn, double wm, double wr, double wl, double wo) {
+  // the marching CTAs' expression of ac_fwd_kernel, term for term (reference order: AcousticOneStepCpu.h:35-44 with
+  // sigma = tau = 0, phi = psi = 0)
+  return (2 - kx2 * c - ky2 * c) * wc + c * rx * rx * (wn + wm) + c * ry * ry * (wr + wl) - wo;
+}
+
+__global__ void __launch_bounds__(AC_FWD_THREADS, 2)
+ac_fwd2_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* __restrict__ wold,
+               const double* __restrict__ c2, double* __restrict__ u1, double* __restrict__ u2, AcPoints srch,
+               const double* __restrict__ srcv_row1, AcPoints src, const double* __restrict__ srcv_row2, AcPoints rcv,
+               double* __restrict__ rcvv_row1, double* __restrict__ rcvv_row2) {
+  pdl_launch_dependents();
+  const int bid = blockIdx.x;
+  const int ld = g.ld;
+  const int ct = bid % t.nct, tr = bid / t.nct;
+  int r0, r1;
+  ac_row_tile(t, tr, &r0, &r1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = t.mc0 + ct * AC_TILE_COLS;
+  const int jb = c0 + warp * AC_WCOLS;
+  const int j = jb + 2 * lane;
+  const bool act = j < t.mc_end;  // stores (both columns j, j+1 are inside the box)
+  pdl_wait();
+  extern __shared__ __align__(128) unsigned char ac_smem[];
+  AcFwd2Stage* stg = reinterpret_cast<AcFwd2Stage*>(ac_smem);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ac_smem + AC_NST_FWD2 * sizeof(AcFwd2Stage));
+  unsigned long long* empty = full + AC_NST_FWD2;
+  const int nrows = r1 - r0;
+  const int nit = nrows + 2;  // intermediate rows q = r0-1 .. r1
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < AC_NST_FWD2; k++) { mbar_init(full + k, 1); mbar_init(empty + k, AC_WARPS); }
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (warp == AC_WARPS) {
+    if (lane == 0) {
+      const unsigned hbytes = (unsigned)min(AC_HCOLS, ld - (c0 - 2)) * 8u;  // never read past the end of a row
+      for (int it = 0; it < nit; it++) {
+        const int sidx = it % AC_NST_FWD2;
+        if (it >= AC_NST_FWD2) { mbar_wait(empty + sidx, (unsigned)(it / AC_NST_FWD2 - 1) & 1u); ring_refill_fence(); }
+        AcFwd2Stage& s = stg[sidx];
+        const i64 ro = (i64)(r0 - 1 + it) * ld + c0 - 2;  // row q, first staged column
+        mbar_arrive_expect_tx(full + sidx, 3u * hbytes);
+        bulk_g2s(s.w, w + ro + ld, hbytes, full + sidx);   // q+1 <= r1+1 <= Hl-1: the box is shrunk by two
+        bulk_g2s(s.wold, wold + ro, hbytes, full + sidx);
+        bulk_g2s(s.c2, c2 + ro, hbytes, full + sidx);
+      }
+    }
+  } else {
+    const bool wact = jb < t.mc_end;
+    const double2 z2 = make_double2(0.0, 0.0);
+    const double kx2 = g.kx2, ky2 = g.ky2, rx = g.rx, ry = g.ry;
+    // u[s] window (rows q-1, q), u[s+1] window (rows q-2, q-1), c^2 of row q-1
+    double2 wm = z2, wc = z2, Im = z2, Ic = z2, cprev = z2;
+    // rim column of this warp (lane 0: column jb-1, lane 31: column jb+64): u[s] window, outer neighbour, u[s+1]
+    double ewm = 0.0, ewc = 0.0, eoc = 0.0, Iec = 0.0;
+    const bool edge = (lane == 0) || (lane == 31);
+    const int ecol = (lane == 0) ? jb - 1 : jb + AC_WCOLS;      // rim column
+    const int ocol = (lane == 0) ? jb - 2 : jb + AC_WCOLS + 1;  // its outer neighbour
+    if (wact) {
+      const i64 ra = (i64)(r0 - 2) * ld, rb_ = ra + ld;  // r0 >= 2
+      if (j + 1 < ld) { wm = ld2(w + ra + j); wc = ld2(w + rb_ + j); }
+      if (edge && ocol < ld) { ewm = w[ra + ecol]; ewc = w[rb_ + ecol]; eoc = w[rb_ + ocol]; }
+    }
+    int ha = 0, hb = 0;
+    if (srch.blk != nullptr && srcv_row1 != nullptr) { ha = srch.blk[bid]; hb = srch.blk[bid + 1]; }
+    const int so = 2 + warp * AC_WCOLS + 2 * lane;              // own pair inside a staged row
+    const int se = (lane == 0) ? so - 1 : so + 2, sx = (lane == 0) ? so - 2 : so + 3;
+    for (int it = 0; it < nit; it++) {
+      const int q = r0 - 1 + it, sidx = it % AC_NST_FWD2;
+      mbar_wait(full + sidx, (unsigned)(it / AC_NST_FWD2) & 1u);
+      const AcFwd2Stage& s = stg[sidx];
+      double2 wn = z2, wo = z2, cc = z2;
+      double ewn = 0.0, eon = 0.0, ewo = 0.0, ecc = 0.0;
+      if (wact) {
+        wn = ld2(s.w + so); wo = ld2(s.wold + so); cc = ld2(s.c2 + so);
+        if (edge) { ewn = s.w[se]; eon = s.w[sx]; ewo = s.wold[se]; ecc = s.c2[se]; }
+      }
+      __syncwarp();  // every lane has read the stage
+      if (lane == 0) mbar_arrive(empty + sidx);
+      if (wact) {
+        // ---- first step: u[s+1] on row q (own pair and the rim column)
+        double lft = __shfl_up_sync(0xffffffffu, wc.y, 1);
+        double rgt = __shfl_down_sync(0xffffffffu, wc.x, 1);
+        if (lane == 0) lft = ewc;
+        if (lane == 31) rgt = ewc;
+        double2 In;
+        In.x = ac_int_cell(cc.x, kx2, ky2, rx, ry, wc.x, wn.x, wm.x, wc.y, lft, wo.x);
+        In.y = ac_int_cell(cc.y, kx2, ky2, rx, ry, wc.y, wn.y, wm.y, rgt, wc.x, wo.y);
+        double Ien = 0.0;
+        if (edge)
+          Ien = (lane == 0) ? ac_int_cell(ecc, kx2, ky2, rx, ry, ewc, ewn, ewm, wc.x, eoc, ewo)
+                            : ac_int_cell(ecc, kx2, ky2, rx, ry, ewc, ewn, ewm, eoc, wc.y, ewo);
+        // sources on (tile + rim) cells of row q: u[s+1][cell] += srcv * dt^2, sequentially per cell (ScatterAddOps)
+        for (int k = ha; k < hb; k++) {
+          const int cell = srch.cell[k];
+          const int row = cell / ld;
+          if (row != q) continue;
+          const int col = cell - row * ld;
+          const bool mx = col == j, my = col == j + 1, me = edge && col == ecol;
+          if (mx || my || me) {
+            double v = mx ? In.x : (my ? In.y : Ien);
+            for (int m = srch.start[k]; m < srch.start[k + 1]; m++) v += srcv_row1[srch.perm[m]] * g.dt2;
+            if (mx) In.x = v; else if (my) In.y = v; else Ien = v;
+          }
+        }
+        if (act && it >= 1 && it <= nrows) st2(u1 + (i64)q * ld + j, In);
+        // ---- second step: u[s+2] on row q-1 from u[s+1] rows q-2, q-1, q; "wold" is u[s] row q-1
+        if (it >= 2) {
+          double l2 = __shfl_up_sync(0xffffffffu, Ic.y, 1);
+          double r2 = __shfl_down_sync(0xffffffffu, Ic.x, 1);
+          if (lane == 0) l2 = Iec;
+          if (lane == 31) r2 = Iec;
+          if (act) {
+            double2 o;
+            o.x = ac_int_cell(cprev.x, kx2, ky2, rx, ry, Ic.x, In.x, Im.x, Ic.y, l2, wm.x);
+            o.y = ac_int_cell(cprev.y, kx2, ky2, rx, ry, Ic.y, In.y, Im.y, r2, Ic.x, wm.y);
+            st2(u2 + (i64)(q - 1) * ld + j, o);
+          }
+        }
+        Im = Ic; Ic = In; Iec = Ien;
+        wm = wc; wc = wn; cprev = cc;
+        ewm = ewc; ewc = ewn; eoc = eon;
+      }
+    }
+  }
+  const AcPoints none{};
+  ac_cta_epilogue(bid, u1, none, nullptr, 0.0, rcv, rcvv_row1, 1.0);          // u[s+1] already carries its sources
+  ac_cta_epilogue(bid, u2, src, srcv_row2, g.dt2, rcv, rcvv_row2, 1.0);
+}

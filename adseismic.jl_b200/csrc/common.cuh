@@ -186,10 +186,8 @@ __device__ __forceinline__ void st2_stream(double* p, double2 v) { __stcs(reinte
 // RN(x / h) from rh = RN(1/h) computed once on the host: q0 = x*rh is within 2 ulp, one FMA correction makes it a
 // faithful quotient and a second one the correctly rounded quotient (Markstein's theorem; the remainders
 // r = x - q*h are exact in an FMA).  Five issue slots instead of the ~40-instruction divide sequence, whose slow
-// path is also taken for every zero wavefield value.  Numerators near the denormal range (inexact remainders)
-// use the divide sequence, so the result is bit-identical to `x / h` for all inputs.
-__device__ __forceinline__ double div_exact(double x, double h, double rh) {
-  if (x != 0.0 && fabs(x) < 1e-280) return x / h;
+// path is also taken for every zero or denormal-range wavefield value.
+__device__ __forceinline__ double div_markstein(double x, double h, double rh) {
   double q = x * rh;
   double r = fma(-q, h, x);
   q = fma(r, rh, q);
@@ -197,15 +195,42 @@ __device__ __forceinline__ double div_exact(double x, double h, double rh) {
   return fma(r, rh, q);
 }
 
-// Branch-free core of div_exact for hot loops: the caller ORs `tiny` over all quotients of an iteration and redoes
-// the iteration with true divisions in the (rare) case that one numerator was near the denormal range.
+// Numerators near the denormal range (|x| < 1e-280: the numerical precursor that runs ahead of every wavefront is a
+// band tens of cells wide of such values) would make the remainders inexact.  They are scaled by 2^400 (exact), divided
+// in the normal range, and scaled back.  Scaling back is exact while the quotient stays normal; for a subnormal result
+// the scaled quotient `q` = RN(2^400 x / h) is first made ROUND-TO-ODD with the sign of its exact remainder, after which
+// the final rounding onto the subnormal grid (>= 2 bits coarser) cannot double-round; the single binade that loses
+// exactly one bit uses the true divide.  Bit-identical to x / h for every input (host model of this routine checked
+// against x / h on 4.4e8 random tiny numerators, 11 divisors: scripts/div_tiny_check.c).  Round 1 fell back to the
+// divide sequence for these numerators instead, which made the elastic forward kernels 2.4x slower once the
+// precursor band had spread over the grid (117 -> 281 us per step at 2000^2, profiles/r02c_elastic_division.md).
+static __device__ __noinline__ double div_fix_tiny(double x, double h, double q) {
+  const double aq = fabs(q);
+  if (aq >= 0x1p-622) return q * 0x1p-400;          // the scaled-back quotient is a normal number: exact
+  if (aq >= 0x1p-623) return x / h;                 // loses exactly one bit: round-to-odd is not enough (rare)
+  const double r = fma(-q, h, x * 0x1p+400);        // exact remainder: its sign tells on which side x/h lies
+  if (r != 0.0) {
+    long long b = __double_as_longlong(q);
+    if ((b & 1LL) == 0) {                           // round to odd: take the other neighbour of the true quotient
+      const bool up = (r > 0.0) == (h > 0.0);       // true quotient > q ?
+      b += ((q > 0.0) == up) ? 1LL : -1LL;
+      q = __longlong_as_double(b);
+    }
+  }
+  return q * 0x1p-400;
+}
+
+__device__ __forceinline__ double div_exact(double x, double h, double rh) {
+  const bool tiny = (x != 0.0) & (fabs(x) < 1e-280);
+  const double q = div_markstein(tiny ? x * 0x1p+400 : x, h, rh);
+  return tiny ? div_fix_tiny(x, h, q) : q;
+}
+
+// Same routine for hot loops (the `tiny` flag of round 1, which made the caller redo the iteration with true
+// divisions, is kept in the signature but no longer raised).
 __device__ __forceinline__ double div_core(double x, double h, double rh, bool& tiny) {
-  tiny |= (x != 0.0) & (fabs(x) < 1e-280);
-  double q = x * rh;
-  double r = fma(-q, h, x);
-  q = fma(r, rh, q);
-  r = fma(-q, h, x);
-  return fma(r, rh, q);
+  (void)tiny;
+  return div_exact(x, h, rh);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -302,9 +302,11 @@ __device__ __forceinline__ double el_st4(double a, double b, double c, double d)
 // instead keeps the inline fast path and the result is discarded)
 __device__ __forceinline__ double el_div_var(double x, double r) {
   const bool z = (x == 0.0);
-  double xs = z ? 1.0 : x;
-  asm volatile("" : "+d"(xs));  // opaque: otherwise the compiler folds the two selects back into x / r
-  const double q = xs / r;
+  const bool tiny = !z & (fabs(x) < 1e-280);       // precursor band: keep the divide on its inline fast path too
+  double xs = z ? 1.0 : (tiny ? x * 0x1p+400 : x);
+  asm volatile("" : "+d"(xs));  // opaque: otherwise the compiler folds the selects back into x / r
+  double q = xs / r;
+  if (tiny) q = div_fix_tiny(x, r, q);             // exact scaling back (see common.cuh)
   return z ? x : q;
 }
 
