@@ -137,13 +137,27 @@ struct adseis_acoustic_plan {
   i64 win_base = -1, win_last = -1;  // slots currently valid in the window: [win_base, win_last]
   // points
   i64 nsrc = 0, nrcv = 0;
+  i64 points_gen = 0;   // bumped whenever a per-point device buffer is reallocated (invalidates captured graphs)
+  // CUDA graphs (single-GPU plans with small step kernels): the whole launch sequence of forward() / gradient() is
+  // captured once and replayed -- every kernel argument is a device address that stays fixed between calls (the
+  // history window, the per-step rows of srcv / rcvv / res / gradsrcv, the per-CTA point lists, which set_points
+  // rewrites in place).  `key` fingerprints those addresses; a mismatch re-captures.
+  struct SpanRec { int phase; i64 launches; cudaEvent_t a, b; };
+  struct GraphSlot { cudaGraphExec_t exec = nullptr; unsigned long long key = 0; i64 launches = 0, recomputed = 0; size_t ev_used = 0; std::vector<SpanRec> spans_copy; };
+  GraphSlot gslot[2];       // 0 = forward(), 1 = gradient()
+  int graphs = -1;          // -1 undecided, 0 off, 1 on
+  bool capturing = false;
   PointSetStorage src, rcv;
   AcPoints srcp{}, rcvp{};
   unsigned char* rcv_owned = nullptr;
   double *srcv = nullptr, *rcvv = nullptr, *obs = nullptr, *res = nullptr, *loss = nullptr;
   i64 srcv_rows = 0;
   // adjoint state
-  double *ub[3] = {nullptr, nullptr, nullptr}, *phib[2] = {nullptr, nullptr}, *psib[2] = {nullptr, nullptr};
+  double *ub[4] = {nullptr, nullptr, nullptr, nullptr}, *phib[2] = {nullptr, nullptr}, *psib[2] = {nullptr, nullptr};
+  int nub = 3;       // rotating ubar planes: 3, or 4 when the two-step adjoint kernel runs (it writes two time levels)
+  bool tb_adj = false;  // two adjoint steps per launch (tb && PropagatorKernel != 0)
+  PointSetStorage rcvH;  // receivers under every box tile whose one-cell rim holds them (two-step adjoint)
+  AcPoints rcvHp{};
   double *G = nullptr, *gradc = nullptr, *gradsrcv = nullptr;
   double* ut[2] = {nullptr, nullptr};  // PropagatorKernel=0: utilde planes (adjoint of the pre-injection outputs)
   bool k0_corr = false;                // ... and some source touches a cell whose phi/psi coefficient is non-zero
@@ -164,7 +178,7 @@ struct adseis_acoustic_plan {
   // per-phase device timing of the last forward()/gradient(): CUDA events on the ctx stream around each run of
   // identical kernels (phase 0 = forward sweep, 1 = forward recomputation, 2 = adjoint sweep)
   std::vector<cudaEvent_t> ev_pool;
-  struct Span { int phase; i64 launches; cudaEvent_t a, b; };
+  typedef SpanRec Span;
   std::vector<Span> spans;
   size_t ev_used = 0;
 };
@@ -177,12 +191,12 @@ static int span_begin(adseis_acoustic_plan* P, int phase, i64 launches) {
   }
   adseis_acoustic_plan::Span sp{phase, launches, P->ev_pool[P->ev_used], P->ev_pool[P->ev_used + 1]};
   P->ev_used += 2;
-  CUDA_TRY(cudaEventRecord(sp.a, P->ctx->stream));
+  CUDA_TRY(cudaEventRecordWithFlags(sp.a, P->ctx->stream, P->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   P->spans.push_back(sp);
   return ADSEIS_OK;
 }
 static int span_end(adseis_acoustic_plan* P) {
-  CUDA_TRY(cudaEventRecord(P->spans.back().b, P->ctx->stream));
+  CUDA_TRY(cudaEventRecordWithFlags(P->spans.back().b, P->ctx->stream, P->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   return ADSEIS_OK;
 }
 
@@ -249,16 +263,17 @@ ADSEIS_API int adseis_acoustic_plan_destroy(adseis_acoustic_plan* P) {
     cudaFree(P->arena);
   } else {
     for (int k = 0; k < 2; k++) { cudaFree(P->phi[k]); cudaFree(P->psi[k]); cudaFree(P->phib[k]); cudaFree(P->psib[k]); }
-    for (int k = 0; k < 3; k++) cudaFree(P->ub[k]);
+    for (int k = 0; k < 4; k++) cudaFree(P->ub[k]);
     cudaFree(P->hist);
   }
   for (double* c : P->ckpt) cudaFree(c);
   free_point_set(&P->src); free_point_set(&P->rcv);
   free_point_set(&P->srcF); free_point_set(&P->rcvF); free_point_set(&P->srcM); free_point_set(&P->rcvM);
-  free_point_set(&P->srcH);
+  free_point_set(&P->srcH); free_point_set(&P->rcvH);
   cudaFree(P->rcv_owned);
   cudaFree(P->srcv); cudaFree(P->rcvv); cudaFree(P->obs); cudaFree(P->res); cudaFree(P->loss);
   cudaFree(P->G); cudaFree(P->gradc); cudaFree(P->gradsrcv); cudaFree(P->ut[0]); cudaFree(P->ut[1]);
+  for (int k = 0; k < 2; k++) if (P->gslot[k].exec) cudaGraphExecDestroy(P->gslot[k].exec);
   for (cudaEvent_t e : P->ev_pool) cudaEventDestroy(e);
   adseis_ctx* ctx = P->ctx;
   delete P;
@@ -332,6 +347,9 @@ static void build_tb_tilings(adseis_acoustic_plan* P) {
   for (int k = f.nrect; k < 4; k++) { f.rblk[k + 1] = f.rblk[f.nrect]; f.rr0[k] = f.rr1[k] = f.rc0[k] = 0; f.rc1[k] = 1; }
   P->nblocksf = f.rblk[f.nrect];
   P->tb = true;
+  const char* ea = getenv("ADSEIS_AC_TB_ADJ");
+  P->tb_adj = P->p.PropagatorKernel != 0 && !(ea && ea[0] == '0');
+  P->nub = P->tb_adj ? 4 : 3;
 }
 
 // Sources / receivers of a plan: keep the points whose padded row is owned (MPIAcoustic.jl:71-78, 98-104), group them
@@ -346,14 +364,18 @@ static int plan_build_points(adseis_acoustic_plan* P, int64_t nsrc, const int64_
   const int H = g.H, W = g.W;
   std::vector<double> sx(H), ty(W);
   TRY(adseis_acoustic_pml_profiles(p, sx.data(), ty.data()));
-  free_point_set(&P->src); free_point_set(&P->rcv);
   P->srcp = AcPoints{}; P->rcvp = AcPoints{};
-  cudaFree(P->rcv_owned); P->rcv_owned = nullptr;
-  cudaFree(P->rcvv); P->rcvv = nullptr;
-  cudaFree(P->obs); P->obs = nullptr;
-  cudaFree(P->res); P->res = nullptr;
-  cudaFree(P->srcv); P->srcv = nullptr; P->srcv_rows = 0;
-  cudaFree(P->gradsrcv); P->gradsrcv = nullptr;
+  // per-point buffers are kept (same device addresses) when the counts do not change: the usual multi-shot case
+  const bool same_counts = (P->rcvv != nullptr) && P->nsrc == nsrc && P->nrcv == nrcv;
+  if (!same_counts) {
+    cudaFree(P->rcv_owned); P->rcv_owned = nullptr;
+    cudaFree(P->rcvv); P->rcvv = nullptr;
+    cudaFree(P->obs); P->obs = nullptr;
+    cudaFree(P->res); P->res = nullptr;
+    cudaFree(P->srcv); P->srcv = nullptr; P->srcv_rows = 0;
+    cudaFree(P->gradsrcv); P->gradsrcv = nullptr;
+    P->points_gen++;
+  }
   P->have_srcv = P->have_obs = P->have_fwd = P->have_grad = false;
   P->k0_corr = false;
   P->nsrc = nsrc; P->nrcv = nrcv;
@@ -398,15 +420,15 @@ static int plan_build_points(adseis_acoustic_plan* P, int64_t nsrc, const int64_
   TRY(build(nrcv, rcvi, rcvj, &P->rcv, &owned, "receiver"));
   if (P->src.nu > 0) P->srcp = AcPoints{P->src.blk, P->src.cell, P->src.start, P->src.perm};
   if (P->rcv.nu > 0) P->rcvp = AcPoints{P->rcv.blk, P->rcv.cell, P->rcv.start, P->rcv.perm};
-  TRY(dev_upload(&P->rcv_owned, owned, st));
-  TRY(dev_alloc_zero(&P->rcvv, (size_t)((p->NSTEP + 1) * nrcv), st));
-  if (P->G) TRY(dev_alloc_zero(&P->gradsrcv, (size_t)(p->NSTEP * nsrc), st));  // adjoint state already exists
+  if (!P->rcv_owned) TRY(dev_alloc(&P->rcv_owned, owned.size()));
+  if (!owned.empty()) CUDA_TRY(cudaMemcpyAsync(P->rcv_owned, owned.data(), owned.size(), cudaMemcpyHostToDevice, st));
+  if (!P->rcvv) TRY(dev_alloc(&P->rcvv, (size_t)((p->NSTEP + 1) * nrcv)));
+  CUDA_TRY(cudaMemsetAsync(P->rcvv, 0, std::max<size_t>((size_t)((p->NSTEP + 1) * nrcv), 1) * 8, st));
+  if (P->G && !P->gradsrcv) TRY(dev_alloc_zero(&P->gradsrcv, (size_t)(p->NSTEP * nsrc), st));  // adjoint state already exists
   // two-step path: the same points grouped by owner under the frame-only tiling (frame points), under the box tiling
   // (box points), and -- sources only -- under every box tile whose one-cell rim contains them (injection into the
   // tile's private copy of the intermediate time level)
-  free_point_set(&P->srcF); free_point_set(&P->rcvF); free_point_set(&P->srcM); free_point_set(&P->rcvM);
-  free_point_set(&P->srcH);
-  P->srcFp = P->rcvFp = P->srcMp = P->rcvMp = P->srcHp = AcPoints{};
+  P->srcFp = P->rcvFp = P->srcMp = P->rcvMp = P->srcHp = P->rcvHp = AcPoints{};
   if (P->tb) {
     const AcTiling &t2 = P->t2, &tf = P->tf;
     auto in_box = [&](int li, int j) { return li >= t2.mr0 && li < t2.mr1 && j >= t2.mc0 && j < t2.mc_end; };
@@ -453,9 +475,10 @@ static int plan_build_points(adseis_acoustic_plan* P, int64_t nsrc, const int64_
     TRY(build2(nsrc, srci, srcj, 1, P->nblocks2, &P->srcM));
     TRY(build2(nrcv, rcvi, rcvj, 1, P->nblocks2, &P->rcvM));
     TRY(build2(nsrc, srci, srcj, 2, P->nblocks2, &P->srcH));
+    TRY(build2(nrcv, rcvi, rcvj, 2, P->nblocks2, &P->rcvH));
     auto view = [](const PointSetStorage& q) { return q.nu > 0 ? AcPoints{q.blk, q.cell, q.start, q.perm} : AcPoints{}; };
     P->srcFp = view(P->srcF); P->rcvFp = view(P->rcvF); P->srcMp = view(P->srcM); P->rcvMp = view(P->rcvM);
-    P->srcHp = view(P->srcH);
+    P->srcHp = view(P->srcH); P->rcvHp = view(P->rcvH);
   }
   return ADSEIS_OK;
 }
@@ -490,6 +513,7 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     CUDA_TRY(cudaFuncSetAttribute(ac_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_FWD_SMEM));
   }
   CUDA_TRY(cudaFuncSetAttribute(ac_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_FWD2_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(ac_adj2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_ADJ2_SMEM));
   if (AC_ADJ_SMEM > 0) {
     CUDA_TRY(cudaFuncSetAttribute(ac_adj_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_ADJ_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(ac_adj_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_ADJ_SMEM));
@@ -950,14 +974,93 @@ static int check_ready(adseis_acoustic_plan* P, bool need_obs) {
   return ADSEIS_OK;
 }
 
+// ---- CUDA-graph replay of a whole sweep ---------------------------------------------------------------------
+static bool graphs_enabled(adseis_acoustic_plan* P) {
+  if (P->graphs < 0) {
+    const char* e = getenv("ADSEIS_GRAPHS");
+    // worth it when a step kernel is short next to its launch cost; large grids keep direct launches (a graph of
+    // tens of thousands of nodes costs more to build than it saves)
+    const bool small = (i64)P->g.H * P->g.W <= (6LL << 20);
+    P->graphs = (P->arena == nullptr) && (e ? e[0] != '0' : small) ? 1 : 0;
+  }
+  return P->graphs == 1;
+}
+
+static unsigned long long graph_key(adseis_acoustic_plan* P, int kind) {
+  unsigned long long h = 1469598103934665603ULL;
+  auto mix = [&](const void* p) { h ^= (unsigned long long)(uintptr_t)p; h *= 1099511628211ULL; };
+  mix(P->hist); mix(P->c2); mix(P->phi[0]); mix(P->psi[0]); mix(P->srcv); mix(P->rcvv); mix(P->perm);
+  const PointSetStorage* ps[] = {&P->src, &P->rcv, &P->srcF, &P->rcvF, &P->srcM, &P->rcvM, &P->srcH, &P->rcvH};
+  for (const PointSetStorage* q : ps) { mix(q->blk); mix(q->cell); mix(q->start); mix(q->perm); mix((void*)(uintptr_t)(q->nu + 1)); }
+  mix((void*)(uintptr_t)(P->nsrc * 131 + P->nrcv + 7)); mix((void*)(uintptr_t)(P->k0_corr ? 3 : 5));
+  if (kind == 1) {
+    mix(P->obs); mix(P->res); mix(P->rcv_owned); mix(P->loss); mix(P->G); mix(P->gradc); mix(P->gradsrcv); mix(P->cvel);
+    for (int k = 0; k < 4; k++) mix(P->ub[k]);
+    mix(P->phib[0]); mix(P->psib[0]); mix(P->ut[0]);
+    for (double* c : P->ckpt) mix(c);
+  }
+  return h | 1ULL;
+}
+
+// Run `body` (which only enqueues work on the context's stream) directly, or -- when graphs are on -- capture it once
+// into a CUDA graph and replay that.  Any failure of the capture path switches graphs off for this plan and falls back.
+template <class Body>
+static int run_captured(adseis_acoustic_plan* P, int kind, Body body) {
+  cudaStream_t st = P->ctx->stream;
+  P->last_launches = 0; P->last_recomputed = 0;
+  P->spans.clear(); P->ev_used = 0;
+  if (!graphs_enabled(P)) return body();
+  adseis_acoustic_plan::GraphSlot& gs = P->gslot[kind];
+  const unsigned long long key = graph_key(P, kind);
+  if (gs.exec && gs.key != key) { cudaGraphExecDestroy(gs.exec); gs.exec = nullptr; }
+  if (!gs.exec) {
+    while (P->ev_pool.size() < 6 * P->seg_b.size() + 8) {   // no event creation inside the capture
+      cudaEvent_t e;
+      CUDA_TRY(cudaEventCreate(&e));
+      P->ev_pool.push_back(e);
+    }
+    const i64 l0 = P->ctx->launches;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); P->graphs = 0; return body(); }
+    P->capturing = true;
+    const int rc = body();
+    P->capturing = false;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    P->ctx->launches = l0;   // nothing has run yet
+    if (rc != ADSEIS_OK || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      P->graphs = 0;
+      if (rc != ADSEIS_OK) return rc;
+      P->last_launches = 0; P->last_recomputed = 0; P->spans.clear(); P->ev_used = 0;
+      return body();
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&gs.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+      cudaGetLastError();
+      gs.exec = nullptr; P->graphs = 0;
+      P->last_launches = 0; P->last_recomputed = 0; P->spans.clear(); P->ev_used = 0;
+      return body();
+    }
+    gs.key = key; gs.launches = P->last_launches; gs.recomputed = P->last_recomputed; gs.ev_used = P->ev_used;
+    gs.spans_copy = P->spans;
+  } else {
+    P->last_launches = gs.launches; P->last_recomputed = gs.recomputed; P->ev_used = gs.ev_used;
+    P->spans = gs.spans_copy;
+  }
+  CUDA_TRY(cudaGraphLaunch(gs.exec, st));
+  P->ctx->launches += gs.launches;
+  return ADSEIS_OK;
+}
+
 ADSEIS_API int adseis_acoustic_plan_forward(adseis_acoustic_plan* P) {
   REQUIRE(P, "acoustic_plan_forward: null");
   TRY(check_ready(P, false));
   CUDA_TRY(cudaSetDevice(P->ctx->device));
-  P->last_launches = 0; P->last_recomputed = 0;
-  P->spans.clear(); P->ev_used = 0;
-  TRY(forward_sweep(P, false, nullptr, nullptr));
+  TRY(run_captured(P, 0, [&]() { return forward_sweep(P, false, nullptr, nullptr); }));
   P->last_segments = (i64)P->seg_b.size();
+  P->win_base = P->seg_b.back(); P->win_last = P->seg_e.back();
   P->have_fwd = true;
   return ADSEIS_OK;
 }
@@ -970,7 +1073,7 @@ static int ensure_adjoint_state(adseis_acoustic_plan* P) {
   const size_t n = (size_t)P->g.plane;
   cudaStream_t st = P->ctx->stream;
   if (!P->arena) {
-    for (int k = 0; k < 3; k++) TRY(dev_alloc_zero(&P->ub[k], n, st));
+    for (int k = 0; k < P->nub; k++) TRY(dev_alloc_zero(&P->ub[k], n, st));
     for (int k = 0; k < 2; k++) { TRY(dev_alloc_zero(&P->phib[k], n, st)); TRY(dev_alloc_zero(&P->psib[k], n, st)); }
   }
   if (P->p.PropagatorKernel == 0)
@@ -981,17 +1084,27 @@ static int ensure_adjoint_state(adseis_acoustic_plan* P) {
   return ADSEIS_OK;
 }
 
+static int gradient_body(adseis_acoustic_plan* P);
+
 ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
   REQUIRE(P, "acoustic_plan_gradient: null");
   TRY(check_ready(P, true));
   CUDA_TRY(cudaSetDevice(P->ctx->device));
+  TRY(ensure_adjoint_state(P));
+  TRY(run_captured(P, 1, [&]() { return gradient_body(P); }));
+  P->last_segments = (i64)P->seg_b.size();
+  P->win_base = P->seg_b.front(); P->win_last = P->seg_e.front();   // the reverse sweep ends in the first segment
+  P->have_fwd = true;
+  P->have_grad = true;
+  return ADSEIS_OK;
+}
+
+static int gradient_body(adseis_acoustic_plan* P) {
   const AcGeom& g = P->g;
   cudaStream_t st = P->ctx->stream;
   const i64 NSTEP = P->p.NSTEP;
   const size_t pb = (size_t)g.plane * 8;
-  P->last_launches = 0; P->last_recomputed = 0;
-  P->spans.clear(); P->ev_used = 0;
-  TRY(ensure_adjoint_state(P));
+  const i64 NUB = P->nub;
   // ---- forward, keeping checkpoints; the last segment stays in the window
   TRY(forward_sweep(P, true, nullptr, nullptr));
   const size_t nseg = P->seg_b.size();
@@ -1003,7 +1116,7 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
   k_residual_final<<<1, RL_BLOCKS, 0, st>>>(P->loss);
   LAUNCH_CHECK(P);
   // ---- reverse sweep
-  for (int k = 0; k < 3; k++) CUDA_TRY(cudaMemsetAsync(P->ub[k], 0, pb, st));
+  for (int k = 0; k < P->nub; k++) CUDA_TRY(cudaMemsetAsync(P->ub[k], 0, pb, st));
   for (int k = 0; k < 2; k++) { CUDA_TRY(cudaMemsetAsync(P->phib[k], 0, pb, st)); CUDA_TRY(cudaMemsetAsync(P->psib[k], 0, pb, st)); }
   CUDA_TRY(cudaMemsetAsync(P->G, 0, pb, st));
   for (int k = 0; k < 2; k++) if (P->ut[k]) CUDA_TRY(cudaMemsetAsync(P->ut[k], 0, pb, st));
@@ -1011,18 +1124,18 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
   TRY(halo_exchange(P, 0, nullptr, nullptr));
   // ubar[NSTEP] = receiver term only; grad_srcv row NSTEP-1
   if (P->rcv.nu > 0) {
-    k_points_inject<<<(P->rcv.nu + 127) / 128, 128, 0, st>>>(P->ub[NSTEP % 3], P->rcvp, P->rcv.nu,
+    k_points_inject<<<(P->rcv.nu + 127) / 128, 128, 0, st>>>(P->ub[NSTEP % NUB], P->rcvp, P->rcv.nu,
                                                              P->res + NSTEP * P->nrcv, 1.0);
     LAUNCH_CHECK(P);
   }
   if (P->src.nu > 0 && NSTEP - 1 >= 1) {
-    k_points_sample<<<(P->src.nu + 127) / 128, 128, 0, st>>>(P->ub[NSTEP % 3], P->srcp, P->src.nu,
+    k_points_sample<<<(P->src.nu + 127) / 128, 128, 0, st>>>(P->ub[NSTEP % NUB], P->srcp, P->src.nu,
                                                              P->gradsrcv + (NSTEP - 1) * P->nsrc, g.dt2);
     LAUNCH_CHECK(P);
   }
   if (P->arena) {
     const int arr[1] = {AR_UB};
-    const i64 idx[1] = {NSTEP % 3};
+    const i64 idx[1] = {NSTEP % NUB};
     TRY(halo_exchange(P, 1, arr, idx));
   }
   AcPoints none{};
@@ -1048,8 +1161,11 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
       P->win_base = b; P->win_last = e;
     }
     TRY(span_begin(P, 2, e - (b + 2) + 1));
-    for (i64 s = e; s >= b + 2; s--) {
-      const AcFuse fuse = make_fuse(P, AR_UB, (s + 2) % 3, AR_PHIB, (s - 1) & 1);
+    // one adjoint step s: ubar[s-1] from ubar[s], ubar[s+1], u[s-1]; `frame_only`: the cells outside the two-step box
+    auto adj_step = [&](i64 s, bool frame_only) -> int {
+      AcFuse fuse;
+      if (frame_only) memset(&fuse, 0, sizeof(fuse));
+      else fuse = make_fuse(P, AR_UB, (s - 1 + NUB) % NUB, AR_PHIB, (s - 1) & 1);
       AcK0 k0{};
       if (P->p.PropagatorKernel == 0) {
         k0.wnew = win_slot(P, b, s); k0.ut_in = P->ut[(s + 1) & 1]; k0.ut_out = P->ut[s & 1];
@@ -1060,14 +1176,33 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
           LAUNCH_CHECK(P);
         }
       }
-      CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), P->p.PropagatorKernel == 0 ? ac_adj_kernel<0> : ac_adj_kernel<1>, P->nblocks, AC_ADJ_THREADS,
-                           AC_ADJ_SMEM, st,
-          g, P->t, P->ub[s % 3], P->ub[(s + 1) % 3], win_slot(P, b, s - 1), P->c2, P->phib[s & 1], P->psib[s & 1],
-          P->sigx, P->tauy, P->ub[(s + 2) % 3] /* == (s-1)%3 */, P->phib[(s - 1) & 1], P->psib[(s - 1) & 1], P->G,
-          P->rcvp, P->nrcv > 0 ? P->res + (s - 1) * P->nrcv : nullptr, (s - 2 >= 1) ? P->srcp : none,
+      const AcPoints rcvp = frame_only ? P->rcvFp : P->rcvp, srcp = frame_only ? P->srcFp : P->srcp;
+      CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), P->p.PropagatorKernel == 0 ? ac_adj_kernel<0> : ac_adj_kernel<1>,
+                           frame_only ? P->nblocksf : P->nblocks, AC_ADJ_THREADS, frame_only ? 0 : AC_ADJ_SMEM, st,
+          g, frame_only ? P->tf : P->t, P->ub[s % NUB], P->ub[(s + 1) % NUB], win_slot(P, b, s - 1), P->c2, P->phib[s & 1],
+          P->psib[s & 1], P->sigx, P->tauy, P->ub[(s - 1 + NUB) % NUB], P->phib[(s - 1) & 1], P->psib[(s - 1) & 1], P->G,
+          rcvp, P->nrcv > 0 ? P->res + (s - 1) * P->nrcv : nullptr, (s - 2 >= 1) ? srcp : none,
           (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr, fuse, k0));
       LAUNCH_CHECK(P);
+      return ADSEIS_OK;
+    };
+    i64 s = e;
+    if (P->tb_adj) {
+      // pairs (s, s-1): frame of step s, box of steps s and s-1 in one launch, frame of step s-1 (which reads the box
+      // cells of ubar[s-1] next to the frame)
+      for (; s - 1 >= b + 2; s -= 2) {
+        TRY(adj_step(s, true));
+        CUDA_TRY(launch_step(true, ac_adj2_kernel, P->nblocks2, AC2_THREADS, AC_ADJ2_SMEM, st,
+            g, P->t2, P->ub[s % NUB], P->ub[(s + 1) % NUB], win_slot(P, b, s - 1), win_slot(P, b, s - 2), P->c2,
+            P->ub[(s - 1 + NUB) % NUB], P->ub[(s - 2 + NUB) % NUB], P->G, P->rcvHp,
+            P->nrcv > 0 ? P->res + (s - 1) * P->nrcv : nullptr, P->rcvMp, P->nrcv > 0 ? P->res + (s - 2) * P->nrcv : nullptr,
+            P->srcMp, (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr,
+            (s - 3 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 3) * P->nsrc : nullptr));
+        LAUNCH_CHECK(P);
+        TRY(adj_step(s - 1, true));
+      }
     }
+    for (; s >= b + 2; s--) TRY(adj_step(s, false));
     TRY(span_end(P));
   }
   CUDA_TRY(cudaMemsetAsync(P->gradc, 0, (size_t)P->model_elems * 8, st));
@@ -1077,8 +1212,6 @@ ADSEIS_API int adseis_acoustic_plan_gradient(adseis_acoustic_plan* P) {
                                         P->p.mpi_convention, P->gradc);
     LAUNCH_CHECK(P);
   }
-  P->have_fwd = true;
-  P->have_grad = true;
   return ADSEIS_OK;
 }
 

@@ -468,6 +468,27 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Adjoint arithmetic of a cell whose whole stencil is PML-free (D = 1, no phibar / psibar terms).  The adjoint is
+// compared with the reference at 1e-10, not bit for bit, so these use explicit fused multiply-adds (the library is
+// compiled with -fmad=false for the forward kernels).  EVERY code path that evaluates such a cell -- the marching CTAs
+// of ac_adj_kernel, the frame CTAs' ac_adj_general_cell, ac_adj2_kernel -- goes through these three functions, so the
+// result does not depend on which path owns the cell (checkpoint segments shift the pairing of steps).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ac_a0(double c, double kx2, double ky2) {      // 2 - kx2 c - ky2 c
+  return __fma_rn(-ky2, c, __fma_rn(-kx2, c, 2.0));
+}
+// ubar[s-1](P) = a0(P) g(P) + rx2 (cg(P+ex) + cg(P-ex)) + ry2 (cg(P+ey) + cg(P-ey)) - ubar[s+1](P),  cg = c^2 ubar[s]
+__device__ __forceinline__ double ac_adj_cell(double a0, double rx2, double ry2, double g, double cgn, double cgm,
+                                              double cgr, double cgl, double u2) {
+  return __fma_rn(a0, g, __fma_rn(rx2, cgn + cgm, __fma_rn(ry2, cgr + cgl, -u2)));
+}
+// cbar(P) = ((-kx2 - ky2) w(P) + rx2 (w(P+ex) + w(P-ex)) + ry2 (w(P+ey) + w(P-ey))) g(P),  w = u[s-1]
+__device__ __forceinline__ double ac_corr_cell(double kk, double rx2, double ry2, double wc, double wn, double wm,
+                                               double wr, double wl, double g) {
+  return __fma_rn(kk, wc, __fma_rn(rx2, wn + wm, ry2 * (wr + wl))) * g;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // adjoint, general cell (gather form of AcousticOneStepCpu.h:76-124)
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ac_adj_general_cell(const AcGeom& g, int li, int j, const double* __restrict__ ub1,
@@ -504,6 +525,18 @@ __device__ __forceinline__ void ac_adj_general_cell(const AcGeom& g, int li, int
   // the adjoint is compared with the reference at 1e-10, not bit for bit: D in [1,2) is inverted once per cell
   // (fast path of the reciprocal sequence) and the constant divisors are folded into rhx, rhy
   const double kx = dt * 0.5 * g.rhx, ky = dt * 0.5 * g.rhy;
+  // A cell whose whole stencil is PML-free (sigma = tau = 0 on it and on its four interior neighbours) is evaluated
+  // with the MARCHING CTAs' expression and summation order, whoever owns it: the frame-only launches of the two-step
+  // path own the rim of the box, which a one-step launch marches -- both must give the same bits, or the result would
+  // depend on how the steps of a sweep happen to be paired (checkpoint segments shift the pairing).
+  if (intP && vxm && vxp && vym && vyp && sg == 0.0 && sgm == 0.0 && sgp == 0.0 && ta == 0.0 && tam == 0.0 && tap == 0.0) {
+    const double rx2 = g.rx * g.rx, ry2 = g.ry * g.ry;
+    ub0[IJ] = ac_adj_cell(ac_a0(cP, g.kx2, g.ky2), rx2, ry2, uP, cxp * uxp, cxm * uxm, cyp * uyp, cym * uym, u2P);
+    phibo[IJ] = (1. - dt * sg) * pb + g.px * (uxm - uxp);   // never used (its coefficient is tau - sigma = 0); kept finite
+    psibo[IJ] = (1. - dt * ta) * qb + g.py * (uym - uyp);
+    G[IJ] = GP + ac_corr_cell(-g.kx2 - g.ky2, rx2, ry2, wC, wU, wD, wR, wL, uP);
+    return;
+  }
   double acc = 0.0, gP = 0.0;
   if (intP) {
     gP = uP * (1.0 / (1 + (sg + ta) / 2 * dt));
@@ -803,16 +836,10 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
           if (lane == 31) { cgr = ecg; wr = ew; }
           if (act) {
             double2 o, Go;
-            {
-              const double c = ccen.x, gg = gc.x;
-              o.x = (2 - kx2 * c - ky2 * c) * gg + rx2 * (cgp.x + cgm.x) + ry2 * (cgc.y + cgl) - u2.x;
-              Go.x = Gr.x + (kk * wc.x + rx2 * (wn.x + wm.x) + ry2 * (wc.y + wl)) * gg;
-            }
-            {
-              const double c = ccen.y, gg = gc.y;
-              o.y = (2 - kx2 * c - ky2 * c) * gg + rx2 * (cgp.y + cgm.y) + ry2 * (cgr + cgc.x) - u2.y;
-              Go.y = Gr.y + (kk * wc.y + rx2 * (wn.y + wm.y) + ry2 * (wr + wc.x)) * gg;
-            }
+            o.x = ac_adj_cell(ac_a0(ccen.x, kx2, ky2), rx2, ry2, gc.x, cgp.x, cgm.x, cgc.y, cgl, u2.x);
+            o.y = ac_adj_cell(ac_a0(ccen.y, kx2, ky2), rx2, ry2, gc.y, cgp.y, cgm.y, cgr, cgc.x, u2.y);
+            Go.x = Gr.x + ac_corr_cell(kk, rx2, ry2, wc.x, wn.x, wm.x, wc.y, wl, gc.x);
+            Go.y = Gr.y + ac_corr_cell(kk, rx2, ry2, wc.y, wn.y, wm.y, wr, wc.x, gc.y);
             st2(ub0 + (i64)li * ld + j, o);
             st2(G + (i64)li * ld + j, Go);
           }
@@ -1008,4 +1035,183 @@ ac_fwd2_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double*
   const AcPoints none{};
   ac_cta_epilogue(bid, u1, none, nullptr, 0.0, rcv, rcvv_row1, 1.0);          // u[s+1] already carries its sources
   ac_cta_epilogue(bid, u2, src, srcv_row2, g.dt2, rcv, rcvv_row2, 1.0);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Two ADJOINT steps per launch (marching CTAs only), the transpose of ac_fwd2_kernel's pair in reverse order:
+//   A = ubar[s-1] = Step^T(ubar[s], ubar[s+1])  on the tile and its one-cell rim (+ the receiver residuals of
+//       slot s-1 that fall on those cells, injected into the register copy),
+//   B = ubar[s-2] = Step^T(A, ubar[s])          one row behind,
+//   Gbar += stencil(u[s-1]) * ubar[s]  +  stencil(u[s-2]) * A     (the same two additions, in the same order, as two
+//       one-step launches: bit-identical to them).
+// HBM traffic per cell and pair: read ubar[s], ubar[s+1], c^2, u[s-1], u[s-2], Gbar; write A, B, Gbar = 72 B, i.e. 36 B
+// per cell-step instead of 56 B.  Four rotating ubar planes (A and B must not overwrite the inputs other tiles read).
+// Mapping: the pair carries seven three-row windows, ~170 live registers with the double2-per-lane layout of the
+// other kernels -- one CTA of 8 warps per SM then runs at 0.2 IPC (measured: 428 us per launch), and two CTAs spill.
+// So here a lane owns ONE column: 16 consumer warps x 32 columns (+ the producer warp) = 544 threads, one CTA per SM,
+// <= 120 registers, four consumer warps per scheduler; lanes 0 / 31 also carry the warp's rim columns.
+// ------------------------------------------------------------------------------------------------------------
+#define AC2_WARPS 16
+#define AC2_WCOLS 32
+#define AC2_THREADS ((AC2_WARPS + 1) * 32)
+#ifndef AC_NST_ADJ2
+#define AC_NST_ADJ2 8
+#endif
+struct __align__(128) AcAdj2Stage {
+  double ub1[AC_HPAD];   // ubar[s]   row q+1, columns c0-2 .. c0+513
+  double c2[AC_HPAD];    // c^2       row q+1
+  double ub2[AC_HPAD];   // ubar[s+1] row q
+  double w1[AC_HPAD];    // u[s-1]    row q+1
+  double w2[AC_HPAD];    // u[s-2]    row q
+  double G[AC_HPAD];     // Gbar      row q-1
+};
+#define AC_ADJ2_SMEM ((int)(AC_NST_ADJ2 * (sizeof(AcAdj2Stage) + 16)))
+
+// first entry of a per-CTA point list (sorted by cell) whose cell is >= key
+__device__ __forceinline__ int ac_lower_bound(const int* __restrict__ cell, int a, int b, int key) {
+  while (a < b) {
+    const int m = (a + b) >> 1;
+    if (cell[m] < key) a = m + 1; else b = m;
+  }
+  return a;
+}
+// v + sum of val[perm[m]] * scale over the points on `key` (sequential, original point order); v if none
+__device__ __noinline__ double ac_add_points(double v, const AcPoints& ps, int a, int b, int key,
+                                             const double* __restrict__ val, double scale) {
+  const int k = ac_lower_bound(ps.cell, a, b, key);
+  if (k < b && ps.cell[k] == key)
+    for (int m = ps.start[k]; m < ps.start[k + 1]; m++) v += val[ps.perm[m]] * scale;
+  return v;
+}
+
+// Shared-memory layout after the ring stages: one private row pair per consumer warp holding c^2 * A of its 32 columns
+// and its two rim columns (double-buffered: row q is written while row q-1 is read).
+#define AC2_PRIV (2 * (AC2_WCOLS + 2))
+#undef AC_ADJ2_SMEM
+#define AC_ADJ2_SMEM ((int)(AC_NST_ADJ2 * (sizeof(AcAdj2Stage) + 16) + AC2_WARPS * AC2_PRIV * sizeof(double)))
+
+// Stage t of a tile carries row r0-2+t of ubar[s], c^2, u[s-1], row r0-3+t of ubar[s+1], u[s-2] and row r0-4+t of Gbar.
+// Iteration `it` (row q = r0-1+it of A, row q-1 of B) reads stages it+2 (rows q+1 / q / q-1), it+1 and it, and releases
+// stage `it` at its end: the three-row stencil windows live in the ring, not in registers (the register-window version
+// of this kernel spent 28 % of its instructions rotating windows and spilled; the ring costs ~33 shared-memory loads
+// per cell pair instead).
+__global__ void __launch_bounds__(AC2_THREADS, 1)
+ac_adj2_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double* __restrict__ ub2,
+               const double* __restrict__ w1, const double* __restrict__ w2, const double* __restrict__ c2,
+               double* __restrict__ ubA, double* __restrict__ ubB, double* __restrict__ G, AcPoints rcvh,
+               const double* __restrict__ res_row1, AcPoints rcv, const double* __restrict__ res_row2, AcPoints src,
+               double* __restrict__ gsrcv_row1, double* __restrict__ gsrcv_row2) {
+  pdl_launch_dependents();
+  const int bid = blockIdx.x;
+  const int ld = g.ld;
+  const int ct = bid % t.nct, tr = bid / t.nct;
+  int r0, r1;
+  ac_row_tile(t, tr, &r0, &r1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = t.mc0 + ct * AC_TILE_COLS;
+  const int jb = c0 + warp * AC2_WCOLS;
+  const int j = jb + lane;
+  const bool act = j < t.mc_end;
+  pdl_wait();
+  extern __shared__ __align__(128) unsigned char ac_smem[];
+  AcAdj2Stage* stg = reinterpret_cast<AcAdj2Stage*>(ac_smem);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ac_smem + AC_NST_ADJ2 * sizeof(AcAdj2Stage));
+  unsigned long long* empty = full + AC_NST_ADJ2;
+  double* priv = reinterpret_cast<double*>(empty + AC_NST_ADJ2) + warp * AC2_PRIV;
+  const int nrows = r1 - r0;
+  const int nit = nrows + 2;   // rows q = r0-1 .. r1 of A
+  const int nst = nit + 2;     // stages (two priming rows)
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < AC_NST_ADJ2; k++) { mbar_init(full + k, 1); mbar_init(empty + k, AC2_WARPS); }
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (warp == AC2_WARPS) {
+    if (lane == 0) {
+      const unsigned hbytes = (unsigned)min(AC_HCOLS, ld - (c0 - 2)) * 8u;
+      for (int k = 0; k < nst; k++) {
+        const int sidx = k % AC_NST_ADJ2;
+        if (k >= AC_NST_ADJ2) { mbar_wait(empty + sidx, (unsigned)(k / AC_NST_ADJ2 - 1) & 1u); ring_refill_fence(); }
+        AcAdj2Stage& s = stg[sidx];
+        const i64 ro = (i64)(r0 - 2 + k) * ld + c0 - 2;   // row r0-2+k >= 1
+        mbar_arrive_expect_tx(full + sidx, (k >= 2 ? 6u : 3u) * hbytes);
+        bulk_g2s(s.ub1, ub1 + ro, hbytes, full + sidx);
+        bulk_g2s(s.c2, c2 + ro, hbytes, full + sidx);
+        bulk_g2s(s.w1, w1 + ro, hbytes, full + sidx);
+        if (k >= 2) {
+          bulk_g2s(s.ub2, ub2 + ro - ld, hbytes, full + sidx);
+          bulk_g2s(s.w2, w2 + ro - ld, hbytes, full + sidx);
+          bulk_g2s(s.G, G + ro - 2 * ld, hbytes, full + sidx);
+        }
+      }
+    }
+  } else {
+    const bool wact = jb < t.mc_end;
+    const double rx2 = g.rx * g.rx, ry2 = g.ry * g.ry, kk = -g.kx2 - g.ky2, kx2 = g.kx2, ky2 = g.ky2;
+    double cAm = 0.0, cAc = 0.0, Ac = 0.0, a0prev = 0.0, t1p = 0.0;   // carried from the previous rows
+    const bool edge = (lane == 0) || (lane == 31);
+    const int so = 2 + warp * AC2_WCOLS + lane;           // own column inside a staged row
+    const int sr = (lane == 0) ? so - 1 : so + 1;         // rim column (lanes 0 / 31)
+    const int sq = (lane == 0) ? so - 2 : so + 2;         // its outer neighbour
+    const int ecol = (lane == 0) ? jb - 1 : jb + AC2_WCOLS;
+    int ha = 0, hb = 0;
+    if (rcvh.blk != nullptr && res_row1 != nullptr) { ha = rcvh.blk[bid]; hb = rcvh.blk[bid + 1]; }
+    mbar_wait(full + 0, 0u);
+    mbar_wait(full + 1, 0u);
+    for (int it = 0; it < nit; it++) {
+      const int q = r0 - 1 + it;
+      const int i0 = (it + 2) % AC_NST_ADJ2, i1 = (it + 1) % AC_NST_ADJ2, i2 = it % AC_NST_ADJ2;
+      mbar_wait(full + i0, (unsigned)((it + 2) / AC_NST_ADJ2) & 1u);
+      if (wact) {
+        const AcAdj2Stage &S0 = stg[i0], &S1 = stg[i1], &S2 = stg[i2];
+        // ---- A = ubar[s-1] on row q
+        const double u_c = S1.ub1[so], c_c = S1.c2[so];
+        const double cgl = S1.c2[so - 1] * S1.ub1[so - 1], cgr = S1.c2[so + 1] * S1.ub1[so + 1];
+        const double cgn = S0.c2[so] * S0.ub1[so], cgm = S2.c2[so] * S2.ub1[so];
+        const double a0 = ac_a0(c_c, kx2, ky2);
+        double A = ac_adj_cell(a0, rx2, ry2, u_c, cgn, cgm, cgr, cgl, S0.ub2[so]);
+        double Ae = 0.0, ecc = 0.0;
+        if (edge) {   // rim column: inner neighbour = own column, outer neighbour = column sq
+          ecc = S1.c2[sr];
+          const double cgo = S1.c2[sq] * S1.ub1[sq], cgi = c_c * u_c;
+          Ae = ac_adj_cell(ac_a0(ecc, kx2, ky2), rx2, ry2, S1.ub1[sr], S0.c2[sr] * S0.ub1[sr], S2.c2[sr] * S2.ub1[sr],
+                           lane == 0 ? cgi : cgo, lane == 0 ? cgo : cgi, S0.ub2[sr]);
+        }
+        // first correlation term of row q: stencil(u[s-1]) * ubar[s]
+        const double t1 = ac_corr_cell(kk, rx2, ry2, S1.w1[so], S0.w1[so], S2.w1[so], S1.w1[so + 1], S1.w1[so - 1], u_c);
+        // receiver residuals of slot s-1 on (tile + rim) cells of row q
+        if (hb > ha) {
+          const int key0 = q * ld + c0 - 1;
+          const int k0 = ac_lower_bound(rcvh.cell, ha, hb, key0);
+          if (k0 < hb && rcvh.cell[k0] <= key0 + AC_TILE_COLS + 1) {   // the row has entries within this tile + rim
+            A = ac_add_points(A, rcvh, k0, hb, q * ld + j, res_row1, 1.0);
+            if (edge) Ae = ac_add_points(Ae, rcvh, k0, hb, q * ld + ecol, res_row1, 1.0);
+          }
+        }
+        if (act && it >= 1 && it <= nrows) ubA[(i64)q * ld + j] = A;
+        const double cAn = c_c * A;
+        double* pw = priv + (it & 1) * (AC2_WCOLS + 2);
+        pw[1 + lane] = cAn;
+        if (edge) pw[lane == 0 ? 0 : AC2_WCOLS + 1] = ecc * Ae;
+        // ---- B = ubar[s-2] on row q-1 and both correlation terms of that row
+        if (it >= 2) {
+          const double* pr = priv + ((it - 1) & 1) * (AC2_WCOLS + 2);   // c^2 A of row q-1 (written one iteration ago)
+          if (act) {
+            const i64 o = (i64)(q - 1) * ld + j;
+            ubB[o] = ac_adj_cell(a0prev, rx2, ry2, Ac, cAn, cAm, pr[lane + 2], pr[lane], S2.ub1[so]);
+            G[o] = (S0.G[so] + t1p) +
+                   ac_corr_cell(kk, rx2, ry2, S1.w2[so], S0.w2[so], S2.w2[so], S1.w2[so + 1], S1.w2[so - 1], Ac);
+          }
+        }
+        cAm = cAc; cAc = cAn; Ac = A; a0prev = a0; t1p = t1;
+      }
+      __syncwarp();   // stage reads and the private-row accesses of this iteration are complete in every lane
+      if (lane == 0) mbar_arrive(empty + i2);
+    }
+    // the last two stages were read but never released inside the loop: nothing waits for them
+  }
+  const AcPoints none{};
+  ac_cta_epilogue(bid, ubA, none, nullptr, 0.0, src, gsrcv_row1, g.dt2);   // A already carries its residuals
+  ac_cta_epilogue(bid, ubB, rcv, res_row2, 1.0, src, gsrcv_row2, g.dt2);
 }

@@ -158,13 +158,27 @@ static inline void build_point_set(const std::vector<int>& owner, const std::vec
 struct PointSetStorage {
   int *blk = nullptr, *cell = nullptr, *start = nullptr, *perm = nullptr, *field = nullptr;
   int nu = 0, npts = 0;
+  size_t cap[5] = {0, 0, 0, 0, 0};  // allocated elements: a re-upload of the same size keeps the device pointers
 };
+static inline int upload_ints_reuse(int** p, size_t* cap, const std::vector<int>& h, cudaStream_t s) {
+  const size_t n = h.empty() ? 1 : h.size();
+  if (*p == nullptr || *cap < n) {
+    cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    TRY(dev_alloc(p, n));
+    *cap = n;
+  }
+  if (!h.empty()) CUDA_TRY(cudaMemcpyAsync(*p, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  return ADSEIS_OK;
+}
+// (re)upload: device buffers are reused when they are large enough, so a plan that is re-pointed at the next shot
+// (same counts) keeps every device address -- kernel arguments, and a captured CUDA graph, stay valid
 static inline int upload_point_set(const PointSetHost& h, PointSetStorage* st, cudaStream_t s) {
-  TRY(dev_upload(&st->blk, h.blk, s));
-  TRY(dev_upload(&st->cell, h.cell, s));
-  TRY(dev_upload(&st->start, h.start, s));
-  TRY(dev_upload(&st->perm, h.perm, s));
-  TRY(dev_upload(&st->field, h.field, s));
+  TRY(upload_ints_reuse(&st->blk, &st->cap[0], h.blk, s));
+  TRY(upload_ints_reuse(&st->cell, &st->cap[1], h.cell, s));
+  TRY(upload_ints_reuse(&st->start, &st->cap[2], h.start, s));
+  TRY(upload_ints_reuse(&st->perm, &st->cap[3], h.perm, s));
+  TRY(upload_ints_reuse(&st->field, &st->cap[4], h.field, s));
   st->nu = (int)h.cell.size();
   st->npts = (int)h.perm.size();
   return ADSEIS_OK;

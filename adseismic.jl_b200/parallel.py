@@ -138,13 +138,15 @@ class ShotPlanCache:
         self.plan, self.key = None, None
 
 
-def compute_loss_and_grads_GPU(param, srcs, rcvs, Rs, model, ctx=None, plan_cache=None, material_grads=True):
+def compute_loss_and_grads_GPU(param, srcs, rcvs, Rs, model, ctx=None, plan_cache=None, material_grads=True,
+                               fetch_traces=True):
     """compute_loss_and_grads_GPU (src/Utils.jl:300-332): sum over shots of sum((rcvv-Rs)^2) and its gradient w.r.t. the
     model.  Acoustic (`srcs` of AcousticSource, `model` = velocity c) or elastic (`srcs` of ElasticSource, `model` =
     (rho, lambda, mu) -> gradient tuple in the same order).  Shots are dealt to the ranks of the current process group
     with the reference's round-robin rule (shot k, 1-based, on device k % n_gpu); the per-rank partial sums are
     all-reduced over NCCL, so every rank returns the full (loss, grad).  Works single-process too.
-    `plan_cache`: a ShotPlanCache kept by the caller across calls (FWI iterations)."""
+    `plan_cache`: a ShotPlanCache kept by the caller across calls (FWI iterations).  `fetch_traces=False` skips the
+    device-to-host copy of every shot's simulated traces into rcvs[k].rcvv (an optimiser only needs loss and gradient)."""
     import torch
     from .structs import ElasticSource
     rank, world, jobs = _shot_context(len(srcs))
@@ -182,7 +184,8 @@ def compute_loss_and_grads_GPU(param, srcs, rcvs, Rs, model, ctx=None, plan_cach
             g += gtmp
             if on_gpu:             # torch's stream must be done with gtmp before it is overwritten
                 torch.cuda.current_stream().synchronize()
-        rcv.rcvv = plan.rcvv()
+        if fetch_traces:
+            rcv.rcvv = plan.rcvv()
         if elastic:
             plan.close()
     if own_cache:

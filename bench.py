@@ -409,14 +409,14 @@ def run_shots(A, ctx, w, steps, warmup, rank, world, dev):
     cache = parallel.ShotPlanCache()
     Rs = parallel.compute_forward_GPU(p, srcs, rcvs, w["model_obs"], ctx=ctx, plan_cache=cache)
     for _ in range(warmup):
-        parallel.compute_loss_and_grads_GPU(p, srcs, rcvs, Rs, w["model"], ctx=ctx, plan_cache=cache)
+        parallel.compute_loss_and_grads_GPU(p, srcs, rcvs, Rs, w["model"], ctx=ctx, plan_cache=cache, fetch_traces=False)
     ctx.sync()
     if world > 1:
         torch.distributed.barrier()
     l0 = ctx.launch_count()
     t0 = time.perf_counter()
     for _ in range(steps):
-        loss, g = parallel.compute_loss_and_grads_GPU(p, srcs, rcvs, Rs, w["model"], ctx=ctx, plan_cache=cache)
+        loss, g = parallel.compute_loss_and_grads_GPU(p, srcs, rcvs, Rs, w["model"], ctx=ctx, plan_cache=cache, fetch_traces=False)
     ctx.sync()
     sec = (time.perf_counter() - t0) / steps
     sec = parallel.all_reduce_scalar(sec, "max", device=dev)
@@ -437,10 +437,10 @@ def run_shots(A, ctx, w, steps, warmup, rank, world, dev):
                                       "final gradient all-reduce)",
                 e2e=dict(value=cells / sec / 1e9, unit=UNIT, ms_per_step=sec * 1e3,
                          note="compute_loss_and_grads_GPU takes host models / traces and returns host gradients: the "
-                              "timed region IS the end-to-end call (per shot H2D of model+srcv+obs, D2H of traces)",
+                              "timed region IS the end-to-end call (per shot H2D of model+srcv+obs, D2H of the loss; gradient D2H once)",
                          h2d_bytes_per_step=int(sum((np.asarray(w["model"]).size + s["srcv"].size + Rs[k].size) * 8
                                                     for k, s in enumerate(w["shots"]))),
-                         d2h_bytes_per_step=int(sum(Rs[k].size * 8 for k in range(len(srcs))) + world * np.asarray(w["model"]).size * 8)),
+                         d2h_bytes_per_step=int(8 * len(srcs) + world * np.asarray(w["model"]).size * 8)),
                 gpu_launches=int(launches), roofline=roof, loss=loss, grad_checksum=checksum(g),
                 config=dict(grid=[p.NX, p.NY], nstep=p.NSTEP, shots=len(srcs), history_slots=info["hist_slots"],
                             segments=info["segments"], parallelism="shots round-robin over %d GPU(s) + NCCL all-reduce" % world))
