@@ -298,7 +298,7 @@ static int validate_params(const adseis_acoustic_params* p) {
 // is the PML-free box shrunk by TWO cells so that the one-cell rim of every tile is made of plain interior cells.
 static void build_tb_tilings(adseis_acoustic_plan* P) {
   P->tb = false;
-  const char* e = getenv("ADSEIS_AC_TB");
+  const char* e = getenv("ADSEIS_AC_TB");   // "0": never, "1": whenever the box is large enough to tile, unset: auto
   if (e && e[0] == '0') return;
   if (P->slab.nranks != 1) return;
   const AcGeom& g = P->g;
@@ -307,9 +307,14 @@ static void build_tb_tilings(adseis_acoustic_plan* P) {
   const int mc0 = round_up(std::max(fj0, 1), 16);
   const int mc_end = mc0 + 2 * ((fj1 + 1 - mc0) / 2);
   if (mr1 - mr0 < 8 || mc_end - mc0 < 32) return;
+  // Auto: a pair costs three launches (frame, box pair, frame) instead of two.  That pays once the box kernels are long
+  // next to the two frame-only launches (~5-10 us each): measured on B200, 2000 x 1000 (C3) is 12 % SLOWER with pairs
+  // (16.2 vs 14.5 us per forward step), 4096^2 is 27 % faster (profiles/r02_temporal_blocking.md).
+  if (!(e && e[0] == '1') && (i64)(mr1 - mr0) * (mc_end - mc0) < (6LL << 20)) return;
   AcTiling& t = P->t2;
   memset(&t, 0, sizeof(t));
   t.mr0 = mr0; t.mr1 = mr1; t.mc0 = mc0; t.mc_end = mc_end;
+  t.fcpt = AC_FRAME_CPT;
   const int nwarpcols = (mc_end - mc0 + AC_WCOLS - 1) / AC_WCOLS;
   t.nct = (nwarpcols + AC_WARPS - 1) / AC_WARPS;
   const int rows = mr1 - mr0;
@@ -332,12 +337,14 @@ static void build_tb_tilings(adseis_acoustic_plan* P) {
   memset(&f, 0, sizeof(f));
   f.mr0 = f.mr1 = P->own0;  // no marched rows
   f.rb = 1;
+  f.fcpt = getenv("ADSEIS_AC_FCPT2") ? std::max(1, atoi(getenv("ADSEIS_AC_FCPT2"))) : 1;  // alone in its launch: all parallelism
+  const int fcells2 = AC_THREADS * f.fcpt;
   auto add_rect = [&](int r0, int r1, int c0, int c1) {
     if (r1 <= r0 || c1 <= c0) return;
     const int k = f.nrect++;
     f.rr0[k] = r0; f.rr1[k] = r1; f.rc0[k] = c0; f.rc1[k] = c1;
     const i64 cells = (i64)(r1 - r0) * (c1 - c0);
-    f.rblk[k + 1] = f.rblk[k] + (int)((cells + AC_FRAME_CELLS - 1) / AC_FRAME_CELLS);
+    f.rblk[k + 1] = f.rblk[k] + (int)((cells + fcells2 - 1) / fcells2);
   };
   f.rblk[0] = 0;
   add_rect(P->own0, mr0, 0, g.W);
@@ -435,7 +442,7 @@ static int plan_build_points(adseis_acoustic_plan* P, int64_t nsrc, const int64_
     auto owner_f = [&](int li, int j) -> int {
       for (int k = 0; k < tf.nrect; k++)
         if (li >= tf.rr0[k] && li < tf.rr1[k] && j >= tf.rc0[k] && j < tf.rc1[k])
-          return tf.rblk[k] + (int)(((i64)(li - tf.rr0[k]) * (tf.rc1[k] - tf.rc0[k]) + (j - tf.rc0[k])) / AC_FRAME_CELLS);
+          return tf.rblk[k] + (int)(((i64)(li - tf.rr0[k]) * (tf.rc1[k] - tf.rc0[k]) + (j - tf.rc0[k])) / (AC_THREADS * tf.fcpt));
       return -1;
     };
     auto build2 = [&](i64 n, const int64_t* pi, const int64_t* pj, int mode, int nblk, PointSetStorage* dst) -> int {
@@ -598,6 +605,7 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     const int fi0 = ia + shrink, fi1 = ib - shrink, fj0 = ja + shrink, fj1 = jb - shrink;
     AcTiling& t = P->t;
     memset(&t, 0, sizeof(t));
+    t.fcpt = AC_FRAME_CPT;
     // marched local rows: owned rows whose global index lies in [fi0, fi1]
     int mr0 = std::max(P->own0, fi0 - g.goff), mr1 = std::min(P->own1, fi1 + 1 - g.goff);
     int mc0 = round_up(std::max(fj0, 1), 16);

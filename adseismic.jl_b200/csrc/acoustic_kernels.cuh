@@ -110,6 +110,8 @@ struct AcTiling {
   int nrect;          // frame rectangles (local rows [rr0,rr1) x columns [rc0,rc1))
   int rr0[4], rr1[4], rc0[4], rc1[4];
   int rblk[5];        // CTA-id prefix of the rectangles, relative to nmarch
+  int fcpt;           // frame cells per thread (a frame CTA covers AC_THREADS * fcpt consecutive cells of its rectangle):
+                      // AC_FRAME_CPT when frame CTAs share a launch with marching CTAs, 1 in frame-only launches
 };
 
 // Row tile tr of the marched rows -> [r0, r1).  Slab plans put a thin tile on the rows next to a neighbour: those CTAs
@@ -289,7 +291,7 @@ __device__ __forceinline__ void ac_frame_locate(const AcTiling& t, int fb, int* 
   for (int k = 1; k < 4; k++)
     if (k < t.nrect && fb >= t.rblk[k]) r = k;
   *rect = r;
-  *idx0 = (fb - t.rblk[r]) * AC_FRAME_CELLS;
+  *idx0 = (fb - t.rblk[r]) * (AC_THREADS * t.fcpt);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -312,12 +314,12 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
     ac_frame_locate(t, bid - t.nmarch, &rect, &idx0);
     wdt = t.rc1[rect] - t.rc0[rect];
     ncell = (t.rr1[rect] - t.rr0[rect]) * wdt;
-    const int rlo = t.rr0[rect] + idx0 / wdt, rhi = t.rr0[rect] + (min(ncell, idx0 + AC_FRAME_CELLS) - 1) / wdt;
+    const int rlo = t.rr0[rect] + idx0 / wdt, rhi = t.rr0[rect] + (min(ncell, idx0 + AC_THREADS * t.fcpt) - 1) / wdt;
     t_lo = f.has_lo && rlo <= f.own0 && f.own0 <= rhi;
     t_hi = f.has_hi && rlo <= f.own_last && f.own_last <= rhi;
     ac_fuse_wait(f, t_lo, t_hi);
-#pragma unroll
-    for (int k = 0; k < AC_FRAME_CPT; k++) {
+#pragma unroll 4
+    for (int k = 0; k < t.fcpt; k++) {
       const int idx = idx0 + k * AC_THREADS + threadIdx.x;
       if (idx < ncell && threadIdx.x < AC_THREADS) {
         const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
@@ -445,8 +447,8 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
   if (t_lo || t_hi) {  // push my piece of the new edge row(s) into the neighbours' halo rows, then publish
     __syncthreads();
     if (bid >= t.nmarch) {
-#pragma unroll
-      for (int k = 0; k < AC_FRAME_CPT; k++) {
+#pragma unroll 4
+      for (int k = 0; k < t.fcpt; k++) {
         const int idx = idx0 + k * AC_THREADS + threadIdx.x;
         if (idx < ncell && threadIdx.x < AC_THREADS) {
           const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
@@ -732,12 +734,12 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
 #endif
     wdt = t.rc1[rect] - t.rc0[rect];
     ncell = (t.rr1[rect] - t.rr0[rect]) * wdt;
-    const int rlo = t.rr0[rect] + idx0 / wdt, rhi = t.rr0[rect] + (min(ncell, idx0 + AC_FRAME_CELLS) - 1) / wdt;
+    const int rlo = t.rr0[rect] + idx0 / wdt, rhi = t.rr0[rect] + (min(ncell, idx0 + AC_THREADS * t.fcpt) - 1) / wdt;
     t_lo = f.has_lo && rlo <= f.own0 && f.own0 <= rhi;
     t_hi = f.has_hi && rlo <= f.own_last && f.own_last <= rhi;
     ac_fuse_wait(f, t_lo, t_hi);
-#pragma unroll
-    for (int k = 0; k < AC_FRAME_CPT; k++) {
+#pragma unroll 4
+    for (int k = 0; k < t.fcpt; k++) {
       const int idx = idx0 + k * AC_THREADS + threadIdx.x;
       if (idx < ncell && threadIdx.x < AC_THREADS) {
         const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
@@ -855,8 +857,8 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
   if (t_lo || t_hi) {
     __syncthreads();
     if (bid >= t.nmarch) {
-#pragma unroll
-      for (int k = 0; k < AC_FRAME_CPT; k++) {
+#pragma unroll 4
+      for (int k = 0; k < t.fcpt; k++) {
         const int idx = idx0 + k * AC_THREADS + threadIdx.x;
         if (idx < ncell && threadIdx.x < AC_THREADS) {
           const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;

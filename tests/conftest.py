@@ -10,6 +10,9 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # The two-steps-per-launch kernels (temporal blocking) switch on automatically only for large grids; the parity tests
+    # run on small ones, so they force the path on (tests that compare it with the one-step path set "0" themselves).
+    os.environ.setdefault("ADSEIS_AC_TB", "1")
 
 
 @pytest.fixture(scope="session")

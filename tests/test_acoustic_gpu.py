@@ -220,3 +220,44 @@ def test_kernel0_vs_oracle(A, ctx, po, shape, mpi):
         plan.close()
     assert out[1][2]["segments"] > 1
     assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
+
+
+@pytest.mark.parametrize("kernel", [1, 0])
+def test_two_step_kernels_equal_one_step_kernels_bitwise(A, ctx, po, monkeypatch, kernel):
+    """Temporal blocking (ac_fwd2_kernel / ac_adj2_kernel + frame-only launches) is an execution schedule, not a
+    different discretisation: traces, loss and both gradients are bit-identical to the one-step kernels, with sources
+    and receivers inside the box, on its rim, in the frame, on tile seams, and with checkpoint segments that shift the
+    pairing of the steps."""
+    NX, NY, NSTEP = 150, 1300, 61
+    rng = np.random.default_rng(31)
+    dx, dt, vp = 10.0, 1e-3, 2500.0
+    sig, tau, c, srci, srcj, srcv, rcvi, rcvj = _case(po, rng, NX, NY, NSTEP, dx, dx, dt, 10, vp, nsrc=6)
+    srci[0], srcj[0] = 14, 18          # first row / column of the two-step box (npml 10: PML-free rows 12.., box 14..)
+    srci[1], srcj[1] = 13, 40          # on the rim of the box (a frame cell whose value the box kernel recomputes)
+    srci[2], srcj[2] = 60, 16 + 512    # first column of the second column tile
+    srci[3], srcj[3] = 60, 16 + 511    # last column of the first one
+    srci[4], srcj[4] = 5, 5            # deep inside the absorbing frame
+    rcvi[:8] = [14, 13, 60, 60, 5, 70, 71, 72]
+    rcvj[:8] = [18, 40, 16 + 512, 16 + 511, 5, 16 + 64, 16 + 63, 16 + 65]
+    p = A.AcousticPropagatorParams(PropagatorKernel=kernel, NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dx, DELTAT=dt,
+                                   vp_ref=vp, NPOINTS_PML=10)
+    pitch = (NY + 2 + 15) // 16 * 16
+    out = {}
+    for tb in ("0", "1"):
+        monkeypatch.setenv("ADSEIS_AC_TB", tb)
+        for slots in (0, 12):
+            plan = A.AcousticPlan(p, srci, srcj, rcvi, rcvj, ctx=ctx, hist_bytes_budget=slots * (NX + 2) * pitch * 8)
+            plan.set_model(c); plan.set_srcv(srcv)
+            plan.forward()
+            r = plan.rcvv()
+            plan.set_obs(0.6 * r)
+            plan.gradient()
+            out[(tb, slots)] = (r, plan.loss(), plan.grad_c(), plan.grad_srcv(), plan.info())
+            plan.close()
+    ref = out[("0", 0)]
+    assert np.abs(ref[0]).max() > 0 and np.abs(ref[2]).max() > 0
+    assert out[("1", 12)][4]["segments"] > 3
+    assert out[("1", 0)][4]["launches"] > ref[4]["launches"]       # three launches per pair of steps instead of two
+    for key, val in out.items():
+        assert np.array_equal(val[0], ref[0]) and val[1] == ref[1], key
+        assert np.array_equal(val[2], ref[2]) and np.array_equal(val[3], ref[3]), key
