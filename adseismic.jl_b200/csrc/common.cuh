@@ -211,22 +211,23 @@ __device__ __forceinline__ double div_markstein(double x, double h, double rh) {
 
 // Numerators near the denormal range (|x| < 1e-280: the numerical precursor that runs ahead of every wavefront is a
 // band tens of cells wide of such values) would make the remainders inexact.  They are scaled by 2^400 (exact), divided
-// in the normal range, and scaled back.  Scaling back is exact while the quotient stays normal; for a subnormal result
-// the scaled quotient `q` = RN(2^400 x / h) is first made ROUND-TO-ODD with the sign of its exact remainder, after which
-// the final rounding onto the subnormal grid (>= 2 bits coarser) cannot double-round; the single binade that loses
-// exactly one bit uses the true divide.  Bit-identical to x / h for every input (host model of this routine checked
-// against x / h on 4.4e8 random tiny numerators, 11 divisors: scripts/div_tiny_check.c).  Round 1 fell back to the
-// divide sequence for these numerators instead, which made the elastic forward kernels 2.4x slower once the
-// precursor band had spread over the grid (117 -> 281 us per step at 2000^2, profiles/r02c_elastic_division.md).
-static __device__ __noinline__ double div_fix_tiny(double x, double h, double q) {
+// in the normal range, and scaled back.  Scaling back is exact while the quotient stays normal.  For a subnormal
+// result the scaled quotient `q` = RN(2^400 x / h) is adjusted with the sign of its exact remainder before the final
+// multiplication rounds it onto the coarser subnormal grid: made ROUND-TO-ODD when >= 2 bits are lost (then the second
+// rounding cannot double-round), and stepped off the rounding boundary towards the true quotient when exactly one bit
+// is lost.  Bit-identical to x / h for every input (host model of this routine checked against x / h on 4.4e8 random
+// tiny numerators, 11 divisors: scripts/div_tiny_check.c); no divide instruction, ~15 inline instructions that only
+// warps holding such a numerator execute.  Round 1 fell back to the divide sequence for these numerators, whose slow
+// path made the CTAs that cross the precursor band several times slower than the rest (a long tail on every launch:
+// elastic forward 117 -> 281 us per step at 2000^2 once the band had spread, profiles/r02c_elastic_division.md).
+__device__ __forceinline__ double div_fix_tiny(double x, double h, double q) {
   const double aq = fabs(q);
-  if (aq >= 0x1p-622) return q * 0x1p-400;          // the scaled-back quotient is a normal number: exact
-  if (aq >= 0x1p-623) return x / h;                 // loses exactly one bit: round-to-odd is not enough (rare)
-  const double r = fma(-q, h, x * 0x1p+400);        // exact remainder: its sign tells on which side x/h lies
-  if (r != 0.0) {
+  if (aq < 0x1p-622) {                                // subnormal result
+    const double r = fma(-q, h, x * 0x1p+400);        // exact remainder: its sign tells on which side x/h lies
     long long b = __double_as_longlong(q);
-    if ((b & 1LL) == 0) {                           // round to odd: take the other neighbour of the true quotient
-      const bool up = (r > 0.0) == (h > 0.0);       // true quotient > q ?
+    const bool one_bit = aq >= 0x1p-623;
+    if (r != 0.0 && (((b & 1LL) == 0) != one_bit)) {
+      const bool up = (r > 0.0) == (h > 0.0);         // true quotient > q ?
       b += ((q > 0.0) == up) ? 1LL : -1LL;
       q = __longlong_as_double(b);
     }

@@ -315,13 +315,29 @@ def acoustic_roofline(A, w, r):
     adj_us = tm["adjoint_ms"] * 1e3 / max(tm["adjoint_launches"], 1)
     nf = tm["forward_launches"] + tm["recompute_launches"]
     fwd_us = (tm["forward_ms"] + tm["recompute_ms"]) * 1e3 / max(nf, 1)
-    roof = roof_entry("ac_adj_kernel", ab["adjoint"], adj_us, peak, peak_src, share=tm["adjoint_ms"] / r["step_ms"],
-                      traffic=ncu_traffic("ac_adj_kernel"))
-    roof["other_kernels"] = dict(ac_fwd_kernel=roof_entry("ac_fwd_kernel", ab["forward"], fwd_us, peak, peak_src,
-                                                          share=(tm["forward_ms"] + tm["recompute_ms"]) / r["step_ms"],
-                                                          traffic=ncu_traffic("ac_fwd_kernel")))
-    # whole gradient against the 8(d) roofline: one forward + one adjoint pass over the grid per counted step
     p = w["param"]
+    # two steps per launch (temporal blocking) switch on automatically for boxes of >= 6 M cells (csrc/acoustic.cu)
+    n = p.NPOINTS_PML + 3
+    tb = os.environ.get("ADSEIS_AC_TB", "") != "0" and (os.environ.get("ADSEIS_AC_TB") == "1" or
+                                                         (p.NX - 2 * n) * (p.NY - 2 * n) >= (6 << 20))
+    half = lambda x: None if x is None else x / 2.0
+    if tb:
+        roof = roof_entry("ac_adj2_kernel (two adjoint steps per launch) + 2 frame-only ac_adj_kernel launches; figures "
+                          "are PER TIME STEP", ab["adjoint"], adj_us, peak, peak_src, share=tm["adjoint_ms"] / r["step_ms"],
+                          traffic=half(ncu_traffic("ac_adj2_kernel")),
+                          note="achieved = SURVEY 8(d) algorithmic bytes of ONE step (56 B/cell) / time per step; the "
+                               "pair kernel moves 36 B per cell-step (ncu traffic above, per step), so frac may exceed 1")
+        roof["other_kernels"] = dict(ac_fwd2_kernel=roof_entry(
+            "ac_fwd2_kernel (two forward steps per launch) + 2 frame-only ac_fwd_kernel launches, per time step",
+            ab["forward"], fwd_us, peak, peak_src, share=(tm["forward_ms"] + tm["recompute_ms"]) / r["step_ms"],
+            traffic=half(ncu_traffic("ac_fwd2_kernel"))))
+    else:
+        roof = roof_entry("ac_adj_kernel", ab["adjoint"], adj_us, peak, peak_src, share=tm["adjoint_ms"] / r["step_ms"],
+                          traffic=ncu_traffic("ac_adj_kernel"))
+        roof["other_kernels"] = dict(ac_fwd_kernel=roof_entry("ac_fwd_kernel", ab["forward"], fwd_us, peak, peak_src,
+                                                              share=(tm["forward_ms"] + tm["recompute_ms"]) / r["step_ms"],
+                                                              traffic=ncu_traffic("ac_fwd_kernel")))
+    # whole gradient against the 8(d) roofline: one forward + one adjoint pass over the grid per counted step
     whole = (ab["forward"] + ab["adjoint"]) * (p.NSTEP - 1) / (r["step_ms"] * 1e-3) / 1e9
     roof["whole_gradient"] = dict(achieved=whole, frac=whole / peak, unit="GB/s",
                                   note="(32+56 B) x cells x counted steps / gradient time; replayed steps are overhead")

@@ -15,11 +15,13 @@ static inline double fix_tiny(double x, double h, double q /* = RN((x * 2^400) /
   const double xs = x * 0x1p+400;
   const double aq = fabs(q);
   if (aq >= 0x1p-622) return q * 0x1p-400;         // the scaled-back quotient is a normal number: exact
-  if (aq >= 0x1p-623) return x / h;                // loses exactly one bit: round-to-odd is not enough (rare binade)
   const double r = fma(-q, h, xs);                 // exact residual: sign tells on which side the true quotient lies
-  if (r != 0.0) {
+  if (r != 0.0) {                                  // (an exact q is rounded correctly by the final multiplication)
     int64_t b; memcpy(&b, &q, 8);
-    if ((b & 1) == 0) {                            // round to odd: take the other neighbour of the true quotient
+    // >= 2 bits lost: round to odd.  Exactly 1 bit lost: q with an odd last bit sits on a rounding boundary of the
+    // coarser grid -- step off it towards the true quotient (lands on the grid: the scaling is then exact)
+    const int one_bit = aq >= 0x1p-623;
+    if (((b & 1) == 0) != one_bit) {
       const int up = (r > 0.0) == (h > 0.0);       // true quotient > q ?
       b += ((q > 0.0) == up) ? 1 : -1;
       memcpy(&q, &b, 8);
