@@ -59,8 +59,10 @@ __global__ void k_grad_finalize(const double* __restrict__ G, const double* __re
 struct AcDesc {
   unsigned long long magic;
   long long Hl, ld, plane, win, own0, own1;
-  long long off_flags, off_hist, off_phi[2], off_psi[2], off_ub[3], off_phib[2], off_psib[2];
+  long long off_flags, off_hist, off_phi[2], off_psi[2], off_ub[4], off_phib[2], off_psib[2];
   long long n_edge_lo, n_edge_hi;  // CTAs of one step launch that own cells of my first / last owned row
+  long long n_edge_lo_f, n_edge_hi_f;  // ... of a frame-only launch of the two-step path (0: that path is off)
+  long long nub;
 };
 #define AC_DESC_MAGIC 0xAD5E15B200ULL
 #define AC_HX_BLOCKS 8
@@ -172,6 +174,9 @@ struct adseis_acoustic_plan {
   unsigned long long sepoch = 0;             // step kernels launched so far (same sequence on every rank)
   int* perm = nullptr;                       // launch order -> logical CTA id (edge CTAs first)
   int n_edge_lo = 0, n_edge_hi = 0;
+  int* perm_f = nullptr;                     // launch order of the frame-only tiling (two-step path on slabs)
+  int n_edge_lo_f = 0, n_edge_hi_f = 0;
+  unsigned long long exp_lo = 0, exp_hi = 0; // signals the neighbours have sent me so far (sum over their fused launches)
   bool connected = false;
   // stats
   i64 last_launches = 0, last_segments = 0, last_recomputed = 0;
@@ -257,7 +262,7 @@ ADSEIS_API int adseis_acoustic_plan_destroy(adseis_acoustic_plan* P) {
   cudaSetDevice(P->ctx->device);
   cudaStreamSynchronize(P->ctx->stream);
   cudaFree(P->c2); cudaFree(P->cvel); cudaFree(P->sigx); cudaFree(P->tauy);
-  cudaFree(P->perm);
+  cudaFree(P->perm); cudaFree(P->perm_f);
   if (P->arena) {
     for (int k = 0; k < 2; k++) if (P->peer[k]) cudaIpcCloseMemHandle(P->peer[k]);
     cudaFree(P->arena);
@@ -294,23 +299,78 @@ static int validate_params(const adseis_acoustic_params* p) {
   return ADSEIS_OK;
 }
 
+// Launch order of a tiling (logical CTA id = perm[blockIdx.x]).  Slab plans: the CTAs that own cells of my first / last
+// owned row next to a neighbour go first, so their halo pushes leave early and the rest of the step hides the NVLink
+// latency.  Then the frame CTAs (latency-bound: one DRAM round trip + fp64 divides, no bandwidth) are spread evenly
+// among the marching CTAs (bandwidth-bound) instead of forming the tail of the launch.
+static void build_launch_order(adseis_acoustic_plan* P, const AcTiling& t, int nblocks, std::vector<int>* order_out,
+                               int* n_edge_lo, int* n_edge_hi) {
+  const bool halo_lo = P->slab.rank > 0, halo_hi = P->slab.rank < P->slab.nranks - 1;
+  const int first = P->own0, last = P->own1 - 1;
+  const int fcells = AC_THREADS * t.fcpt;
+  std::vector<int> edge, march, frame;
+  *n_edge_lo = *n_edge_hi = 0;
+  for (int b = 0; b < nblocks; b++) {
+    int rlo, rhi;
+    if (b < t.nmarch) {
+      int a0, a1;
+      ac_row_tile(t, b / t.nct, &a0, &a1);
+      rlo = a0; rhi = a1 - 1;
+    } else {
+      int fb = b - t.nmarch, r = 0;
+      for (int k = 1; k < t.nrect; k++) if (fb >= t.rblk[k]) r = k;
+      const int w = t.rc1[r] - t.rc0[r];
+      const i64 ncell = (i64)(t.rr1[r] - t.rr0[r]) * w, i0 = (i64)(fb - t.rblk[r]) * fcells;
+      rlo = t.rr0[r] + (int)(i0 / w);
+      rhi = t.rr0[r] + (int)((std::min<i64>(ncell, i0 + fcells) - 1) / w);
+    }
+    const bool tl = halo_lo && rlo <= first && first <= rhi, th = halo_hi && rlo <= last && last <= rhi;
+    if (tl) (*n_edge_lo)++;
+    if (th) (*n_edge_hi)++;
+    if (tl || th) edge.push_back(b);
+    else (b < t.nmarch ? march : frame).push_back(b);
+  }
+  std::vector<int>& order = *order_out;
+  order = edge;
+  size_t im = 0, ifr = 0;
+  const size_t nm = march.size(), nf = frame.size();
+  while (im < nm || ifr < nf) {  // Bresenham merge: frame CTA k goes after ~k*nm/nf marching CTAs
+    if (ifr < nf && (im >= nm || ifr * nm <= im * nf)) order.push_back(frame[ifr++]);
+    else order.push_back(march[im++]);
+  }
+}
+
 // Temporal blocking: tilings of the two-step forward path (see ac_fwd2_kernel).  Single-GPU plans only; the marched box
 // is the PML-free box shrunk by TWO cells so that the one-cell rim of every tile is made of plain interior cells.
 static void build_tb_tilings(adseis_acoustic_plan* P) {
   P->tb = false;
   const char* e = getenv("ADSEIS_AC_TB");   // "0": never, "1": whenever the box is large enough to tile, unset: auto
   if (e && e[0] == '0') return;
-  if (P->slab.nranks != 1) return;
   const AcGeom& g = P->g;
+  const bool slab = P->slab.nranks > 1;
+  const int has_lo = P->slab.rank > 0 ? 1 : 0, has_hi = P->slab.rank < P->slab.nranks - 1 ? 1 : 0;
+  if (slab) {
+    // Slab plans: the two rows next to a neighbour are advanced by the frame-only launches (which carry the fused halo
+    // exchange of the one-step kernels, one halo row, unchanged); the box pair kernel then reads owned rows only and
+    // never touches a halo.  EVERY rank must take the same decision (the launch sequences must match): it depends on
+    // global quantities only.
+    const char* es = getenv("ADSEIS_AC_TB_SLAB");
+    if (es && es[0] == '0') return;
+    if (P->p.PropagatorKernel == 0) return;
+    const i64 rows_min = (i64)g.H / P->slab.nranks - (P->p.NPOINTS_PML + 4) - 5;
+    const i64 cells = rows_min * (i64)(g.W - 2 * (P->p.NPOINTS_PML + 4));
+    const i64 min_cells = getenv("ADSEIS_AC_TB_SLAB_MIN") ? atoll(getenv("ADSEIS_AC_TB_SLAB_MIN")) : (3LL << 19);
+    if (rows_min < 16 || (!(e && e[0] == '1') && cells < min_cells)) return;
+  }
   const int fi0 = P->box_i0 + 2, fi1 = P->box_i1 - 2, fj0 = P->box_j0 + 2, fj1 = P->box_j1 - 2;
-  const int mr0 = std::max(P->own0, fi0 - g.goff), mr1 = std::min(P->own1, fi1 + 1 - g.goff);
+  const int mr0 = std::max(P->own0 + 2 * has_lo, fi0 - g.goff), mr1 = std::min(P->own1 - 2 * has_hi, fi1 + 1 - g.goff);
   const int mc0 = round_up(std::max(fj0, 1), 16);
   const int mc_end = mc0 + 2 * ((fj1 + 1 - mc0) / 2);
   if (mr1 - mr0 < 8 || mc_end - mc0 < 32) return;
   // Auto: a pair costs three launches (frame, box pair, frame) instead of two.  That pays once the box kernels are long
   // next to the two frame-only launches (~5-10 us each): measured on B200, 2000 x 1000 (C3) is 12 % SLOWER with pairs
   // (16.2 vs 14.5 us per forward step), 4096^2 is 27 % faster (profiles/r02_temporal_blocking.md).
-  if (!(e && e[0] == '1') && (i64)(mr1 - mr0) * (mc_end - mc0) < (6LL << 20)) return;
+  if (!slab && !(e && e[0] == '1') && (i64)(mr1 - mr0) * (mc_end - mc0) < (6LL << 20)) return;
   AcTiling& t = P->t2;
   memset(&t, 0, sizeof(t));
   t.mr0 = mr0; t.mr1 = mr1; t.mc0 = mc0; t.mc_end = mc_end;
@@ -354,6 +414,11 @@ static void build_tb_tilings(adseis_acoustic_plan* P) {
   for (int k = f.nrect; k < 4; k++) { f.rblk[k + 1] = f.rblk[f.nrect]; f.rr0[k] = f.rr1[k] = f.rc0[k] = 0; f.rc1[k] = 1; }
   P->nblocksf = f.rblk[f.nrect];
   P->tb = true;
+  if (slab) {
+    std::vector<int> order;
+    build_launch_order(P, f, P->nblocksf, &order, &P->n_edge_lo_f, &P->n_edge_hi_f);
+    if (dev_upload(&P->perm_f, order, P->ctx->stream) != ADSEIS_OK) { P->tb = false; return; }
+  }
   const char* ea = getenv("ADSEIS_AC_TB_ADJ");
   P->tb_adj = P->p.PropagatorKernel != 0 && !(ea && ea[0] == '0');
   P->nub = P->tb_adj ? 4 : 3;
@@ -665,40 +730,8 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     P->nblocks = t.nmarch + t.rblk[t.nrect];
   }
   {
-    // Launch order (logical CTA id = perm[blockIdx.x]).  Slab plans: the CTAs that own cells of my first / last
-    // owned row next to a neighbour go first, so their halo pushes leave early and the rest of the step hides the
-    // NVLink latency.  Then the frame CTAs (latency-bound: one DRAM round trip + fp64 divides, no bandwidth) are
-    // spread evenly among the marching CTAs (bandwidth-bound) instead of forming the tail of the launch.
-    const AcTiling& t = P->t;
-    const int first = P->own0, last = P->own1 - 1;
-    std::vector<int> edge, march, frame;
-    for (int b = 0; b < P->nblocks; b++) {
-      int rlo, rhi;
-      if (b < t.nmarch) {
-        int a0, a1;
-        ac_row_tile(t, b / t.nct, &a0, &a1);
-        rlo = a0; rhi = a1 - 1;
-      } else {
-        int fb = b - t.nmarch, r = 0;
-        for (int k = 1; k < t.nrect; k++) if (fb >= t.rblk[k]) r = k;
-        const int w = t.rc1[r] - t.rc0[r];
-        const i64 ncell = (i64)(t.rr1[r] - t.rr0[r]) * w, i0 = (i64)(fb - t.rblk[r]) * AC_FRAME_CELLS;
-        rlo = t.rr0[r] + (int)(i0 / w);
-        rhi = t.rr0[r] + (int)((std::min<i64>(ncell, i0 + AC_FRAME_CELLS) - 1) / w);
-      }
-      const bool tl = halo_lo && rlo <= first && first <= rhi, th = halo_hi && rlo <= last && last <= rhi;
-      if (tl) P->n_edge_lo++;
-      if (th) P->n_edge_hi++;
-      if (tl || th) edge.push_back(b);
-      else (b < t.nmarch ? march : frame).push_back(b);
-    }
-    std::vector<int> order(edge);
-    size_t im = 0, ifr = 0;
-    const size_t nm = march.size(), nf = frame.size();
-    while (im < nm || ifr < nf) {  // Bresenham merge: frame CTA k goes after ~k*nm/nf marching CTAs
-      if (ifr < nf && (im >= nm || ifr * nm <= im * nf)) order.push_back(frame[ifr++]);
-      else order.push_back(march[im++]);
-    }
+    std::vector<int> order;
+    build_launch_order(P, P->t, P->nblocks, &order, &P->n_edge_lo, &P->n_edge_hi);
     PTRY(dev_upload(&P->perm, order, st));
   }
 
@@ -745,13 +778,14 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     AcDesc& d = P->desc;
     d.magic = AC_DESC_MAGIC; d.Hl = g.Hl; d.ld = g.ld; d.plane = g.plane; d.win = P->win; d.own0 = P->own0; d.own1 = P->own1;
     d.n_edge_lo = P->n_edge_lo; d.n_edge_hi = P->n_edge_hi;
+    d.n_edge_lo_f = P->tb ? P->n_edge_lo_f : 0; d.n_edge_hi_f = P->tb ? P->n_edge_hi_f : 0; d.nub = P->nub;
     long long off = 512;  // bytes; descriptor lives in [0,512)
     d.off_flags = off; off += 512;
     auto take = [&](long long nplanes) { long long o = off; off += nplanes * (long long)plane_bytes; return o; };
     d.off_hist = take(P->win);
     for (int k = 0; k < 2; k++) d.off_phi[k] = take(1);
     for (int k = 0; k < 2; k++) d.off_psi[k] = take(1);
-    for (int k = 0; k < 3; k++) d.off_ub[k] = take(1);
+    for (int k = 0; k < 4; k++) d.off_ub[k] = (k < P->nub) ? take(1) : 0;
     for (int k = 0; k < 2; k++) d.off_phib[k] = take(1);
     for (int k = 0; k < 2; k++) d.off_psib[k] = take(1);
     P->arena_bytes = (size_t)off;
@@ -767,7 +801,7 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     char* base = (char*)P->arena;
     P->hist = (double*)(base + d.off_hist);
     for (int k = 0; k < 2; k++) { P->phi[k] = (double*)(base + d.off_phi[k]); P->psi[k] = (double*)(base + d.off_psi[k]); }
-    for (int k = 0; k < 3; k++) P->ub[k] = (double*)(base + d.off_ub[k]);
+    for (int k = 0; k < P->nub; k++) P->ub[k] = (double*)(base + d.off_ub[k]);
     for (int k = 0; k < 2; k++) { P->phib[k] = (double*)(base + d.off_phib[k]); P->psib[k] = (double*)(base + d.off_psib[k]); }
     PCUDA(cudaStreamSynchronize(st));
   }
@@ -854,12 +888,14 @@ ADSEIS_API int adseis_acoustic_plan_set_obs(adseis_acoustic_plan* P, const doubl
 
 // ---- forward steps s_first..s_last of segment k into the window (slot s at index s - base) -----------------
 // Peer pointers and flag expectations of the next step launch (slab plans); arr_u/arr_p: the arrays it produces.
-static AcFuse make_fuse(adseis_acoustic_plan* P, int arr_u, i64 idx_u, int arr_p, i64 idx_p) {
+// `frame_only`: the launch uses the frame-only tiling of the two-step path (its own launch order and edge-CTA counts).
+// The flag a rank waits on counts the signals of ALL fused launches its neighbour has issued so far; both ranks issue
+// the same sequence of launches, so the expectation is accumulated on the host, launch by launch.
+static AcFuse make_fuse(adseis_acoustic_plan* P, int arr_u, i64 idx_u, int arr_p, i64 idx_p, bool frame_only = false) {
   AcFuse f;
   memset(&f, 0, sizeof(f));
-  f.perm = P->perm;
+  f.perm = frame_only ? P->perm_f : P->perm;
   if (!P->arena) return f;
-  const AcGeom& g = P->g;
   f.own0 = P->own0; f.own_last = P->own1 - 1;
   f.has_lo = P->peer[0] != nullptr; f.has_hi = P->peer[1] != nullptr;
   P->sepoch++;
@@ -868,17 +904,18 @@ static AcFuse make_fuse(adseis_acoustic_plan* P, int arr_u, i64 idx_u, int arr_p
     f.lo_u = (double*)(P->peer[0] + desc_off(d, arr_u, idx_u)) + (d.Hl - 1) * d.ld;
     f.lo_p = (double*)(P->peer[0] + desc_off(d, arr_p, idx_p)) + (d.Hl - 1) * d.ld;
     f.sig_lo = (unsigned long long*)(P->peer[0] + d.off_flags) + 4;
-    f.expect_lo = (unsigned long long)d.n_edge_hi * (P->sepoch - 1);
+    f.expect_lo = P->exp_lo;
+    P->exp_lo += (unsigned long long)(frame_only ? d.n_edge_hi_f : d.n_edge_hi);
   }
   if (f.has_hi) {  // my last owned row -> rank+1's lower halo row (its local row 0)
     const AcDesc& d = P->dpeer[1];
     f.hi_u = (double*)(P->peer[1] + desc_off(d, arr_u, idx_u));
     f.hi_p = (double*)(P->peer[1] + desc_off(d, arr_p, idx_p));
     f.sig_hi = (unsigned long long*)(P->peer[1] + d.off_flags) + 3;
-    f.expect_hi = (unsigned long long)d.n_edge_lo * (P->sepoch - 1);
+    f.expect_hi = P->exp_hi;
+    P->exp_hi += (unsigned long long)(frame_only ? d.n_edge_lo_f : d.n_edge_lo);
   }
   f.my_flags = (unsigned long long*)((char*)P->arena + P->desc.off_flags);
-  (void)g;
   return f;
 }
 
@@ -889,10 +926,11 @@ static int launch_forward_step(adseis_acoustic_plan* P, i64 base, i64 s, bool sa
   cudaStream_t st = P->ctx->stream;
   AcPoints none{};
   AcFuse fuse;
-  if (frame_only) memset(&fuse, 0, sizeof(fuse));
-  else fuse = make_fuse(P, AR_HIST, s - base, AR_PHI, s & 1);
+  if (frame_only && !P->arena) memset(&fuse, 0, sizeof(fuse));
+  else fuse = make_fuse(P, AR_HIST, s - base, AR_PHI, s & 1, frame_only);
   const AcPoints srcp = frame_only ? P->srcFp : P->srcp, rcvp = frame_only ? P->rcvFp : P->rcvp;
-  CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), P->p.PropagatorKernel == 0 ? ac_fwd_kernel<0> : ac_fwd_kernel<1>,
+  CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab() || (frame_only && adseis_pdl_tb_slab()),
+                       P->p.PropagatorKernel == 0 ? ac_fwd_kernel<0> : ac_fwd_kernel<1>,
                        frame_only ? P->nblocksf : P->nblocks, AC_FWD_THREADS, frame_only ? 0 : AC_FWD_SMEM, st,
       g, frame_only ? P->tf : P->t, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, P->phi[(s - 1) & 1],
       P->psi[(s - 1) & 1], P->sigx, P->tauy, win_slot(P, base, s), P->phi[s & 1], P->psi[s & 1], srcp,
@@ -916,7 +954,7 @@ static int run_forward_steps(adseis_acoustic_plan* P, i64 base, i64 s_first, i64
     // levels s-1 and s-2 only; the second frame launch reads the box cells of slot s next to the frame.
     for (; s + 1 <= s_last; s += 2) {
       TRY(launch_forward_step(P, base, s, sample, true));
-      CUDA_TRY(launch_step(true, ac_fwd2_kernel, P->nblocks2, AC_FWD_THREADS, AC_FWD2_SMEM, st,
+      CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_tb_slab(), ac_fwd2_kernel, P->nblocks2, AC_FWD_THREADS, AC_FWD2_SMEM, st,
           g, P->t2, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, win_slot(P, base, s), win_slot(P, base, s + 1),
           P->srcHp, P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, P->srcMp,
           P->nsrc > 0 ? P->srcv + s * P->nsrc : nullptr, sample ? P->rcvMp : none,
@@ -1172,8 +1210,8 @@ static int gradient_body(adseis_acoustic_plan* P) {
     // one adjoint step s: ubar[s-1] from ubar[s], ubar[s+1], u[s-1]; `frame_only`: the cells outside the two-step box
     auto adj_step = [&](i64 s, bool frame_only) -> int {
       AcFuse fuse;
-      if (frame_only) memset(&fuse, 0, sizeof(fuse));
-      else fuse = make_fuse(P, AR_UB, (s - 1 + NUB) % NUB, AR_PHIB, (s - 1) & 1);
+      if (frame_only && !P->arena) memset(&fuse, 0, sizeof(fuse));
+      else fuse = make_fuse(P, AR_UB, (s - 1 + NUB) % NUB, AR_PHIB, (s - 1) & 1, frame_only);
       AcK0 k0{};
       if (P->p.PropagatorKernel == 0) {
         k0.wnew = win_slot(P, b, s); k0.ut_in = P->ut[(s + 1) & 1]; k0.ut_out = P->ut[s & 1];
@@ -1185,7 +1223,8 @@ static int gradient_body(adseis_acoustic_plan* P) {
         }
       }
       const AcPoints rcvp = frame_only ? P->rcvFp : P->rcvp, srcp = frame_only ? P->srcFp : P->srcp;
-      CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), P->p.PropagatorKernel == 0 ? ac_adj_kernel<0> : ac_adj_kernel<1>,
+      CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab() || (frame_only && adseis_pdl_tb_slab()),
+                           P->p.PropagatorKernel == 0 ? ac_adj_kernel<0> : ac_adj_kernel<1>,
                            frame_only ? P->nblocksf : P->nblocks, AC_ADJ_THREADS, frame_only ? 0 : AC_ADJ_SMEM, st,
           g, frame_only ? P->tf : P->t, P->ub[s % NUB], P->ub[(s + 1) % NUB], win_slot(P, b, s - 1), P->c2, P->phib[s & 1],
           P->psib[s & 1], P->sigx, P->tauy, P->ub[(s - 1 + NUB) % NUB], P->phib[(s - 1) & 1], P->psib[(s - 1) & 1], P->G,
@@ -1200,7 +1239,7 @@ static int gradient_body(adseis_acoustic_plan* P) {
       // cells of ubar[s-1] next to the frame)
       for (; s - 1 >= b + 2; s -= 2) {
         TRY(adj_step(s, true));
-        CUDA_TRY(launch_step(true, ac_adj2_kernel, P->nblocks2, AC2_THREADS, AC_ADJ2_SMEM, st,
+        CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_tb_slab(), ac_adj2_kernel, P->nblocks2, AC2_THREADS, AC_ADJ2_SMEM, st,
             g, P->t2, P->ub[s % NUB], P->ub[(s + 1) % NUB], win_slot(P, b, s - 1), win_slot(P, b, s - 2), P->c2,
             P->ub[(s - 1 + NUB) % NUB], P->ub[(s - 2 + NUB) % NUB], P->G, P->rcvHp,
             P->nrcv > 0 ? P->res + (s - 1) * P->nrcv : nullptr, P->rcvMp, P->nrcv > 0 ? P->res + (s - 2) * P->nrcv : nullptr,
@@ -1345,7 +1384,8 @@ ADSEIS_API int adseis_acoustic_plan_ipc_connect(adseis_acoustic_plan* P, const v
     P->peer[k] = (char*)ptr;
     CUDA_TRY(cudaMemcpy(&P->dpeer[k], ptr, sizeof(AcDesc), cudaMemcpyDeviceToHost));
     const AcDesc& d = P->dpeer[k];
-    if (d.magic != AC_DESC_MAGIC || d.ld != P->desc.ld || d.win != P->desc.win) {
+    if (d.magic != AC_DESC_MAGIC || d.ld != P->desc.ld || d.win != P->desc.win || d.nub != P->desc.nub ||
+        (d.n_edge_lo_f + d.n_edge_hi_f > 0) != (P->desc.n_edge_lo_f + P->desc.n_edge_hi_f > 0)) {
       adseis_set_error("acoustic_plan_ipc_connect: neighbour %d has an incompatible layout (magic %llx ld %lld win %lld; "
                        "mine ld %lld win %lld)", P->slab.rank + (k ? 1 : -1), d.magic, d.ld, d.win, P->desc.ld, P->desc.win);
       return ADSEIS_ECOMM;
