@@ -62,6 +62,7 @@ struct AcDesc {
   long long off_flags, off_hist, off_phi[2], off_psi[2], off_ub[4], off_phib[2], off_psib[2];
   long long n_edge_lo, n_edge_hi;  // CTAs of one step launch that own cells of my first / last owned row
   long long n_edge_lo_f, n_edge_hi_f;  // ... of a frame-only launch of the two-step path (0: that path is off)
+  long long n_edge_lo_w, n_edge_hi_w;  // ... of a WIDE frame-only launch (frame + rim ring of the box)
   long long nub;
 };
 #define AC_DESC_MAGIC 0xAD5E15B200ULL
@@ -120,11 +121,29 @@ struct adseis_acoustic_plan {
   // temporal blocking (two forward steps per launch; single-GPU plans with a large enough PML-free box):
   //   t2 = marching-only tiling of the box shrunk by two cells, tf = frame-only tiling of everything else
   bool tb = false;
-  AcTiling t2{}, tf{};
-  int nblocks2 = 0, nblocksf = 0;
+  AcTiling t2{};
+  int nblocks2 = 0;
   int box_i0 = 0, box_i1 = -1, box_j0 = 0, box_j1 = -1;  // PML-free box (global padded indices, inclusive)
-  PointSetStorage srcF, rcvF, srcM, rcvM, srcH;          // points by owner under tf (frame) / t2 (box) / t2 + rim
-  AcPoints srcFp{}, rcvFp{}, srcMp{}, rcvMp{}, srcHp{};
+  // frame-only tilings of the two-step path: [0] = everything outside the box, [1] = the same plus the rim ring of the box
+  // (a "wide" launch: the next frame launch then depends on it alone, not on the concurrent box-pair launch)
+  struct FrameKind {
+    AcTiling t{};
+    int nblocks = 0;
+    int* perm = nullptr;
+    int n_edge_lo = 0, n_edge_hi = 0;
+    PointSetStorage src, rcv;       // all points the tiling owns
+    AcPoints srcp{}, rcvp{};
+    // wide kind only: the points outside the box (epilogue injection) and the points on the rim ring of the box
+    // (injected in registers, see AcFuse::rim)
+    PointSetStorage srcN, rcvN, srcR, rcvR;
+    AcPoints srcNp{}, rcvNp{}, srcRp{}, rcvRp{};
+  };
+  FrameKind fk[2];
+  bool tb_overlap = false;                               // box-pair launches and frame launches on two streams
+  cudaStream_t sb = nullptr;                             // the frames' stream
+  cudaEvent_t evA[2] = {nullptr, nullptr}, evB[2] = {nullptr, nullptr};
+  PointSetStorage srcM, rcvM, srcH;                      // points by owner under t2 (box) / t2 + rim
+  AcPoints srcMp{}, rcvMp{}, srcHp{};
   int fast_rows = 0; // rows of the PML-free box owned by this GPU
   int own0, own1;  // owned local rows [own0, own1)
   i64 model_elems; // elements of the caller's model array
@@ -174,8 +193,6 @@ struct adseis_acoustic_plan {
   unsigned long long sepoch = 0;             // step kernels launched so far (same sequence on every rank)
   int* perm = nullptr;                       // launch order -> logical CTA id (edge CTAs first)
   int n_edge_lo = 0, n_edge_hi = 0;
-  int* perm_f = nullptr;                     // launch order of the frame-only tiling (two-step path on slabs)
-  int n_edge_lo_f = 0, n_edge_hi_f = 0;
   unsigned long long exp_lo = 0, exp_hi = 0; // signals the neighbours have sent me so far (sum over their fused launches)
   bool connected = false;
   // stats
@@ -262,7 +279,13 @@ ADSEIS_API int adseis_acoustic_plan_destroy(adseis_acoustic_plan* P) {
   cudaSetDevice(P->ctx->device);
   cudaStreamSynchronize(P->ctx->stream);
   cudaFree(P->c2); cudaFree(P->cvel); cudaFree(P->sigx); cudaFree(P->tauy);
-  cudaFree(P->perm); cudaFree(P->perm_f);
+  cudaFree(P->perm);
+  for (int k = 0; k < 2; k++) {
+    cudaFree(P->fk[k].perm); free_point_set(&P->fk[k].src); free_point_set(&P->fk[k].rcv);
+    free_point_set(&P->fk[k].srcN); free_point_set(&P->fk[k].rcvN); free_point_set(&P->fk[k].srcR); free_point_set(&P->fk[k].rcvR);
+  }
+  if (P->sb) cudaStreamDestroy(P->sb);
+  for (int k = 0; k < 2; k++) { if (P->evA[k]) cudaEventDestroy(P->evA[k]); if (P->evB[k]) cudaEventDestroy(P->evB[k]); }
   if (P->arena) {
     for (int k = 0; k < 2; k++) if (P->peer[k]) cudaIpcCloseMemHandle(P->peer[k]);
     cudaFree(P->arena);
@@ -273,7 +296,7 @@ ADSEIS_API int adseis_acoustic_plan_destroy(adseis_acoustic_plan* P) {
   }
   for (double* c : P->ckpt) cudaFree(c);
   free_point_set(&P->src); free_point_set(&P->rcv);
-  free_point_set(&P->srcF); free_point_set(&P->rcvF); free_point_set(&P->srcM); free_point_set(&P->rcvM);
+  free_point_set(&P->srcM); free_point_set(&P->rcvM);
   free_point_set(&P->srcH); free_point_set(&P->rcvH);
   cudaFree(P->rcv_owned);
   cudaFree(P->srcv); cudaFree(P->rcvv); cudaFree(P->obs); cudaFree(P->res); cudaFree(P->loss);
@@ -392,32 +415,40 @@ static void build_tb_tilings(adseis_acoustic_plan* P) {
   t.ntr = (rows + t.rb - 1) / t.rb;
   t.nmarch = t.nct * t.ntr;
   P->nblocks2 = t.nmarch;
-  // frame-only tiling: everything outside [mr0, mr1) x [mc0, mc_end)
-  AcTiling& f = P->tf;
-  memset(&f, 0, sizeof(f));
-  f.mr0 = f.mr1 = P->own0;  // no marched rows
-  f.rb = 1;
-  f.fcpt = getenv("ADSEIS_AC_FCPT2") ? std::max(1, atoi(getenv("ADSEIS_AC_FCPT2"))) : 1;  // alone in its launch: all parallelism
-  const int fcells2 = AC_THREADS * f.fcpt;
-  auto add_rect = [&](int r0, int r1, int c0, int c1) {
-    if (r1 <= r0 || c1 <= c0) return;
-    const int k = f.nrect++;
-    f.rr0[k] = r0; f.rr1[k] = r1; f.rc0[k] = c0; f.rc1[k] = c1;
-    const i64 cells = (i64)(r1 - r0) * (c1 - c0);
-    f.rblk[k + 1] = f.rblk[k] + (int)((cells + fcells2 - 1) / fcells2);
-  };
-  f.rblk[0] = 0;
-  add_rect(P->own0, mr0, 0, g.W);
-  add_rect(mr1, P->own1, 0, g.W);
-  add_rect(mr0, mr1, 0, mc0);
-  add_rect(mr0, mr1, mc_end, g.W);
-  for (int k = f.nrect; k < 4; k++) { f.rblk[k + 1] = f.rblk[f.nrect]; f.rr0[k] = f.rr1[k] = f.rc0[k] = 0; f.rc1[k] = 1; }
-  P->nblocksf = f.rblk[f.nrect];
-  P->tb = true;
-  if (slab) {
+  // frame-only tilings: [0] everything outside [mr0, mr1) x [mc0, mc_end); [1] the same plus the rim ring of that box
+  for (int kind = 0; kind < 2; kind++) {
+    adseis_acoustic_plan::FrameKind& F = P->fk[kind];
+    AcTiling& f = F.t;
+    memset(&f, 0, sizeof(f));
+    f.mr0 = f.mr1 = P->own0;  // no marched rows
+    f.rb = 1;
+    f.fcpt = getenv("ADSEIS_AC_FCPT2") ? std::max(1, atoi(getenv("ADSEIS_AC_FCPT2"))) : 1;  // alone in its launch: all parallelism
+    const int fcells2 = AC_THREADS * f.fcpt;
+    auto add_rect = [&](int r0, int r1, int c0, int c1) {
+      if (r1 <= r0 || c1 <= c0) return;
+      const int k = f.nrect++;
+      f.rr0[k] = r0; f.rr1[k] = r1; f.rc0[k] = c0; f.rc1[k] = c1;
+      const i64 cells = (i64)(r1 - r0) * (c1 - c0);
+      f.rblk[k + 1] = f.rblk[k] + (int)((cells + fcells2 - 1) / fcells2);
+    };
+    f.rblk[0] = 0;
+    const int w = kind;   // rim width taken from the box
+    add_rect(P->own0, mr0 + w, 0, g.W);
+    add_rect(mr1 - w, P->own1, 0, g.W);
+    add_rect(mr0 + w, mr1 - w, 0, mc0 + w);
+    add_rect(mr0 + w, mr1 - w, mc_end - w, g.W);
+    for (int k = f.nrect; k < 4; k++) { f.rblk[k + 1] = f.rblk[f.nrect]; f.rr0[k] = f.rr1[k] = f.rc0[k] = 0; f.rc1[k] = 1; }
+    if (kind == 1) { f.bx_r0 = mr0; f.bx_r1 = mr1; f.bx_c0 = mc0; f.bx_c1 = mc_end; }
+    F.nblocks = f.rblk[f.nrect];
     std::vector<int> order;
-    build_launch_order(P, f, P->nblocksf, &order, &P->n_edge_lo_f, &P->n_edge_hi_f);
-    if (dev_upload(&P->perm_f, order, P->ctx->stream) != ADSEIS_OK) { P->tb = false; return; }
+    build_launch_order(P, f, F.nblocks, &order, &F.n_edge_lo, &F.n_edge_hi);
+    cudaFree(F.perm); F.perm = nullptr;
+    if (slab && dev_upload(&F.perm, order, P->ctx->stream) != ADSEIS_OK) return;
+  }
+  P->tb = true;
+  {
+    const char* eo = getenv("ADSEIS_AC_TB_OVERLAP");
+    P->tb_overlap = !(eo && eo[0] == '0');
   }
   const char* ea = getenv("ADSEIS_AC_TB_ADJ");
   P->tb_adj = P->p.PropagatorKernel != 0 && !(ea && ea[0] == '0');
@@ -500,11 +531,14 @@ static int plan_build_points(adseis_acoustic_plan* P, int64_t nsrc, const int64_
   // two-step path: the same points grouped by owner under the frame-only tiling (frame points), under the box tiling
   // (box points), and -- sources only -- under every box tile whose one-cell rim contains them (injection into the
   // tile's private copy of the intermediate time level)
-  P->srcFp = P->rcvFp = P->srcMp = P->rcvMp = P->srcHp = P->rcvHp = AcPoints{};
+  P->srcMp = P->rcvMp = P->srcHp = P->rcvHp = AcPoints{};
+  for (int k = 0; k < 2; k++) P->fk[k].srcp = P->fk[k].rcvp = P->fk[k].srcNp = P->fk[k].rcvNp = P->fk[k].srcRp = P->fk[k].rcvRp = AcPoints{};
   if (P->tb) {
-    const AcTiling &t2 = P->t2, &tf = P->tf;
-    auto in_box = [&](int li, int j) { return li >= t2.mr0 && li < t2.mr1 && j >= t2.mc0 && j < t2.mc_end; };
-    auto owner_f = [&](int li, int j) -> int {
+    const AcTiling& t2 = P->t2;
+    auto in_box = [&](int li, int j, int w) {   // strictly inside the box shrunk by w
+      return li >= t2.mr0 + w && li < t2.mr1 - w && j >= t2.mc0 + w && j < t2.mc_end - w;
+    };
+    auto owner_f = [&](const AcTiling& tf, int li, int j) -> int {
       for (int k = 0; k < tf.nrect; k++)
         if (li >= tf.rr0[k] && li < tf.rr1[k] && j >= tf.rc0[k] && j < tf.rc1[k])
           return tf.rblk[k] + (int)(((i64)(li - tf.rr0[k]) * (tf.rc1[k] - tf.rc0[k]) + (j - tf.rc0[k])) / (AC_THREADS * tf.fcpt));
@@ -515,13 +549,16 @@ static int plan_build_points(adseis_acoustic_plan* P, int64_t nsrc, const int64_
       for (i64 k = 0; k < n; k++) {
         const i64 gi = pi[k] + ioff, gj = pj[k] + ioff;
         const int li = (int)(gi - g.goff), j = (int)gj;
-        if (mode == 0) {          // frame
-          if (in_box(li, j)) continue;
-          const int o = owner_f(li, j);
+        if (mode == 0 || mode >= 3) {   // frame; 3: wide frame = frame + rim ring of the box, 4: its frame part, 5: its rim part
+          const int w = mode >= 3 ? 1 : 0;
+          if (in_box(li, j, w)) continue;
+          if (mode == 4 && in_box(li, j, 0)) continue;
+          if (mode == 5 && !in_box(li, j, 0)) continue;
+          const int o = owner_f(P->fk[w].t, li, j);
           REQUIRE(o >= 0, "acoustic plan: internal error: frame cell (%d,%d) has no owner CTA", li, j);
           own.push_back(o); cells.push_back(li * g.ld + j); gid.push_back((int)k);
         } else if (mode == 1) {   // box
-          if (!in_box(li, j)) continue;
+          if (!in_box(li, j, 0)) continue;
           own.push_back(ac_row_tile_of(t2, li) * t2.nct + (j - t2.mc0) / AC_TILE_COLS);
           cells.push_back(li * g.ld + j); gid.push_back((int)k);
         } else {                  // every box tile whose (tile + rim) holds the cell
@@ -542,14 +579,23 @@ static int plan_build_points(adseis_acoustic_plan* P, int64_t nsrc, const int64_
       build_point_set(own, cells, gid, none, nblk, &h);
       return upload_point_set(h, dst, st);
     };
-    TRY(build2(nsrc, srci, srcj, 0, P->nblocksf, &P->srcF));
-    TRY(build2(nrcv, rcvi, rcvj, 0, P->nblocksf, &P->rcvF));
+    for (int k = 0; k < 2; k++) {
+      TRY(build2(nsrc, srci, srcj, k ? 3 : 0, P->fk[k].nblocks, &P->fk[k].src));
+      TRY(build2(nrcv, rcvi, rcvj, k ? 3 : 0, P->fk[k].nblocks, &P->fk[k].rcv));
+    }
+    TRY(build2(nsrc, srci, srcj, 4, P->fk[1].nblocks, &P->fk[1].srcN));
+    TRY(build2(nrcv, rcvi, rcvj, 4, P->fk[1].nblocks, &P->fk[1].rcvN));
+    TRY(build2(nsrc, srci, srcj, 5, P->fk[1].nblocks, &P->fk[1].srcR));
+    TRY(build2(nrcv, rcvi, rcvj, 5, P->fk[1].nblocks, &P->fk[1].rcvR));
     TRY(build2(nsrc, srci, srcj, 1, P->nblocks2, &P->srcM));
     TRY(build2(nrcv, rcvi, rcvj, 1, P->nblocks2, &P->rcvM));
     TRY(build2(nsrc, srci, srcj, 2, P->nblocks2, &P->srcH));
     TRY(build2(nrcv, rcvi, rcvj, 2, P->nblocks2, &P->rcvH));
     auto view = [](const PointSetStorage& q) { return q.nu > 0 ? AcPoints{q.blk, q.cell, q.start, q.perm} : AcPoints{}; };
-    P->srcFp = view(P->srcF); P->rcvFp = view(P->rcvF); P->srcMp = view(P->srcM); P->rcvMp = view(P->rcvM);
+    for (int k = 0; k < 2; k++) { P->fk[k].srcp = view(P->fk[k].src); P->fk[k].rcvp = view(P->fk[k].rcv); }
+    P->fk[1].srcNp = view(P->fk[1].srcN); P->fk[1].rcvNp = view(P->fk[1].rcvN);
+    P->fk[1].srcRp = view(P->fk[1].srcR); P->fk[1].rcvRp = view(P->fk[1].rcvR);
+    P->srcMp = view(P->srcM); P->rcvMp = view(P->rcvM);
     P->srcHp = view(P->srcH); P->rcvHp = view(P->rcvH);
   }
   return ADSEIS_OK;
@@ -778,7 +824,8 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     AcDesc& d = P->desc;
     d.magic = AC_DESC_MAGIC; d.Hl = g.Hl; d.ld = g.ld; d.plane = g.plane; d.win = P->win; d.own0 = P->own0; d.own1 = P->own1;
     d.n_edge_lo = P->n_edge_lo; d.n_edge_hi = P->n_edge_hi;
-    d.n_edge_lo_f = P->tb ? P->n_edge_lo_f : 0; d.n_edge_hi_f = P->tb ? P->n_edge_hi_f : 0; d.nub = P->nub;
+    d.n_edge_lo_f = P->tb ? P->fk[0].n_edge_lo : 0; d.n_edge_hi_f = P->tb ? P->fk[0].n_edge_hi : 0; d.nub = P->nub;
+    d.n_edge_lo_w = P->tb ? P->fk[1].n_edge_lo : 0; d.n_edge_hi_w = P->tb ? P->fk[1].n_edge_hi : 0;
     long long off = 512;  // bytes; descriptor lives in [0,512)
     d.off_flags = off; off += 512;
     auto take = [&](long long nplanes) { long long o = off; off += nplanes * (long long)plane_bytes; return o; };
@@ -891,10 +938,10 @@ ADSEIS_API int adseis_acoustic_plan_set_obs(adseis_acoustic_plan* P, const doubl
 // `frame_only`: the launch uses the frame-only tiling of the two-step path (its own launch order and edge-CTA counts).
 // The flag a rank waits on counts the signals of ALL fused launches its neighbour has issued so far; both ranks issue
 // the same sequence of launches, so the expectation is accumulated on the host, launch by launch.
-static AcFuse make_fuse(adseis_acoustic_plan* P, int arr_u, i64 idx_u, int arr_p, i64 idx_p, bool frame_only = false) {
+static AcFuse make_fuse(adseis_acoustic_plan* P, int arr_u, i64 idx_u, int arr_p, i64 idx_p, int fkind = 0) {
   AcFuse f;
   memset(&f, 0, sizeof(f));
-  f.perm = frame_only ? P->perm_f : P->perm;
+  f.perm = fkind ? P->fk[fkind - 1].perm : P->perm;
   if (!P->arena) return f;
   f.own0 = P->own0; f.own_last = P->own1 - 1;
   f.has_lo = P->peer[0] != nullptr; f.has_hi = P->peer[1] != nullptr;
@@ -905,7 +952,7 @@ static AcFuse make_fuse(adseis_acoustic_plan* P, int arr_u, i64 idx_u, int arr_p
     f.lo_p = (double*)(P->peer[0] + desc_off(d, arr_p, idx_p)) + (d.Hl - 1) * d.ld;
     f.sig_lo = (unsigned long long*)(P->peer[0] + d.off_flags) + 4;
     f.expect_lo = P->exp_lo;
-    P->exp_lo += (unsigned long long)(frame_only ? d.n_edge_hi_f : d.n_edge_hi);
+    P->exp_lo += (unsigned long long)(fkind == 2 ? d.n_edge_hi_w : fkind == 1 ? d.n_edge_hi_f : d.n_edge_hi);
   }
   if (f.has_hi) {  // my last owned row -> rank+1's lower halo row (its local row 0)
     const AcDesc& d = P->dpeer[1];
@@ -913,26 +960,78 @@ static AcFuse make_fuse(adseis_acoustic_plan* P, int arr_u, i64 idx_u, int arr_p
     f.hi_p = (double*)(P->peer[1] + desc_off(d, arr_p, idx_p));
     f.sig_hi = (unsigned long long*)(P->peer[1] + d.off_flags) + 3;
     f.expect_hi = P->exp_hi;
-    P->exp_hi += (unsigned long long)(frame_only ? d.n_edge_lo_f : d.n_edge_lo);
+    P->exp_hi += (unsigned long long)(fkind == 2 ? d.n_edge_lo_w : fkind == 1 ? d.n_edge_lo_f : d.n_edge_lo);
   }
   f.my_flags = (unsigned long long*)((char*)P->arena + P->desc.off_flags);
   return f;
 }
 
-// one forward step s (slot s from slots s-1, s-2) with the one-step kernel; `frame_only`: only the cells outside the
-// two-step box (tiling tf) -- the box cells of that slot are written by ac_fwd2_kernel
-static int launch_forward_step(adseis_acoustic_plan* P, i64 base, i64 s, bool sample, bool frame_only) {
+// Two-stream pipeline of the two-step path: box-pair launches stay on the context's stream (A), frame launches go to a
+// second stream (B).  Within a pair they are independent -- the box kernel reads the two previous time levels only and
+// the FIRST frame launch of a pair is a wide one (it also recomputes the rim ring of the box, so the second frame launch
+// depends on it alone).  Across pairs the streams leapfrog: A(p) waits for B(p-1), B(p) waits for A(p-1).
+struct TbPipe {
+  adseis_acoustic_plan* P;
+  bool on = false, first = true;
+  int n = 0;
+  int begin() {
+    if (!P->tb_overlap) return ADSEIS_OK;
+    if (!P->sb) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&P->sb, cudaStreamNonBlocking));
+      for (int k = 0; k < 2; k++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&P->evA[k], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&P->evB[k], cudaEventDisableTiming));
+      }
+    }
+    on = true; first = true; n = 0;
+    return ADSEIS_OK;
+  }
+  cudaStream_t frames() const { return on ? P->sb : P->ctx->stream; }
+  int pre_frames() {   // before the frame launches of pair n
+    if (!on) return ADSEIS_OK;
+    if (first) {       // everything enqueued on A so far (memsets, copies, earlier launches) precedes the first frames
+      CUDA_TRY(cudaEventRecord(P->evA[1], P->ctx->stream));
+      CUDA_TRY(cudaStreamWaitEvent(P->sb, P->evA[1], 0));
+    } else {
+      CUDA_TRY(cudaStreamWaitEvent(P->sb, P->evA[(n + 1) & 1], 0));   // box pair n-1
+    }
+    return ADSEIS_OK;
+  }
+  int post_frames() {
+    if (on) CUDA_TRY(cudaEventRecord(P->evB[n & 1], P->sb));
+    return ADSEIS_OK;
+  }
+  int pre_box() {
+    if (on && !first) CUDA_TRY(cudaStreamWaitEvent(P->ctx->stream, P->evB[(n + 1) & 1], 0));   // frames of pair n-1
+    return ADSEIS_OK;
+  }
+  int post_box() {
+    if (on) { CUDA_TRY(cudaEventRecord(P->evA[n & 1], P->ctx->stream)); first = false; n++; }
+    return ADSEIS_OK;
+  }
+  int end() {          // join: later work on A sees every frame launch
+    if (on && !first) CUDA_TRY(cudaStreamWaitEvent(P->ctx->stream, P->evB[(n + 1) & 1], 0));
+    on = false;
+    return ADSEIS_OK;
+  }
+};
+
+// one forward step s (slot s from slots s-1, s-2) with the one-step kernel.  fkind 0: the full tiling (marching + frame
+// CTAs); 1: only the cells outside the two-step box -- the box cells of that slot are written by ac_fwd2_kernel; 2: the
+// same plus the rim ring of the box
+static int launch_forward_step(adseis_acoustic_plan* P, i64 base, i64 s, bool sample, int fkind, cudaStream_t st) {
   const AcGeom& g = P->g;
-  cudaStream_t st = P->ctx->stream;
   AcPoints none{};
   AcFuse fuse;
-  if (frame_only && !P->arena) memset(&fuse, 0, sizeof(fuse));
-  else fuse = make_fuse(P, AR_HIST, s - base, AR_PHI, s & 1, frame_only);
-  const AcPoints srcp = frame_only ? P->srcFp : P->srcp, rcvp = frame_only ? P->rcvFp : P->rcvp;
-  CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab() || (frame_only && adseis_pdl_tb_slab()),
+  if (fkind && !P->arena) memset(&fuse, 0, sizeof(fuse));
+  else fuse = make_fuse(P, AR_HIST, s - base, AR_PHI, s & 1, fkind);
+  const adseis_acoustic_plan::FrameKind* F = fkind ? &P->fk[fkind - 1] : nullptr;
+  const AcPoints srcp = fkind == 2 ? F->srcNp : (F ? F->srcp : P->srcp), rcvp = F ? F->rcvp : P->rcvp;
+  if (fkind == 2) fuse.rim = F->srcRp;
+  CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab() || (fkind && adseis_pdl_tb_slab()),
                        P->p.PropagatorKernel == 0 ? ac_fwd_kernel<0> : ac_fwd_kernel<1>,
-                       frame_only ? P->nblocksf : P->nblocks, AC_FWD_THREADS, frame_only ? 0 : AC_FWD_SMEM, st,
-      g, frame_only ? P->tf : P->t, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, P->phi[(s - 1) & 1],
+                       F ? F->nblocks : P->nblocks, AC_FWD_THREADS, F ? 0 : AC_FWD_SMEM, st,
+      g, F ? F->t : P->t, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, P->phi[(s - 1) & 1],
       P->psi[(s - 1) & 1], P->sigx, P->tauy, win_slot(P, base, s), P->phi[s & 1], P->psi[s & 1], srcp,
       P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, sample ? rcvp : none,
       (sample && P->nrcv > 0) ? P->rcvv + s * P->nrcv : nullptr, fuse));
@@ -950,10 +1049,21 @@ static int run_forward_steps(adseis_acoustic_plan* P, i64 base, i64 s_first, i64
   }
   i64 s = s_first;
   if (P->tb) {
-    // pairs of steps (s, s+1): frame of s, box of s and s+1 in one launch, frame of s+1.  The box launch reads time
-    // levels s-1 and s-2 only; the second frame launch reads the box cells of slot s next to the frame.
+    // pairs of steps (s, s+1): frame of s, frame of s+1, box of s and s+1 in one launch.  The box launch reads time
+    // levels s-1 and s-2 only.  One stream: narrow frame, box, narrow frame (the second frame launch reads the box cells
+    // of slot s next to the frame).  Two streams: wide frame + narrow frame on B, box on A, concurrently.
+    TbPipe pipe{P};
+    TRY(pipe.begin());
     for (; s + 1 <= s_last; s += 2) {
-      TRY(launch_forward_step(P, base, s, sample, true));
+      if (pipe.on) {
+        TRY(pipe.pre_frames());
+        TRY(launch_forward_step(P, base, s, sample, 2, pipe.frames()));
+        TRY(launch_forward_step(P, base, s + 1, sample, 1, pipe.frames()));
+        TRY(pipe.post_frames());
+        TRY(pipe.pre_box());
+      } else {
+        TRY(launch_forward_step(P, base, s, sample, 1, st));
+      }
       CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_tb_slab(), ac_fwd2_kernel, P->nblocks2, AC_FWD_THREADS, AC_FWD2_SMEM, st,
           g, P->t2, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, win_slot(P, base, s), win_slot(P, base, s + 1),
           P->srcHp, P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, P->srcMp,
@@ -961,10 +1071,12 @@ static int run_forward_steps(adseis_acoustic_plan* P, i64 base, i64 s_first, i64
           (sample && P->nrcv > 0) ? P->rcvv + s * P->nrcv : nullptr,
           (sample && P->nrcv > 0) ? P->rcvv + (s + 1) * P->nrcv : nullptr));
       LAUNCH_CHECK(P);
-      TRY(launch_forward_step(P, base, s + 1, sample, true));
+      if (pipe.on) TRY(pipe.post_box());
+      else TRY(launch_forward_step(P, base, s + 1, sample, 1, st));
     }
+    TRY(pipe.end());
   }
-  for (; s <= s_last; s++) TRY(launch_forward_step(P, base, s, sample, false));
+  for (; s <= s_last; s++) TRY(launch_forward_step(P, base, s, sample, 0, st));
   return ADSEIS_OK;
 }
 
@@ -1036,7 +1148,7 @@ static unsigned long long graph_key(adseis_acoustic_plan* P, int kind) {
   unsigned long long h = 1469598103934665603ULL;
   auto mix = [&](const void* p) { h ^= (unsigned long long)(uintptr_t)p; h *= 1099511628211ULL; };
   mix(P->hist); mix(P->c2); mix(P->phi[0]); mix(P->psi[0]); mix(P->srcv); mix(P->rcvv); mix(P->perm);
-  const PointSetStorage* ps[] = {&P->src, &P->rcv, &P->srcF, &P->rcvF, &P->srcM, &P->rcvM, &P->srcH, &P->rcvH};
+  const PointSetStorage* ps[] = {&P->src, &P->rcv, &P->fk[0].src, &P->fk[0].rcv, &P->fk[1].src, &P->fk[1].rcv, &P->srcM, &P->rcvM, &P->srcH, &P->rcvH};
   for (const PointSetStorage* q : ps) { mix(q->blk); mix(q->cell); mix(q->start); mix(q->perm); mix((void*)(uintptr_t)(q->nu + 1)); }
   mix((void*)(uintptr_t)(P->nsrc * 131 + P->nrcv + 7)); mix((void*)(uintptr_t)(P->k0_corr ? 3 : 5));
   if (kind == 1) {
@@ -1207,26 +1319,28 @@ static int gradient_body(adseis_acoustic_plan* P) {
       P->win_base = b; P->win_last = e;
     }
     TRY(span_begin(P, 2, e - (b + 2) + 1));
-    // one adjoint step s: ubar[s-1] from ubar[s], ubar[s+1], u[s-1]; `frame_only`: the cells outside the two-step box
-    auto adj_step = [&](i64 s, bool frame_only) -> int {
+    // one adjoint step s: ubar[s-1] from ubar[s], ubar[s+1], u[s-1]; fkind as in launch_forward_step
+    auto adj_step = [&](i64 s, int fkind, cudaStream_t stl) -> int {
       AcFuse fuse;
-      if (frame_only && !P->arena) memset(&fuse, 0, sizeof(fuse));
-      else fuse = make_fuse(P, AR_UB, (s - 1 + NUB) % NUB, AR_PHIB, (s - 1) & 1, frame_only);
+      if (fkind && !P->arena) memset(&fuse, 0, sizeof(fuse));
+      else fuse = make_fuse(P, AR_UB, (s - 1 + NUB) % NUB, AR_PHIB, (s - 1) & 1, fkind);
       AcK0 k0{};
       if (P->p.PropagatorKernel == 0) {
         k0.wnew = win_slot(P, b, s); k0.ut_in = P->ut[(s + 1) & 1]; k0.ut_out = P->ut[s & 1];
         if (P->k0_corr && P->src.nu > 0) {
-          k_ac_k0_src_corr<<<(P->src.nu + 127) / 128, 128, 0, st>>>(g, P->src.cell, P->src.start, P->src.perm, P->src.nu,
-                                                                    P->srcv + (s - 1) * P->nsrc, P->phib[s & 1],
-                                                                    P->psib[s & 1], P->sigx, P->tauy, P->G);
+          k_ac_k0_src_corr<<<(P->src.nu + 127) / 128, 128, 0, stl>>>(g, P->src.cell, P->src.start, P->src.perm, P->src.nu,
+                                                                     P->srcv + (s - 1) * P->nsrc, P->phib[s & 1],
+                                                                     P->psib[s & 1], P->sigx, P->tauy, P->G);
           LAUNCH_CHECK(P);
         }
       }
-      const AcPoints rcvp = frame_only ? P->rcvFp : P->rcvp, srcp = frame_only ? P->srcFp : P->srcp;
-      CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab() || (frame_only && adseis_pdl_tb_slab()),
+      const adseis_acoustic_plan::FrameKind* F = fkind ? &P->fk[fkind - 1] : nullptr;
+      const AcPoints rcvp = fkind == 2 ? F->rcvNp : (F ? F->rcvp : P->rcvp), srcp = F ? F->srcp : P->srcp;
+      if (fkind == 2) fuse.rim = F->rcvRp;
+      CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab() || (fkind && adseis_pdl_tb_slab()),
                            P->p.PropagatorKernel == 0 ? ac_adj_kernel<0> : ac_adj_kernel<1>,
-                           frame_only ? P->nblocksf : P->nblocks, AC_ADJ_THREADS, frame_only ? 0 : AC_ADJ_SMEM, st,
-          g, frame_only ? P->tf : P->t, P->ub[s % NUB], P->ub[(s + 1) % NUB], win_slot(P, b, s - 1), P->c2, P->phib[s & 1],
+                           F ? F->nblocks : P->nblocks, AC_ADJ_THREADS, F ? 0 : AC_ADJ_SMEM, stl,
+          g, F ? F->t : P->t, P->ub[s % NUB], P->ub[(s + 1) % NUB], win_slot(P, b, s - 1), P->c2, P->phib[s & 1],
           P->psib[s & 1], P->sigx, P->tauy, P->ub[(s - 1 + NUB) % NUB], P->phib[(s - 1) & 1], P->psib[(s - 1) & 1], P->G,
           rcvp, P->nrcv > 0 ? P->res + (s - 1) * P->nrcv : nullptr, (s - 2 >= 1) ? srcp : none,
           (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr, fuse, k0));
@@ -1235,10 +1349,20 @@ static int gradient_body(adseis_acoustic_plan* P) {
     };
     i64 s = e;
     if (P->tb_adj) {
-      // pairs (s, s-1): frame of step s, box of steps s and s-1 in one launch, frame of step s-1 (which reads the box
-      // cells of ubar[s-1] next to the frame)
+      // pairs (s, s-1): frame of step s, frame of step s-1, box of steps s and s-1 in one launch; streams as in the
+      // forward sweep (one stream: narrow frame, box, narrow frame)
+      TbPipe pipe{P};
+      TRY(pipe.begin());
       for (; s - 1 >= b + 2; s -= 2) {
-        TRY(adj_step(s, true));
+        if (pipe.on) {
+          TRY(pipe.pre_frames());
+          TRY(adj_step(s, 2, pipe.frames()));
+          TRY(adj_step(s - 1, 1, pipe.frames()));
+          TRY(pipe.post_frames());
+          TRY(pipe.pre_box());
+        } else {
+          TRY(adj_step(s, 1, st));
+        }
         CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_tb_slab(), ac_adj2_kernel, P->nblocks2, AC2_THREADS, AC_ADJ2_SMEM, st,
             g, P->t2, P->ub[s % NUB], P->ub[(s + 1) % NUB], win_slot(P, b, s - 1), win_slot(P, b, s - 2), P->c2,
             P->ub[(s - 1 + NUB) % NUB], P->ub[(s - 2 + NUB) % NUB], P->G, P->rcvHp,
@@ -1246,10 +1370,12 @@ static int gradient_body(adseis_acoustic_plan* P) {
             P->srcMp, (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr,
             (s - 3 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 3) * P->nsrc : nullptr));
         LAUNCH_CHECK(P);
-        TRY(adj_step(s - 1, true));
+        if (pipe.on) TRY(pipe.post_box());
+        else TRY(adj_step(s - 1, 1, st));
       }
+      TRY(pipe.end());
     }
-    for (; s >= b + 2; s--) TRY(adj_step(s, false));
+    for (; s >= b + 2; s--) TRY(adj_step(s, 0, st));
     TRY(span_end(P));
   }
   CUDA_TRY(cudaMemsetAsync(P->gradc, 0, (size_t)P->model_elems * 8, st));

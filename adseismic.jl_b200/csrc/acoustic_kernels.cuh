@@ -110,6 +110,9 @@ struct AcTiling {
   int nrect;          // frame rectangles (local rows [rr0,rr1) x columns [rc0,rc1))
   int rr0[4], rr1[4], rc0[4], rc1[4];
   int rblk[5];        // CTA-id prefix of the rectangles, relative to nmarch
+  int bx_r0, bx_r1, bx_c0, bx_c1;  // frame cells inside this box (the rim ring a WIDE frame-only launch recomputes so that the
+                      // next frame launch does not depend on the concurrent box-pair launch) store their state only: the
+                      // box kernel owns their Gbar / phibar / psibar updates
   int fcpt;           // frame cells per thread (a frame CTA covers AC_THREADS * fcpt consecutive cells of its rectangle):
                       // AC_FRAME_CPT when frame CTAs share a launch with marching CTAs, 1 in frame-only launches
 };
@@ -140,6 +143,23 @@ struct AcPoints {
   const int* perm;
 };
 
+// first entry of a per-CTA point list (sorted by cell) whose cell is >= key
+__device__ __forceinline__ int ac_lower_bound(const int* __restrict__ cell, int a, int b, int key) {
+  while (a < b) {
+    const int m = (a + b) >> 1;
+    if (cell[m] < key) a = m + 1; else b = m;
+  }
+  return a;
+}
+// v + sum of val[perm[m]] * scale over the points on `key` (sequential, original point order); v if none
+__device__ __noinline__ double ac_add_points(double v, const AcPoints& ps, int a, int b, int key,
+                                             const double* __restrict__ val, double scale) {
+  const int k = ac_lower_bound(ps.cell, a, b, key);
+  if (k < b && ps.cell[k] == key)
+    for (int m = ps.start[k]; m < ps.start[k + 1]; m++) v += val[ps.perm[m]] * scale;
+  return v;
+}
+
 // Slab decomposition, fused into the step kernels (all null / zero on a single GPU).  The CTAs whose cells include
 // my first (last) owned row are scheduled first (perm), wait until the neighbour's previous step has delivered the
 // halo row they read, and -- after their epilogue -- store their piece of the new edge row straight into the
@@ -154,6 +174,10 @@ struct AcFuse {
   unsigned long long *sig_lo, *sig_hi;   // neighbour flags to bump (peer pointers)
   unsigned long long* my_flags;          // [3] bumped by rank-1's step kernels, [4] by rank+1's, [2] error
   unsigned long long expect_lo, expect_hi;
+  // wide frame-only launches: the injected points (sources forward, receiver residuals adjoint) that sit on the rim
+  // ring of the box.  They are added in registers BEFORE the cell's single store -- the concurrent box-pair launch
+  // stores the same final value, so neither launch may read-modify-write such a cell
+  AcPoints rim;
 };
 
 __device__ __forceinline__ void ac_fuse_wait(const AcFuse& f, bool t_lo, bool t_hi) {
@@ -188,7 +212,9 @@ __device__ __forceinline__ void ac_fwd_general_cell(const AcGeom& g, int li, int
                                                     const double* __restrict__ phi, const double* __restrict__ psi,
                                                     const double* __restrict__ sigx, const double* __restrict__ tauy,
                                                     double* __restrict__ u, double* __restrict__ phio,
-                                                    double* __restrict__ psio) {
+                                                    double* __restrict__ psio, const AcPoints* rim = nullptr,
+                                                    int rim_a = 0, int rim_n = 0, const double* __restrict__ rim_val = nullptr,
+                                                    double rim_scale = 0.0) {
   const int gi = g.goff + li;
   const i64 IJ = (i64)li * g.ld + j;
   if (j >= g.W) { u[IJ] = 0.0; return; }
@@ -204,7 +230,9 @@ __device__ __forceinline__ void ac_fwd_general_cell(const AcGeom& g, int li, int
              g.px * (phi[IpJ] - phi[InJ]) +
              g.py * (psi[IJp] - psi[IJn]) -
              (1 - (sg + ta) * dt / 2) * wold[IJ];
-  u[IJ] = (v == 0.0) ? v : v / (1 + (sg + ta) / 2 * dt);  // zero numerators would take the divide's slow path
+  v = (v == 0.0) ? v : v / (1 + (sg + ta) / 2 * dt);  // zero numerators would take the divide's slow path
+  if (rim_n > 0) v = ac_add_points(v, *rim, rim_a, rim_a + rim_n, (int)IJ, rim_val, rim_scale);
+  u[IJ] = v;
   phio[IJ] = (1. - dt * sg) * phi[IJ] + div_exact(dt * c * (ta - sg) / 2.0, g.hx, g.rhx) * (w[IpJ] - w[InJ]);
   psio[IJ] = (1. - dt * ta) * psi[IJ] + div_exact(dt * c * (sg - ta) / 2.0, g.hy, g.rhy) * (w[IJp] - w[IJn]);
 }
@@ -236,7 +264,9 @@ __device__ __forceinline__ void ac_fwd_general_cell_k0(const AcGeom& g, int li, 
                                                        const double* __restrict__ phi, const double* __restrict__ psi,
                                                        const double* __restrict__ sigx, const double* __restrict__ tauy,
                                                        double* __restrict__ u, double* __restrict__ phio,
-                                                       double* __restrict__ psio) {
+                                                       double* __restrict__ psio, const AcPoints* rim = nullptr,
+                                                    int rim_a = 0, int rim_n = 0, const double* __restrict__ rim_val = nullptr,
+                                                    double rim_scale = 0.0) {
   const int gi = g.goff + li;
   const i64 IJ = (i64)li * g.ld + j;
   if (j >= g.W) { u[IJ] = 0.0; return; }
@@ -252,7 +282,7 @@ __device__ __forceinline__ void ac_fwd_general_cell_k0(const AcGeom& g, int li, 
   const double uxm = ac_uprime(g, vxm ? gi - 1 : gi, j, vxm ? IJ - g.ld : IJ, w, wold, c2, phi, psi, sigx, tauy);
   const double uyp = ac_uprime(g, gi, vyp ? j + 1 : j, vyp ? IJ + 1 : IJ, w, wold, c2, phi, psi, sigx, tauy);
   const double uym = ac_uprime(g, gi, vym ? j - 1 : j, vym ? IJ - 1 : IJ, w, wold, c2, phi, psi, sigx, tauy);
-  u[IJ] = uP;
+  u[IJ] = (rim_n > 0) ? ac_add_points(uP, *rim, rim_a, rim_a + rim_n, (int)IJ, rim_val, rim_scale) : uP;
   const double a = div_exact(dt * c * (ta - sg) / 2.0, g.hx, g.rhx);
   const double b = div_exact(dt * c * (sg - ta) / 2.0, g.hy, g.rhy);
   phio[IJ] = (1. - dt * sg) * phi[IJ] + a * ((vxp ? uxp : 0.0) - (vxm ? uxm : 0.0));
@@ -318,13 +348,16 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
     t_lo = f.has_lo && rlo <= f.own0 && f.own0 <= rhi;
     t_hi = f.has_hi && rlo <= f.own_last && f.own_last <= rhi;
     ac_fuse_wait(f, t_lo, t_hi);
+    int rim_a = 0, rim_n = 0;
+    if (f.rim.blk != nullptr && srcv_row != nullptr) { rim_a = f.rim.blk[bid]; rim_n = f.rim.blk[bid + 1] - rim_a; }
 #pragma unroll 4
     for (int k = 0; k < t.fcpt; k++) {
       const int idx = idx0 + k * AC_THREADS + threadIdx.x;
       if (idx < ncell && threadIdx.x < AC_THREADS) {
         const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
-        if constexpr (PK == 0) ac_fwd_general_cell_k0(g, li, j, w, wold, c2, phi, psi, sigx, tauy, u, phio, psio);
-        else ac_fwd_general_cell(g, li, j, w, wold, c2, phi, psi, sigx, tauy, u, phio, psio);
+        const bool inbox = rim_n > 0 && li >= t.bx_r0 && li < t.bx_r1 && j >= t.bx_c0 && j < t.bx_c1;
+        if constexpr (PK == 0) ac_fwd_general_cell_k0(g, li, j, w, wold, c2, phi, psi, sigx, tauy, u, phio, psio, &f.rim, rim_a, inbox ? rim_n : 0, srcv_row, g.dt2);
+        else ac_fwd_general_cell(g, li, j, w, wold, c2, phi, psi, sigx, tauy, u, phio, psio, &f.rim, rim_a, inbox ? rim_n : 0, srcv_row, g.dt2);
       }
     }
   } else {
@@ -499,7 +532,9 @@ __device__ __forceinline__ void ac_adj_general_cell(const AcGeom& g, int li, int
                                                     const double* __restrict__ psib,
                                                     const double* __restrict__ sigx, const double* __restrict__ tauy,
                                                     double* __restrict__ ub0, double* __restrict__ phibo,
-                                                    double* __restrict__ psibo, double* __restrict__ G) {
+                                                    double* __restrict__ psibo, double* __restrict__ G,
+                                                    bool state_only = false, const AcPoints* rim = nullptr, int rim_a = 0,
+                                                    int rim_n = 0, const double* __restrict__ rim_val = nullptr) {
   // All loads are issued up front from always-valid (clamped) addresses and the validity predicates only select
   // terms afterwards: a frame cell then costs ONE memory round trip instead of one per neighbour branch (the
   // frame is ~2 % of the cells but its dependent DRAM round trips used to form the tail of every launch).
@@ -533,7 +568,10 @@ __device__ __forceinline__ void ac_adj_general_cell(const AcGeom& g, int li, int
   // depend on how the steps of a sweep happen to be paired (checkpoint segments shift the pairing).
   if (intP && vxm && vxp && vym && vyp && sg == 0.0 && sgm == 0.0 && sgp == 0.0 && ta == 0.0 && tam == 0.0 && tap == 0.0) {
     const double rx2 = g.rx * g.rx, ry2 = g.ry * g.ry;
-    ub0[IJ] = ac_adj_cell(ac_a0(cP, g.kx2, g.ky2), rx2, ry2, uP, cxp * uxp, cxm * uxm, cyp * uyp, cym * uym, u2P);
+    double a_ = ac_adj_cell(ac_a0(cP, g.kx2, g.ky2), rx2, ry2, uP, cxp * uxp, cxm * uxm, cyp * uyp, cym * uym, u2P);
+    if (state_only && rim_n > 0) a_ = ac_add_points(a_, *rim, rim_a, rim_a + rim_n, (int)IJ, rim_val, 1.0);
+    ub0[IJ] = a_;
+    if (state_only) return;   // a rim cell of the box recomputed by a wide frame launch: the box kernel accumulates Gbar
     phibo[IJ] = (1. - dt * sg) * pb + g.px * (uxm - uxp);   // never used (its coefficient is tau - sigma = 0); kept finite
     psibo[IJ] = (1. - dt * ta) * qb + g.py * (uym - uyp);
     G[IJ] = GP + ac_corr_cell(-g.kx2 - g.ky2, rx2, ry2, wC, wU, wD, wR, wL, uP);
@@ -738,13 +776,16 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
     t_lo = f.has_lo && rlo <= f.own0 && f.own0 <= rhi;
     t_hi = f.has_hi && rlo <= f.own_last && f.own_last <= rhi;
     ac_fuse_wait(f, t_lo, t_hi);
+    int rim_a = 0, rim_n = 0;
+    if (f.rim.blk != nullptr && res_row != nullptr) { rim_a = f.rim.blk[bid]; rim_n = f.rim.blk[bid + 1] - rim_a; }
 #pragma unroll 4
     for (int k = 0; k < t.fcpt; k++) {
       const int idx = idx0 + k * AC_THREADS + threadIdx.x;
       if (idx < ncell && threadIdx.x < AC_THREADS) {
         const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
         if constexpr (PK == 0) ac_adj_general_cell_k0(g, li, j, ub1, wf, c2, phib, psib, sigx, tauy, ub0, phibo, psibo, G, k0);
-        else ac_adj_general_cell(g, li, j, ub1, ub2, wf, c2, phib, psib, sigx, tauy, ub0, phibo, psibo, G);
+        else ac_adj_general_cell(g, li, j, ub1, ub2, wf, c2, phib, psib, sigx, tauy, ub0, phibo, psibo, G,
+                                 li >= t.bx_r0 && li < t.bx_r1 && j >= t.bx_c0 && j < t.bx_c1, &f.rim, rim_a, rim_n, res_row);
       }
     }
   } else {
@@ -1069,22 +1110,6 @@ struct __align__(128) AcAdj2Stage {
 };
 #define AC_ADJ2_SMEM ((int)(AC_NST_ADJ2 * (sizeof(AcAdj2Stage) + 16)))
 
-// first entry of a per-CTA point list (sorted by cell) whose cell is >= key
-__device__ __forceinline__ int ac_lower_bound(const int* __restrict__ cell, int a, int b, int key) {
-  while (a < b) {
-    const int m = (a + b) >> 1;
-    if (cell[m] < key) a = m + 1; else b = m;
-  }
-  return a;
-}
-// v + sum of val[perm[m]] * scale over the points on `key` (sequential, original point order); v if none
-__device__ __noinline__ double ac_add_points(double v, const AcPoints& ps, int a, int b, int key,
-                                             const double* __restrict__ val, double scale) {
-  const int k = ac_lower_bound(ps.cell, a, b, key);
-  if (k < b && ps.cell[k] == key)
-    for (int m = ps.start[k]; m < ps.start[k + 1]; m++) v += val[ps.perm[m]] * scale;
-  return v;
-}
 
 // Shared-memory layout after the ring stages: one private row pair per consumer warp holding c^2 * A of its 32 columns
 // and its two rim columns (double-buffered: row q is written while row q-1 is read).

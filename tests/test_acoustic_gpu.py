@@ -239,12 +239,16 @@ def test_two_step_kernels_equal_one_step_kernels_bitwise(A, ctx, po, monkeypatch
     srci[4], srcj[4] = 5, 5            # deep inside the absorbing frame
     rcvi[:8] = [14, 13, 60, 60, 5, 70, 71, 72]
     rcvj[:8] = [18, 40, 16 + 512, 16 + 511, 5, 16 + 64, 16 + 63, 16 + 65]
+    rcvi[8:14] = [15, 15, 16, 40, 40, 15]        # on and next to the first row / column of the box (its rim ring), duplicates
+    rcvj[8:14] = [17, 18, 17, 17, 18, 17]
+    srci[5], srcj[5] = 15, 17                    # a source on the corner cell of the rim ring
     p = A.AcousticPropagatorParams(PropagatorKernel=kernel, NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dx, DELTAT=dt,
                                    vp_ref=vp, NPOINTS_PML=10)
     pitch = (NY + 2 + 15) // 16 * 16
     out = {}
-    for tb in ("0", "1"):
-        monkeypatch.setenv("ADSEIS_AC_TB", tb)
+    for tb in ("0", "1", "1s"):       # one-step kernels; pairs with frame / box launches on two streams; pairs on one stream
+        monkeypatch.setenv("ADSEIS_AC_TB", tb[0])
+        monkeypatch.setenv("ADSEIS_AC_TB_OVERLAP", "0" if tb == "1s" else "1")
         for slots in (0, 12):
             plan = A.AcousticPlan(p, srci, srcj, rcvi, rcvj, ctx=ctx, hist_bytes_budget=slots * (NX + 2) * pitch * 8)
             plan.set_model(c); plan.set_srcv(srcv)
