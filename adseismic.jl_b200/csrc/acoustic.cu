@@ -382,7 +382,10 @@ static void build_tb_tilings(adseis_acoustic_plan* P) {
     if (P->p.PropagatorKernel == 0) return;
     const i64 rows_min = (i64)g.H / P->slab.nranks - (P->p.NPOINTS_PML + 4) - 5;
     const i64 cells = rows_min * (i64)(g.W - 2 * (P->p.NPOINTS_PML + 4));
-    const i64 min_cells = getenv("ADSEIS_AC_TB_SLAB_MIN") ? atoll(getenv("ADSEIS_AC_TB_SLAB_MIN")) : (3LL << 19);
+    // measured on B200s, C4 (4096^2): pairs win on 2 slabs (8.3 M box cells each: 103.5 -> 126.3 Gcell-upd/s), are neutral
+    // on 4 (4.2 M: 199 -> 206) and lose on 8 (2.1 M: 361 -> 275 -- the chain of frame-only launches with their fused
+    // halo waits, two per pair, is then longer than the box-pair kernel it should hide behind)
+    const i64 min_cells = getenv("ADSEIS_AC_TB_SLAB_MIN") ? atoll(getenv("ADSEIS_AC_TB_SLAB_MIN")) : (6LL << 20);
     if (rows_min < 16 || (!(e && e[0] == '1') && cells < min_cells)) return;
   }
   const int fi0 = P->box_i0 + 2, fi1 = P->box_i1 - 2, fj0 = P->box_j0 + 2, fj1 = P->box_j1 - 2;
