@@ -64,6 +64,7 @@ struct AcDesc {
   long long n_edge_lo_f, n_edge_hi_f;  // ... of a frame-only launch of the two-step path (0: that path is off)
   long long n_edge_lo_w, n_edge_hi_w;  // ... of a WIDE frame-only launch (frame + rim ring of the box)
   long long nub;
+  long long off_ll;   // packed halo rows: [from lo, from hi][u, p][parity] rows of ld 16-byte words (0: not present)
 };
 #define AC_DESC_MAGIC 0xAD5E15B200ULL
 #define AC_HX_BLOCKS 8
@@ -193,6 +194,8 @@ struct adseis_acoustic_plan {
   unsigned long long sepoch = 0;             // step kernels launched so far (same sequence on every rank)
   int* perm = nullptr;                       // launch order -> logical CTA id (edge CTAs first)
   int n_edge_lo = 0, n_edge_hi = 0;
+  bool ll = false;                           // packed halo rows instead of fence + flag (ADSEIS_AC_LL=0 switches back)
+  int ll_prev_kind = 0; i64 ll_prev_s = 0;   // the last fused launch: 1 forward / 2 adjoint step s (0: none, or an explicit exchange since)
   unsigned long long exp_lo = 0, exp_hi = 0; // signals the neighbours have sent me so far (sum over their fused launches)
   bool connected = false;
   // stats
@@ -230,6 +233,63 @@ static inline double* win_slot(adseis_acoustic_plan* P, i64 base, i64 s) { retur
     (P)->last_launches++;                 \
     CUDA_TRY(cudaGetLastError());         \
   } while (0)
+
+// Development aid (-DADSEIS_TIMELINE): a timed event after every step launch on the stream it went to; the dump lists,
+// per launch, when it finished.  ADSEIS_TIMELINE=<marks to keep>, ADSEIS_TIMELINE_SKIP=<launches to skip first>.
+#ifdef ADSEIS_TIMELINE
+struct TlMark { cudaEvent_t ev; int tag; long long s; unsigned long long* dev; };
+static std::vector<TlMark> g_tl;
+static long long g_tl_seen = 0, g_tl_cap = -1, g_tl_skip = 0;
+static unsigned long long* g_tl_dev = nullptr;   // 5 device time stamps per mark
+static unsigned long long* g_tl_next = nullptr;  // slot handed to the launch that tl_mark() follows
+static void tl_init() {
+  if (g_tl_cap >= 0) return;
+  const char* e = getenv("ADSEIS_TIMELINE"); g_tl_cap = e ? atoll(e) : 0;
+  const char* k = getenv("ADSEIS_TIMELINE_SKIP"); g_tl_skip = k ? atoll(k) : 0;
+  if (g_tl_cap > 0 && cudaMalloc(&g_tl_dev, (size_t)g_tl_cap * 5 * 8) == cudaSuccess) {
+    std::vector<unsigned long long> init((size_t)g_tl_cap * 5, 0ULL);
+    for (long long i = 0; i < g_tl_cap; i++) init[(size_t)i * 5] = ~0ULL;
+    cudaMemcpy(g_tl_dev, init.data(), init.size() * 8, cudaMemcpyHostToDevice);
+  }
+}
+// device slot for the NEXT marked launch (null when that launch is not kept)
+static unsigned long long* tl_slot() {
+  tl_init();
+  g_tl_next = nullptr;
+  if (g_tl_seen < g_tl_skip || (long long)g_tl.size() >= g_tl_cap || !g_tl_dev) return nullptr;
+  return g_tl_next = g_tl_dev + g_tl.size() * 5;
+}
+static void tl_mark(cudaStream_t st, int tag, long long s) {
+  tl_init();
+  if (g_tl_seen++ < g_tl_skip || (long long)g_tl.size() >= g_tl_cap) return;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, st);
+  g_tl.push_back({ev, tag, s, g_tl_next});
+  g_tl_next = nullptr;
+}
+extern "C" __attribute__((visibility("default"))) int adseis_debug_timeline_dump(const char* path) {
+  cudaDeviceSynchronize();
+  FILE* f = fopen(path, "w");
+  if (!f) return -1;
+  unsigned long long t00 = 0;
+  for (size_t k = 0; k < g_tl.size(); k++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_tl[0].ev, g_tl[k].ev);
+    unsigned long long d[5] = {0, 0, 0, 0, 0};
+    if (g_tl[k].dev) cudaMemcpy(d, g_tl[k].dev, sizeof(d), cudaMemcpyDeviceToHost);
+    if (!t00 && g_tl[k].dev) t00 = d[0];
+    double r[5];
+    for (int q = 0; q < 5; q++) r[q] = (g_tl[k].dev && d[q] && d[q] != ~0ULL) ? (double)(long long)(d[q] - t00) * 1e-3 : -1.0;
+    fprintf(f, "%zu %d %lld %.3f %.3f %.3f %.3f %.3f %.3f\n", k, g_tl[k].tag, g_tl[k].s, ms * 1e3, r[0], r[1], r[2], r[3], r[4]);
+  }
+  fclose(f);
+  return (int)g_tl.size();
+}
+#define TL_MARK(st, tag, s) tl_mark(st, tag, s)
+#else
+#define TL_MARK(st, tag, s) do {} while (0)
+#endif
 
 enum AcArr { AR_HIST, AR_PHI, AR_PSI, AR_UB, AR_PHIB, AR_PSIB };  // arrays with halo rows (slab plans)
 static int halo_exchange(adseis_acoustic_plan* P, int narr, const int* arr, const i64* idx);
@@ -330,7 +390,7 @@ static void build_launch_order(adseis_acoustic_plan* P, const AcTiling& t, int n
                                int* n_edge_lo, int* n_edge_hi) {
   const bool halo_lo = P->slab.rank > 0, halo_hi = P->slab.rank < P->slab.nranks - 1;
   const int first = P->own0, last = P->own1 - 1;
-  const int fcells = AC_THREADS * t.fcpt;
+  const int fcells = t.fthr * t.fcpt;
   std::vector<int> edge, march, frame;
   *n_edge_lo = *n_edge_hi = 0;
   for (int b = 0; b < nblocks; b++) {
@@ -400,7 +460,7 @@ static void build_tb_tilings(adseis_acoustic_plan* P) {
   AcTiling& t = P->t2;
   memset(&t, 0, sizeof(t));
   t.mr0 = mr0; t.mr1 = mr1; t.mc0 = mc0; t.mc_end = mc_end;
-  t.fcpt = AC_FRAME_CPT;
+  t.fcpt = AC_FRAME_CPT; t.fthr = AC_THREADS;
   const int nwarpcols = (mc_end - mc0 + AC_WCOLS - 1) / AC_WCOLS;
   t.nct = (nwarpcols + AC_WARPS - 1) / AC_WARPS;
   const int rows = mr1 - mr0;
@@ -426,7 +486,8 @@ static void build_tb_tilings(adseis_acoustic_plan* P) {
     f.mr0 = f.mr1 = P->own0;  // no marched rows
     f.rb = 1;
     f.fcpt = getenv("ADSEIS_AC_FCPT2") ? std::max(1, atoi(getenv("ADSEIS_AC_FCPT2"))) : 1;  // alone in its launch: all parallelism
-    const int fcells2 = AC_THREADS * f.fcpt;
+    f.fthr = AC_FO_THREADS;
+    const int fcells2 = f.fthr * f.fcpt;
     auto add_rect = [&](int r0, int r1, int c0, int c1) {
       if (r1 <= r0 || c1 <= c0) return;
       const int k = f.nrect++;
@@ -544,7 +605,7 @@ static int plan_build_points(adseis_acoustic_plan* P, int64_t nsrc, const int64_
     auto owner_f = [&](const AcTiling& tf, int li, int j) -> int {
       for (int k = 0; k < tf.nrect; k++)
         if (li >= tf.rr0[k] && li < tf.rr1[k] && j >= tf.rc0[k] && j < tf.rc1[k])
-          return tf.rblk[k] + (int)(((i64)(li - tf.rr0[k]) * (tf.rc1[k] - tf.rc0[k]) + (j - tf.rc0[k])) / (AC_THREADS * tf.fcpt));
+          return tf.rblk[k] + (int)(((i64)(li - tf.rr0[k]) * (tf.rc1[k] - tf.rc0[k]) + (j - tf.rc0[k])) / (tf.fthr * tf.fcpt));
       return -1;
     };
     auto build2 = [&](i64 n, const int64_t* pi, const int64_t* pj, int mode, int nblk, PointSetStorage* dst) -> int {
@@ -719,7 +780,7 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     const int fi0 = ia + shrink, fi1 = ib - shrink, fj0 = ja + shrink, fj1 = jb - shrink;
     AcTiling& t = P->t;
     memset(&t, 0, sizeof(t));
-    t.fcpt = AC_FRAME_CPT;
+    t.fcpt = AC_FRAME_CPT; t.fthr = AC_THREADS;
     // marched local rows: owned rows whose global index lies in [fi0, fi1]
     int mr0 = std::max(P->own0, fi0 - g.goff), mr1 = std::min(P->own1, fi1 + 1 - g.goff);
     int mc0 = round_up(std::max(fj0, 1), 16);
@@ -838,6 +899,12 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     for (int k = 0; k < 4; k++) d.off_ub[k] = (k < P->nub) ? take(1) : 0;
     for (int k = 0; k < 2; k++) d.off_phib[k] = take(1);
     for (int k = 0; k < 2; k++) d.off_psib[k] = take(1);
+    {
+      const char* ell = getenv("ADSEIS_AC_LL");
+      P->ll = !(ell && ell[0] == '0');
+      d.off_ll = 0;
+      if (P->ll) { d.off_ll = off; off += 8LL * g.ld * 16; off = (off + 511) / 512 * 512; }
+    }
     P->arena_bytes = (size_t)off;
     cudaError_t e = cudaMalloc((void**)&P->arena, P->arena_bytes);
     if (e != cudaSuccess) {
@@ -941,7 +1008,8 @@ ADSEIS_API int adseis_acoustic_plan_set_obs(adseis_acoustic_plan* P, const doubl
 // `frame_only`: the launch uses the frame-only tiling of the two-step path (its own launch order and edge-CTA counts).
 // The flag a rank waits on counts the signals of ALL fused launches its neighbour has issued so far; both ranks issue
 // the same sequence of launches, so the expectation is accumulated on the host, launch by launch.
-static AcFuse make_fuse(adseis_acoustic_plan* P, int arr_u, i64 idx_u, int arr_p, i64 idx_p, int fkind = 0) {
+static AcFuse make_fuse(adseis_acoustic_plan* P, int arr_u, i64 idx_u, int arr_p, i64 idx_p, int fkind = 0,
+                        bool recv = false, double* in_u = nullptr, double* in_p = nullptr) {
   AcFuse f;
   memset(&f, 0, sizeof(f));
   f.perm = fkind ? P->fk[fkind - 1].perm : P->perm;
@@ -949,6 +1017,27 @@ static AcFuse make_fuse(adseis_acoustic_plan* P, int arr_u, i64 idx_u, int arr_p
   f.own0 = P->own0; f.own_last = P->own1 - 1;
   f.has_lo = P->peer[0] != nullptr; f.has_hi = P->peer[1] != nullptr;
   P->sepoch++;
+  if (P->ll) {
+    // LL rows: region (from, array, parity); I am rank-1's "hi" and rank+1's "lo" neighbour
+    auto row = [&](char* base, const AcDesc& d, int from, int arr, unsigned long long ep) {
+      return (ulonglong2*)(base + d.off_ll + (long long)((from * 2 + arr) * 2 + (int)(ep & 1ULL)) * d.ld * 16);
+    };
+    const unsigned long long es = P->sepoch, er = P->sepoch - 1;
+    f.ll = 1;
+    f.ep_send = (unsigned)(es % 0xFFFFFFFEULL) + 1u;
+    f.ep_recv = recv ? (unsigned)(er % 0xFFFFFFFEULL) + 1u : 0u;
+    f.in_u = in_u; f.in_p = in_p;
+    f.my_flags = (unsigned long long*)((char*)P->arena + P->desc.off_flags);
+    if (f.has_lo) {
+      f.tx_lo_u = row(P->peer[0], P->dpeer[0], 1, 0, es); f.tx_lo_p = row(P->peer[0], P->dpeer[0], 1, 1, es);
+      f.rx_lo_u = row((char*)P->arena, P->desc, 0, 0, er); f.rx_lo_p = row((char*)P->arena, P->desc, 0, 1, er);
+    }
+    if (f.has_hi) {
+      f.tx_hi_u = row(P->peer[1], P->dpeer[1], 0, 0, es); f.tx_hi_p = row(P->peer[1], P->dpeer[1], 0, 1, es);
+      f.rx_hi_u = row((char*)P->arena, P->desc, 1, 0, er); f.rx_hi_p = row((char*)P->arena, P->desc, 1, 1, er);
+    }
+    return f;
+  }
   if (f.has_lo) {  // my first owned row -> rank-1's upper halo row; it bumps my flags[3], I bump its flags[4]
     const AcDesc& d = P->dpeer[0];
     f.lo_u = (double*)(P->peer[0] + desc_off(d, arr_u, idx_u)) + (d.Hl - 1) * d.ld;
@@ -1027,18 +1116,27 @@ static int launch_forward_step(adseis_acoustic_plan* P, i64 base, i64 s, bool sa
   AcPoints none{};
   AcFuse fuse;
   if (fkind && !P->arena) memset(&fuse, 0, sizeof(fuse));
-  else fuse = make_fuse(P, AR_HIST, s - base, AR_PHI, s & 1, fkind);
+  else {
+    fuse = make_fuse(P, AR_HIST, s - base, AR_PHI, s & 1, fkind, P->ll_prev_kind == 1 && P->ll_prev_s == s - 1,
+                     win_slot(P, base, s - 1), P->phi[(s - 1) & 1]);
+    P->ll_prev_kind = 1; P->ll_prev_s = s;
+  }
   const adseis_acoustic_plan::FrameKind* F = fkind ? &P->fk[fkind - 1] : nullptr;
   const AcPoints srcp = fkind == 2 ? F->srcNp : (F ? F->srcp : P->srcp), rcvp = F ? F->rcvp : P->rcvp;
   if (fkind == 2) fuse.rim = F->srcRp;
+#ifdef ADSEIS_TIMELINE
+  fuse.tl = tl_slot();
+#endif
   CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab() || (fkind && adseis_pdl_tb_slab()),
-                       P->p.PropagatorKernel == 0 ? ac_fwd_kernel<0> : ac_fwd_kernel<1>,
-                       F ? F->nblocks : P->nblocks, AC_FWD_THREADS, F ? 0 : AC_FWD_SMEM, st,
+                       F ? (P->p.PropagatorKernel == 0 ? ac_fwd_kernel<0, 1> : ac_fwd_kernel<1, 1>)
+                         : (P->p.PropagatorKernel == 0 ? ac_fwd_kernel<0, 0> : ac_fwd_kernel<1, 0>),
+                       F ? F->nblocks : P->nblocks, F ? AC_FO_THREADS : AC_FWD_THREADS, F ? 0 : AC_FWD_SMEM, st,
       g, F ? F->t : P->t, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, P->phi[(s - 1) & 1],
       P->psi[(s - 1) & 1], P->sigx, P->tauy, win_slot(P, base, s), P->phi[s & 1], P->psi[s & 1], srcp,
       P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, sample ? rcvp : none,
       (sample && P->nrcv > 0) ? P->rcvv + s * P->nrcv : nullptr, fuse));
   LAUNCH_CHECK(P);
+  TL_MARK(st, fkind, s);
   return ADSEIS_OK;
 }
 
@@ -1067,13 +1165,14 @@ static int run_forward_steps(adseis_acoustic_plan* P, i64 base, i64 s_first, i64
       } else {
         TRY(launch_forward_step(P, base, s, sample, 1, st));
       }
-      CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_tb_slab(), ac_fwd2_kernel, P->nblocks2, AC_FWD_THREADS, AC_FWD2_SMEM, st,
+      CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_tb_slab() == 2, ac_fwd2_kernel, P->nblocks2, AC_FWD_THREADS, AC_FWD2_SMEM, st,
           g, P->t2, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, win_slot(P, base, s), win_slot(P, base, s + 1),
           P->srcHp, P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, P->srcMp,
           P->nsrc > 0 ? P->srcv + s * P->nsrc : nullptr, sample ? P->rcvMp : none,
           (sample && P->nrcv > 0) ? P->rcvv + s * P->nrcv : nullptr,
           (sample && P->nrcv > 0) ? P->rcvv + (s + 1) * P->nrcv : nullptr));
       LAUNCH_CHECK(P);
+      TL_MARK(st, 3, s);
       if (pipe.on) TRY(pipe.post_box());
       else TRY(launch_forward_step(P, base, s + 1, sample, 1, st));
     }
@@ -1102,10 +1201,18 @@ static int forward_sweep(adseis_acoustic_plan* P, bool save_ckpt, segment_cb cb,
   for (size_t k = 0; k < nseg; k++) {
     const i64 b = P->seg_b[k], e = P->seg_e[k];
     if (k > 0) {
-      // slab plans: the neighbours' last pushes must have landed before halo rows are copied
-      TRY(halo_exchange(P, 0, nullptr, nullptr));
-      // window index 0,1 <- slots b, b+1 (the last two slots of the previous segment)
+      // slab plans: the neighbours' last pushes must have landed before halo rows are copied.  Packed halo rows are
+      // unpacked by the NEXT step launch, so the halo rows of the last slot and of its phi are exchanged explicitly
+      // here (they go into the checkpoint and into the rebased window)
       const i64 pbse = P->seg_b[k - 1];
+      if (P->ll) {
+        const int arr[2] = {AR_HIST, AR_PHI};
+        const i64 idx[2] = {b + 1 - pbse, (b + 1) & 1};
+        TRY(halo_exchange(P, 2, arr, idx));
+      } else {
+        TRY(halo_exchange(P, 0, nullptr, nullptr));
+      }
+      // window index 0,1 <- slots b, b+1 (the last two slots of the previous segment)
       double* s0 = win_slot(P, pbse, b);
       double* s1 = win_slot(P, pbse, b + 1);
       if (save_ckpt) {
@@ -1320,13 +1427,23 @@ static int gradient_body(adseis_acoustic_plan* P) {
       TRY(span_end(P));
       P->last_recomputed += e - (b + 2) + 1;
       P->win_base = b; P->win_last = e;
+      if (P->arena && P->ll) {
+        // packed halo rows: the adjoint rows sent by the last adjoint launch before the replay were never unpacked
+        const int arr[2] = {AR_UB, AR_PHIB};
+        const i64 idx[2] = {e % NUB, e & 1};
+        TRY(halo_exchange(P, 2, arr, idx));
+      }
     }
     TRY(span_begin(P, 2, e - (b + 2) + 1));
     // one adjoint step s: ubar[s-1] from ubar[s], ubar[s+1], u[s-1]; fkind as in launch_forward_step
     auto adj_step = [&](i64 s, int fkind, cudaStream_t stl) -> int {
       AcFuse fuse;
       if (fkind && !P->arena) memset(&fuse, 0, sizeof(fuse));
-      else fuse = make_fuse(P, AR_UB, (s - 1 + NUB) % NUB, AR_PHIB, (s - 1) & 1, fkind);
+      else {
+        fuse = make_fuse(P, AR_UB, (s - 1 + NUB) % NUB, AR_PHIB, (s - 1) & 1, fkind, P->ll_prev_kind == 2 && P->ll_prev_s == s + 1,
+                         P->ub[s % NUB], P->phib[s & 1]);
+        P->ll_prev_kind = 2; P->ll_prev_s = s;
+      }
       AcK0 k0{};
       if (P->p.PropagatorKernel == 0) {
         k0.wnew = win_slot(P, b, s); k0.ut_in = P->ut[(s + 1) & 1]; k0.ut_out = P->ut[s & 1];
@@ -1340,14 +1457,19 @@ static int gradient_body(adseis_acoustic_plan* P) {
       const adseis_acoustic_plan::FrameKind* F = fkind ? &P->fk[fkind - 1] : nullptr;
       const AcPoints rcvp = fkind == 2 ? F->rcvNp : (F ? F->rcvp : P->rcvp), srcp = F ? F->srcp : P->srcp;
       if (fkind == 2) fuse.rim = F->rcvRp;
+#ifdef ADSEIS_TIMELINE
+      fuse.tl = tl_slot();
+#endif
       CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab() || (fkind && adseis_pdl_tb_slab()),
-                           P->p.PropagatorKernel == 0 ? ac_adj_kernel<0> : ac_adj_kernel<1>,
-                           F ? F->nblocks : P->nblocks, AC_ADJ_THREADS, F ? 0 : AC_ADJ_SMEM, stl,
+                           F ? (P->p.PropagatorKernel == 0 ? ac_adj_kernel<0, 1> : ac_adj_kernel<1, 1>)
+                             : (P->p.PropagatorKernel == 0 ? ac_adj_kernel<0, 0> : ac_adj_kernel<1, 0>),
+                           F ? F->nblocks : P->nblocks, F ? AC_FO_THREADS : AC_ADJ_THREADS, F ? 0 : AC_ADJ_SMEM, stl,
           g, F ? F->t : P->t, P->ub[s % NUB], P->ub[(s + 1) % NUB], win_slot(P, b, s - 1), P->c2, P->phib[s & 1],
           P->psib[s & 1], P->sigx, P->tauy, P->ub[(s - 1 + NUB) % NUB], P->phib[(s - 1) & 1], P->psib[(s - 1) & 1], P->G,
           rcvp, P->nrcv > 0 ? P->res + (s - 1) * P->nrcv : nullptr, (s - 2 >= 1) ? srcp : none,
           (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr, fuse, k0));
       LAUNCH_CHECK(P);
+      TL_MARK(stl, 10 + fkind, s);
       return ADSEIS_OK;
     };
     i64 s = e;
@@ -1366,13 +1488,14 @@ static int gradient_body(adseis_acoustic_plan* P) {
         } else {
           TRY(adj_step(s, 1, st));
         }
-        CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_tb_slab(), ac_adj2_kernel, P->nblocks2, AC2_THREADS, AC_ADJ2_SMEM, st,
+        CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_tb_slab() == 2, ac_adj2_kernel, P->nblocks2, AC2_THREADS, AC_ADJ2_SMEM, st,
             g, P->t2, P->ub[s % NUB], P->ub[(s + 1) % NUB], win_slot(P, b, s - 1), win_slot(P, b, s - 2), P->c2,
             P->ub[(s - 1 + NUB) % NUB], P->ub[(s - 2 + NUB) % NUB], P->G, P->rcvHp,
             P->nrcv > 0 ? P->res + (s - 1) * P->nrcv : nullptr, P->rcvMp, P->nrcv > 0 ? P->res + (s - 2) * P->nrcv : nullptr,
             P->srcMp, (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr,
             (s - 3 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 3) * P->nsrc : nullptr));
         LAUNCH_CHECK(P);
+        TL_MARK(st, 13, s);
         if (pipe.on) TRY(pipe.post_box());
         else TRY(adj_step(s - 1, 1, st));
       }
@@ -1570,6 +1693,7 @@ static int halo_exchange(adseis_acoustic_plan* P, int narr, const int* arr, cons
   if (a.has_hi) a.sig_hi = (unsigned long long*)(P->peer[1] + P->dpeer[1].off_flags) + 0;
   a.my_flags = (unsigned long long*)(base + P->desc.off_flags);
   P->epoch++;
+  P->ll_prev_kind = 0;   // the next fused launch finds its halo rows in place
   a.expect = (unsigned long long)AC_HX_BLOCKS * P->epoch;
   k_halo_exchange<<<AC_HX_BLOCKS, 256, 0, P->ctx->stream>>>(a);
   LAUNCH_CHECK(P);

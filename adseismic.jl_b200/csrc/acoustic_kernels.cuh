@@ -113,9 +113,15 @@ struct AcTiling {
   int bx_r0, bx_r1, bx_c0, bx_c1;  // frame cells inside this box (the rim ring a WIDE frame-only launch recomputes so that the
                       // next frame launch does not depend on the concurrent box-pair launch) store their state only: the
                       // box kernel owns their Gbar / phibar / psibar updates
-  int fcpt;           // frame cells per thread (a frame CTA covers AC_THREADS * fcpt consecutive cells of its rectangle):
+  int fcpt;           // frame cells per thread (a frame CTA covers fthr * fcpt consecutive cells of its rectangle):
                       // AC_FRAME_CPT when frame CTAs share a launch with marching CTAs, 1 in frame-only launches
+  int fthr;           // threads of a frame CTA that own cells: AC_THREADS in a full launch, AC_FO_THREADS in a frame-only one
 };
+// Frame-only launches of the two-step path run CONCURRENTLY with the box-pair kernel (second stream).  That only works if
+// their CTAs fit into what two resident box-pair CTAs leave of an SM (10 K registers next to ac_fwd2_kernel, 13 K next to
+// ac_adj2_kernel): 128 threads at <= 80 registers.  With the 288-thread CTAs of the full kernels the frame launches sat
+// in the queue until the box kernel drained (measured: 7 us between the first and the last CTA entering).
+#define AC_FO_THREADS 128
 
 // Row tile tr of the marched rows -> [r0, r1).  Slab plans put a thin tile on the rows next to a neighbour: those CTAs
 // are launched first and finish within a couple of microseconds, so the halo rows they push travel over NVLink while
@@ -152,7 +158,7 @@ __device__ __forceinline__ int ac_lower_bound(const int* __restrict__ cell, int 
   return a;
 }
 // v + sum of val[perm[m]] * scale over the points on `key` (sequential, original point order); v if none
-__device__ __noinline__ double ac_add_points(double v, const AcPoints& ps, int a, int b, int key,
+__device__ __noinline__ double ac_add_points(double v, AcPoints ps, int a, int b, int key,
                                              const double* __restrict__ val, double scale) {
   const int k = ac_lower_bound(ps.cell, a, b, key);
   if (k < b && ps.cell[k] == key)
@@ -178,11 +184,87 @@ struct AcFuse {
   // ring of the box.  They are added in registers BEFORE the cell's single store -- the concurrent box-pair launch
   // stores the same final value, so neither launch may read-modify-write such a cell
   AcPoints rim;
+  // Packed halo rows ("LL": every 8-byte word carries 32 data bits and the 32-bit epoch of the launch that sent it, so
+  // the data is its own flag).  The sender stores its edge row into the neighbour's LL row and is done -- no
+  // system-scope fence, no flag, nothing on its critical path; the receiving CTA (next fused launch of the neighbour)
+  // polls the words of the columns it owns, writes the doubles into the halo row of the array it is about to read
+  // and goes on.  One NVLink one-way latency per step instead of store + fence round trip + flag + poll.
+  int ll;
+  unsigned ep_send, ep_recv;                               // epoch stamped on my rows; epoch to wait for (0: nothing to receive)
+  ulonglong2 *tx_lo_u, *tx_lo_p, *tx_hi_u, *tx_hi_p;       // the neighbours' LL rows (peer pointers), one entry per column
+  const ulonglong2 *rx_lo_u, *rx_lo_p, *rx_hi_u, *rx_hi_p; // my LL rows, filled by the neighbours' previous fused launch
+  double *in_u, *in_p;                                     // the arrays this launch READS with halo rows (unpack targets)
+#ifdef ADSEIS_TIMELINE
+  unsigned long long* tl;   // [5]: min entry, max entry, max after-wait (edge CTAs), max end of compute, max after signal
+#endif
 };
+#ifdef ADSEIS_TIMELINE
+__device__ __forceinline__ unsigned long long tl_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TL_DEV(f, k) do { if ((f).tl && threadIdx.x == 0) { if ((k) == 0) atomicMin((f).tl, tl_now()); atomicMax((f).tl + ((k) == 0 ? 1 : (k) + 1), tl_now()); } } while (0)
+#else
+#define TL_DEV(f, k) do {} while (0)
+#endif
+
+__device__ __forceinline__ void ll_put(ulonglong2* row, int j, double v, unsigned ep) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v), e = (unsigned long long)ep << 32;
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(row + j), "l"(e | (b & 0xffffffffULL)), "l"(e | (b >> 32))
+               : "memory");
+}
+__device__ __forceinline__ double ll_get(const ulonglong2* row, int j, unsigned ep, unsigned long long* my_flags) {
+  unsigned long long x, y, spins = 0;
+  while (true) {
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "l"(row + j) : "memory");
+    if ((unsigned)(x >> 32) == ep && (unsigned)(y >> 32) == ep) break;
+    if (++spins > (1ULL << 24)) { my_flags[2] = 1ULL; break; }  // neighbour lost: report, do not hang
+  }
+  return __longlong_as_double((long long)((x & 0xffffffffULL) | (y << 32)));
+}
+// The helpers below are out of line and take plain values: the step kernels keep their register budget, and the
+// parameter block is not copied to local memory (which passing `const AcFuse&` to a real call would force).
+struct AcLLRx { const ulonglong2 *lo_u, *lo_p, *hi_u, *hi_p; double *in_u, *in_p; unsigned long long* my_flags; int own0, own_last; unsigned ep; };
+struct AcLLTx { ulonglong2 *lo_u, *lo_p, *hi_u, *hi_p; unsigned ep; };
+__device__ __forceinline__ AcLLRx ac_ll_rx(const AcFuse& f) {
+  return AcLLRx{f.rx_lo_u, f.rx_lo_p, f.rx_hi_u, f.rx_hi_p, f.in_u, f.in_p, f.my_flags, f.own0, f.own_last, f.ep_recv};
+}
+__device__ __forceinline__ AcLLTx ac_ll_tx(const AcFuse& f) { return AcLLTx{f.tx_lo_u, f.tx_lo_p, f.tx_hi_u, f.tx_hi_p, f.ep_send}; }
+// frame cell (li, j) on an edge row: fetch the halo values next to it (the thread that unpacks a value is the thread
+// that reads it afterwards)
+__device__ __noinline__ void ac_ll_recv_cell(AcLLRx r, bool lo, bool hi, int j, int ld) {
+  if (lo) {
+    const double a = ll_get(r.lo_u, j, r.ep, r.my_flags), b = ll_get(r.lo_p, j, r.ep, r.my_flags);
+    r.in_u[(i64)(r.own0 - 1) * ld + j] = a; r.in_p[(i64)(r.own0 - 1) * ld + j] = b;
+  }
+  if (hi) {
+    const double a = ll_get(r.hi_u, j, r.ep, r.my_flags), b = ll_get(r.hi_p, j, r.ep, r.my_flags);
+    r.in_u[(i64)(r.own_last + 1) * ld + j] = a; r.in_p[(i64)(r.own_last + 1) * ld + j] = b;
+  }
+}
+// marching CTA: columns j, j+1 of the halo row(s); the rows are then read by bulk copies (async proxy) of this CTA, so
+// the writes are fenced to that proxy here and ordered before the producer by the __syncthreads() that follows the call
+__device__ __noinline__ void ac_ll_recv_march(AcLLRx r, int j, bool mine, bool t_lo, bool t_hi, int ld) {
+  if (mine) {
+    if (t_lo) {
+      double2 v;
+      v.x = ll_get(r.lo_u, j, r.ep, r.my_flags); v.y = ll_get(r.lo_u, j + 1, r.ep, r.my_flags);
+      st2(r.in_u + (i64)(r.own0 - 1) * ld + j, v);
+    }
+    if (t_hi) {
+      double2 v;
+      v.x = ll_get(r.hi_u, j, r.ep, r.my_flags); v.y = ll_get(r.hi_u, j + 1, r.ep, r.my_flags);
+      st2(r.in_u + (i64)(r.own_last + 1) * ld + j, v);
+    }
+  }
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+// the matching sends (frame cell: u and its phi companion; marching cells are PML-free: companion = 0)
+__device__ __noinline__ void ac_ll_send_cell(AcLLTx x, bool lo, bool hi, int j, double u, double p) {
+  if (lo) { ll_put(x.lo_u, j, u, x.ep); ll_put(x.lo_p, j, p, x.ep); }
+  if (hi) { ll_put(x.hi_u, j, u, x.ep); ll_put(x.hi_p, j, p, x.ep); }
+}
 
 __device__ __forceinline__ void ac_fuse_wait(const AcFuse& f, bool t_lo, bool t_hi) {
   pdl_wait();  // (programmatic dependent launch) everything the previous launch wrote is visible from here on
-  if (!(t_lo || t_hi)) return;  // CTA-uniform
+  if (f.ll || !(t_lo || t_hi)) return;  // CTA-uniform
   if (threadIdx.x == 0) {
     volatile unsigned long long* fl = f.my_flags;
     unsigned long long spins = 0;
@@ -195,7 +277,7 @@ __device__ __forceinline__ void ac_fuse_wait(const AcFuse& f, bool t_lo, bool t_
 }
 
 __device__ __forceinline__ void ac_fuse_signal(const AcFuse& f, bool t_lo, bool t_hi) {
-  if (!(t_lo || t_hi)) return;
+  if (f.ll || !(t_lo || t_hi)) return;
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -212,7 +294,7 @@ __device__ __forceinline__ void ac_fwd_general_cell(const AcGeom& g, int li, int
                                                     const double* __restrict__ phi, const double* __restrict__ psi,
                                                     const double* __restrict__ sigx, const double* __restrict__ tauy,
                                                     double* __restrict__ u, double* __restrict__ phio,
-                                                    double* __restrict__ psio, const AcPoints* rim = nullptr,
+                                                    double* __restrict__ psio, AcPoints rim = AcPoints{},
                                                     int rim_a = 0, int rim_n = 0, const double* __restrict__ rim_val = nullptr,
                                                     double rim_scale = 0.0) {
   const int gi = g.goff + li;
@@ -231,7 +313,7 @@ __device__ __forceinline__ void ac_fwd_general_cell(const AcGeom& g, int li, int
              g.py * (psi[IJp] - psi[IJn]) -
              (1 - (sg + ta) * dt / 2) * wold[IJ];
   v = (v == 0.0) ? v : v / (1 + (sg + ta) / 2 * dt);  // zero numerators would take the divide's slow path
-  if (rim_n > 0) v = ac_add_points(v, *rim, rim_a, rim_a + rim_n, (int)IJ, rim_val, rim_scale);
+  if (rim_n > 0) v = ac_add_points(v, rim, rim_a, rim_a + rim_n, (int)IJ, rim_val, rim_scale);
   u[IJ] = v;
   phio[IJ] = (1. - dt * sg) * phi[IJ] + div_exact(dt * c * (ta - sg) / 2.0, g.hx, g.rhx) * (w[IpJ] - w[InJ]);
   psio[IJ] = (1. - dt * ta) * psi[IJ] + div_exact(dt * c * (sg - ta) / 2.0, g.hy, g.rhy) * (w[IJp] - w[IJn]);
@@ -264,7 +346,7 @@ __device__ __forceinline__ void ac_fwd_general_cell_k0(const AcGeom& g, int li, 
                                                        const double* __restrict__ phi, const double* __restrict__ psi,
                                                        const double* __restrict__ sigx, const double* __restrict__ tauy,
                                                        double* __restrict__ u, double* __restrict__ phio,
-                                                       double* __restrict__ psio, const AcPoints* rim = nullptr,
+                                                       double* __restrict__ psio, AcPoints rim = AcPoints{},
                                                     int rim_a = 0, int rim_n = 0, const double* __restrict__ rim_val = nullptr,
                                                     double rim_scale = 0.0) {
   const int gi = g.goff + li;
@@ -282,7 +364,7 @@ __device__ __forceinline__ void ac_fwd_general_cell_k0(const AcGeom& g, int li, 
   const double uxm = ac_uprime(g, vxm ? gi - 1 : gi, j, vxm ? IJ - g.ld : IJ, w, wold, c2, phi, psi, sigx, tauy);
   const double uyp = ac_uprime(g, gi, vyp ? j + 1 : j, vyp ? IJ + 1 : IJ, w, wold, c2, phi, psi, sigx, tauy);
   const double uym = ac_uprime(g, gi, vym ? j - 1 : j, vym ? IJ - 1 : IJ, w, wold, c2, phi, psi, sigx, tauy);
-  u[IJ] = (rim_n > 0) ? ac_add_points(uP, *rim, rim_a, rim_a + rim_n, (int)IJ, rim_val, rim_scale) : uP;
+  u[IJ] = (rim_n > 0) ? ac_add_points(uP, rim, rim_a, rim_a + rim_n, (int)IJ, rim_val, rim_scale) : uP;
   const double a = div_exact(dt * c * (ta - sg) / 2.0, g.hx, g.rhx);
   const double b = div_exact(dt * c * (sg - ta) / 2.0, g.hy, g.rhy);
   phio[IJ] = (1. - dt * sg) * phi[IJ] + a * ((vxp ? uxp : 0.0) - (vxm ? uxm : 0.0));
@@ -321,43 +403,55 @@ __device__ __forceinline__ void ac_frame_locate(const AcTiling& t, int fb, int* 
   for (int k = 1; k < 4; k++)
     if (k < t.nrect && fb >= t.rblk[k]) r = k;
   *rect = r;
-  *idx0 = (fb - t.rblk[r]) * (AC_THREADS * t.fcpt);
+  *idx0 = (fb - t.rblk[r]) * (t.fthr * t.fcpt);
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // forward kernel
 // ------------------------------------------------------------------------------------------------------------
-template <int PK>  // PropagatorKernel: 1 = custom-op scheme (phi, psi from the old wavefield), 0 = TF-op scheme
-__global__ void __launch_bounds__(AC_FWD_THREADS, AC_MINB_FWD)
+template <int PK, int FO = 0>  // PropagatorKernel: 1 = custom-op scheme (phi, psi from the old wavefield), 0 = TF-op scheme; FO: frame-only launch
+__global__ void __launch_bounds__(FO ? AC_FO_THREADS : AC_FWD_THREADS, FO ? 6 : AC_MINB_FWD)
 ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* __restrict__ wold,
               const double* __restrict__ c2, const double* __restrict__ phi, const double* __restrict__ psi,
               const double* __restrict__ sigx, const double* __restrict__ tauy, double* __restrict__ u,
               double* __restrict__ phio, double* __restrict__ psio, AcPoints src,
               const double* __restrict__ srcv_row, AcPoints rcv, double* __restrict__ rcvv_row, AcFuse f) {
   pdl_launch_dependents();
+  TL_DEV(f, 0);
   const int bid = f.perm ? f.perm[blockIdx.x] : blockIdx.x;
   const int ld = g.ld;
   bool t_lo = false, t_hi = false;  // this CTA owns cells of my first / last owned row next to a neighbour
   int rect = 0, idx0 = 0, wdt = 1, ncell = 0;
-  if (bid >= t.nmarch) {
+  if (FO || bid >= t.nmarch) {
     // ---------------- frame CTA ----------------
     ac_frame_locate(t, bid - t.nmarch, &rect, &idx0);
     wdt = t.rc1[rect] - t.rc0[rect];
     ncell = (t.rr1[rect] - t.rr0[rect]) * wdt;
-    const int rlo = t.rr0[rect] + idx0 / wdt, rhi = t.rr0[rect] + (min(ncell, idx0 + AC_THREADS * t.fcpt) - 1) / wdt;
+    const int rlo = t.rr0[rect] + idx0 / wdt, rhi = t.rr0[rect] + (min(ncell, idx0 + t.fthr * t.fcpt) - 1) / wdt;
     t_lo = f.has_lo && rlo <= f.own0 && f.own0 <= rhi;
     t_hi = f.has_hi && rlo <= f.own_last && f.own_last <= rhi;
     ac_fuse_wait(f, t_lo, t_hi);
+    if (f.ll && f.ep_recv != 0u && (t_lo || t_hi)) {
+      for (int k = 0; k < t.fcpt; k++) {
+        const int idx = idx0 + k * t.fthr + threadIdx.x;
+        if (idx < ncell && threadIdx.x < t.fthr) {
+          const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
+          const bool lo = t_lo && li == f.own0, hi = t_hi && li == f.own_last;
+          if (lo || hi) ac_ll_recv_cell(ac_ll_rx(f), lo, hi, j, ld);
+        }
+      }
+    }
+    if (t_lo || t_hi) TL_DEV(f, 1);
     int rim_a = 0, rim_n = 0;
     if (f.rim.blk != nullptr && srcv_row != nullptr) { rim_a = f.rim.blk[bid]; rim_n = f.rim.blk[bid + 1] - rim_a; }
 #pragma unroll 4
     for (int k = 0; k < t.fcpt; k++) {
-      const int idx = idx0 + k * AC_THREADS + threadIdx.x;
-      if (idx < ncell && threadIdx.x < AC_THREADS) {
+      const int idx = idx0 + k * t.fthr + threadIdx.x;
+      if (idx < ncell && threadIdx.x < t.fthr) {
         const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
         const bool inbox = rim_n > 0 && li >= t.bx_r0 && li < t.bx_r1 && j >= t.bx_c0 && j < t.bx_c1;
-        if constexpr (PK == 0) ac_fwd_general_cell_k0(g, li, j, w, wold, c2, phi, psi, sigx, tauy, u, phio, psio, &f.rim, rim_a, inbox ? rim_n : 0, srcv_row, g.dt2);
-        else ac_fwd_general_cell(g, li, j, w, wold, c2, phi, psi, sigx, tauy, u, phio, psio, &f.rim, rim_a, inbox ? rim_n : 0, srcv_row, g.dt2);
+        if constexpr (PK == 0) ac_fwd_general_cell_k0(g, li, j, w, wold, c2, phi, psi, sigx, tauy, u, phio, psio, f.rim, rim_a, inbox ? rim_n : 0, srcv_row, g.dt2);
+        else ac_fwd_general_cell(g, li, j, w, wold, c2, phi, psi, sigx, tauy, u, phio, psio, f.rim, rim_a, inbox ? rim_n : 0, srcv_row, g.dt2);
       }
     }
   } else {
@@ -374,6 +468,8 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
     t_lo = f.has_lo && r0 <= f.own0 && f.own0 < r1;
     t_hi = f.has_hi && r0 <= f.own_last && f.own_last < r1;
     ac_fuse_wait(f, t_lo, t_hi);
+    if (f.ll && f.ep_recv != 0u && (t_lo || t_hi)) ac_ll_recv_march(ac_ll_rx(f), j, act && threadIdx.x < AC_THREADS, t_lo, t_hi, ld);
+    if (t_lo || t_hi) TL_DEV(f, 1);
     extern __shared__ __align__(128) unsigned char ac_smem[];
     AcFwdStage* stg = reinterpret_cast<AcFwdStage*>(ac_smem);
     unsigned long long* full = reinterpret_cast<unsigned long long*>(ac_smem + AC_NST_FWD * sizeof(AcFwdStage));
@@ -477,28 +573,39 @@ ac_fwd_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* 
     }
   }
   ac_cta_epilogue(bid, u, src, srcv_row, g.dt2, rcv, rcvv_row, 1.0);
+  TL_DEV(f, 2);
   if (t_lo || t_hi) {  // push my piece of the new edge row(s) into the neighbours' halo rows, then publish
     __syncthreads();
-    if (bid >= t.nmarch) {
+    if (FO || bid >= t.nmarch) {
 #pragma unroll 4
       for (int k = 0; k < t.fcpt; k++) {
-        const int idx = idx0 + k * AC_THREADS + threadIdx.x;
-        if (idx < ncell && threadIdx.x < AC_THREADS) {
+        const int idx = idx0 + k * t.fthr + threadIdx.x;
+        if (idx < ncell && threadIdx.x < t.fthr) {
           const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
           const i64 IJ = (i64)li * ld + j;
-          if (t_lo && li == f.own0) { f.lo_u[j] = u[IJ]; f.lo_p[j] = phio[IJ]; }
-          if (t_hi && li == f.own_last) { f.hi_u[j] = u[IJ]; f.hi_p[j] = phio[IJ]; }
+          if (f.ll) {
+            ac_ll_send_cell(ac_ll_tx(f), t_lo && li == f.own0, t_hi && li == f.own_last, j, u[IJ], phio[IJ]);
+          } else {
+            if (t_lo && li == f.own0) { f.lo_u[j] = u[IJ]; f.lo_p[j] = phio[IJ]; }
+            if (t_hi && li == f.own_last) { f.hi_u[j] = u[IJ]; f.hi_p[j] = phio[IJ]; }
+          }
         }
       }
     } else {
       const int ct = bid % t.nct;
       const int j = t.mc0 + ct * AC_TILE_COLS + 2 * threadIdx.x;
       if (j < t.mc_end && threadIdx.x < AC_THREADS) {
-        if (t_lo) st2(f.lo_u + j, ld2(u + (i64)f.own0 * ld + j));
-        if (t_hi) st2(f.hi_u + j, ld2(u + (i64)f.own_last * ld + j));
+        if (f.ll) {
+          if (t_lo) { const double2 v = ld2(u + (i64)f.own0 * ld + j); ac_ll_send_cell(ac_ll_tx(f), true, false, j, v.x, 0.0); ac_ll_send_cell(ac_ll_tx(f), true, false, j + 1, v.y, 0.0); }
+          if (t_hi) { const double2 v = ld2(u + (i64)f.own_last * ld + j); ac_ll_send_cell(ac_ll_tx(f), false, true, j, v.x, 0.0); ac_ll_send_cell(ac_ll_tx(f), false, true, j + 1, v.y, 0.0); }
+        } else {
+          if (t_lo) st2(f.lo_u + j, ld2(u + (i64)f.own0 * ld + j));
+          if (t_hi) st2(f.hi_u + j, ld2(u + (i64)f.own_last * ld + j));
+        }
       }
     }
     ac_fuse_signal(f, t_lo, t_hi);
+    TL_DEV(f, 3);
   }
 }
 
@@ -533,7 +640,7 @@ __device__ __forceinline__ void ac_adj_general_cell(const AcGeom& g, int li, int
                                                     const double* __restrict__ sigx, const double* __restrict__ tauy,
                                                     double* __restrict__ ub0, double* __restrict__ phibo,
                                                     double* __restrict__ psibo, double* __restrict__ G,
-                                                    bool state_only = false, const AcPoints* rim = nullptr, int rim_a = 0,
+                                                    bool state_only = false, AcPoints rim = AcPoints{}, int rim_a = 0,
                                                     int rim_n = 0, const double* __restrict__ rim_val = nullptr) {
   // All loads are issued up front from always-valid (clamped) addresses and the validity predicates only select
   // terms afterwards: a frame cell then costs ONE memory round trip instead of one per neighbour branch (the
@@ -569,7 +676,7 @@ __device__ __forceinline__ void ac_adj_general_cell(const AcGeom& g, int li, int
   if (intP && vxm && vxp && vym && vyp && sg == 0.0 && sgm == 0.0 && sgp == 0.0 && ta == 0.0 && tam == 0.0 && tap == 0.0) {
     const double rx2 = g.rx * g.rx, ry2 = g.ry * g.ry;
     double a_ = ac_adj_cell(ac_a0(cP, g.kx2, g.ky2), rx2, ry2, uP, cxp * uxp, cxm * uxm, cyp * uyp, cym * uym, u2P);
-    if (state_only && rim_n > 0) a_ = ac_add_points(a_, *rim, rim_a, rim_a + rim_n, (int)IJ, rim_val, 1.0);
+    if (state_only && rim_n > 0) a_ = ac_add_points(a_, rim, rim_a, rim_a + rim_n, (int)IJ, rim_val, 1.0);
     ub0[IJ] = a_;
     if (state_only) return;   // a rim cell of the box recomputed by a wide frame launch: the box kernel accumulates Gbar
     phibo[IJ] = (1. - dt * sg) * pb + g.px * (uxm - uxp);   // never used (its coefficient is tau - sigma = 0); kept finite
@@ -746,8 +853,8 @@ __global__ void k_ac_k0_src_corr(AcGeom g, const int* __restrict__ cell, const i
 // ------------------------------------------------------------------------------------------------------------
 // adjoint kernel: ub0 = ubar[s-1] from ub1 = ubar[s], ub2 = ubar[s+1], wf = u[s-1]
 // ------------------------------------------------------------------------------------------------------------
-template <int PK>
-__global__ void __launch_bounds__(AC_ADJ_THREADS, AC_MINB_ADJ)
+template <int PK, int FO = 0>
+__global__ void __launch_bounds__(FO ? AC_FO_THREADS : AC_ADJ_THREADS, FO ? 5 : AC_MINB_ADJ)
 ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double* __restrict__ ub2,
               const double* __restrict__ wf, const double* __restrict__ c2, const double* __restrict__ phib,
               const double* __restrict__ psib, const double* __restrict__ sigx, const double* __restrict__ tauy,
@@ -755,6 +862,7 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
               double* __restrict__ G, AcPoints rcv, const double* __restrict__ res_row, AcPoints src,
               double* __restrict__ gsrcv_row, AcFuse f, AcK0 k0) {
   pdl_launch_dependents();
+  TL_DEV(f, 0);
   const int bid = f.perm ? f.perm[blockIdx.x] : blockIdx.x;
 #ifdef AC_DEBUG_SKIP_FRAME   // timing experiments only (wrong results)
   if (bid >= t.nmarch) return;
@@ -765,27 +873,38 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
   const int ld = g.ld;
   bool t_lo = false, t_hi = false;
   int rect = 0, idx0 = 0, wdt = 1, ncell = 0;
-  if (bid >= t.nmarch) {
+  if (FO || bid >= t.nmarch) {
     ac_frame_locate(t, bid - t.nmarch, &rect, &idx0);
 #ifdef AC_DEBUG_RECTS
     if (!((AC_DEBUG_RECTS >> rect) & 1)) return;
 #endif
     wdt = t.rc1[rect] - t.rc0[rect];
     ncell = (t.rr1[rect] - t.rr0[rect]) * wdt;
-    const int rlo = t.rr0[rect] + idx0 / wdt, rhi = t.rr0[rect] + (min(ncell, idx0 + AC_THREADS * t.fcpt) - 1) / wdt;
+    const int rlo = t.rr0[rect] + idx0 / wdt, rhi = t.rr0[rect] + (min(ncell, idx0 + t.fthr * t.fcpt) - 1) / wdt;
     t_lo = f.has_lo && rlo <= f.own0 && f.own0 <= rhi;
     t_hi = f.has_hi && rlo <= f.own_last && f.own_last <= rhi;
     ac_fuse_wait(f, t_lo, t_hi);
+    if (f.ll && f.ep_recv != 0u && (t_lo || t_hi)) {
+      for (int k = 0; k < t.fcpt; k++) {
+        const int idx = idx0 + k * t.fthr + threadIdx.x;
+        if (idx < ncell && threadIdx.x < t.fthr) {
+          const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
+          const bool lo = t_lo && li == f.own0, hi = t_hi && li == f.own_last;
+          if (lo || hi) ac_ll_recv_cell(ac_ll_rx(f), lo, hi, j, ld);
+        }
+      }
+    }
+    if (t_lo || t_hi) TL_DEV(f, 1);
     int rim_a = 0, rim_n = 0;
     if (f.rim.blk != nullptr && res_row != nullptr) { rim_a = f.rim.blk[bid]; rim_n = f.rim.blk[bid + 1] - rim_a; }
 #pragma unroll 4
     for (int k = 0; k < t.fcpt; k++) {
-      const int idx = idx0 + k * AC_THREADS + threadIdx.x;
-      if (idx < ncell && threadIdx.x < AC_THREADS) {
+      const int idx = idx0 + k * t.fthr + threadIdx.x;
+      if (idx < ncell && threadIdx.x < t.fthr) {
         const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
         if constexpr (PK == 0) ac_adj_general_cell_k0(g, li, j, ub1, wf, c2, phib, psib, sigx, tauy, ub0, phibo, psibo, G, k0);
         else ac_adj_general_cell(g, li, j, ub1, ub2, wf, c2, phib, psib, sigx, tauy, ub0, phibo, psibo, G,
-                                 li >= t.bx_r0 && li < t.bx_r1 && j >= t.bx_c0 && j < t.bx_c1, &f.rim, rim_a, rim_n, res_row);
+                                 li >= t.bx_r0 && li < t.bx_r1 && j >= t.bx_c0 && j < t.bx_c1, f.rim, rim_a, rim_n, res_row);
       }
     }
   } else {
@@ -801,6 +920,8 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
     t_lo = f.has_lo && r0 <= f.own0 && f.own0 < r1;
     t_hi = f.has_hi && r0 <= f.own_last && f.own_last < r1;
     ac_fuse_wait(f, t_lo, t_hi);
+    if (f.ll && f.ep_recv != 0u && (t_lo || t_hi)) ac_ll_recv_march(ac_ll_rx(f), j, act && threadIdx.x < AC_THREADS, t_lo, t_hi, ld);
+    if (t_lo || t_hi) TL_DEV(f, 1);
     extern __shared__ __align__(128) unsigned char ac_smem[];
     AcAdjStage* stg = reinterpret_cast<AcAdjStage*>(ac_smem);
     unsigned long long* full = reinterpret_cast<unsigned long long*>(ac_smem + AC_NST_ADJ * sizeof(AcAdjStage));
@@ -895,28 +1016,39 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
     }
   }
   ac_cta_epilogue(bid, ub0, rcv, res_row, 1.0, src, gsrcv_row, g.dt2);
+  TL_DEV(f, 2);
   if (t_lo || t_hi) {
     __syncthreads();
-    if (bid >= t.nmarch) {
+    if (FO || bid >= t.nmarch) {
 #pragma unroll 4
       for (int k = 0; k < t.fcpt; k++) {
-        const int idx = idx0 + k * AC_THREADS + threadIdx.x;
-        if (idx < ncell && threadIdx.x < AC_THREADS) {
+        const int idx = idx0 + k * t.fthr + threadIdx.x;
+        if (idx < ncell && threadIdx.x < t.fthr) {
           const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
           const i64 IJ = (i64)li * ld + j;
-          if (t_lo && li == f.own0) { f.lo_u[j] = ub0[IJ]; f.lo_p[j] = phibo[IJ]; }
-          if (t_hi && li == f.own_last) { f.hi_u[j] = ub0[IJ]; f.hi_p[j] = phibo[IJ]; }
+          if (f.ll) {
+            ac_ll_send_cell(ac_ll_tx(f), t_lo && li == f.own0, t_hi && li == f.own_last, j, ub0[IJ], phibo[IJ]);
+          } else {
+            if (t_lo && li == f.own0) { f.lo_u[j] = ub0[IJ]; f.lo_p[j] = phibo[IJ]; }
+            if (t_hi && li == f.own_last) { f.hi_u[j] = ub0[IJ]; f.hi_p[j] = phibo[IJ]; }
+          }
         }
       }
     } else {
       const int ct = bid % t.nct;
       const int j = t.mc0 + ct * AC_TILE_COLS + 2 * threadIdx.x;
       if (j < t.mc_end && threadIdx.x < AC_THREADS) {
-        if (t_lo) st2(f.lo_u + j, ld2(ub0 + (i64)f.own0 * ld + j));
-        if (t_hi) st2(f.hi_u + j, ld2(ub0 + (i64)f.own_last * ld + j));
+        if (f.ll) {
+          if (t_lo) { const double2 v = ld2(ub0 + (i64)f.own0 * ld + j); ac_ll_send_cell(ac_ll_tx(f), true, false, j, v.x, 0.0); ac_ll_send_cell(ac_ll_tx(f), true, false, j + 1, v.y, 0.0); }
+          if (t_hi) { const double2 v = ld2(ub0 + (i64)f.own_last * ld + j); ac_ll_send_cell(ac_ll_tx(f), false, true, j, v.x, 0.0); ac_ll_send_cell(ac_ll_tx(f), false, true, j + 1, v.y, 0.0); }
+        } else {
+          if (t_lo) st2(f.lo_u + j, ld2(ub0 + (i64)f.own0 * ld + j));
+          if (t_hi) st2(f.hi_u + j, ld2(ub0 + (i64)f.own_last * ld + j));
+        }
       }
     }
     ac_fuse_signal(f, t_lo, t_hi);
+    TL_DEV(f, 3);
   }
 }
 

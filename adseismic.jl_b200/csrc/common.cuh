@@ -96,10 +96,10 @@ static inline bool adseis_pdl_slab() {  // ADSEIS_PDL_SLAB=1: tuning experiments
 }
 // ADSEIS_PDL_TBSLAB=1: PDL for the two-step path on slab plans too (experiments).  Measured on 2 B200s, C4: 107.7
 // Gcell-upd/s with, 118.4 without -- CTAs of the next launch that become resident early spin on the neighbour's flags.
-static inline bool adseis_pdl_tb_slab() {
+static inline int adseis_pdl_tb_slab() {  // 0 off, 1 frame-only launches, 2 box-pair launches too
   static int on = -1;
-  if (on < 0) { const char* e = getenv("ADSEIS_PDL_TBSLAB"); on = (e && e[0] == '1') ? 1 : 0; }
-  return on != 0;
+  if (on < 0) { const char* e = getenv("ADSEIS_PDL_TBSLAB"); on = (e && e[0] >= '1' && e[0] <= '2') ? e[0] - '0' : 0; }
+  return on;
 }
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
