@@ -72,8 +72,8 @@ struct AcDesc {
 
 struct AcHaloArgs {
   int nrow;                 // rows to push (0 = pure barrier)
-  const double* src[4];     // my rows (ld doubles each)
-  double* dst[4];           // the neighbour's halo rows (peer pointers)
+  const double* src[12];    // my rows (ld doubles each)
+  double* dst[12];          // the neighbour's halo rows (peer pointers)
   int ld;
   int has_lo, has_hi;
   unsigned long long* sig_lo;   // neighbour's "flag_from_hi" / "flag_from_lo" (peer pointers)
@@ -194,6 +194,9 @@ struct adseis_acoustic_plan {
   unsigned long long sepoch = 0;             // step kernels launched so far (same sequence on every rank)
   int* perm = nullptr;                       // launch order -> logical CTA id (edge CTAs first)
   int n_edge_lo = 0, n_edge_hi = 0;
+  int hd = 1;                                // halo rows per neighbour (2 for PropagatorKernel = 0, whose phi'/psi' read u' one row further)
+  bool unfused = false;                      // slab plan whose step launches do not exchange: an explicit exchange follows every launch
+  PointSetStorage srcK{};                    // PropagatorKernel = 0 on slabs: sources within one row of my rows (c-gradient correction)
   bool ll = false;                           // packed halo rows instead of fence + flag (ADSEIS_AC_LL=0 switches back)
   int ll_prev_kind = 0; i64 ll_prev_s = 0;   // the last fused launch: 1 forward / 2 adjoint step s (0: none, or an explicit exchange since)
   unsigned long long exp_lo = 0, exp_hi = 0; // signals the neighbours have sent me so far (sum over their fused launches)
@@ -292,7 +295,7 @@ extern "C" __attribute__((visibility("default"))) int adseis_debug_timeline_dump
 #endif
 
 enum AcArr { AR_HIST, AR_PHI, AR_PSI, AR_UB, AR_PHIB, AR_PSIB };  // arrays with halo rows (slab plans)
-static int halo_exchange(adseis_acoustic_plan* P, int narr, const int* arr, const i64* idx);
+static int halo_exchange(adseis_acoustic_plan* P, int narr, const int* arr, const i64* idx, const int* depth = nullptr);
 static int halo_check(adseis_acoustic_plan* P);
 struct AcDesc;
 static long long desc_off(const AcDesc& d, int arr, i64 idx);
@@ -355,7 +358,7 @@ ADSEIS_API int adseis_acoustic_plan_destroy(adseis_acoustic_plan* P) {
     cudaFree(P->hist);
   }
   for (double* c : P->ckpt) cudaFree(c);
-  free_point_set(&P->src); free_point_set(&P->rcv);
+  free_point_set(&P->src); free_point_set(&P->rcv); free_point_set(&P->srcK);
   free_point_set(&P->srcM); free_point_set(&P->rcvM);
   free_point_set(&P->srcH); free_point_set(&P->rcvH);
   cudaFree(P->rcv_owned);
@@ -584,6 +587,18 @@ static int plan_build_points(adseis_acoustic_plan* P, int64_t nsrc, const int64_
     }
   std::vector<unsigned char> owned;
   TRY(build(nsrc, srci, srcj, &P->src, nullptr, "source"));
+  if (P->unfused) {   // sources on my rows and on the neighbours' rows next to them, grouped by cell (no owner CTA needed)
+    std::vector<int> own, cells, gid, none;
+    for (i64 k = 0; k < nsrc; k++) {
+      const i64 gi = srci[k] + ioff, gj = srcj[k] + ioff;
+      if (gi >= sl.row0 - 1 && gi < sl.row1 + 1) {
+        own.push_back(0); cells.push_back((int)(gi - g.goff) * g.ld + (int)gj); gid.push_back((int)k);
+      }
+    }
+    PointSetHost h;
+    build_point_set(own, cells, gid, none, 1, &h);
+    TRY(upload_point_set(h, &P->srcK, st));
+  }
   TRY(build(nrcv, rcvi, rcvj, &P->rcv, &owned, "receiver"));
   if (P->src.nu > 0) P->srcp = AcPoints{P->src.blk, P->src.cell, P->src.start, P->src.perm};
   if (P->rcv.nu > 0) P->rcvp = AcPoints{P->rcv.blk, P->rcv.cell, P->rcv.start, P->rcv.perm};
@@ -700,9 +715,6 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     CUDA_TRY(cudaFuncSetAttribute(ac_adj_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_ADJ_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(ac_adj_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC_ADJ_SMEM));
   }
-  REQUIRE(p->PropagatorKernel != 0 || !slab || slab->nranks <= 1,
-          "acoustic_plan_create: PropagatorKernel=0 is implemented for single-GPU plans (and shot parallelism); slab "
-          "decomposition needs PropagatorKernel=1");
   cudaStream_t st = ctx->stream;
   adseis_acoustic_plan* P = new adseis_acoustic_plan();
   P->ctx = ctx;
@@ -721,7 +733,19 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
                      (long long)sl.row0, (long long)sl.row1);
     return ADSEIS_EINVAL;
   }
-  const int halo_lo = sl.rank > 0 ? 1 : 0, halo_hi = sl.rank < sl.nranks - 1 ? 1 : 0;
+  // PropagatorKernel = 0 (phi', psi' from the NEW wavefield, MPIAcoustic.jl:212-246): an edge-row frame cell re-evaluates
+  // u' of the neighbour's edge row, which reads one row further -- two halo rows, exchanged by an explicit kernel after
+  // every step launch (the reference exchanges u' inside its one_step the same way, with mpi_halo_exchange)
+  P->hd = (p->PropagatorKernel == 0 && sl.nranks > 1) ? 2 : 1;
+  P->unfused = P->hd == 2;
+  if (sl.nranks > 1 && sl.row1 - sl.row0 < P->hd) {
+    const int need = P->hd;
+    delete P;
+    ctx->plans--;
+    adseis_set_error("acoustic_plan_create: a slab needs at least %d rows", need);
+    return ADSEIS_EINVAL;
+  }
+  const int halo_lo = sl.rank > 0 ? P->hd : 0, halo_hi = sl.rank < sl.nranks - 1 ? P->hd : 0;
   AcGeom& g = P->g;
   g.H = H; g.W = W;
   g.goff = (int)sl.row0 - halo_lo;
@@ -901,7 +925,7 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
     for (int k = 0; k < 2; k++) d.off_psib[k] = take(1);
     {
       const char* ell = getenv("ADSEIS_AC_LL");
-      P->ll = !(ell && ell[0] == '0');
+      P->ll = !(ell && ell[0] == '0') && !P->unfused;
       d.off_ll = 0;
       if (P->ll) { d.off_ll = off; off += 8LL * g.ld * 16; off = (off + 511) / 512 * 512; }
     }
@@ -1013,7 +1037,7 @@ static AcFuse make_fuse(adseis_acoustic_plan* P, int arr_u, i64 idx_u, int arr_p
   AcFuse f;
   memset(&f, 0, sizeof(f));
   f.perm = fkind ? P->fk[fkind - 1].perm : P->perm;
-  if (!P->arena) return f;
+  if (!P->arena || P->unfused) return f;
   f.own0 = P->own0; f.own_last = P->own1 - 1;
   f.has_lo = P->peer[0] != nullptr; f.has_hi = P->peer[1] != nullptr;
   P->sepoch++;
@@ -1137,6 +1161,11 @@ static int launch_forward_step(adseis_acoustic_plan* P, i64 base, i64 s, bool sa
       (sample && P->nrcv > 0) ? P->rcvv + s * P->nrcv : nullptr, fuse));
   LAUNCH_CHECK(P);
   TL_MARK(st, fkind, s);
+  if (P->arena && P->unfused) {
+    const int arr[3] = {AR_HIST, AR_PHI, AR_PSI}, dep[3] = {2, 2, 1};
+    const i64 idx[3] = {s - base, s & 1, s & 1};
+    TRY(halo_exchange(P, 3, arr, idx, dep));
+  }
   return ADSEIS_OK;
 }
 
@@ -1447,10 +1476,11 @@ static int gradient_body(adseis_acoustic_plan* P) {
       AcK0 k0{};
       if (P->p.PropagatorKernel == 0) {
         k0.wnew = win_slot(P, b, s); k0.ut_in = P->ut[(s + 1) & 1]; k0.ut_out = P->ut[s & 1];
-        if (P->k0_corr && P->src.nu > 0) {
-          k_ac_k0_src_corr<<<(P->src.nu + 127) / 128, 128, 0, stl>>>(g, P->src.cell, P->src.start, P->src.perm, P->src.nu,
-                                                                     P->srcv + (s - 1) * P->nsrc, P->phib[s & 1],
-                                                                     P->psib[s & 1], P->sigx, P->tauy, P->G);
+        const PointSetStorage& K = P->unfused ? P->srcK : P->src;   // slabs: incl. the neighbours' sources next to my rows
+        if (P->k0_corr && K.nu > 0) {
+          k_ac_k0_src_corr<<<(K.nu + 127) / 128, 128, 0, stl>>>(g, K.cell, K.start, K.perm, K.nu,
+                                                                P->srcv + (s - 1) * P->nsrc, P->phib[s & 1],
+                                                                P->psib[s & 1], P->sigx, P->tauy, P->G, P->own0, P->own1);
           LAUNCH_CHECK(P);
         }
       }
@@ -1470,6 +1500,11 @@ static int gradient_body(adseis_acoustic_plan* P) {
           (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr, fuse, k0));
       LAUNCH_CHECK(P);
       TL_MARK(stl, 10 + fkind, s);
+      if (P->arena && P->unfused) {
+        const int arr[3] = {AR_UB, AR_PHIB, AR_PSIB}, dep[3] = {1, 2, 1};
+        const i64 idx[3] = {(s - 1 + NUB) % NUB, (s - 1) & 1, (s - 1) & 1};
+        TRY(halo_exchange(P, 3, arr, idx, dep));
+      }
       return ADSEIS_OK;
     };
     i64 s = e;
@@ -1660,7 +1695,7 @@ static long long desc_off(const AcDesc& d, int arr, i64 idx) {
 
 // Push the first / last owned row of up to two arrays to the neighbours and wait for theirs (nothing to do on a
 // single GPU).  narr == 0 is a pure barrier.
-static int halo_exchange(adseis_acoustic_plan* P, int narr, const int* arr, const i64* idx) {
+static int halo_exchange(adseis_acoustic_plan* P, int narr, const int* arr, const i64* idx, const int* depth) {
   if (!P->arena) return ADSEIS_OK;
   if (!P->connected) {
     adseis_set_error("acoustic slab plan: adseis_acoustic_plan_ipc_connect has not been called");
@@ -1675,17 +1710,20 @@ static int halo_exchange(adseis_acoustic_plan* P, int narr, const int* arr, cons
   char* base = (char*)P->arena;
   for (int k = 0; k < narr; k++) {
     const double* mine = (const double*)(base + desc_off(P->desc, arr[k], idx[k]));
-    if (a.has_lo) {  // my first owned row -> rank-1's upper halo row (its local row Hl-1)
-      const AcDesc& d = P->dpeer[0];
-      a.src[a.nrow] = mine + (i64)P->own0 * g.ld;
-      a.dst[a.nrow] = (double*)(P->peer[0] + desc_off(d, arr[k], idx[k])) + (d.Hl - 1) * d.ld;
-      a.nrow++;
-    }
-    if (a.has_hi) {  // my last owned row -> rank+1's lower halo row (its local row 0)
-      const AcDesc& d = P->dpeer[1];
-      a.src[a.nrow] = mine + (i64)(P->own1 - 1) * g.ld;
-      a.dst[a.nrow] = (double*)(P->peer[1] + desc_off(d, arr[k], idx[k]));
-      a.nrow++;
+    const int dep = depth ? depth[k] : 1;
+    for (int r = 0; r < dep; r++) {
+      if (a.has_lo) {  // my first owned rows -> rank-1's upper halo rows (its local rows own1, own1+1, ...)
+        const AcDesc& d = P->dpeer[0];
+        a.src[a.nrow] = mine + (i64)(P->own0 + r) * g.ld;
+        a.dst[a.nrow] = (double*)(P->peer[0] + desc_off(d, arr[k], idx[k])) + (d.own1 + r) * d.ld;
+        a.nrow++;
+      }
+      if (a.has_hi) {  // my last owned rows -> rank+1's lower halo rows (its local rows own0-dep .. own0-1)
+        const AcDesc& d = P->dpeer[1];
+        a.src[a.nrow] = mine + (i64)(P->own1 - dep + r) * g.ld;
+        a.dst[a.nrow] = (double*)(P->peer[1] + desc_off(d, arr[k], idx[k])) + (d.own0 - dep + r) * d.ld;
+        a.nrow++;
+      }
     }
   }
   // rank-1 sees me as its "hi" neighbour: I add to its flag[1]; rank+1 sees me as "lo": its flag[0]

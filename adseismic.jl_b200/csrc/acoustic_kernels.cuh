@@ -823,7 +823,8 @@ __global__ void k_ac_k0_src_corr(AcGeom g, const int* __restrict__ cell, const i
                                  const int* __restrict__ perm, int nu, const double* __restrict__ srcv_row,
                                  const double* __restrict__ phib, const double* __restrict__ psib,
                                  const double* __restrict__ sigx, const double* __restrict__ tauy,
-                                 double* __restrict__ G) {
+                                 double* __restrict__ G, int own0, int own1) {
+  // slab plans: the point list holds the sources within one row of my rows; only cells of rows [own0, own1) are mine
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nu) return;
   double v = 0.0;
@@ -832,19 +833,20 @@ __global__ void k_ac_k0_src_corr(AcGeom g, const int* __restrict__ cell, const i
   const int li = cell[k] / g.ld, j = cell[k] % g.ld, gi = g.goff + li;
   const i64 S = cell[k];
   const double kx = g.dt * 0.5 * g.rhx, ky = g.dt * 0.5 * g.rhy;
-  if (ac_interior(g, gi - 1, j)) {
+  const bool mine = li >= own0 && li < own1;
+  if (ac_interior(g, gi - 1, j) && li - 1 >= own0 && li - 1 < own1) {
     const double cf = (tauy[j] - sigx[gi - 1]) * kx;
     if (cf != 0.0) atomicAdd(&G[S - g.ld], -(cf * v * phib[S - g.ld]));
   }
-  if (ac_interior(g, gi + 1, j)) {
+  if (ac_interior(g, gi + 1, j) && li + 1 >= own0 && li + 1 < own1) {
     const double cf = (tauy[j] - sigx[gi + 1]) * kx;
     if (cf != 0.0) atomicAdd(&G[S + g.ld], cf * v * phib[S + g.ld]);
   }
-  if (ac_interior(g, gi, j - 1)) {
+  if (ac_interior(g, gi, j - 1) && mine) {
     const double cf = (sigx[gi] - tauy[j - 1]) * ky;
     if (cf != 0.0) atomicAdd(&G[S - 1], -(cf * v * psib[S - 1]));
   }
-  if (ac_interior(g, gi, j + 1)) {
+  if (ac_interior(g, gi, j + 1) && mine) {
     const double cf = (sigx[gi] - tauy[j + 1]) * ky;
     if (cf != 0.0) atomicAdd(&G[S + 1], cf * v * psib[S + 1]);
   }

@@ -250,12 +250,17 @@ class DomainDecomposedAcoustic:
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.param = param
         self.ctx = ctx or _lib.default_context()
-        self.geo = slab_geometry(param.NX, param.NY, self.world, self.rank)
+        # PropagatorKernel = 0 (phi', psi' from the new wavefield, MPIAcoustic.jl:212-246) keeps two halo rows per neighbour
+        k0 = param.PropagatorKernel == 0 and self.world > 1
+        self.geo = slab_geometry(param.NX, param.NY, self.world, self.rank, halo=2 if k0 else 1)
         self.dev = torch.device("cuda", torch.cuda.current_device())
         plane_bytes = self.geo["Hl"] * self.geo["ld"] * 8
         srci, srcj, rcvi, rcvj = (np.atleast_1d(np.asarray(x, dtype=np.int64)) for x in (srci, srcj, rcvi, rcvj))
         self.nsrc, self.nrcv = len(srci), len(rcvi)
-        self.smask = owned_points(srci, self.geo["row0"], self.geo["row1"], param.mpi_convention)
+        # the plan keeps the points it owns and ignores the rest; with PropagatorKernel = 0 it also needs the neighbours'
+        # sources next to its rows (their injected part is removed from its c-gradient terms, csrc k_ac_k0_src_corr)
+        self.smask = owned_points(srci, self.geo["row0"] - (1 if k0 else 0), self.geo["row1"] + (1 if k0 else 0),
+                                  param.mpi_convention)
         self.rmask = owned_points(rcvi, self.geo["row0"], self.geo["row1"], param.mpi_convention)
         if self.world == 1:
             self.plan = AcousticPlan(param, srci, srcj, rcvi, rcvj, ctx=self.ctx)

@@ -70,7 +70,8 @@ typedef struct {
   int64_t NPOINTS_PML;
   double Rcoef, vp_ref;
   int32_t mpi_convention;   /* 0: AcousticPropagatorSolver inputs; 1: MPIAcousticPropagatorSolver inputs */
-  int32_t PropagatorKernel; /* 0: TF-op scheme, phi/psi from the NEW wavefield (Core.jl:528-549; single-GPU plans);
+  int32_t PropagatorKernel; /* 0: TF-op scheme, phi/psi from the NEW wavefield (Core.jl:528-549, MPIAcoustic.jl:212-246; slab plans
+                                  keep two halo rows and exchange them after every step);
                                1: custom-op scheme, phi/psi from the OLD wavefield (AcousticOneStepCpu.h); 2 == 1 */
 } adseis_acoustic_params;
 

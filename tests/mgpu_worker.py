@@ -62,6 +62,41 @@ def main():
             print("DD x%d slots=%s ok: loss rel %.1e grad_c rel %.1e grad_srcv rel %.1e segments %d" %
                   (world, slots, abs(L - L0) / L0, relerr(g, g0), relerr(s, s0), info["segments"]), flush=True)
         dd.close()
+    # ---------------- PropagatorKernel = 0 on slabs (MPIAcousticPropagatorSolver's scheme, MPIAcoustic.jl:212-246) ----------------
+    # phi', psi' are driven by the new wavefield: two halo rows, explicit exchange after every step launch.  Sources sit
+    # on both sides of every slab boundary (their injected part is removed from the NEIGHBOUR's c-gradient terms too).
+    srci0, srcj0 = srci.copy(), srcj.copy()
+    for k, (r0_, r1_) in enumerate(bounds[:-1]):
+        srci0[(2 * k) % nsrc] = r1_; srci0[(2 * k + 1) % nsrc] = r1_ + 1
+        srcj0[(2 * k) % nsrc] = 3 + k; srcj0[(2 * k + 1) % nsrc] = NY - 2 - k      # inside the absorbing frame columns
+    u0k, up0k, r0k = po.acoustic_forward(NX, NY, NSTEP, dt, dx, dx, sig, tau, c, srci0, srcj0, srcv, rcvi, rcvj, kernel=0)
+    obsk = 0.7 * r0k + 0.02 * np.abs(r0k).max() * rng.standard_normal(r0k.shape)
+    L0k, g0k, s0k = po.acoustic_misfit_grad(NX, NY, NSTEP, dt, dx, dx, sig, tau, c, srci0, srcj0, rcvi, rcvj, obsk, u0k,
+                                            upre_hist=up0k)
+    p0 = A.AcousticPropagatorParams(PropagatorKernel=0, NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dx, DELTAT=dt, vp_ref=vp,
+                                    NPOINTS_PML=8)
+    one = A.AcousticPlan(p0, srci0, srcj0, rcvi, rcvj, ctx=ctx)            # the undecomposed CUDA path, on every rank
+    one.set_model(c); one.set_srcv(srcv); one.set_obs(obsk); one.gradient()
+    r1k, g1k, s1k = one.rcvv(), one.grad_c(), one.grad_srcv()
+    one.close()
+    assert relerr(r1k, r0k) < 1e-12
+    for slots in (None, 14):
+        dd = parallel.DomainDecomposedAcoustic(p0, srci0, srcj0, rcvi, rcvj, ctx=ctx, hist_slots=slots)
+        dd.set_model(c); dd.set_srcv(srcv); dd.set_obs(obsk)
+        dd.forward()
+        r = dd.rcvv()
+        assert np.array_equal(r, r1k), "rank %d: PropagatorKernel=0 DD traces differ from the undecomposed run (max %g)" % (
+            rank, np.abs(r - r1k).max())
+        dd.gradient()
+        L, g, s_ = dd.loss(), dd.grad_c().cpu().numpy(), dd.grad_srcv()
+        assert abs(L - L0k) / L0k < 1e-12, (L, L0k)
+        assert relerr(g, g0k) < 1e-10, relerr(g, g0k)
+        assert relerr(s_, s0k) < 1e-10, relerr(s_, s0k)
+        assert relerr(g, g1k) < 1e-13 and relerr(s_, s1k) < 1e-13, (relerr(g, g1k), relerr(s_, s1k))
+        if rank == 0:
+            print("DD x%d PropagatorKernel=0 slots=%s ok: grad_c rel %.1e grad_srcv rel %.1e segments %d" %
+                  (world, slots, relerr(g, g0k), relerr(s_, s0k), dd.plan.info()["segments"]), flush=True)
+        dd.close()
     # ---------------- elastic domain decomposition (both reference variants) ----------------
     # the reference's own test is decomposed == undecomposed (examples/mpi_elastic/verification/verify_backward.jl)
     for variant, (NX, NY, NSTEP) in ((1, (36 * world + 3, 150, 24)), (0, (34 * world + 1, 140, 22))):
