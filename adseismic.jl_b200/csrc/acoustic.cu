@@ -265,9 +265,13 @@ static unsigned long long* tl_slot() {
 static void tl_mark(cudaStream_t st, int tag, long long s) {
   tl_init();
   if (g_tl_seen++ < g_tl_skip || (long long)g_tl.size() >= g_tl_cap) return;
-  cudaEvent_t ev;
-  if (cudaEventCreate(&ev) != cudaSuccess) return;
-  cudaEventRecord(ev, st);
+  static int with_events = -1;
+  if (with_events < 0) { const char* e = getenv("ADSEIS_TIMELINE_EVENTS"); with_events = (e && e[0] == '0') ? 0 : 1; }
+  cudaEvent_t ev = nullptr;
+  if (with_events) {   // (an event record between two launches costs ~6 us of stream time: off for undisturbed device stamps)
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, st);
+  }
   g_tl.push_back({ev, tag, s, g_tl_next});
   g_tl_next = nullptr;
 }
@@ -278,7 +282,7 @@ extern "C" __attribute__((visibility("default"))) int adseis_debug_timeline_dump
   unsigned long long t00 = 0;
   for (size_t k = 0; k < g_tl.size(); k++) {
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, g_tl[0].ev, g_tl[k].ev);
+    if (g_tl[0].ev && g_tl[k].ev) cudaEventElapsedTime(&ms, g_tl[0].ev, g_tl[k].ev);
     unsigned long long d[5] = {0, 0, 0, 0, 0};
     if (g_tl[k].dev) cudaMemcpy(d, g_tl[k].dev, sizeof(d), cudaMemcpyDeviceToHost);
     if (!t00 && g_tl[k].dev) t00 = d[0];
@@ -445,10 +449,10 @@ static void build_tb_tilings(adseis_acoustic_plan* P) {
     if (P->p.PropagatorKernel == 0) return;
     const i64 rows_min = (i64)g.H / P->slab.nranks - (P->p.NPOINTS_PML + 4) - 5;
     const i64 cells = rows_min * (i64)(g.W - 2 * (P->p.NPOINTS_PML + 4));
-    // measured on B200s, C4 (4096^2): pairs win on 2 slabs (8.3 M box cells each: 103.5 -> 126.3 Gcell-upd/s), are neutral
-    // on 4 (4.2 M: 199 -> 206) and lose on 8 (2.1 M: 361 -> 275 -- the chain of frame-only launches with their fused
-    // halo waits, two per pair, is then longer than the box-pair kernel it should hide behind)
-    const i64 min_cells = getenv("ADSEIS_AC_TB_SLAB_MIN") ? atoll(getenv("ADSEIS_AC_TB_SLAB_MIN")) : (6LL << 20);
+    // measured on B200s with packed halo rows and 128-thread frame-only CTAs (profiles/r02_slab_latency.md), us per step
+    // pair one-step -> pairs: 2048-row slabs of 4096 columns 2 x faster than one GPU either way, 1024 rows 85.5 -> 64.9,
+    // 512 rows 41.3 -> 39.6; below that the box-pair kernel has too few rows per CTA to amortise its ring prologue
+    const i64 min_cells = getenv("ADSEIS_AC_TB_SLAB_MIN") ? atoll(getenv("ADSEIS_AC_TB_SLAB_MIN")) : (3LL << 19);
     if (rows_min < 16 || (!(e && e[0] == '1') && cells < min_cells)) return;
   }
   const int fi0 = P->box_i0 + 2, fi1 = P->box_i1 - 2, fj0 = P->box_j0 + 2, fj1 = P->box_j1 - 2;
@@ -1088,8 +1092,8 @@ static AcFuse make_fuse(adseis_acoustic_plan* P, int arr_u, i64 idx_u, int arr_p
 // depends on it alone).  Across pairs the streams leapfrog: A(p) waits for B(p-1), B(p) waits for A(p-1).
 struct TbPipe {
   adseis_acoustic_plan* P;
-  bool on = false, first = true;
-  int n = 0;
+  bool on = false, box_first = false;
+  int n = 0;   // index of the current pair
   int begin() {
     if (!P->tb_overlap) return ADSEIS_OK;
     if (!P->sb) {
@@ -1099,34 +1103,36 @@ struct TbPipe {
         CUDA_TRY(cudaEventCreateWithFlags(&P->evB[k], cudaEventDisableTiming));
       }
     }
-    on = true; first = true; n = 0;
+    on = true; n = 0;
+    // slab plans: the box-pair kernel is the critical path of a pair (two launches that become eligible together are
+    // started ~3 us apart), so it is enqueued first; on one GPU the frames go first (the measured configuration)
+    const char* e = getenv("ADSEIS_AC_TB_BOXFIRST");
+    box_first = e ? e[0] == '1' : P->arena != nullptr;
+    // everything enqueued on A so far (memsets, copies, earlier launches) precedes the first frames
+    CUDA_TRY(cudaEventRecord(P->evA[1], P->ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(P->sb, P->evA[1], 0));
     return ADSEIS_OK;
   }
   cudaStream_t frames() const { return on ? P->sb : P->ctx->stream; }
-  int pre_frames() {   // before the frame launches of pair n
-    if (!on) return ADSEIS_OK;
-    if (first) {       // everything enqueued on A so far (memsets, copies, earlier launches) precedes the first frames
-      CUDA_TRY(cudaEventRecord(P->evA[1], P->ctx->stream));
-      CUDA_TRY(cudaStreamWaitEvent(P->sb, P->evA[1], 0));
-    } else {
-      CUDA_TRY(cudaStreamWaitEvent(P->sb, P->evA[(n + 1) & 1], 0));   // box pair n-1
-    }
+  int pre_frames() {   // frames of pair n follow the box launch of pair n-1
+    if (on && n > 0) CUDA_TRY(cudaStreamWaitEvent(P->sb, P->evA[(n - 1) & 1], 0));
     return ADSEIS_OK;
   }
   int post_frames() {
     if (on) CUDA_TRY(cudaEventRecord(P->evB[n & 1], P->sb));
     return ADSEIS_OK;
   }
-  int pre_box() {
-    if (on && !first) CUDA_TRY(cudaStreamWaitEvent(P->ctx->stream, P->evB[(n + 1) & 1], 0));   // frames of pair n-1
+  int pre_box() {      // the box launch of pair n follows the frames of pair n-1
+    if (on && n > 0) CUDA_TRY(cudaStreamWaitEvent(P->ctx->stream, P->evB[(n - 1) & 1], 0));
     return ADSEIS_OK;
   }
   int post_box() {
-    if (on) { CUDA_TRY(cudaEventRecord(P->evA[n & 1], P->ctx->stream)); first = false; n++; }
+    if (on) CUDA_TRY(cudaEventRecord(P->evA[n & 1], P->ctx->stream));
     return ADSEIS_OK;
   }
+  void next() { n++; }
   int end() {          // join: later work on A sees every frame launch
-    if (on && !first) CUDA_TRY(cudaStreamWaitEvent(P->ctx->stream, P->evB[(n + 1) & 1], 0));
+    if (on && n > 0) CUDA_TRY(cudaStreamWaitEvent(P->ctx->stream, P->evB[(n - 1) & 1], 0));
     on = false;
     return ADSEIS_OK;
   }
@@ -1185,25 +1191,39 @@ static int run_forward_steps(adseis_acoustic_plan* P, i64 base, i64 s_first, i64
     TbPipe pipe{P};
     TRY(pipe.begin());
     for (; s + 1 <= s_last; s += 2) {
-      if (pipe.on) {
+      auto frames = [&]() -> int {
         TRY(pipe.pre_frames());
         TRY(launch_forward_step(P, base, s, sample, 2, pipe.frames()));
         TRY(launch_forward_step(P, base, s + 1, sample, 1, pipe.frames()));
         TRY(pipe.post_frames());
+        return ADSEIS_OK;
+      };
+      auto box = [&]() -> int {
         TRY(pipe.pre_box());
-      } else {
+        CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_tb_slab() == 2, ac_fwd2_kernel, P->nblocks2, AC_FWD_THREADS, AC_FWD2_SMEM, st,
+            g, P->t2, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, win_slot(P, base, s), win_slot(P, base, s + 1),
+            P->srcHp, P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, P->srcMp,
+            P->nsrc > 0 ? P->srcv + s * P->nsrc : nullptr, sample ? P->rcvMp : none,
+            (sample && P->nrcv > 0) ? P->rcvv + s * P->nrcv : nullptr,
+            (sample && P->nrcv > 0) ? P->rcvv + (s + 1) * P->nrcv : nullptr
+#ifdef ADSEIS_TIMELINE
+            , tl_slot()
+#endif
+            ));
+        LAUNCH_CHECK(P);
+        TL_MARK(st, 3, s);
+        TRY(pipe.post_box());
+        return ADSEIS_OK;
+      };
+      if (pipe.on) {
+        if (pipe.box_first) { TRY(box()); TRY(frames()); }
+        else { TRY(frames()); TRY(box()); }
+        pipe.next();
+      } else {   // one stream: narrow frame, box, narrow frame (the second frame launch reads the box cells of slot s)
         TRY(launch_forward_step(P, base, s, sample, 1, st));
+        TRY(box());
+        TRY(launch_forward_step(P, base, s + 1, sample, 1, st));
       }
-      CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_tb_slab() == 2, ac_fwd2_kernel, P->nblocks2, AC_FWD_THREADS, AC_FWD2_SMEM, st,
-          g, P->t2, win_slot(P, base, s - 1), win_slot(P, base, s - 2), P->c2, win_slot(P, base, s), win_slot(P, base, s + 1),
-          P->srcHp, P->nsrc > 0 ? P->srcv + (s - 1) * P->nsrc : nullptr, P->srcMp,
-          P->nsrc > 0 ? P->srcv + s * P->nsrc : nullptr, sample ? P->rcvMp : none,
-          (sample && P->nrcv > 0) ? P->rcvv + s * P->nrcv : nullptr,
-          (sample && P->nrcv > 0) ? P->rcvv + (s + 1) * P->nrcv : nullptr));
-      LAUNCH_CHECK(P);
-      TL_MARK(st, 3, s);
-      if (pipe.on) TRY(pipe.post_box());
-      else TRY(launch_forward_step(P, base, s + 1, sample, 1, st));
     }
     TRY(pipe.end());
   }
@@ -1514,25 +1534,39 @@ static int gradient_body(adseis_acoustic_plan* P) {
       TbPipe pipe{P};
       TRY(pipe.begin());
       for (; s - 1 >= b + 2; s -= 2) {
-        if (pipe.on) {
+        auto frames = [&]() -> int {
           TRY(pipe.pre_frames());
           TRY(adj_step(s, 2, pipe.frames()));
           TRY(adj_step(s - 1, 1, pipe.frames()));
           TRY(pipe.post_frames());
+          return ADSEIS_OK;
+        };
+        auto box = [&]() -> int {
           TRY(pipe.pre_box());
+          CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_tb_slab() == 2, ac_adj2_kernel, P->nblocks2, AC2_THREADS, AC_ADJ2_SMEM, st,
+              g, P->t2, P->ub[s % NUB], P->ub[(s + 1) % NUB], win_slot(P, b, s - 1), win_slot(P, b, s - 2), P->c2,
+              P->ub[(s - 1 + NUB) % NUB], P->ub[(s - 2 + NUB) % NUB], P->G, P->rcvHp,
+              P->nrcv > 0 ? P->res + (s - 1) * P->nrcv : nullptr, P->rcvMp, P->nrcv > 0 ? P->res + (s - 2) * P->nrcv : nullptr,
+              P->srcMp, (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr,
+              (s - 3 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 3) * P->nsrc : nullptr
+#ifdef ADSEIS_TIMELINE
+              , tl_slot()
+#endif
+              ));
+          LAUNCH_CHECK(P);
+          TL_MARK(st, 13, s);
+          TRY(pipe.post_box());
+          return ADSEIS_OK;
+        };
+        if (pipe.on) {
+          if (pipe.box_first) { TRY(box()); TRY(frames()); }
+          else { TRY(frames()); TRY(box()); }
+          pipe.next();
         } else {
           TRY(adj_step(s, 1, st));
+          TRY(box());
+          TRY(adj_step(s - 1, 1, st));
         }
-        CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_tb_slab() == 2, ac_adj2_kernel, P->nblocks2, AC2_THREADS, AC_ADJ2_SMEM, st,
-            g, P->t2, P->ub[s % NUB], P->ub[(s + 1) % NUB], win_slot(P, b, s - 1), win_slot(P, b, s - 2), P->c2,
-            P->ub[(s - 1 + NUB) % NUB], P->ub[(s - 2 + NUB) % NUB], P->G, P->rcvHp,
-            P->nrcv > 0 ? P->res + (s - 1) * P->nrcv : nullptr, P->rcvMp, P->nrcv > 0 ? P->res + (s - 2) * P->nrcv : nullptr,
-            P->srcMp, (s - 2 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr,
-            (s - 3 >= 1 && P->nsrc > 0) ? P->gradsrcv + (s - 3) * P->nsrc : nullptr));
-        LAUNCH_CHECK(P);
-        TL_MARK(st, 13, s);
-        if (pipe.on) TRY(pipe.post_box());
-        else TRY(adj_step(s - 1, 1, st));
       }
       TRY(pipe.end());
     }

@@ -1092,7 +1092,15 @@ __global__ void __launch_bounds__(AC_FWD_THREADS, 2)
 ac_fwd2_kernel(AcGeom g, AcTiling t, const double* __restrict__ w, const double* __restrict__ wold,
                const double* __restrict__ c2, double* __restrict__ u1, double* __restrict__ u2, AcPoints srch,
                const double* __restrict__ srcv_row1, AcPoints src, const double* __restrict__ srcv_row2, AcPoints rcv,
-               double* __restrict__ rcvv_row1, double* __restrict__ rcvv_row2) {
+               double* __restrict__ rcvv_row1, double* __restrict__ rcvv_row2
+#ifdef ADSEIS_TIMELINE
+               , unsigned long long* tl
+#endif
+               ) {
+#ifdef ADSEIS_TIMELINE
+  struct TlExit { unsigned long long* p; __device__ ~TlExit() { if (p && threadIdx.x == 0) atomicMax(p + 3, tl_now()); } } tl_exit{tl};
+  if (tl && threadIdx.x == 0) { atomicMin(tl, tl_now()); atomicMax(tl + 1, tl_now()); }
+#endif
   pdl_launch_dependents();
   const int bid = blockIdx.x;
   const int ld = g.ld;
@@ -1261,7 +1269,15 @@ ac_adj2_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const doubl
                const double* __restrict__ w1, const double* __restrict__ w2, const double* __restrict__ c2,
                double* __restrict__ ubA, double* __restrict__ ubB, double* __restrict__ G, AcPoints rcvh,
                const double* __restrict__ res_row1, AcPoints rcv, const double* __restrict__ res_row2, AcPoints src,
-               double* __restrict__ gsrcv_row1, double* __restrict__ gsrcv_row2) {
+               double* __restrict__ gsrcv_row1, double* __restrict__ gsrcv_row2
+#ifdef ADSEIS_TIMELINE
+               , unsigned long long* tl
+#endif
+               ) {
+#ifdef ADSEIS_TIMELINE
+  struct TlExit { unsigned long long* p; __device__ ~TlExit() { if (p && threadIdx.x == 0) atomicMax(p + 3, tl_now()); } } tl_exit{tl};
+  if (tl && threadIdx.x == 0) { atomicMin(tl, tl_now()); atomicMax(tl + 1, tl_now()); }
+#endif
   pdl_launch_dependents();
   const int bid = blockIdx.x;
   const int ld = g.ld;

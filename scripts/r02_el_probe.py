@@ -15,3 +15,9 @@ plan.forward(); ctx.sync()
 cs = B.ClockSampler(0); cs.start()
 ctx.sync(); t0 = time.perf_counter(); plan.forward(); ctx.sync(); t1 = time.perf_counter()
 print("C5 forward nstep %d: %.1f us/step" % (nstep, (t1 - t0) * 1e6 / nstep), cs.stop(), flush=True)
+if os.environ.get("PGRAD"):
+    r = plan.rcvv()
+    plan.set_obs(0.5 * r)
+    plan.gradient(True); ctx.sync()
+    t0 = time.perf_counter(); plan.gradient(True); ctx.sync(); t1 = time.perf_counter()
+    print("C5 material gradient nstep %d: %.1f us/step (fwd+adj), loss %.17g" % (nstep, (t1 - t0) * 1e6 / nstep, plan.loss()), flush=True)

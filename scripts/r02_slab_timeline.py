@@ -68,4 +68,21 @@ if os.environ.get("ADSEIS_TIMELINE"):
         if len(fr) > 4:
             print("  previous launch published -> next launch's first CTA enters: median %.2f us" %
                   float(np.median(fr[1:, 4] - fr[:-1, 8])))
+        # pair structure of the two-step path from device stamps alone (run with ADSEIS_TIMELINE_EVENTS=0): for each pair the
+        # start / end of the box launch, the wide and the narrow frame launch, relative to the start of the pair's box launch
+        for box, wide, nar, label in ((3, 2, 1, "fwd"), (13, 12, 11, "adj")):
+            B_ = rows[(rows[:, 1] == box) & (rows[:, 4] >= 0)]
+            out = []
+            for b in B_[2:-2]:
+                s0 = b[2]
+                wd = rows[(rows[:, 1] == wide) & (rows[:, 2] == s0)]
+                nr = rows[(rows[:, 1] == nar) & (rows[:, 2] == (s0 + 1 if box == 3 else s0 - 1))]
+                if len(wd) == 1 and len(nr) == 1 and wd[0, 4] >= 0 and nr[0, 4] >= 0:
+                    e = lambda r: max(r[7], r[8]) if r[8] >= 0 else r[7]
+                    out.append([wd[0, 4] - b[4], e(wd[0]) - b[4], nr[0, 4] - b[4], e(nr[0]) - b[4], b[7] - b[4]])
+            if len(out) > 4:
+                o = np.median(np.array(out), axis=0)
+                per = np.median(np.diff(B_[2:-2, 4]))
+                print("  %s pair (us after the box launch's first CTA): wide %.1f..%.1f  narrow %.1f..%.1f  box ..%.1f   period %.1f" %
+                      (label, o[0], o[1], o[2], o[3], o[4], per))
 dd.close()
