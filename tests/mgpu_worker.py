@@ -62,6 +62,40 @@ def main():
             print("DD x%d slots=%s ok: loss rel %.1e grad_c rel %.1e grad_srcv rel %.1e segments %d" %
                   (world, slots, abs(L - L0) / L0, relerr(g, g0), relerr(s, s0), info["segments"]), flush=True)
         dd.close()
+    # ---------------- the halo protocol is an execution detail: packed rows == fence + flag, run to run, bit for bit ----------------
+    # (a taller grid so that the two-step path with its frame-only launches is exercised on slabs as well)
+    NXb = 64 * world + 30
+    sigb, taub = po.acoustic_pml(NXb, NY, dx, dx, npml=8, vp_ref=vp)
+    cb = vp * (1 + 0.1 * rng.random((NXb + 2, NY + 2)))
+    pb = A.AcousticPropagatorParams(PropagatorKernel=1, NX=NXb, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dx, DELTAT=dt, vp_ref=vp,
+                                    NPOINTS_PML=8)
+    bnd = [parallel.slab_partition(NXb, world, r) for r in range(world)]
+    sib = rng.integers(1, NXb + 2, nsrc); rib = rng.integers(1, NXb + 2, nrcv)
+    for k, (r0_, r1_) in enumerate(bnd[:-1]):
+        sib[k % nsrc] = r1_ + (k & 1); rib[2 * k] = r1_; rib[2 * k + 1] = r1_ + 1
+    ub, rb_ = po.acoustic_forward(NXb, NY, NSTEP, dt, dx, dx, sigb, taub, cb, sib, srcj, srcv, rib, rcvj)
+    obsb = 0.6 * rb_
+    Lb, gb, sb_ = po.acoustic_misfit_grad(NXb, NY, NSTEP, dt, dx, dx, sigb, taub, cb, sib, srcj, rib, rcvj, obsb, ub)
+    got = {}
+    for tb in ("0", "1"):
+        for ll in ("1", "0"):
+            os.environ["ADSEIS_AC_TB_SLAB"] = tb; os.environ["ADSEIS_AC_TB_SLAB_MIN"] = "0"; os.environ["ADSEIS_AC_LL"] = ll
+            for rep in range(2):
+                dd = parallel.DomainDecomposedAcoustic(pb, sib, srcj, rib, rcvj, ctx=ctx, hist_slots=None if rep == 0 else 14)
+                dd.set_model(cb); dd.set_srcv(srcv); dd.set_obs(obsb)
+                dd.gradient()
+                got[(tb, ll, rep)] = (dd.rcvv(), dd.loss(), dd.grad_c().cpu().numpy(), dd.grad_srcv())
+                dd.close()
+    for k in ("ADSEIS_AC_TB_SLAB", "ADSEIS_AC_TB_SLAB_MIN", "ADSEIS_AC_LL"):
+        os.environ.pop(k)
+    ref_ = got[("0", "0", 0)]
+    assert np.array_equal(ref_[0], rb_) and relerr(ref_[2], gb) < 1e-10 and relerr(ref_[3], sb_) < 1e-10
+    for key, val in got.items():
+        assert np.array_equal(val[0], ref_[0]) and val[1] == ref_[1] and np.array_equal(val[2], ref_[2]) and \
+            np.array_equal(val[3], ref_[3]), "slab run %s differs from the fence+flag one-step run" % (key,)
+    if rank == 0:
+        print("DD x%d halo protocols ok: one-step / two-step x packed / flags x resident / checkpointed: identical bits" % world,
+              flush=True)
     # ---------------- PropagatorKernel = 0 on slabs (MPIAcousticPropagatorSolver's scheme, MPIAcoustic.jl:212-246) ----------------
     # phi', psi' are driven by the new wavefield: two halo rows, explicit exchange after every step launch.  Sources sit
     # on both sides of every slab boundary (their injected part is removed from the NEIGHBOUR's c-gradient terms too).
