@@ -194,6 +194,13 @@ struct adseis_acoustic_plan {
   unsigned long long sepoch = 0;             // step kernels launched so far (same sequence on every rank)
   int* perm = nullptr;                       // launch order -> logical CTA id (edge CTAs first)
   int n_edge_lo = 0, n_edge_hi = 0;
+  // whole sweep in one cooperative launch (small single-GPU grids whose tape is resident): tiling of ALL cells as general
+  // cells, the points grouped by its CTAs, the barrier counter
+  bool persist = false;
+  AcTiling tp{};
+  int nblocksP = 0;
+  PointSetStorage srcP{}, rcvP{};
+  unsigned long long* pbar = nullptr;
   int hd = 1;                                // halo rows per neighbour (2 for PropagatorKernel = 0, whose phi'/psi' read u' one row further)
   bool unfused = false;                      // slab plan whose step launches do not exchange: an explicit exchange follows every launch
   PointSetStorage srcK{};                    // PropagatorKernel = 0 on slabs: sources within one row of my rows (c-gradient correction)
@@ -363,6 +370,7 @@ ADSEIS_API int adseis_acoustic_plan_destroy(adseis_acoustic_plan* P) {
   }
   for (double* c : P->ckpt) cudaFree(c);
   free_point_set(&P->src); free_point_set(&P->rcv); free_point_set(&P->srcK);
+  free_point_set(&P->srcP); free_point_set(&P->rcvP); cudaFree(P->pbar);
   free_point_set(&P->srcM); free_point_set(&P->rcvM);
   free_point_set(&P->srcH); free_point_set(&P->rcvH);
   cudaFree(P->rcv_owned);
@@ -529,6 +537,46 @@ static void build_tb_tilings(adseis_acoustic_plan* P) {
 // Sources / receivers of a plan: keep the points whose padded row is owned (MPIAcoustic.jl:71-78, 98-104), group them
 // by owner CTA (per-CTA CSR lists, see PointSet in common.cuh) and size the per-point buffers.  Called by plan_create
 // and by adseis_acoustic_plan_set_points (one plan per GPU serves all shots of a multi-shot gradient).
+// Whole-sweep (persistent) path: every owned cell is a general cell of ONE rectangle, split evenly over CTAs that are all
+// resident at once (cooperative launch).  Built for small single-GPU grids; used when the tape is resident (one segment).
+static void build_persist_tiling(adseis_acoustic_plan* P) {
+  P->persist = false;
+  const char* e = getenv("ADSEIS_AC_PERSIST");
+  if (P->slab.nranks > 1 || (e && e[0] == '0')) return;
+  const AcGeom& g = P->g;
+  const i64 cells = (i64)(P->own1 - P->own0) * g.W;
+  // measured on B200 (profiles/r02_small_grids.md): one launch per step costs ~8 / 10 us (forward / adjoint) whatever the
+  // grid; the resident kernel costs a grid barrier plus one general cell per thread and step
+  // 401 x 133: 16.9 -> 8.0 us per step pair (scheme 1), 25.6 -> 10.7 (scheme 0); break-even near 250 k cells (scheme 1) and
+  // 150 k (scheme 0, whose frame cells re-evaluate their neighbours)
+  if (!(e && e[0] == '1') && cells > ((P->p.PropagatorKernel == 0) ? (1LL << 17) : (1LL << 18))) return;
+  int dev_coop = 0;
+  if (cudaDeviceGetAttribute(&dev_coop, cudaDevAttrCooperativeLaunch, P->ctx->device) != cudaSuccess || !dev_coop) return;
+  int per_sm = 0, per_sm2 = 0;
+  const bool k0 = P->p.PropagatorKernel == 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k0 ? ac_fwd_persist_kernel<0> : ac_fwd_persist_kernel<1>, AC_PS_THREADS, 0) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k0 ? ac_adj_persist_kernel<0> : ac_adj_persist_kernel<1>, AC_PS_THREADS, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  const i64 max_ctas = (i64)std::min(per_sm, per_sm2) * P->ctx->sm_count;
+  if (max_ctas < 1) return;
+  AcTiling& t = P->tp;
+  memset(&t, 0, sizeof(t));
+  t.mr0 = t.mr1 = P->own0;
+  t.rb = 1;
+  t.fthr = AC_PS_THREADS;
+  t.fcpt = (int)std::max<i64>(1, (cells + AC_PS_THREADS * max_ctas - 1) / (AC_PS_THREADS * max_ctas));
+  if (getenv("ADSEIS_AC_PERSIST_CPT")) t.fcpt = std::max(t.fcpt, atoi(getenv("ADSEIS_AC_PERSIST_CPT")));
+  const i64 per = (i64)t.fthr * t.fcpt;
+  t.nrect = 1;
+  t.rr0[0] = P->own0; t.rr1[0] = P->own1; t.rc0[0] = 0; t.rc1[0] = g.W;
+  t.rblk[0] = 0; t.rblk[1] = (int)((cells + per - 1) / per);
+  for (int k = 1; k < 4; k++) { t.rblk[k + 1] = t.rblk[1]; t.rr0[k] = t.rr1[k] = t.rc0[k] = 0; t.rc1[k] = 1; }
+  P->nblocksP = t.rblk[1];
+  P->persist = P->nblocksP >= 1 && P->nblocksP <= max_ctas;
+}
+
 static int plan_build_points(adseis_acoustic_plan* P, int64_t nsrc, const int64_t* srci, const int64_t* srcj,
                              int64_t nrcv, const int64_t* rcvi, const int64_t* rcvj) {
   const adseis_acoustic_params* p = &P->p;
@@ -604,6 +652,23 @@ static int plan_build_points(adseis_acoustic_plan* P, int64_t nsrc, const int64_
     TRY(upload_point_set(h, &P->srcK, st));
   }
   TRY(build(nrcv, rcvi, rcvj, &P->rcv, &owned, "receiver"));
+  if (P->persist) {   // the same points grouped by the CTAs of the whole-sweep tiling
+    auto buildp = [&](i64 n, const int64_t* pi, const int64_t* pj, PointSetStorage* dst) -> int {
+      std::vector<int> own, cells, gid, none;
+      const i64 per = (i64)P->tp.fthr * P->tp.fcpt;
+      for (i64 k = 0; k < n; k++) {
+        const i64 gi = pi[k] + ioff, gj = pj[k] + ioff;
+        const int li = (int)(gi - g.goff);
+        own.push_back((int)(((i64)(li - P->own0) * g.W + gj) / per));
+        cells.push_back(li * g.ld + (int)gj); gid.push_back((int)k);
+      }
+      PointSetHost h;
+      build_point_set(own, cells, gid, none, P->nblocksP, &h);
+      return upload_point_set(h, dst, st);
+    };
+    TRY(buildp(nsrc, srci, srcj, &P->srcP));
+    TRY(buildp(nrcv, rcvi, rcvj, &P->rcvP));
+  }
   if (P->src.nu > 0) P->srcp = AcPoints{P->src.blk, P->src.cell, P->src.start, P->src.perm};
   if (P->rcv.nu > 0) P->rcvp = AcPoints{P->rcv.blk, P->rcv.cell, P->rcv.start, P->rcv.perm};
   if (!P->rcv_owned) TRY(dev_alloc(&P->rcv_owned, owned.size()));
@@ -874,6 +939,7 @@ ADSEIS_API int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acousti
   }
 
   build_tb_tilings(P);
+  build_persist_tiling(P);
   PTRY(dev_upload(&P->sigx, sx, st));
   PTRY(dev_upload(&P->tauy, ty, st));
   PTRY(dev_alloc_zero(&P->c2, (size_t)g.plane, st));
@@ -1233,6 +1299,39 @@ static int run_forward_steps(adseis_acoustic_plan* P, i64 base, i64 s_first, i64
 
 typedef int (*segment_cb)(adseis_acoustic_plan* P, size_t k, void* user);
 
+// ---- whole sweep in one cooperative launch (small grids) --------------------------------------------------------------
+static bool use_persist(adseis_acoustic_plan* P) {
+  return P->persist && !P->arena && P->seg_b.size() == 1 && !(P->p.PropagatorKernel == 0 && P->k0_corr);
+}
+static AcPersist persist_args(adseis_acoustic_plan* P) {
+  AcPersist a;
+  memset(&a, 0, sizeof(a));
+  a.hist = P->hist; a.plane = P->g.plane;
+  for (int k = 0; k < 2; k++) { a.phi[k] = P->phi[k]; a.psi[k] = P->psi[k]; a.phib[k] = P->phib[k]; a.psib[k] = P->psib[k]; a.ut[k] = P->ut[k]; }
+  a.c2 = P->c2; a.sigx = P->sigx; a.tauy = P->tauy;
+  auto view = [](const PointSetStorage& q) { return q.nu > 0 ? AcPoints{q.blk, q.cell, q.start, q.perm} : AcPoints{}; };
+  a.src = view(P->srcP); a.rcv = view(P->rcvP);
+  a.srcv = P->srcv; a.nsrc = (int)P->nsrc; a.nrcv = (int)P->nrcv;
+  for (int k = 0; k < 4; k++) a.ub[k] = P->ub[k];
+  a.nub = P->nub;
+  a.G = P->G; a.res = P->res; a.gradsrcv = P->gradsrcv;
+  a.bar = P->pbar;
+  return a;
+}
+template <class K>
+static int launch_persist(adseis_acoustic_plan* P, K kernel, AcPersist a) {
+  cudaStream_t st = P->ctx->stream;
+  if (!P->pbar) TRY(dev_alloc_zero(&P->pbar, 1, st));
+  a.bar = P->pbar;
+  CUDA_TRY(cudaMemsetAsync(P->pbar, 0, 8, st));
+  AcGeom g = P->g;
+  AcTiling t = P->tp;
+  void* args[3] = {&g, &t, &a};
+  CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kernel, dim3(P->nblocksP), dim3(AC_PS_THREADS), args, 0, st));
+  LAUNCH_CHECK(P);
+  return ADSEIS_OK;
+}
+
 // Full forward sweep, segment by segment.  After segment k finishes (slots seg_b[k]..seg_e[k] in the window)
 // `cb` is invoked (may be null).  Saves the start state of every later segment when save_ckpt.
 static int forward_sweep(adseis_acoustic_plan* P, bool save_ckpt, segment_cb cb, void* user) {
@@ -1275,7 +1374,14 @@ static int forward_sweep(adseis_acoustic_plan* P, bool save_ckpt, segment_cb cb,
       CUDA_TRY(cudaMemcpyAsync(P->hist + g.plane, s1, pb, cudaMemcpyDeviceToDevice, st));
     }
     TRY(span_begin(P, 0, e - (b + 2) + 1));
-    TRY(run_forward_steps(P, b, b + 2, e, true));
+    if (use_persist(P) && e >= b + 2) {
+      AcPersist a = persist_args(P);
+      a.s_first = b + 2; a.s_last = e; a.rcvv = P->rcvv;
+      if (P->p.PropagatorKernel == 0) TRY(launch_persist(P, ac_fwd_persist_kernel<0>, a));
+      else TRY(launch_persist(P, ac_fwd_persist_kernel<1>, a));
+    } else {
+      TRY(run_forward_steps(P, b, b + 2, e, true));
+    }
     TRY(span_end(P));
     P->win_base = b; P->win_last = e;
     if (cb) TRY(cb(P, k, user));
@@ -1298,7 +1404,7 @@ static bool graphs_enabled(adseis_acoustic_plan* P) {
     // worth it when a step kernel is short next to its launch cost; large grids keep direct launches (a graph of
     // tens of thousands of nodes costs more to build than it saves)
     const bool small = (i64)P->g.H * P->g.W <= (6LL << 20);
-    P->graphs = (P->arena == nullptr) && (e ? e[0] != '0' : small) ? 1 : 0;
+    P->graphs = (P->arena == nullptr) && !use_persist(P) && (e ? e[0] != '0' : small) ? 1 : 0;   // (a cooperative launch is not captured)
   }
   return P->graphs == 1;
 }
@@ -1495,7 +1601,7 @@ static int gradient_body(adseis_acoustic_plan* P) {
       }
       AcK0 k0{};
       if (P->p.PropagatorKernel == 0) {
-        k0.wnew = win_slot(P, b, s); k0.ut_in = P->ut[(s + 1) & 1]; k0.ut_out = P->ut[s & 1];
+        k0.wnew = win_slot(P, b, s); k0.ut_in = P->ut[(s + 1) & 1]; k0.ut_out = P->ut[s & 1]; k0.ub2 = P->ub[(s + 1) % NUB];
         const PointSetStorage& K = P->unfused ? P->srcK : P->src;   // slabs: incl. the neighbours' sources next to my rows
         if (P->k0_corr && K.nu > 0) {
           k_ac_k0_src_corr<<<(K.nu + 127) / 128, 128, 0, stl>>>(g, K.cell, K.start, K.perm, K.nu,
@@ -1528,6 +1634,13 @@ static int gradient_body(adseis_acoustic_plan* P) {
       return ADSEIS_OK;
     };
     i64 s = e;
+    if (use_persist(P) && e >= b + 2) {
+      AcPersist a = persist_args(P);
+      a.s_first = b + 2; a.s_last = e;
+      if (P->p.PropagatorKernel == 0) TRY(launch_persist(P, ac_adj_persist_kernel<0>, a));
+      else TRY(launch_persist(P, ac_adj_persist_kernel<1>, a));
+      s = b + 1;
+    }
     if (P->tb_adj) {
       // pairs (s, s-1): frame of step s, frame of step s-1, box of steps s and s-1 in one launch; streams as in the
       // forward sweep (one stream: narrow frame, box, narrow frame)

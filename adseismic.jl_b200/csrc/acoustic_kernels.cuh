@@ -731,6 +731,7 @@ struct AcK0 {
   const double* wnew;   // u[s] (post-injection), history slot s
   const double* ut_in;  // utilde_{s+1} (frame cells)
   double* ut_out;       // utilde_s
+  const double* ub2;    // ubar_{s+1} (== utilde_{s+1} wherever every cell within two rows / columns is PML-free)
 };
 
 __device__ __forceinline__ bool ac_interior(const AcGeom& g, int gi, int j) {
@@ -777,6 +778,19 @@ __device__ __forceinline__ void ac_adj_general_cell_k0(const AcGeom& g, int li, 
   const bool vyp = rowok && j + 1 >= 1 && j + 1 <= g.W - 2;
   // every evaluation runs on an interior cell: invalid ones are redirected to a valid one and dropped.  A ring cell P
   // has at most one interior neighbour; `safe` is that neighbour (or P itself when P is interior).
+  // A cell with nothing but PML-free interior cells within two rows / columns (the region the marching CTAs cover, and a
+  // few columns more) has utilde == ubar on itself and its neighbours: it is evaluated with the marching CTAs' expression
+  // and summation order, whoever owns it -- a frame CTA of a step launch or the whole-sweep kernel -- so that the bits
+  // of the gradient do not depend on the schedule.
+  if (gi - 2 >= 1 && gi + 2 <= g.H - 2 && j - 2 >= 1 && j + 2 <= g.W - 2 && sigx[gi - 2] == 0.0 && sigx[gi - 1] == 0.0 &&
+      sigx[gi] == 0.0 && sigx[gi + 1] == 0.0 && sigx[gi + 2] == 0.0 && tauy[j - 2] == 0.0 && tauy[j - 1] == 0.0 &&
+      tauy[j] == 0.0 && tauy[j + 1] == 0.0 && tauy[j + 2] == 0.0) {
+    const double rx2 = g.rx * g.rx, ry2 = g.ry * g.ry, uP = ub1[IJ];
+    ub0[IJ] = ac_adj_cell(ac_a0(c2[IJ], g.kx2, g.ky2), rx2, ry2, uP, c2[IJ + g.ld] * ub1[IJ + g.ld], c2[IJ - g.ld] * ub1[IJ - g.ld],
+                          c2[IJ + 1] * ub1[IJ + 1], c2[IJ - 1] * ub1[IJ - 1], k0.ub2[IJ]);
+    G[IJ] = G[IJ] + ac_corr_cell(-g.kx2 - g.ky2, rx2, ry2, wf[IJ], wf[IJ + g.ld], wf[IJ - g.ld], wf[IJ + 1], wf[IJ - 1], uP);
+    return;
+  }
   const int sgi = intP ? gi : (vxm ? gi - 1 : (vxp ? gi + 1 : gi)), sj = intP ? j : (vym ? j - 1 : (vyp ? j + 1 : j));
   const bool any = intP || vxm || vxp || vym || vyp;
   if (!any) { ub0[IJ] = 0.0; return; }  // ring corners: no interior neighbour at all
@@ -1051,6 +1065,105 @@ ac_adj_kernel(AcGeom g, AcTiling t, const double* __restrict__ ub1, const double
     }
     ac_fuse_signal(f, t_lo, t_hi);
     TL_DEV(f, 3);
+  }
+}
+
+// ============================================================================================================
+// WHOLE SWEEP in one launch (small grids).  When a step is a few hundred thousand cells its kernel is all launch latency
+// (C1, 401 x 133: 6.5 / 10 us per forward / adjoint launch for 0.3 us of HBM time).  Here one cooperative launch runs
+// every step of a sweep: all cells are evaluated as general cells by CTAs that stay resident, own the same cells for
+// the whole sweep (so the per-CTA point lists work unchanged) and meet at a grid barrier after every step.  Same
+// expressions as the step kernels (interior cells of the adjoint go through the shared FMA helpers), so the results
+// are the same bits.  State lives in the same arrays as for the step kernels; between steps it is L2 traffic.
+// ============================================================================================================
+#define AC_PS_THREADS 256
+struct AcPersist {
+  double* hist; i64 plane;                 // forward history: slot k at hist + k * plane (single segment, base 0)
+  double *phi[2], *psi[2];
+  const double *c2, *sigx, *tauy;
+  AcPoints src, rcv;
+  const double* srcv; int nsrc;
+  double* rcvv; int nrcv;                  // forward: traces out (null: no sampling)
+  i64 s_first, s_last;
+  // adjoint
+  double* ub[4]; int nub;
+  double *phib[2], *psib[2], *G;
+  double* ut[2];                           // PropagatorKernel = 0: utilde side planes
+  const double* res; double* gradsrcv;
+  unsigned long long* bar;                 // grid barrier counter (zero at launch)
+};
+
+// all CTAs of the (cooperative) launch; `target` = arrivals expected so far
+__device__ __forceinline__ void ac_grid_barrier(unsigned long long* bar, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1ULL);
+    unsigned long long v;
+    do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory"); } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int PK>
+__global__ void __launch_bounds__(AC_PS_THREADS, 2) ac_fwd_persist_kernel(AcGeom g, AcTiling t, AcPersist a) {
+  const int bid = blockIdx.x;
+  int rect, idx0;
+  ac_frame_locate(t, bid, &rect, &idx0);
+  const int wdt = t.rc1[rect] - t.rc0[rect];
+  const int ncell = (t.rr1[rect] - t.rr0[rect]) * wdt;
+  AcPoints none{};
+  unsigned long long arrivals = 0;
+  for (i64 s = a.s_first; s <= a.s_last; s++) {
+    // plain (non-__restrict__) views: these arrays are written by other CTAs during this launch
+    double* w = a.hist + (s - 1) * a.plane;
+    double* wold = a.hist + (s - 2) * a.plane;
+    double* u = a.hist + s * a.plane;
+    double *phi = a.phi[(s - 1) & 1], *psi = a.psi[(s - 1) & 1], *phio = a.phi[s & 1], *psio = a.psi[s & 1];
+    for (int k = 0; k < t.fcpt; k++) {
+      const int idx = idx0 + k * t.fthr + threadIdx.x;
+      if (idx < ncell) {
+        const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
+        if constexpr (PK == 0) ac_fwd_general_cell_k0(g, li, j, w, wold, a.c2, phi, psi, a.sigx, a.tauy, u, phio, psio);
+        else ac_fwd_general_cell(g, li, j, w, wold, a.c2, phi, psi, a.sigx, a.tauy, u, phio, psio);
+      }
+    }
+    ac_cta_epilogue(bid, u, a.src, a.nsrc > 0 ? a.srcv + (s - 1) * a.nsrc : nullptr, g.dt2, a.rcvv ? a.rcv : none,
+                    (a.rcvv && a.nrcv > 0) ? a.rcvv + s * a.nrcv : nullptr, 1.0);
+    arrivals += gridDim.x;
+    ac_grid_barrier(a.bar, arrivals);
+  }
+}
+
+template <int PK>
+__global__ void __launch_bounds__(AC_PS_THREADS, 2) ac_adj_persist_kernel(AcGeom g, AcTiling t, AcPersist a) {
+  const int bid = blockIdx.x;
+  int rect, idx0;
+  ac_frame_locate(t, bid, &rect, &idx0);
+  const int wdt = t.rc1[rect] - t.rc0[rect];
+  const int ncell = (t.rr1[rect] - t.rr0[rect]) * wdt;
+  AcPoints none{};
+  const int NUB = a.nub;
+  unsigned long long arrivals = 0;
+  for (i64 s = a.s_last; s >= a.s_first; s--) {   // ubar[s-1] from ubar[s], ubar[s+1], u[s-1]
+    double *ub1 = a.ub[s % NUB], *ub2 = a.ub[(s + 1) % NUB], *ub0 = a.ub[(s - 1 + NUB) % NUB];
+    double* wf = a.hist + (s - 1) * a.plane;
+    double *phib = a.phib[s & 1], *psib = a.psib[s & 1], *phibo = a.phib[(s - 1) & 1], *psibo = a.psib[(s - 1) & 1];
+    AcK0 k0{};
+    if constexpr (PK == 0) { k0.wnew = a.hist + s * a.plane; k0.ut_in = a.ut[(s + 1) & 1]; k0.ut_out = a.ut[s & 1]; k0.ub2 = ub2; }
+    for (int k = 0; k < t.fcpt; k++) {
+      const int idx = idx0 + k * t.fthr + threadIdx.x;
+      if (idx < ncell) {
+        const int li = t.rr0[rect] + idx / wdt, j = t.rc0[rect] + idx % wdt;
+        if constexpr (PK == 0) ac_adj_general_cell_k0(g, li, j, ub1, wf, a.c2, phib, psib, a.sigx, a.tauy, ub0, phibo, psibo, a.G, k0);
+        else ac_adj_general_cell(g, li, j, ub1, ub2, wf, a.c2, phib, psib, a.sigx, a.tauy, ub0, phibo, psibo, a.G);
+      }
+    }
+    ac_cta_epilogue(bid, ub0, a.rcv, a.nrcv > 0 ? a.res + (s - 1) * a.nrcv : nullptr, 1.0, (s - 2 >= 1) ? a.src : none,
+                    (s - 2 >= 1 && a.nsrc > 0) ? a.gradsrcv + (s - 2) * a.nsrc : nullptr, g.dt2);
+    arrivals += gridDim.x;
+    ac_grid_barrier(a.bar, arrivals);
   }
 }
 

@@ -249,6 +249,7 @@ def test_two_step_kernels_equal_one_step_kernels_bitwise(A, ctx, po, monkeypatch
                                    vp_ref=vp, NPOINTS_PML=10)
     pitch = (NY + 2 + 15) // 16 * 16
     out = {}
+    monkeypatch.setenv("ADSEIS_AC_PERSIST", "0")      # this test is about the step kernels (the whole-sweep kernel has its own)
     for tb in ("0", "1", "1s"):       # one-step kernels; pairs with frame / box launches on two streams; pairs on one stream
         monkeypatch.setenv("ADSEIS_AC_TB", tb[0])
         monkeypatch.setenv("ADSEIS_AC_TB_OVERLAP", "0" if tb == "1s" else "1")
@@ -268,3 +269,39 @@ def test_two_step_kernels_equal_one_step_kernels_bitwise(A, ctx, po, monkeypatch
     for key, val in out.items():
         assert np.array_equal(val[0], ref[0]) and val[1] == ref[1], key
         assert np.array_equal(val[2], ref[2]) and np.array_equal(val[3], ref[3]), key
+
+
+@pytest.mark.parametrize("kernel,frame_sources", [(1, True), (0, False), (0, True)])
+def test_whole_sweep_kernel_equals_step_kernels_bitwise(A, ctx, po, monkeypatch, kernel, frame_sources):
+    """Small grids run a whole sweep in ONE cooperative launch (ac_fwd_persist_kernel / ac_adj_persist_kernel: resident
+    CTAs, a grid barrier per step).  It is a schedule, not a discretisation: same bits as one launch per step, for both
+    schemes; with PropagatorKernel=0 and sources inside the absorbing frame (c-gradient correction kernel between the
+    adjoint launches) the plan falls back to the step kernels."""
+    NX, NY, NSTEP = 133, 401, 90
+    rng = np.random.default_rng(77)
+    dx, dt, vp = 10.0, 1e-3, 2500.0
+    sig, tau, c, srci, srcj, srcv, rcvi, rcvj = _case(po, rng, NX, NY, NSTEP, dx, dx, dt, 12, vp, nsrc=4)
+    srci[:] = [40, 41, 70, 100]; srcj[:] = [200, 200, 30, 380]
+    if frame_sources:
+        srci[0], srcj[0] = 5, 6; srci[1], srcj[1] = 1, NY // 2
+    rcvi[:4] = [5, 1, 40, 41]; rcvj[:4] = [6, NY // 2, 200, 200]
+    p = A.AcousticPropagatorParams(PropagatorKernel=kernel, NX=NX, NY=NY, NSTEP=NSTEP, DELTAX=dx, DELTAY=dx, DELTAT=dt,
+                                   vp_ref=vp, NPOINTS_PML=12)
+    out = {}
+    for ps in ("0", "1"):
+        monkeypatch.setenv("ADSEIS_AC_PERSIST", ps)
+        plan = A.AcousticPlan(p, srci, srcj, rcvi, rcvj, ctx=ctx)
+        plan.set_model(c); plan.set_srcv(srcv)
+        plan.forward()
+        r = plan.rcvv()
+        plan.set_obs(0.6 * r)
+        for rep in range(2):
+            plan.gradient()
+        out[ps] = (r, plan.loss(), plan.grad_c(), plan.grad_srcv(), plan.snapshot(NSTEP), plan.info())
+        plan.close()
+    a, b = out["0"], out["1"]
+    assert np.abs(a[0]).max() > 0 and np.abs(a[2]).max() > 0
+    expect_persist = not (kernel == 0 and frame_sources)
+    assert (b[5]["launches"] < a[5]["launches"] / 10) == expect_persist, (a[5], b[5])
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1] and np.array_equal(a[4], b[4])
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
