@@ -332,11 +332,15 @@ def acoustic_roofline(A, w, r):
             ab["forward"], fwd_us, peak, peak_src, share=(tm["forward_ms"] + tm["recompute_ms"]) / r["step_ms"],
             traffic=half(ncu_traffic("ac_fwd2_kernel"))))
     else:
-        roof = roof_entry("ac_adj_kernel", ab["adjoint"], adj_us, peak, peak_src, share=tm["adjoint_ms"] / r["step_ms"],
-                          traffic=ncu_traffic("ac_adj_kernel"))
-        roof["other_kernels"] = dict(ac_fwd_kernel=roof_entry("ac_fwd_kernel", ab["forward"], fwd_us, peak, peak_src,
+        # small grids run a whole sweep in one cooperative launch (csrc: ac_*_persist_kernel): a handful of launches per gradient
+        sweep = r["info"]["launches"] < p.NSTEP // 2
+        ka, kf = ("ac_adj_persist_kernel (whole sweep in one launch; figures are PER TIME STEP)",
+                  "ac_fwd_persist_kernel (whole sweep in one launch, per time step)") if sweep else ("ac_adj_kernel", "ac_fwd_kernel")
+        roof = roof_entry(ka, ab["adjoint"], adj_us, peak, peak_src, share=tm["adjoint_ms"] / r["step_ms"],
+                          traffic=None if sweep else ncu_traffic("ac_adj_kernel"))
+        roof["other_kernels"] = dict(ac_fwd_kernel=roof_entry(kf, ab["forward"], fwd_us, peak, peak_src,
                                                               share=(tm["forward_ms"] + tm["recompute_ms"]) / r["step_ms"],
-                                                              traffic=ncu_traffic("ac_fwd_kernel")))
+                                                              traffic=None if sweep else ncu_traffic("ac_fwd_kernel")))
     # whole gradient against the 8(d) roofline: one forward + one adjoint pass over the grid per counted step
     whole = (ab["forward"] + ab["adjoint"]) * (p.NSTEP - 1) / (r["step_ms"] * 1e-3) / 1e9
     roof["whole_gradient"] = dict(achieved=whole, frac=whole / peak, unit="GB/s",
