@@ -457,10 +457,11 @@ static void build_tb_tilings(adseis_acoustic_plan* P) {
     if (P->p.PropagatorKernel == 0) return;
     const i64 rows_min = (i64)g.H / P->slab.nranks - (P->p.NPOINTS_PML + 4) - 5;
     const i64 cells = rows_min * (i64)(g.W - 2 * (P->p.NPOINTS_PML + 4));
-    // measured on B200s with packed halo rows and 128-thread frame-only CTAs (profiles/r02_slab_latency.md), us per step
-    // pair one-step -> pairs: 2048-row slabs of 4096 columns 2 x faster than one GPU either way, 1024 rows 85.5 -> 64.9,
-    // 512 rows 41.3 -> 39.6; below that the box-pair kernel has too few rows per CTA to amortise its ring prologue
-    const i64 min_cells = getenv("ADSEIS_AC_TB_SLAB_MIN") ? atoll(getenv("ADSEIS_AC_TB_SLAB_MIN")) : (3LL << 19);
+    // measured on B200s with packed halo rows and 128-thread frame-only CTAs (profiles/r02_slab_latency.md), C4 (4096^2),
+    // Gcell-upd/s one step per launch -> pairs: 2 GPUs (8.3 M box cells per slab) 103.5 -> 126+, 4 GPUs (4.1 M) 197 -> 227,
+    // 8 GPUs (2.0 M) 406 -> 357: an interior slab waits on two neighbours in every frame-only launch, and its box-pair kernel
+    // has 14 rows per CTA (two of them rim rows) -- below ~3 M cells one step per launch wins
+    const i64 min_cells = getenv("ADSEIS_AC_TB_SLAB_MIN") ? atoll(getenv("ADSEIS_AC_TB_SLAB_MIN")) : (3LL << 20);
     if (rows_min < 16 || (!(e && e[0] == '1') && cells < min_cells)) return;
   }
   const int fi0 = P->box_i0 + 2, fi1 = P->box_i1 - 2, fj0 = P->box_j0 + 2, fj1 = P->box_j1 - 2;
