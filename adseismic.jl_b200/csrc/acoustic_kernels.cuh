@@ -205,20 +205,6 @@ __device__ __forceinline__ unsigned long long tl_now() { unsigned long long t; a
 #define TL_DEV(f, k) do {} while (0)
 #endif
 
-__device__ __forceinline__ void ll_put(ulonglong2* row, int j, double v, unsigned ep) {
-  const unsigned long long b = (unsigned long long)__double_as_longlong(v), e = (unsigned long long)ep << 32;
-  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(row + j), "l"(e | (b & 0xffffffffULL)), "l"(e | (b >> 32))
-               : "memory");
-}
-__device__ __forceinline__ double ll_get(const ulonglong2* row, int j, unsigned ep, unsigned long long* my_flags) {
-  unsigned long long x, y, spins = 0;
-  while (true) {
-    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "l"(row + j) : "memory");
-    if ((unsigned)(x >> 32) == ep && (unsigned)(y >> 32) == ep) break;
-    if (++spins > (1ULL << 24)) { my_flags[2] = 1ULL; break; }  // neighbour lost: report, do not hang
-  }
-  return __longlong_as_double((long long)((x & 0xffffffffULL) | (y << 32)));
-}
 // The helpers below are out of line and take plain values: the step kernels keep their register budget, and the
 // parameter block is not copied to local memory (which passing `const AcFuse&` to a real call would force).
 struct AcLLRx { const ulonglong2 *lo_u, *lo_p, *hi_u, *hi_p; double *in_u, *in_p; unsigned long long* my_flags; int own0, own_last; unsigned ep; };

@@ -196,6 +196,22 @@ static inline void free_point_set(PointSetStorage* st) {
 }
 
 #ifdef __CUDACC__
+// Packed halo words ("LL"): an 8-byte word = 32 data bits + the 32-bit epoch of the launch that sent it; two words per
+// double.  8-byte stores are single-copy atomic, so a word whose epoch matches carries valid data -- no fence, no flag.
+__device__ __forceinline__ void ll_put(ulonglong2* row, int j, double v, unsigned ep) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v), e = (unsigned long long)ep << 32;
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(row + j), "l"(e | (b & 0xffffffffULL)), "l"(e | (b >> 32))
+               : "memory");
+}
+__device__ __forceinline__ double ll_get(const ulonglong2* row, int j, unsigned ep, unsigned long long* my_flags) {
+  unsigned long long x, y, spins = 0;
+  while (true) {
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "l"(row + j) : "memory");
+    if ((unsigned)(x >> 32) == ep && (unsigned)(y >> 32) == ep) break;
+    if (++spins > (1ULL << 27)) { my_flags[2] = 1ULL; break; }  // neighbour lost (minutes): report, do not hang
+  }
+  return __longlong_as_double((long long)((x & 0xffffffffULL) | (y << 32)));
+}
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }

@@ -128,9 +128,13 @@ struct adseis_elastic_plan {
     long long Hl, ld, plane, slot_sz, win, own0, own1;
     long long off_flags, off_hist, off_adj, off_gacc;
     long long n_edge_lo, n_edge_hi;
+    long long off_ll;   // packed halo rows: [from lo, from hi][parity][field 0..2][row 0..1] rows of ld 16-byte words (0: absent)
   } desc{}, dpeer[2];
   char* peer[2] = {nullptr, nullptr};
   unsigned long long epoch = 0, sepoch = 0;
+  bool ll = false;              // packed halo rows instead of fence + flag (ADSEIS_EL_LL=0 switches back)
+  int ll_prev_nf = 0;           // planes the previous fused launch produced (= the planes whose halo rows the next one reads)
+  struct { int arr; long long idx; int field; } ll_prev[3];
   int* perm = nullptr;
   int n_edge_lo = 0, n_edge_hi = 0;
   bool connected = false;
@@ -536,6 +540,15 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
     d.off_hist = off; off += (long long)((size_t)P->win * slot_bytes);
     d.off_adj = off; off += (long long)(adj_elems * 8);
     d.off_gacc = off; off += (long long)(5 * (size_t)g.plane * 8);
+    {
+      // opt-in (ADSEIS_EL_LL=1): measured on 2 B200s (C5, 1002-row slabs) the packed rows change nothing -- forward 75.1 vs
+      // 74.9 us per step, material gradient 203.7 vs 204.0 -- and one full-size run reported a halo time-out that the
+      // remaining GPU budget of the round did not allow to chase; parity tests pass with it (tests/mgpu_worker.py)
+      const char* ell = getenv("ADSEIS_EL_LL");
+      P->ll = (ell && ell[0] == '1');
+      d.off_ll = 0;
+      if (P->ll) { d.off_ll = off; off += 2LL * 2 * 3 * EL_HALO * g.ld * 16; off = (off + 511) / 512 * 512; }
+    }
     P->arena_bytes = (size_t)off;
     cudaError_t e = cudaMalloc((void**)&P->arena, P->arena_bytes);
     if (e != cudaSuccess) {
@@ -640,7 +653,9 @@ static inline long long el_plane_off(const adseis_elastic_plan::Desc& d, const E
   return base + (long long)r.field * d.plane * 8;
 }
 
-static ElFuse el_make_fuse(adseis_elastic_plan* P, int nf, const ElPlaneRef* planes) {
+// `recv`: the previous fused launch produced the planes whose halo rows this launch reads (false for the first launch of a
+// sweep / segment / replay and after an explicit exchange: the halo rows are then in place already)
+static ElFuse el_make_fuse(adseis_elastic_plan* P, int nf, const ElPlaneRef* planes, bool recv) {
   ElFuse f;
   memset(&f, 0, sizeof(f));
   f.perm = P->perm;
@@ -648,6 +663,27 @@ static ElFuse el_make_fuse(adseis_elastic_plan* P, int nf, const ElPlaneRef* pla
   f.has_lo = P->peer[0] != nullptr; f.has_hi = P->peer[1] != nullptr;
   f.nf = nf;
   P->sepoch++;
+  if (P->ll) {
+    auto rows = [&](char* base, const adseis_elastic_plan::Desc& d, int from, unsigned long long ep) {
+      return (ulonglong2*)(base + d.off_ll + (long long)(from * 2 + (int)(ep & 1ULL)) * 3 * EL_HALO * d.ld * 16);
+    };
+    const unsigned long long es = P->sepoch, er = P->sepoch - 1;
+    f.ll = 1;
+    f.ep_send = (unsigned)(es % 0xFFFFFFFEULL) + 1u;
+    f.ep_recv = (recv && P->ll_prev_nf > 0) ? (unsigned)(er % 0xFFFFFFFEULL) + 1u : 0u;
+    f.my_flags = (unsigned long long*)((char*)P->arena + P->desc.off_flags);
+    for (int k = 0; k < nf; k++) f.src[k] = (const double*)((char*)P->arena + el_plane_off(P->desc, planes[k]));
+    if (f.has_lo) { f.tx_lo = rows(P->peer[0], P->dpeer[0], 1, es); f.rx_lo = rows((char*)P->arena, P->desc, 0, er); }
+    if (f.has_hi) { f.tx_hi = rows(P->peer[1], P->dpeer[1], 0, es); f.rx_hi = rows((char*)P->arena, P->desc, 1, er); }
+    f.nf_in = P->ll_prev_nf;
+    for (int k = 0; k < P->ll_prev_nf; k++) {
+      const ElPlaneRef r{P->ll_prev[k].arr, P->ll_prev[k].idx, P->ll_prev[k].field};
+      f.in[k] = (double*)((char*)P->arena + el_plane_off(P->desc, r));
+    }
+    P->ll_prev_nf = nf;
+    for (int k = 0; k < nf; k++) { P->ll_prev[k].arr = planes[k].arr; P->ll_prev[k].idx = planes[k].idx; P->ll_prev[k].field = planes[k].field; }
+    return f;
+  }
   for (int k = 0; k < nf; k++) {
     f.src[k] = (const double*)((char*)P->arena + el_plane_off(P->desc, planes[k]));
     if (f.has_lo) f.lo[k] = (double*)(P->peer[0] + el_plane_off(P->dpeer[0], planes[k])) + (P->dpeer[0].Hl - EL_HALO) * P->dpeer[0].ld;
@@ -711,6 +747,8 @@ __global__ void __launch_bounds__(256) k_el_halo_exchange(ElHaloArgs a) {
 }
 
 static int el_halo_exchange(adseis_elastic_plan* P, int nf, const ElPlaneRef* planes) {
+  P->ll_prev_nf = 0;   // packed rows: the next fused launch finds its halo rows in place
+
   if (!P->arena) return ADSEIS_OK;
   if (!P->connected) {
     adseis_set_error("elastic slab plan: adseis_elastic_plan_ipc_connect has not been called");
@@ -749,6 +787,16 @@ static int el_halo_check(adseis_elastic_plan* P) {
   return ADSEIS_OK;
 }
 
+// Packed halo rows are unpacked by the NEXT step launch; the velocity planes of the last slot of a sweep / segment /
+// replay have none, so their halo rows are exchanged explicitly (they go into checkpoints and are read by the
+// material-gradient kernels).  Also ends the chain: the following launch receives nothing.
+static int el_finish_slot(adseis_elastic_plan* P, i64 widx) {
+  if (!P->arena) return ADSEIS_OK;
+  if (!P->ll) return el_halo_exchange(P, 0, nullptr);
+  const ElPlaneRef v[2] = {{EA_HIST, widx, 0}, {EA_HIST, widx, 1}};
+  return el_halo_exchange(P, 2, v);
+}
+
 // one forward step s: slot `in` (s-1) -> slot `out` (s); in == out is allowed (in-place stepping)
 static int el_step_forward(adseis_elastic_plan* P, i64 s, double* in, double* out, bool sample) {
   cudaStream_t st = P->ctx->stream;
@@ -760,12 +808,12 @@ static int el_step_forward(adseis_elastic_plan* P, i64 s, double* in, double* ou
   const double* prev = (P->nsrc > 0 && s >= 2) ? P->srcv + (s - 2) * P->nsrc : nullptr;
   const i64 widx = (out - P->hist) / P->slot_sz;
   const ElPlaneRef sig_planes[2] = {{EA_HIST, widx, 2}, {EA_HIST, widx, 4}};  // fw3/fw4 difference sxx, sxy along x
-  CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), el_sigma_fwd, P->nblocks, EL_NT, el_ring_bytes<ElSigFwdT>(), st, P->g, P->ctas, si, so, mt, cf, P->src.dev, prev, el_make_fuse(P, 2, sig_planes)));
+  CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), el_sigma_fwd, P->nblocks, EL_NT, el_ring_bytes<ElSigFwdT>(), st, P->g, P->ctas, si, so, mt, cf, P->src.dev, prev, el_make_fuse(P, 2, sig_planes, true)));
   EL_LAUNCH_CHECK(P);
   const ElPlaneRef vel_planes[2] = {{EA_HIST, widx, 0}, {EA_HIST, widx, 1}};
   CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), el_vel_fwd, P->nblocks, EL_NT, el_ring_bytes<ElVelFwdT>(), st, P->g, P->ctas, si, so, mt, cf, P->src.dev, row, sample ? P->rcv.dev : none,
                                          (sample && P->nrcv > 0) ? P->rcvv : nullptr, (int)(P->p.NSTEP + 1), (int)s,
-                                         el_make_fuse(P, 2, vel_planes)));
+                                         el_make_fuse(P, 2, vel_planes, true)));
   EL_LAUNCH_CHECK(P);
   return ADSEIS_OK;
 }
@@ -787,6 +835,7 @@ static int el_forward_sweep(adseis_elastic_plan* P, bool keep, bool save_ckpt) {
   TRY(el_barrier(P));  // slab plans: nobody pushes halo rows before everybody's memsets are done
   if (!keep) {
     for (i64 s = 1; s <= P->p.NSTEP; s++) TRY(el_step_forward(P, s, P->hist, P->hist, true));
+    if (P->ll) TRY(el_finish_slot(P, 0));
     P->win_base = P->win_last = P->p.NSTEP;
     P->inplace_last = true;
     return ADSEIS_OK;
@@ -795,7 +844,8 @@ static int el_forward_sweep(adseis_elastic_plan* P, bool keep, bool save_ckpt) {
   for (size_t k = 0; k < nseg; k++) {
     const i64 b = P->seg_b[k], e = P->seg_e[k];
     if (k > 0) {
-      TRY(el_barrier(P));  // slab plans: the neighbours' last pushes must have landed before halo rows are copied
+      // slab plans: the neighbours' last pushes must have landed before halo rows are copied
+      TRY(el_finish_slot(P, b - P->seg_b[k - 1]));
       double* last = win_ptr(P, P->seg_b[k - 1], b);
       if (save_ckpt) CUDA_TRY(cudaMemcpyAsync(P->ckpt[k - 1], last, sb, cudaMemcpyDeviceToDevice, st));
       CUDA_TRY(cudaMemcpyAsync(P->hist, last, sb, cudaMemcpyDeviceToDevice, st));
@@ -805,6 +855,7 @@ static int el_forward_sweep(adseis_elastic_plan* P, bool keep, bool save_ckpt) {
     for (i64 s = b + 1; s <= e; s++) TRY(el_step_forward(P, s, win_ptr(P, b, s - 1), win_ptr(P, b, s), true));
     P->win_base = b; P->win_last = e;
   }
+  if (P->ll && nseg > 0) TRY(el_finish_slot(P, P->seg_e[nseg - 1] - P->seg_b[nseg - 1]));
   P->inplace_last = false;
   return ADSEIS_OK;
 }
@@ -892,9 +943,14 @@ ADSEIS_API int adseis_elastic_plan_gradient(adseis_elastic_plan* P, int want_mat
       if (k != (i64)nseg - 1) {  // restore the first slot of segment k and replay its forward steps
         if (k == 0) CUDA_TRY(cudaMemsetAsync(P->hist, 0, sb, st));
         else CUDA_TRY(cudaMemcpyAsync(P->hist, P->ckpt[k - 1], sb, cudaMemcpyDeviceToDevice, st));
+        P->ll_prev_nf = 0;   // the previous fused launch was an adjoint one: nothing to receive
         for (i64 s = b + 1; s <= e; s++) TRY(el_step_forward(P, s, win_ptr(P, b, s - 1), win_ptr(P, b, s), false));
         P->last_recomputed += e - b;
         P->win_base = b; P->win_last = e;
+        if (P->ll && P->arena) {
+          TRY(el_finish_slot(P, e - b));
+          TRY(el_halo_exchange(P, 2, vb_planes));   // vbar rows sent by the last adjoint launch before the replay
+        }
       }
     }
     for (i64 s = e; s >= b + 1; s--) {
@@ -906,21 +962,21 @@ ADSEIS_API int adseis_elastic_plan_gradient(adseis_elastic_plan* P, int want_mat
       double* grow = (s - 2 >= 0 && P->nsrc > 0 && s >= 2) ? P->gradsrcv + (s - 2) * P->nsrc : nullptr;
       if (mat) {
         CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), el_vel_adj<true>, P->nblocks, EL_NT, el_ring_bytes<ElVelAdjT<true>>(), st, g, P->ctas, bi, bo, fs, mt, cf, P->Gr3, P->Gr4, P->rcv.dev, resp, stride, (int)s,
-                                                     el_make_fuse(P, 3, sb_planes)));
+                                                     el_make_fuse(P, 3, sb_planes, true)));
         EL_LAUNCH_CHECK(P);
         CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), el_sigma_adj<true>, P->nblocks, EL_NT, el_ring_bytes<ElSigAdjT<true>>(), st, g, P->ctas, bi, bo, fp, fs, mt, cf, P->Gl, P->Gm1, P->Gm2,
                                                        s >= 2 ? P->rcv.dev : none, s >= 2 ? resp : nullptr, stride,
                                                        (int)(s - 1), s >= 2 ? P->src.dev : none, grow,
-                                                       el_make_fuse(P, 2, vb_planes)));
+                                                       el_make_fuse(P, 2, vb_planes, true)));
         EL_LAUNCH_CHECK(P);
       } else {
         CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), el_vel_adj<false>, P->nblocks, EL_NT, el_ring_bytes<ElVelAdjT<false>>(), st, g, P->ctas, bi, bo, zero, mt, cf, nullptr, nullptr, P->rcv.dev, resp, stride,
-                                                      (int)s, el_make_fuse(P, 3, sb_planes)));
+                                                      (int)s, el_make_fuse(P, 3, sb_planes, true)));
         EL_LAUNCH_CHECK(P);
         CUDA_TRY(launch_step(P->arena == nullptr || adseis_pdl_slab(), el_sigma_adj<false>, P->nblocks, EL_NT, el_ring_bytes<ElSigAdjT<false>>(), st, g, P->ctas, bi, bo, zero, zero, mt, cf, nullptr, nullptr, nullptr,
                                                         s >= 2 ? P->rcv.dev : none, s >= 2 ? resp : nullptr, stride,
                                                         (int)(s - 1), s >= 2 ? P->src.dev : none, grow,
-                                                        el_make_fuse(P, 2, vb_planes)));
+                                                        el_make_fuse(P, 2, vb_planes, true)));
         EL_LAUNCH_CHECK(P);
       }
     }

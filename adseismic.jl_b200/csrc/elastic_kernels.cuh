@@ -123,6 +123,16 @@ struct ElFuse {
   unsigned long long *sig_lo, *sig_hi;   // neighbour flags to bump (peer pointers)
   unsigned long long* my_flags;          // [3] bumped by rank-1's step kernels, [4] by rank+1's, [2] error
   unsigned long long expect_lo, expect_hi;
+  // packed halo rows (see common.cuh: ll_put / ll_get and csrc/acoustic_kernels.cuh AcFuse): the sender stores its
+  // EL_HALO edge rows of the planes it produces into the neighbour's packed rows [field][row][column] and is done; the
+  // receiving CTA of the neighbour's NEXT launch unpacks the columns it owns into the halo rows of the planes it reads
+  // (= the planes the previous launch produced).
+  int ll;
+  unsigned ep_send, ep_recv;             // epoch stamped on my rows; epoch to wait for (0: nothing to receive)
+  ulonglong2 *tx_lo, *tx_hi;             // the neighbours' packed rows (peer pointers)
+  const ulonglong2 *rx_lo, *rx_hi;       // mine, filled by the neighbours' previous fused launch
+  int nf_in;
+  double* in[3];                         // my planes whose halo rows this launch reads
 };
 
 __device__ __forceinline__ int el_bid(const ElFuse& f) { return f.perm ? f.perm[blockIdx.x] : blockIdx.x; }
@@ -142,9 +152,51 @@ __device__ __forceinline__ void el_cta_edges(const ElGeom& g, const ElFuse& f, c
   *t_hi = f.has_hi && d.r1 > g.own1 - EL_HALO;
 }
 
-__device__ __forceinline__ void el_fuse_wait(const ElFuse& f, bool t_lo, bool t_hi) {
+// out of line, plain values (keeps the step kernels' register budget and their parameter block out of local memory)
+__device__ __noinline__ void el_ll_recv(const ulonglong2* rx_lo, const ulonglong2* rx_hi, double* in0, double* in1, double* in2,
+                                        int nf_in, unsigned ep, unsigned long long* my_flags, int own0, int own1, int ld,
+                                        int c0, int c1, bool t_lo, bool t_hi) {
+  double* in[3] = {in0, in1, in2};
+  for (int k = 0; k < nf_in; k++) {
+#pragma unroll
+    for (int r = 0; r < EL_HALO; r++) {
+      const ulonglong2* lo = rx_lo + (i64)(k * EL_HALO + r) * ld;
+      const ulonglong2* hi = rx_hi + (i64)(k * EL_HALO + r) * ld;
+      for (int q = c0 + threadIdx.x; q < c1; q += EL_NT) {
+        if (t_lo) in[k][(i64)(own0 - EL_HALO + r) * ld + q] = ll_get(lo, q, ep, my_flags);
+        if (t_hi) in[k][(i64)(own1 + r) * ld + q] = ll_get(hi, q, ep, my_flags);
+      }
+    }
+  }
+  asm volatile("fence.proxy.async.global;" ::: "memory");   // the halo rows are read by bulk copies of this CTA
+}
+__device__ __noinline__ void el_ll_send(ulonglong2* tx_lo, ulonglong2* tx_hi, const double* s0, const double* s1, const double* s2,
+                                        int nf, unsigned ep, int own0, int own1, int ld, int r0, int r1, int c0, int c1,
+                                        bool t_lo, bool t_hi) {
+  const double* src[3] = {s0, s1, s2};
+  for (int k = 0; k < nf; k++) {
+#pragma unroll
+    for (int r = 0; r < EL_HALO; r++) {
+      const int lo_row = own0 + r, hi_row = own1 - EL_HALO + r;
+      if (t_lo && lo_row >= r0 && lo_row < r1)
+        for (int q = c0 + threadIdx.x; q < c1; q += EL_NT) ll_put(tx_lo + (i64)(k * EL_HALO + r) * ld, q, src[k][(i64)lo_row * ld + q], ep);
+      if (t_hi && hi_row >= r0 && hi_row < r1)
+        for (int q = c0 + threadIdx.x; q < c1; q += EL_NT) ll_put(tx_hi + (i64)(k * EL_HALO + r) * ld, q, src[k][(i64)hi_row * ld + q], ep);
+    }
+  }
+}
+
+__device__ __forceinline__ void el_fuse_wait(const ElGeom& g, const ElFuse& f, const ElCta& d, bool t_lo, bool t_hi) {
   pdl_wait();  // (programmatic dependent launch) everything the previous launch wrote is visible from here on
   if (!(t_lo || t_hi)) return;  // CTA-uniform
+  if (f.ll) {
+    if (f.ep_recv != 0u) {
+      el_ll_recv(f.rx_lo, f.rx_hi, f.in[0], f.in[1], f.in[2], f.nf_in, f.ep_recv, f.my_flags, g.own0, g.own1, g.ld, d.c0, d.c1,
+                 t_lo, t_hi);
+      __syncthreads();
+    }
+    return;
+  }
   if (threadIdx.x == 0) {
     volatile unsigned long long* fl = f.my_flags;
     unsigned long long spins = 0;
@@ -160,6 +212,10 @@ __device__ __forceinline__ void el_fuse_wait(const ElFuse& f, bool t_lo, bool t_
 __device__ __forceinline__ void el_fuse_push(const ElGeom& g, const ElFuse& f, const ElCta& d, bool t_lo, bool t_hi) {
   if (!(t_lo || t_hi)) return;
   __syncthreads();  // all cells (and point injections) of this CTA are written
+  if (f.ll) {
+    el_ll_send(f.tx_lo, f.tx_hi, f.src[0], f.src[1], f.src[2], f.nf, f.ep_send, g.own0, g.own1, g.ld, d.r0, d.r1, d.c0, d.c1, t_lo, t_hi);
+    return;
+  }
   for (int k = 0; k < f.nf; k++) {
 #pragma unroll
     for (int r = 0; r < EL_HALO; r++) {
@@ -467,7 +523,7 @@ el_sigma_fwd(ElGeom g, const ElCta* __restrict__ ctas, ElSlot in, ElSlot out, El
 #endif
   bool t_lo, t_hi;
   el_cta_edges(g, f, d, &t_lo, &t_hi);
-  el_fuse_wait(f, t_lo, t_hi);
+  el_fuse_wait(g, f, d, t_lo, t_hi);
   int sa = 0, sb = 0;
   if (src.blk != nullptr && srcv_prev != nullptr) { sa = src.blk[bid]; sb = src.blk[bid + 1]; }
   if (d.kind == 0) {
@@ -623,7 +679,7 @@ el_vel_fwd(ElGeom g, const ElCta* __restrict__ ctas, ElSlot in, ElSlot out, ElMa
 #endif
   bool t_lo, t_hi;
   el_cta_edges(g, f, d, &t_lo, &t_hi);
-  el_fuse_wait(f, t_lo, t_hi);
+  el_fuse_wait(g, f, d, t_lo, t_hi);
   if (d.kind == 0) {
     double* ring = reinterpret_cast<double*>(el_smem + 64);
     el_vel_fwd_march(g, d, in, out, mt, ring, reinterpret_cast<unsigned long long*>(el_smem));
@@ -957,7 +1013,7 @@ el_vel_adj(ElGeom g, const ElCta* __restrict__ ctas, ElSlot b, ElSlot bout, ElSl
 #endif
   bool t_lo, t_hi;
   el_cta_edges(g, f, d, &t_lo, &t_hi);
-  el_fuse_wait(f, t_lo, t_hi);
+  el_fuse_wait(g, f, d, t_lo, t_hi);
   int ra = 0, rb = 0;
   if (rcv.blk != nullptr && res != nullptr) { ra = rcv.blk[bid]; rb = rcv.blk[bid + 1]; }
   if (d.kind == 0) {
@@ -1226,7 +1282,7 @@ el_sigma_adj(ElGeom g, const ElCta* __restrict__ ctas, ElSlot b, ElSlot bout, El
 #endif
   bool t_lo, t_hi;
   el_cta_edges(g, f, d, &t_lo, &t_hi);
-  el_fuse_wait(f, t_lo, t_hi);
+  el_fuse_wait(g, f, d, t_lo, t_hi);
   if (d.kind == 0) {
     double* ring = reinterpret_cast<double*>(el_smem + 64);
     el_sigma_adj_march<MATGRAD>(g, d, b, bout, fwdv, mt, Gl, Gm1, Gm2, ring, reinterpret_cast<unsigned long long*>(el_smem));
