@@ -395,9 +395,10 @@ ADSEIS_API int adseis_elastic_plan_create(adseis_ctx* ctx, const adseis_elastic_
           ctas.push_back(ElCta{0, mrt[tr], mrt[tr + 1], c0 + tc * EL_TCOLS, std::min(c1, c0 + (tc + 1) * EL_TCOLS), 0, 0, 0});
     }
     P->nmarch = (int)ctas.size();
-    // cells per thread of a generic CTA: 4 on large grids (fewer CTAs); 1 on slabs / small grids, where the launch
-    // is a single wave and its duration is the latency chain of the longest CTA
-    int gen_cpt = (sl.nranks > 1 || (i64)g.Hl * g.W < (i64)1500 * 1500) ? 1 : 4;
+    // cells per thread of a generic CTA: 2 on large grids (measured on B200, C5 2000^2, us per step forward / material
+    // gradient: 1 -> 148.5 / 392, 2 -> 148.7 / 368.5, 3 -> 146.9 / 382.6, 4 -> 146.8 / 395.6); 1 on slabs / small grids, where
+    // the launch is a single wave and its duration is the latency chain of the longest CTA
+    int gen_cpt = (sl.nranks > 1 || (i64)g.Hl * g.W < (i64)1500 * 1500) ? 1 : 2;
     if (getenv("ADSEIS_EL_CPT")) gen_cpt = std::max(1, atoi(getenv("ADSEIS_EL_CPT")));
     auto add_rect = [&](int rr0, int rr1, int cc0, int cc1) {
       if (rr1 <= rr0 || cc1 <= cc0) return;
