@@ -10,14 +10,16 @@
 #     SimulatedObservation!(ap, rcv)                                          (src/Core.jl:726)
 #     ElasticPropagatorParams / ElasticSource / ElasticReceiver               (src/Struct.jl:4-62)
 #     ElasticPropagatorSolver(param, src, ρ, λ, μ)                            (src/Core.jl:31)
-#     compute_loss_and_grads(param, src, rcv, Rs, c)                          (src/Utils.jl:300-332, one device)
+#     AcousticPlan / set_points! / gradient!, compute_loss_and_grads_GPU      (src/Utils.jl:300-332, shot k on device k % n)
+#     LBFGS!(loss_and_grad, x0)                                               (src/Optim.jl:135-193)
 module ADSeismicB200
 
 using Parameters
 export AcousticPropagatorParams, AcousticSource, AcousticReceiver, AcousticPropagator,
        AcousticPropagatorSolver, SimulatedObservation!, acoustic_misfit_grad,
        ElasticPropagatorParams, ElasticSource, ElasticReceiver, ElasticPropagator,
-       ElasticPropagatorSolver, elastic_misfit_grad
+       ElasticPropagatorSolver, elastic_misfit_grad,
+       AcousticPlan, set_points!, set_model!, set_srcv!, set_obs!, gradient!, compute_loss_and_grads_GPU, LBFGS!
 
 const libadseis = get(ENV, "ADSEIS_B200_LIB", joinpath(@__DIR__, "..", "adseismic.jl_b200", "libadseis_b200.so"))
 
@@ -121,6 +123,97 @@ function acoustic_misfit_grad(param::AcousticPropagatorParams, src::AcousticSour
         rcv.rcvi, rcv.rcvj, rowmajor(obs), loss, rcvv, gc, gs))
     rcv.rcvv = fromrowmajor(rcvv, param.NSTEP + 1, nrcv)
     loss[], fromrowmajor(gc, size(c, 1), size(c, 2)), fromrowmajor(gs, param.NSTEP, nsrc)
+end
+
+# ---- device-resident plan: one per GPU, re-pointed per shot (include/adseis.h: adseis_acoustic_plan_*) ----------------
+# The reference re-runs one Session graph per L-BFGS iteration and places shot k on device k % n_gpu
+# (src/Optim.jl:135-193, src/Utils.jl:300-332).  Here the device state (history window, checkpoints, adjoint planes)
+# lives in a plan that is created once per device; set_points! moves it to the next shot.
+mutable struct AcousticPlan
+    handle::Ptr{Cvoid}
+    param::AcousticPropagatorParams
+    nsrc::Int; nrcv::Int; shape::Tuple{Int,Int}
+    function AcousticPlan(param::AcousticPropagatorParams, src::AcousticSource, rcv::AcousticReceiver; context = ctx(),
+                          hist_bytes_budget::Integer = 0)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:adseis_acoustic_plan_create, libadseis), Cint,
+            (Ptr{Cvoid}, Ref{CAcousticParams}, Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64},
+             Csize_t, Ref{Ptr{Cvoid}}),
+            context.handle, toC(param), C_NULL, length(src.srci), src.srci, src.srcj, length(rcv.rcvi), rcv.rcvi, rcv.rcvj,
+            hist_bytes_budget, h))
+        shape = param.mpi_convention ? (param.NX, param.NY) : (param.NX + 2, param.NY + 2)
+        pl = new(h[], param, length(src.srci), length(rcv.rcvi), shape)
+        finalizer(x -> ccall((:adseis_acoustic_plan_destroy, libadseis), Cint, (Ptr{Cvoid},), x.handle), pl)
+        pl
+    end
+end
+function set_points!(pl::AcousticPlan, src::AcousticSource, rcv::AcousticReceiver)
+    check(ccall((:adseis_acoustic_plan_set_points, libadseis), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}),
+        pl.handle, length(src.srci), src.srci, src.srcj, length(rcv.rcvi), rcv.rcvi, rcv.rcvj))
+    pl.nsrc = length(src.srci); pl.nrcv = length(rcv.rcvi); pl
+end
+set_model!(pl::AcousticPlan, c::Matrix{Float64}) =
+    check(ccall((:adseis_acoustic_plan_set_model, libadseis), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), pl.handle, rowmajor(c), 0))
+set_srcv!(pl::AcousticPlan, srcv::Matrix{Float64}) =
+    check(ccall((:adseis_acoustic_plan_set_srcv, libadseis), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Cint),
+                pl.handle, rowmajor(srcv), size(srcv, 1), 0))
+set_obs!(pl::AcousticPlan, obs::Matrix{Float64}) =
+    check(ccall((:adseis_acoustic_plan_set_obs, libadseis), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), pl.handle, rowmajor(obs), 0))
+"forward + reverse sweep; returns (loss, grad_c) -- ADSEIS_GET_LOSS = 2, ADSEIS_GET_GRAD_C = 3 (include/adseis.h:125-129)"
+function gradient!(pl::AcousticPlan)
+    check(ccall((:adseis_acoustic_plan_gradient, libadseis), Cint, (Ptr{Cvoid},), pl.handle))
+    loss = Vector{Float64}(undef, 1); gc = Vector{Float64}(undef, prod(pl.shape))
+    check(ccall((:adseis_acoustic_plan_get, libadseis), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint), pl.handle, 2, loss, 0))
+    check(ccall((:adseis_acoustic_plan_get, libadseis), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint), pl.handle, 3, gc, 0))
+    loss[1], fromrowmajor(gc, pl.shape[1], pl.shape[2])
+end
+
+"""
+compute_loss_and_grads_GPU(param, srcs, rcvs, Rs, c; contexts): src/Utils.jl:300-332 -- sum over shots of
+sum((rcvv - Rs[k]).^2) and its gradient w.r.t. c.  Shot k (1-based) runs on contexts[k % n + 1 ...] exactly as the
+reference deals shots to `/gpu:(k % n_gpu)`; one plan per device is created on first use and re-pointed per shot.
+(One Julia task per device; the C calls of different contexts do not share state.)
+"""
+function compute_loss_and_grads_GPU(param::AcousticPropagatorParams, srcs::Vector{AcousticSource},
+                                    rcvs::Vector{AcousticReceiver}, Rs::Vector{Matrix{Float64}}, c::Matrix{Float64};
+                                    contexts::Vector{Context} = [ctx()], plans = Dict{Int,AcousticPlan}())
+    n = length(contexts)
+    partial = Vector{Tuple{Float64,Matrix{Float64}}}(undef, n)
+    @sync for d in 1:n
+        Threads.@spawn begin
+            L = 0.0; G = zeros(size(c))
+            for k in 1:length(srcs)
+                k % n == d - 1 || continue                       # src/Utils.jl:326
+                pl = get!(plans, d) do
+                    AcousticPlan(param, srcs[k], rcvs[k]; context = contexts[d])
+                end
+                set_points!(pl, srcs[k], rcvs[k]); set_model!(pl, c); set_srcv!(pl, srcs[k].srcv); set_obs!(pl, Rs[k])
+                l, g = gradient!(pl)
+                L += l; G .+= g
+            end
+            partial[d] = (L, G)
+        end
+    end
+    sum(first, partial), sum(last, partial)
+end
+
+"""
+LBFGS!(loss_and_grad, x0; max_iter): the role of src/Optim.jl:135-193 (`LBFGS!(sess, loss, grads, vars)` around
+Optim.jl's L-BFGS) without a TensorFlow session: `loss_and_grad(x) -> (loss, grad)` is evaluated eagerly.
+"""
+function LBFGS!(loss_and_grad::Function, x0::Array{Float64}; max_iter::Int = 15000, callback = nothing)
+    Optim = Base.require(Base.PkgId(Base.UUID("429524aa-4258-5aef-a3af-852621145aeb"), "Optim"))
+    losses = Float64[]
+    fg!(F, G, x) = begin
+        l, g = loss_and_grad(x)
+        G === nothing || (G .= g)
+        push!(losses, l)
+        l
+    end
+    Base.invokelatest(Optim.optimize, Optim.only_fg!(fg!), x0, Optim.LBFGS(),
+                      Optim.Options(iterations = max_iter, callback = callback === nothing ? (_ -> false) : callback))
+    losses
 end
 
 # ---- elastic -----------------------------------------------------------------------------------------------------
