@@ -200,7 +200,7 @@ struct adseis_acoustic_plan {
   AcTiling tp{};
   int nblocksP = 0;
   PointSetStorage srcP{}, rcvP{};
-  unsigned long long* pbar = nullptr;
+  unsigned long long* pbar = nullptr;        // [0] grid barrier counter, [1 ...] per-CTA progress
   int hd = 1;                                // halo rows per neighbour (2 for PropagatorKernel = 0, whose phi'/psi' read u' one row further)
   bool unfused = false;                      // slab plan whose step launches do not exchange: an explicit exchange follows every launch
   PointSetStorage srcK{};                    // PropagatorKernel = 0 on slabs: sources within one row of my rows (c-gradient correction)
@@ -1322,9 +1322,21 @@ static AcPersist persist_args(adseis_acoustic_plan* P) {
 template <class K>
 static int launch_persist(adseis_acoustic_plan* P, K kernel, AcPersist a) {
   cudaStream_t st = P->ctx->stream;
-  if (!P->pbar) TRY(dev_alloc_zero(&P->pbar, 1, st));
+  const size_t nb = (size_t)P->nblocksP + 1;
+  if (!P->pbar) TRY(dev_alloc_zero(&P->pbar, nb, st));
   a.bar = P->pbar;
-  CUDA_TRY(cudaMemsetAsync(P->pbar, 0, 8, st));
+  CUDA_TRY(cudaMemsetAsync(P->pbar, 0, nb * 8, st));
+  {
+    // grid barrier (default) or per-CTA progress flags of the neighbours only (ADSEIS_AC_PERSIST_SYNC=1; a step reads one
+    // row / column around a cell with scheme 1, two with scheme 0).  Measured on B200, C1: the flags are SLOWER -- 12.0 vs
+    // 8.1 us per step pair (a release fence + up to nine acquire polls per CTA and step against one atomic + one poll)
+    const char* e = getenv("ADSEIS_AC_PERSIST_SYNC");
+    const i64 per = (i64)P->tp.fthr * P->tp.fcpt, reach = (P->p.PropagatorKernel == 0 ? 2 : 1) * (i64)P->g.W + 2;
+    const i64 dep = (reach + per - 1) / per;
+    if ((e && e[0] == '1') && 2 * dep + 1 <= AC_PS_THREADS) {
+      a.prog = P->pbar + 1; a.dep_lo = (int)dep; a.dep_hi = (int)dep;
+    }
+  }
   AcGeom g = P->g;
   AcTiling t = P->tp;
   void* args[3] = {&g, &t, &a};

@@ -1077,6 +1077,12 @@ struct AcPersist {
   double* ut[2];                           // PropagatorKernel = 0: utilde side planes
   const double* res; double* gradsrcv;
   unsigned long long* bar;                 // grid barrier counter (zero at launch)
+  // Neighbour synchronisation instead of the grid barrier: prog[b] = steps CTA b has finished.  A CTA's cells are a
+  // contiguous range of the row-major cell list, and a step reads at most `reach` rows / columns around a cell, so CTA b
+  // depends on the CTAs covering [first - reach*W, last + reach*W] only.  The same wait covers the write-after-read
+  // hazard of the ping-pong arrays (my dependents are my dependencies).
+  unsigned long long* prog;                // null: grid barrier
+  int dep_lo, dep_hi;                      // CTA b waits for CTAs b - dep_lo .. b + dep_hi (clipped to the grid)
 };
 
 // all CTAs of the (cooperative) launch; `target` = arrivals expected so far
@@ -1088,6 +1094,26 @@ __device__ __forceinline__ void ac_grid_barrier(unsigned long long* bar, unsigne
     unsigned long long v;
     do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory"); } while (v < target);
     __threadfence();
+  }
+  __syncthreads();
+}
+
+// step `done` of this CTA is finished (all its stores issued): publish, then wait until the CTAs it depends on have
+// finished the same step
+__device__ __forceinline__ void ac_neighbour_sync(const AcPersist& a, unsigned long long done) {
+  __syncthreads();
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(a.prog + b), "l"(done) : "memory");
+  }
+  const int n = a.dep_lo + a.dep_hi + 1;
+  if ((int)threadIdx.x < n) {
+    const int q = b - a.dep_lo + (int)threadIdx.x;
+    if (q >= 0 && q < (int)gridDim.x && q != b) {
+      unsigned long long v;
+      do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.prog + q) : "memory"); } while (v < done);
+    }
   }
   __syncthreads();
 }
@@ -1118,7 +1144,8 @@ __global__ void __launch_bounds__(AC_PS_THREADS, 2) ac_fwd_persist_kernel(AcGeom
     ac_cta_epilogue(bid, u, a.src, a.nsrc > 0 ? a.srcv + (s - 1) * a.nsrc : nullptr, g.dt2, a.rcvv ? a.rcv : none,
                     (a.rcvv && a.nrcv > 0) ? a.rcvv + s * a.nrcv : nullptr, 1.0);
     arrivals += gridDim.x;
-    ac_grid_barrier(a.bar, arrivals);
+    if (a.prog) ac_neighbour_sync(a, arrivals / gridDim.x);
+    else ac_grid_barrier(a.bar, arrivals);
   }
 }
 
@@ -1149,7 +1176,8 @@ __global__ void __launch_bounds__(AC_PS_THREADS, 2) ac_adj_persist_kernel(AcGeom
     ac_cta_epilogue(bid, ub0, a.rcv, a.nrcv > 0 ? a.res + (s - 1) * a.nrcv : nullptr, 1.0, (s - 2 >= 1) ? a.src : none,
                     (s - 2 >= 1 && a.nsrc > 0) ? a.gradsrcv + (s - 2) * a.nsrc : nullptr, g.dt2);
     arrivals += gridDim.x;
-    ac_grid_barrier(a.bar, arrivals);
+    if (a.prog) ac_neighbour_sync(a, arrivals / gridDim.x);
+    else ac_grid_barrier(a.bar, arrivals);
   }
 }
 
