@@ -192,3 +192,34 @@ def test_plan_window_budget():
             assert W + 1 + 4 * (nseg1 - 1) > slots
     with pytest.raises(MemoryError):
         plan_window(1000, 5)
+
+
+def test_packed_halo_words_roundtrip():
+    """The slab halo rows travel as 8-byte words = 32 data bits + the sender's 32-bit launch epoch, two words per double
+    (csrc/common.cuh: ll_put / ll_get).  NumPy restatement of that packing: every bit pattern survives (NaN payloads, -0.0,
+    denormals), and a pair whose words carry different epochs -- a torn or stale read -- is never accepted."""
+    rng = np.random.default_rng(5)
+    bits = rng.integers(0, 2**64, 4096, dtype=np.uint64)
+    bits[:6] = np.array([0.0, -0.0, 5e-324, np.inf, -np.inf, np.nan]).view(np.uint64)
+    ep = np.uint64(0x9E3779B9)
+
+    def put(b, e):
+        return (e << np.uint64(32)) | (b & np.uint64(0xFFFFFFFF)), (e << np.uint64(32)) | (b >> np.uint64(32))
+
+    def get(x, y, e):
+        ok = ((x >> np.uint64(32)) == e) & ((y >> np.uint64(32)) == e)
+        return ok, (x & np.uint64(0xFFFFFFFF)) | (y << np.uint64(32))
+
+    x, y = put(bits, ep)
+    ok, back = get(x, y, ep)
+    assert ok.all() and np.array_equal(back, bits)
+    # the receiver of launch n+2 polls the same parity buffer that still holds epoch n: not accepted
+    ok_old, _ = get(x, y, ep + np.uint64(2))
+    assert not ok_old.any()
+    # torn pair: low word already rewritten by the next sender, high word still the old one
+    x2, _ = put(bits ^ np.uint64(1), ep + np.uint64(2))
+    ok_torn, _ = get(x2, y, ep + np.uint64(2))
+    assert not ok_torn.any()
+    # epoch 0 is "never written" (the arena is zero-filled): a launch that expects epoch >= 1 never accepts zeros
+    ok_zero, _ = get(np.zeros(4, np.uint64), np.zeros(4, np.uint64), np.uint64(1))
+    assert not ok_zero.any()
