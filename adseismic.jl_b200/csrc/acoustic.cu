@@ -1579,6 +1579,10 @@ static int gradient_body(adseis_acoustic_plan* P) {
     const i64 b = P->seg_b[k], e = P->seg_e[k];
     if (k != (i64)nseg - 1) {
       // restore the start state of segment k and recompute its forward steps (bit-identical replay)
+      // (packed halo rows: the first replay launch receives nothing, so nothing proves that the neighbour has consumed
+      // the words its own last adjoint launch still needs before this rank overwrites them two launches later -- a
+      // handshake closes that window)
+      if (P->arena && P->ll) TRY(halo_exchange(P, 0, nullptr, nullptr));
       if (k == 0) {
         CUDA_TRY(cudaMemsetAsync(P->hist, 0, 2 * pb, st));
         CUDA_TRY(cudaMemsetAsync(P->phi[1], 0, pb, st));

@@ -950,6 +950,7 @@ ADSEIS_API int adseis_elastic_plan_gradient(adseis_elastic_plan* P, int want_mat
       if (k != (i64)nseg - 1) {  // restore the first slot of segment k and replay its forward steps
         if (k == 0) CUDA_TRY(cudaMemsetAsync(P->hist, 0, sb, st));
         else CUDA_TRY(cudaMemcpyAsync(P->hist, P->ckpt[k - 1], sb, cudaMemcpyDeviceToDevice, st));
+        if (P->ll) TRY(el_barrier(P));   // handshake: the neighbour is done with the words of my last adjoint launches
         P->ll_prev_nf = 0;   // the previous fused launch was an adjoint one: nothing to receive
         for (i64 s = b + 1; s <= e; s++) TRY(el_step_forward(P, s, win_ptr(P, b, s - 1), win_ptr(P, b, s), false));
         P->last_recomputed += e - b;
