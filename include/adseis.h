@@ -97,7 +97,10 @@ int adseis_slab_partition(int64_t NX, int32_t nranks, int32_t rank, adseis_slab*
  * When the full history (NSTEP+1 snapshots) does not fit, gradients use segment checkpointing with one
  * bit-identical forward recomputation per segment.
  * slab == NULL: single GPU.  Sources / receivers are given with GLOBAL indices; a slab plan keeps the ones it
- * owns (MPIAcoustic.jl:71-78, 98-104). */
+ * owns (MPIAcoustic.jl:71-78, 98-104) and ignores the rest, so every rank may pass the full lists.  With
+ * PropagatorKernel = 0 a slab plan must at least be given, besides its own sources, the sources on the row just
+ * outside either end of its slab (their injected part is removed from c-gradient terms of its own cells);
+ * srcv / grad_srcv keep one column per source passed, columns of sources owned elsewhere stay zero. */
 int adseis_acoustic_plan_create(adseis_ctx* ctx, const adseis_acoustic_params* p, const adseis_slab* slab,
                                 int64_t nsrc, const int64_t* srci, const int64_t* srcj, int64_t nrcv,
                                 const int64_t* rcvi, const int64_t* rcvj, size_t hist_bytes_budget,
